@@ -1,0 +1,139 @@
+/*
+ * relpose_b200 -- C ABI of the B200 (sm_100a) compute library behind the rel_pose hot path.
+ *
+ * The reference (crockwell/rel_pose @35d1352) is pure Python: its "operator interface" for this
+ * path is the nn.Module `ViTEss` (src/model.py:11-191) plus the third-party `lietorch.SE3`
+ * type (environment.yml:20).  There is no FFI in the reference; this header is the boundary a
+ * maintainer would bind with ctypes.  Each entry point cites the reference
+ * lines whose arithmetic it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - tensors are dense row-major float32 unless stated otherwise, 16-byte aligned;
+ *   - `device` is the CUDA ordinal that owns the buffers, `stream` a cudaStream_t on it
+ *     (passed as void*); the call enqueues work and returns, it never synchronises, allocates
+ *     or frees;
+ *   - the caller owns inputs, outputs and workspaces and keeps them alive until the stream has
+ *     passed the call;
+ *   - return 0 on success; a negative RP_E* code for bad arguments; a positive cudaError_t for
+ *     CUDA failures.  rp_last_error() returns a thread-local message.  Nothing throws.
+ *   - stateless and re-entrant (autograd calls the *_bwd entry points from its own threads).
+ */
+#ifndef RELPOSE_B200_H
+#define RELPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RP_OK 0
+#define RP_EINVAL (-1)    /* bad shape / null pointer / unsupported size */
+#define RP_EALIGN (-2)    /* pointer not 16-byte aligned */
+#define RP_EWORKSPACE (-3) /* workspace too small */
+
+/* epilogue activations of rp_linear_f32 */
+#define RP_ACT_NONE 0
+#define RP_ACT_GELU 1     /* exact erf GELU, vit_layers/mlp.py:22 */
+#define RP_ACT_RELU 2     /* src/model.py:93,95 */
+
+/* fixed geometry of the path (src/model.py:19-23, vision_transformer.py:409-424) */
+#define RP_GRID 24
+#define RP_NTOK 576
+#define RP_EMBED 192
+#define RP_HEADS 3
+#define RP_HDIM 64
+#define RP_NPOS 6
+#define RP_EMW 70         /* HDIM + NPOS */
+
+const char* rp_last_error(void);
+int rp_version(void);
+/* Compute capability major*10+minor of `device` (100 on B200), or a negative code. */
+int rp_device_arch(int device);
+
+/* ---- A1  src/model.py:114-125 -------------------------------------------------------------
+ * images [n_img,3,H,W] BGR 0..255  ->  out [n_img,3,224,224] RGB, (x/255-mean)/std, legacy
+ * nearest resize (src = floor(dst*in/out)).  Bit-exact w.r.t. the reference's float32 ops. */
+int rp_preprocess_f32(const float* images, float* out, int n_img, int H, int W, int device, void* stream);
+/* same from uint8 pixels (cv2.imread layout converted to NCHW by the caller) */
+int rp_preprocess_u8(const uint8_t* images, float* out, int n_img, int H, int W, int device, void* stream);
+
+/* ---- src/model.py:100-109 + vision_transformer.py:117-145 -----------------------------------
+ * In place: fx,cx *= 24/W ; fy,cy *= 24/H on intrinsics [B,2,4]; writes kxy [B,2] =
+ * (1/(fx/cx), 1/(fy/cy)) of view 0 (the diagonal of the reference's K^-1) and sets
+ * flags[0] |= 1 if any pair has intrinsics[:,0] != intrinsics[:,1], |= 2 if cx*cy == 0 for
+ * pair 0 (the two conditions the reference asserts on).  flags must be zeroed by the caller. */
+int rp_intrinsics_prepare_f32(float* intrinsics, float* kxy, int* flags, int B, int H, int W, int device, void* stream);
+
+/* ---- A4  src/model.py:136-141,172 ---------------------------------------------------------
+ * fmap [n_img,192,576] (NCHW feature map, 24x24 flattened) -> x [n_img,576,192] + pos_embed[576,192] */
+int rp_tokens_posembed_f32(const float* fmap, const float* pos_embed, float* x, int n_img, int device, void* stream);
+
+/* ---- LayerNorm  vision_transformer.py:396 (eps 1e-6), rows x cols, cols <= 1024 ------------ */
+int rp_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int rows, int cols,
+                     float eps, int device, void* stream);
+
+/* ---- nn.Linear with fused epilogue  (vision_transformer.py:323,331; mlp.py:21-24; model.py:91-98)
+ * C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) + residual[M,N]    (bias, residual may be NULL;
+ * residual may alias C).  K % 4 == 0.  workspace: rp_linear_workspace_bytes(M,N,K) bytes (may be 0). */
+size_t rp_linear_workspace_bytes(int M, int N, int K);
+int rp_linear_f32(const float* A, const float* W, const float* bias, const float* residual, float* C,
+                  int M, int N, int K, int act, void* workspace, size_t workspace_bytes, int device, void* stream);
+
+/* ---- A5 attention core  vision_transformer.py:323-329 --------------------------------------
+ * qkv [n_img,576,576] (column = s*192+h*64+d)  ->  out [n_img,576,192] (column = h*64+d),
+ * out = softmax(q k^T * 0.125) v per image and head; nothing is materialised in HBM. */
+int rp_self_attention_f32(const float* qkv, float* out, int n_img, int device, void* stream);
+
+/* ---- A6  vision_transformer.py:90-158 ------------------------------------------------------
+ * pos [B,576,6] = [p3^2,p4^2,p3*p4,p3,p4,1], p3 = ys[i%24]*ky, p4 = xs[i/24]*kx (transposed grid).
+ * lin24: host pointer to the 24 floats of torch.linspace(-1,1,24); kxy [B,2] from
+ * rp_intrinsics_prepare_f32 or NULL (intrinsics=None: kx = ky = 1 without multiplication). */
+int rp_posenc_f32(const float* kxy, const float* host_lin24, float* pos, int B, int device, void* stream);
+
+/* ---- A7 Essential Matrix Module core  vision_transformer.py:198-223 -------------------------
+ * qkv [2B,576,576] with the two views of pair b at rows 2b, 2b+1; pos [B,576,6] or NULL
+ * (no_pos_encoding); out bil [B,2,3,W,W], W = 70 (64 if pos == NULL):
+ *   bil[b,0,h] = V1^T A1 V1,  A1 = softmax(S1,-1)*softmax(S1,-2),  S1 = q2 k1^T * 0.125
+ *   bil[b,1,h] = V2^T A2 V2,  A2 likewise from S2 = q1 k2^T * 0.125,   V = [v | pos].
+ * The 576x576 affinities never leave the chip.  workspace: rp_essential_workspace_bytes(B). */
+size_t rp_essential_workspace_bytes(int B);
+int rp_essential_f32(const float* qkv, const float* pos, float* bil, int B, void* workspace,
+                     size_t workspace_bytes, int device, void* stream);
+
+/* ---- A7 tail  vision_transformer.py:229-238 + :292-294 --------------------------------------
+ * Z[b,c,h*70+a] = bil[b,dir,h,a,c];  Y = Z W^T + bias (proj_fundamental, W [192,210]);
+ * out [2B,70,192] with out[2b] = Y from bil[b,1] and out[2b+1] = Y from bil[b,0] (the flip). */
+int rp_em_project_f32(const float* bil, const float* W, const float* bias, float* out, int B, int device, void* stream);
+
+/* ---- A10  src/model.py:145-152 --------------------------------------------------------------
+ * raw [B,2,7], Gs [B,2,7] -> out [B,2,7]: out[:,0] = Gs[:,0]; out[:,1] = raw[:,1] with the
+ * quaternion divided by max(||q||, 0.01). */
+int rp_normalize_pose_f32(const float* raw, const float* Gs, float* out, int B, int device, void* stream);
+
+/* ---- A12 lietorch SE3 (lietorch==0.2; call sites src/geom/losses.py:8-10) --------------------
+ * Elements are 7 floats [t, q_xyzw]; tangents 6 floats [tau, phi].  n = number of elements.
+ * Quaternions are re-normalised on load, as lietorch's SO3 constructor does.
+ * Backward = lietorch's convention: gradient of a LEFT perturbation exp(d)X, written into the
+ * first 6 of 7 slots (slot 7 = 0). */
+int rp_se3_mul_fwd_f32(const float* X, const float* Y, float* Z, int64_t n, int device, void* stream);
+int rp_se3_mul_bwd_f32(const float* dZ, const float* X, const float* Y, float* dX, float* dY, int64_t n, int device, void* stream);
+int rp_se3_inv_fwd_f32(const float* X, float* Y, int64_t n, int device, void* stream);
+int rp_se3_inv_bwd_f32(const float* dY, const float* X, float* dX, int64_t n, int device, void* stream);
+int rp_se3_log_fwd_f32(const float* X, float* a, int64_t n, int device, void* stream);
+int rp_se3_log_bwd_f32(const float* da, const float* X, float* dX, int64_t n, int device, void* stream);
+int rp_se3_exp_fwd_f32(const float* a, float* X, int64_t n, int device, void* stream);
+int rp_se3_exp_bwd_f32(const float* dX, const float* a, float* da, int64_t n, int device, void* stream);
+
+/* ---- BASELINE.json config 3 (no reference counterpart; oracle = LAPACK, parity unpinned) -----
+ * E [n,3,3] -> U [n,3,3], S [n,3] (descending, >= 0), V [n,3,3] with E = U diag(S) V^T. */
+int rp_svd3_f32(const float* E, float* U, float* S, float* V, int64_t n, int device, void* stream);
+/* E [n,3,3] -> R1 = U W V^T, R2 = U W^T V^T (det +1), t = U[:,2]   ([n,3,3],[n,3,3],[n,3]) */
+int rp_essential_to_rt_f32(const float* E, float* R1, float* R2, float* t, int64_t n, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RELPOSE_B200_H */

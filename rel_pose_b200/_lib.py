@@ -1,0 +1,93 @@
+"""ctypes binding of librelpose_b200.so (the C ABI declared in include/relpose_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or cannot be loaded every
+compute entry point raises.  Build it with `python -c "import __graft_entry__ as g; g.build()"`
+or `make -C rel_pose_b200/csrc`.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librelpose_b200.so")
+
+_c_int = ctypes.c_int
+_c_i64 = ctypes.c_int64
+_c_f32 = ctypes.c_float
+_c_size = ctypes.c_size_t
+_ptr = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/relpose_b200.h one to one
+_SIGNATURES = {
+    "rp_last_error": (ctypes.c_char_p, []),
+    "rp_version": (_c_int, []),
+    "rp_device_arch": (_c_int, [_c_int]),
+    "rp_preprocess_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_preprocess_u8": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_intrinsics_prepare_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_tokens_posembed_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_layernorm_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_f32, _c_int, _ptr]),
+    "rp_linear_workspace_bytes": (_c_size, [_c_int, _c_int, _c_int]),
+    "rp_linear_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _c_size, _c_int, _ptr]),
+    "rp_self_attention_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_posenc_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_essential_workspace_bytes": (_c_size, [_c_int]),
+    "rp_essential_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _ptr, _c_size, _c_int, _ptr]),
+    "rp_em_project_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_normalize_pose_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_se3_mul_fwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_se3_mul_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_se3_inv_fwd_f32": (_c_int, [_ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_se3_inv_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_se3_log_fwd_f32": (_c_int, [_ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_se3_log_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_se3_exp_fwd_f32": (_c_int, [_ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_se3_exp_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_svd3_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_essential_to_rt_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class RelposeLibraryError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises RelposeLibraryError if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise RelposeLibraryError(
+                f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+                "(run `make -C rel_pose_b200/csrc`); rel_pose_b200 has no CPU / PyTorch fallback.")
+        try:
+            handle = ctypes.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise RelposeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(handle, name)
+            except AttributeError as e:
+                raise RelposeLibraryError(f"{LIB_PATH} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().rp_last_error()
+        msg = msg.decode("utf-8", "replace") if msg else ""
+        raise RelposeLibraryError(f"{what or 'relpose_b200'} failed (code {rc}): {msg}")

@@ -1,0 +1,257 @@
+// Elementwise / gather / normalisation kernels of the rel_pose hot path (HBM-bound work).
+// Reference rows: A1 (src/model.py:114-125), A4 (:136-141,172), LayerNorm (vision_transformer.py:396),
+// A6 (vision_transformer.py:90-158), A10 (src/model.py:145-152).
+#include "common.cuh"
+
+#include <string.h>
+
+namespace rp {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace rp
+
+extern "C" const char* rp_last_error(void) { return rp::g_err; }
+extern "C" int rp_version(void) { return 100; }
+extern "C" int rp_device_arch(int device) {
+    int major = 0, minor = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+    if (e != cudaSuccess) {
+        rp::set_error("rp_device_arch: %s", cudaGetErrorString(e));
+        return -(int)e;
+    }
+    return major * 10 + minor;
+}
+
+// ------------------------------------------------------------------------------------------ A1
+// One thread per output pixel (all three channels): out[n,c,oy,ox] = ((img[n,2-c,iy,ix]/255)-mean[c])/std[c].
+// Writes are fully coalesced; reads are a strided gather inside one input row (L1/L2 absorb it).
+template <typename T>
+__global__ void __launch_bounds__(256) preprocess_kernel(const T* __restrict__ img, float* __restrict__ out,
+                                                          int n_img, int H, int W, float scale_h, float scale_w) {
+    const int OUT = 224;
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float stdv[3] = {0.229f, 0.224f, 0.225f};
+    long long total = (long long)n_img * OUT * OUT;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int ox = (int)(idx % OUT);
+        int oy = (int)((idx / OUT) % OUT);
+        int n = (int)(idx / (OUT * OUT));
+        int ix = min((int)floorf(__fmul_rn((float)ox, scale_w)), W - 1);
+        int iy = min((int)floorf(__fmul_rn((float)oy, scale_h)), H - 1);
+        const T* src = img + ((long long)n * 3) * H * W + (long long)iy * W + ix;
+        float* dst = out + ((long long)n * 3) * OUT * OUT + (long long)oy * OUT + ox;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = (float)src[(long long)(2 - c) * H * W];       // BGR -> RGB
+            v = __fdiv_rn(v, 255.0f);
+            v = __fsub_rn(v, mean[c]);
+            v = __fdiv_rn(v, stdv[c]);
+            dst[(long long)c * OUT * OUT] = v;
+        }
+    }
+}
+
+template <typename T>
+static int preprocess_launch(const T* images, float* out, int n_img, int H, int W, int device, void* stream) {
+    RP_REQUIRE(images && out, RP_EINVAL, "rp_preprocess: null pointer");
+    RP_REQUIRE(n_img > 0 && H > 0 && W > 0, RP_EINVAL, "rp_preprocess: bad shape n_img=%d H=%d W=%d", n_img, H, W);
+    RP_GUARD(device);
+    long long total = (long long)n_img * 224 * 224;
+    int blocks = (int)min((total + 255) / 256, (long long)rp::num_sms(device) * 16);
+    float sh = (float)H / (float)224, sw = (float)W / (float)224;   // ATen: scale = (float)in / out
+    preprocess_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(images, out, n_img, H, W, sh, sw);
+    return rp::finish_launch("rp_preprocess");
+}
+
+extern "C" int rp_preprocess_f32(const float* images, float* out, int n_img, int H, int W, int device, void* stream) {
+    return preprocess_launch<float>(images, out, n_img, H, W, device, stream);
+}
+extern "C" int rp_preprocess_u8(const uint8_t* images, float* out, int n_img, int H, int W, int device, void* stream) {
+    return preprocess_launch<uint8_t>(images, out, n_img, H, W, device, stream);
+}
+
+// ------------------------------------------------------------------- intrinsics (model.py:100-109)
+__global__ void intrinsics_prepare_kernel(float* __restrict__ intr, float* __restrict__ kxy, int* __restrict__ flags,
+                                          int B, float sx, float sy) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float k[2][4];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        float4 q = reinterpret_cast<float4*>(intr)[b * 2 + v];
+        k[v][0] = __fmul_rn(sx, q.x);   // fx
+        k[v][1] = __fmul_rn(sy, q.y);   // fy
+        k[v][2] = __fmul_rn(sx, q.z);   // cx
+        k[v][3] = __fmul_rn(sy, q.w);   // cy
+        reinterpret_cast<float4*>(intr)[b * 2 + v] = make_float4(k[v][0], k[v][1], k[v][2], k[v][3]);
+    }
+    int f = 0;
+    if (k[0][0] != k[1][0] || k[0][1] != k[1][1] || k[0][2] != k[1][2] || k[0][3] != k[1][3]) f |= 1;
+    if (b == 0 && __fmul_rn(k[0][2], k[0][3]) == 0.0f) f |= 2;
+    if (f) atomicOr(flags, f);
+    // K = diag(fx/cx, fy/cy, 1) after the reference's pixel->[-1,1] normalisation; K^-1 diagonal:
+    float fxn = __fmul_rn(__fdiv_rn(k[0][0], __fmul_rn(k[0][2], 2.0f)), 2.0f);
+    float fyn = __fmul_rn(__fdiv_rn(k[0][1], __fmul_rn(k[0][3], 2.0f)), 2.0f);
+    kxy[b * 2 + 0] = __fdiv_rn(1.0f, fxn);
+    kxy[b * 2 + 1] = __fdiv_rn(1.0f, fyn);
+}
+
+extern "C" int rp_intrinsics_prepare_f32(float* intrinsics, float* kxy, int* flags, int B, int H, int W, int device,
+                                         void* stream) {
+    RP_REQUIRE(intrinsics && kxy && flags, RP_EINVAL, "rp_intrinsics_prepare: null pointer");
+    RP_REQUIRE(B > 0 && H > 0 && W > 0, RP_EINVAL, "rp_intrinsics_prepare: bad shape");
+    RP_REQUIRE(rp::aligned16(intrinsics), RP_EALIGN, "rp_intrinsics_prepare: intrinsics not 16-byte aligned");
+    RP_GUARD(device);
+    float sx = (float)(24.0 / (double)W), sy = (float)(24.0 / (double)H);
+    intrinsics_prepare_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(intrinsics, kxy, flags, B, sx, sy);
+    return rp::finish_launch("rp_intrinsics_prepare");
+}
+
+// ------------------------------------------------------------------------------------------ A4
+// [n,192,576] -> [n,576,192] (+pos_embed): 32x32 shared-memory tile transpose, both sides coalesced.
+__global__ void __launch_bounds__(256) tokens_posembed_kernel(const float* __restrict__ fmap,
+                                                              const float* __restrict__ pos, float* __restrict__ x) {
+    __shared__ float tile[32][33];
+    const int C = RP_EMBED, N = RP_NTOK;
+    int n = blockIdx.z;
+    int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const float* src = fmap + (long long)n * C * N;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = src[(long long)(c0 + r) * N + t0 + tx];
+    __syncthreads();
+    float* dst = x + (long long)n * N * C;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        int t = t0 + r, c = c0 + tx;
+        dst[(long long)t * C + c] = tile[tx][r] + pos[t * C + c];
+    }
+}
+
+extern "C" int rp_tokens_posembed_f32(const float* fmap, const float* pos_embed, float* x, int n_img, int device,
+                                      void* stream) {
+    RP_REQUIRE(fmap && pos_embed && x && n_img > 0, RP_EINVAL, "rp_tokens_posembed: bad argument");
+    RP_GUARD(device);
+    dim3 grid(RP_NTOK / 32, RP_EMBED / 32, n_img);
+    tokens_posembed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fmap, pos_embed, x);
+    return rp::finish_launch("rp_tokens_posembed");
+}
+
+// ----------------------------------------------------------------------------------- LayerNorm
+// One warp per row; the row lives in registers (cols <= 32*PER); two-pass mean / variance.
+template <int PER>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                        const float* __restrict__ b, float* __restrict__ y, int rows,
+                                                        int cols, float eps) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* xr = x + (long long)warp * cols;
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        v[i] = (c < cols) ? xr[c] : 0.f;
+        s += v[i];
+    }
+    float mean = rp::warp_sum(s) / (float)cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        float d = (c < cols) ? v[i] - mean : 0.f;
+        q += d * d;
+    }
+    float rstd = 1.0f / sqrtf(rp::warp_sum(q) / (float)cols + eps);   // IEEE sqrt + div (no fast-math)
+    float* yr = y + (long long)warp * cols;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        if (c < cols) yr[c] = (v[i] - mean) * rstd * g[c] + b[c];
+    }
+}
+
+extern "C" int rp_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int rows, int cols,
+                                float eps, int device, void* stream) {
+    RP_REQUIRE(x && gamma && beta && y, RP_EINVAL, "rp_layernorm: null pointer");
+    RP_REQUIRE(rows > 0 && cols > 0 && cols <= 1024, RP_EINVAL, "rp_layernorm: bad shape rows=%d cols=%d", rows, cols);
+    RP_GUARD(device);
+    int blocks = (rows + 7) / 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cols <= 256)
+        layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps);
+    else
+        layernorm_kernel<32><<<blocks, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps);
+    return rp::finish_launch("rp_layernorm");
+}
+
+// ------------------------------------------------------------------------------------------ A6
+struct Lin24 {
+    float v[RP_GRID];
+};
+
+__global__ void posenc_kernel(const float* __restrict__ kxy, Lin24 lin, float* __restrict__ pos, int B) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * RP_NTOK) return;
+    int b = idx / RP_NTOK, i = idx % RP_NTOK;
+    float p3 = lin.v[i % RP_GRID];   // "y" runs with the FAST token index (transposed grid)
+    float p4 = lin.v[i / RP_GRID];
+    if (kxy) {
+        p4 = __fmul_rn(kxy[b * 2 + 0], p4);
+        p3 = __fmul_rn(kxy[b * 2 + 1], p3);
+    }
+    float* o = pos + (long long)idx * RP_NPOS;
+    o[0] = __fmul_rn(p3, p3);
+    o[1] = __fmul_rn(p4, p4);
+    o[2] = __fmul_rn(p3, p4);
+    o[3] = p3;
+    o[4] = p4;
+    o[5] = 1.0f;
+}
+
+extern "C" int rp_posenc_f32(const float* kxy, const float* host_lin24, float* pos, int B, int device, void* stream) {
+    RP_REQUIRE(host_lin24 && pos && B > 0, RP_EINVAL, "rp_posenc: bad argument");
+    RP_GUARD(device);
+    Lin24 lin;
+    memcpy(lin.v, host_lin24, sizeof(lin.v));
+    int total = B * RP_NTOK;
+    posenc_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kxy, lin, pos, B);
+    return rp::finish_launch("rp_posenc");
+}
+
+// ----------------------------------------------------------------------------------------- A10
+__global__ void normalize_pose_kernel(const float* __restrict__ raw, const float* __restrict__ Gs,
+                                      float* __restrict__ out, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* g = Gs + (long long)b * 14;
+    const float* r = raw + (long long)b * 14 + 7;
+    float* o = out + (long long)b * 14;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) o[i] = g[i];
+    float qx = r[3], qy = r[4], qz = r[5], qw = r[6];
+    float n = sqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
+    float d = fmaxf(n, 0.01f);
+    o[7] = r[0];
+    o[8] = r[1];
+    o[9] = r[2];
+    o[10] = __fdiv_rn(qx, d);
+    o[11] = __fdiv_rn(qy, d);
+    o[12] = __fdiv_rn(qz, d);
+    o[13] = __fdiv_rn(qw, d);
+}
+
+extern "C" int rp_normalize_pose_f32(const float* raw, const float* Gs, float* out, int B, int device, void* stream) {
+    RP_REQUIRE(raw && Gs && out && B > 0, RP_EINVAL, "rp_normalize_pose: bad argument");
+    RP_GUARD(device);
+    normalize_pose_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(raw, Gs, out, B);
+    return rp::finish_launch("rp_normalize_pose");
+}

@@ -1,0 +1,20 @@
+"""Geodesic pose loss -- mirror of /root/reference/src/geom/losses.py:3-21 on top of the SE3 kernels."""
+import torch
+
+
+def geodesic_loss(Ps, Gs, train_val="train"):
+    """Ps: ground-truth SE3 [B,2]; Gs: list holding the predicted SE3 [B,2] (model output).
+    d = log((G_j G_i^-1) (P_j P_i^-1)^-1) for (i,j) in ((0,1),(1,0)); mean |tau|, mean |phi|."""
+    ii = torch.tensor([0, 1], device=Ps.data.device)
+    jj = torch.tensor([1, 0], device=Ps.data.device)
+    dP = Ps[:, jj] * Ps[:, ii].inv()
+    dG = Gs[0][:, jj] * Gs[0][:, ii].inv()
+    d = (dG * dP.inv()).log()
+    tau, phi = d.split([3, 3], dim=-1)
+    loss_tr = tau.norm(dim=-1).mean()
+    loss_rot = phi.norm(dim=-1).mean()
+    metrics = {
+        train_val + "_geo_loss_tr": loss_tr.detach().item(),
+        train_val + "_geo_loss_rot": loss_rot.detach().item(),
+    }
+    return loss_tr, loss_rot, metrics

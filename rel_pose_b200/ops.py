@@ -1,0 +1,360 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch is plumbing only here: it owns device memory and
+streams; every computation below is a call into librelpose_b200.so.  Inputs must be CUDA tensors --
+there is no CPU or eager-PyTorch fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+NTOK, EMBED, HEADS, HDIM, NPOS, EMW = 576, 192, 3, 64, 6, 70
+
+_launch_count = 0     # number of kernels launched through the library (bench.py reports it)
+_timer = None         # optional StageTimer: CUDA-event timing of every library call (bench.py)
+
+
+def launches():
+    return _launch_count
+
+
+class StageTimer:
+    """Collects (name, start_event, end_event, flops, bytes) for calls made while installed.
+    Events are recorded on the stream the kernels are launched on (torch's current stream)."""
+
+    def __init__(self):
+        self.records = []
+        self._open = None
+
+    def begin(self, name, flops=0.0, nbytes=0.0):
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        self._open = (name, ev0, ev1, flops, nbytes)
+
+    def end(self):
+        name, ev0, ev1, flops, nbytes = self._open
+        ev1.record()
+        self.records.append((name, ev0, ev1, flops, nbytes))
+        self._open = None
+
+    def summary(self):
+        """name -> dict(calls, ms, flops, bytes); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, ev0, ev1, flops, nbytes in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["calls"] += 1
+            d["ms"] += ev0.elapsed_time(ev1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+def set_timer(timer):
+    global _timer
+    _timer = timer
+
+
+def _count(n=1):
+    global _launch_count
+    _launch_count += n
+    if _timer is not None and _timer._open is not None:
+        _timer.end()
+
+
+def _tbegin(name, flops=0.0, nbytes=0.0):
+    if _timer is not None:
+        _timer.begin(name, flops, nbytes)
+
+
+def _tend():
+    if _timer is not None and _timer._open is not None:
+        _timer.end()
+
+
+def _req(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise _lib.RelposeLibraryError(
+            f"{name}: tensor is on {t.device}; rel_pose_b200 runs on CUDA devices only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _ctx(t):
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    return dev, ctypes.c_void_p(stream)
+
+
+# ------------------------------------------------------------------------------------------ A1
+def preprocess(images):
+    """[B,2,3,H,W] (float32 BGR 0..255, or uint8) -> [2B,3,224,224] float32."""
+    if images.dtype == torch.uint8:
+        _req(images, "images", torch.uint8)
+        fn = _lib.lib().rp_preprocess_u8
+    else:
+        _req(images, "images")
+        fn = _lib.lib().rp_preprocess_f32
+    B, V, C, H, W = images.shape
+    assert C == 3
+    out = torch.empty((B * V, 3, 224, 224), dtype=torch.float32, device=images.device)
+    dev, st = _ctx(images)
+    _tbegin("preprocess", 0.0, float(images.numel() * images.element_size()) + 4.0 * B * V * 3 * 224 * 224)
+    _lib.check(fn(_p(images), _p(out), B * V, H, W, dev, st), "rp_preprocess")
+    _count()
+    return out
+
+
+def intrinsics_prepare(intrinsics, H, W):
+    """In place rescale of [B,2,4] intrinsics to the 24x24 grid; returns (kxy [B,2], flags int32[1])."""
+    _req(intrinsics, "intrinsics")
+    B = intrinsics.shape[0]
+    assert tuple(intrinsics.shape[1:]) == (2, 4)
+    kxy = torch.empty((B, 2), dtype=torch.float32, device=intrinsics.device)
+    flags = torch.zeros((1,), dtype=torch.int32, device=intrinsics.device)
+    dev, st = _ctx(intrinsics)
+    _lib.check(_lib.lib().rp_intrinsics_prepare_f32(_p(intrinsics), _p(kxy), _p(flags), B, H, W, dev, st),
+               "rp_intrinsics_prepare")
+    _count()
+    return kxy, flags
+
+
+# ------------------------------------------------------------------------------------------ A4
+def tokens_posembed(fmap, pos_embed):
+    """[n,192,24,24] -> [n,576,192] + pos_embed."""
+    _req(fmap, "fmap"); _req(pos_embed, "pos_embed")
+    n = fmap.shape[0]
+    assert fmap.numel() == n * EMBED * NTOK and pos_embed.numel() == NTOK * EMBED
+    x = torch.empty((n, NTOK, EMBED), dtype=torch.float32, device=fmap.device)
+    dev, st = _ctx(fmap)
+    _tbegin("tokens_posembed", 0.0, 8.0 * n * NTOK * EMBED)
+    _lib.check(_lib.lib().rp_tokens_posembed_f32(_p(fmap), _p(pos_embed), _p(x), n, dev, st), "rp_tokens_posembed")
+    _count()
+    return x
+
+
+def layernorm(x, gamma, beta, eps=1e-6):
+    _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    y = torch.empty_like(x)
+    dev, st = _ctx(x)
+    _tbegin("layernorm", 0.0, 8.0 * rows * cols)
+    _lib.check(_lib.lib().rp_layernorm_f32(_p(x), _p(gamma), _p(beta), _p(y), rows, cols, float(eps), dev, st),
+               "rp_layernorm")
+    _count()
+    return y
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, residual=None, out=None):
+    """act(x @ weight.T + bias) + residual through rp_linear_f32."""
+    _req(x, "x"); _req(weight, "weight")
+    N, K = weight.shape
+    assert x.shape[-1] == K
+    M = x.numel() // K
+    if bias is not None:
+        _req(bias, "bias")
+    if residual is not None:
+        _req(residual, "residual")
+        assert residual.numel() == M * N
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws_bytes = L.rp_linear_workspace_bytes(M, N, K)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x.device) if ws_bytes else None
+    dev, st = _ctx(x)
+    _tbegin(f"linear[{N}x{K}]", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
+    _lib.check(L.rp_linear_f32(_p(x), _p(weight), _p(bias), _p(residual), _p(out), M, N, K, int(act),
+                               _p(ws), ws_bytes, dev, st), "rp_linear")
+    _count(2 if ws_bytes else 1)
+    return out
+
+
+def self_attention(qkv):
+    """qkv [n,576,576] -> [n,576,192]."""
+    _req(qkv, "qkv")
+    n = qkv.shape[0]
+    assert tuple(qkv.shape[1:]) == (NTOK, 3 * EMBED)
+    out = torch.empty((n, NTOK, EMBED), dtype=torch.float32, device=qkv.device)
+    dev, st = _ctx(qkv)
+    _tbegin("self_attention", 4.0 * n * HEADS * NTOK * NTOK * HDIM, 4.0 * n * NTOK * 4 * EMBED)
+    _lib.check(_lib.lib().rp_self_attention_f32(_p(qkv), _p(out), n, dev, st), "rp_self_attention")
+    _count()
+    return out
+
+
+_LIN24 = None
+
+
+def lin24():
+    """torch.linspace(-1,1,24) evaluated on the host exactly like the reference does
+    (vision_transformer.py:108-109) -- 24 floats handed to the kernel by value."""
+    global _LIN24
+    if _LIN24 is None:
+        _LIN24 = torch.linspace(-1, 1, steps=24, dtype=torch.float32).contiguous()
+    return _LIN24
+
+
+def posenc(B, kxy, device):
+    """[B,576,6] positional monomials; kxy [B,2] or None (intrinsics=None)."""
+    pos = torch.empty((B, NTOK, NPOS), dtype=torch.float32, device=device)
+    if kxy is not None:
+        _req(kxy, "kxy")
+    t = lin24()
+    dev, st = _ctx(pos)
+    _lib.check(_lib.lib().rp_posenc_f32(_p(kxy), ctypes.c_void_p(t.data_ptr()), _p(pos), B, dev, st), "rp_posenc")
+    _count()
+    return pos
+
+
+def essential(qkv, pos):
+    """qkv [2B,576,576], pos [B,576,6] or None -> bilinear forms [B,2,3,W,W]."""
+    _req(qkv, "qkv")
+    B = qkv.shape[0] // 2
+    assert qkv.shape[0] == 2 * B and tuple(qkv.shape[1:]) == (NTOK, 3 * EMBED)
+    width = EMW if pos is not None else HDIM
+    if pos is not None:
+        _req(pos, "pos")
+        assert tuple(pos.shape) == (B, NTOK, NPOS)
+    bil = torch.empty((B, 2, HEADS, width, width), dtype=torch.float32, device=qkv.device)
+    L = _lib.lib()
+    ws_bytes = L.rp_essential_workspace_bytes(B)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=qkv.device)
+    dev, st = _ctx(qkv)
+    # per (pair, head, direction): scores 2*N*N*64 (x3: two stat passes + recompute), A*V 2*N*N*W, V^T*T 2*N*W*W
+    _tbegin("essential", B * 2.0 * HEADS * (2.0 * NTOK * NTOK * HDIM + 2.0 * NTOK * NTOK * width + 2.0 * NTOK * width * width),
+            4.0 * (2 * B * NTOK * 3 * EMBED + B * 2 * HEADS * width * width))
+    _lib.check(L.rp_essential_f32(_p(qkv), _p(pos), _p(bil), B, _p(ws), ws_bytes, dev, st), "rp_essential")
+    _count(3)
+    return bil
+
+
+def em_project(bil, weight, bias):
+    """bil [B,2,3,70,70] -> [2B,70,192] (proj_fundamental + the reference's output flip)."""
+    _req(bil, "bil"); _req(weight, "weight"); _req(bias, "bias")
+    B = bil.shape[0]
+    assert tuple(bil.shape[1:]) == (2, HEADS, EMW, EMW) and tuple(weight.shape) == (EMBED, HEADS * EMW)
+    out = torch.empty((2 * B, EMW, EMBED), dtype=torch.float32, device=bil.device)
+    dev, st = _ctx(bil)
+    _tbegin("em_project", 2.0 * B * 2 * EMW * HEADS * EMW * EMBED, 4.0 * (bil.numel() + 2 * B * EMW * EMBED))
+    _lib.check(_lib.lib().rp_em_project_f32(_p(bil), _p(weight), _p(bias), _p(out), B, dev, st), "rp_em_project")
+    _count()
+    return out
+
+
+def normalize_pose(raw, Gs):
+    _req(raw, "raw"); _req(Gs, "Gs")
+    B = raw.shape[0]
+    assert tuple(raw.shape) == (B, 2, 7) and tuple(Gs.shape) == (B, 2, 7)
+    out = torch.empty_like(raw)
+    dev, st = _ctx(raw)
+    _lib.check(_lib.lib().rp_normalize_pose_f32(_p(raw), _p(Gs), _p(out), B, dev, st), "rp_normalize_pose")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ A12
+def _se3_unary(fn_name, x, in_w, out_w):
+    _req(x, fn_name)
+    assert x.shape[-1] == in_w
+    n = x.numel() // in_w
+    out = torch.empty(x.shape[:-1] + (out_w,), dtype=torch.float32, device=x.device)
+    if n:
+        dev, st = _ctx(x)
+        _lib.check(getattr(_lib.lib(), fn_name)(_p(x), _p(out), n, dev, st), fn_name)
+        _count()
+    return out
+
+
+def se3_inv_fwd(X):
+    return _se3_unary("rp_se3_inv_fwd_f32", X, 7, 7)
+
+
+def se3_log_fwd(X):
+    return _se3_unary("rp_se3_log_fwd_f32", X, 7, 6)
+
+
+def se3_exp_fwd(a):
+    return _se3_unary("rp_se3_exp_fwd_f32", a, 6, 7)
+
+
+def se3_mul_fwd(X, Y):
+    _req(X, "X"); _req(Y, "Y")
+    assert X.shape == Y.shape and X.shape[-1] == 7
+    Z = torch.empty_like(X)
+    n = X.numel() // 7
+    if n:
+        dev, st = _ctx(X)
+        _lib.check(_lib.lib().rp_se3_mul_fwd_f32(_p(X), _p(Y), _p(Z), n, dev, st), "rp_se3_mul_fwd")
+        _count()
+    return Z
+
+
+def se3_mul_bwd(dZ, X, Y):
+    _req(dZ, "dZ"); _req(X, "X"); _req(Y, "Y")
+    dX, dY = torch.empty_like(X), torch.empty_like(Y)
+    n = X.numel() // 7
+    if n:
+        dev, st = _ctx(X)
+        _lib.check(_lib.lib().rp_se3_mul_bwd_f32(_p(dZ), _p(X), _p(Y), _p(dX), _p(dY), n, dev, st), "rp_se3_mul_bwd")
+        _count()
+    return dX, dY
+
+
+def _se3_bwd(fn_name, g, x, out_w):
+    _req(g, "grad"); _req(x, "x")
+    n = x.numel() // x.shape[-1]
+    out = torch.empty(x.shape[:-1] + (out_w,), dtype=torch.float32, device=x.device)
+    if n:
+        dev, st = _ctx(x)
+        _lib.check(getattr(_lib.lib(), fn_name)(_p(g), _p(x), _p(out), n, dev, st), fn_name)
+        _count()
+    return out
+
+
+def se3_inv_bwd(dY, X):
+    return _se3_bwd("rp_se3_inv_bwd_f32", dY, X, 7)
+
+
+def se3_log_bwd(da, X):
+    return _se3_bwd("rp_se3_log_bwd_f32", da, X, 7)
+
+
+def se3_exp_bwd(dX, a):
+    return _se3_bwd("rp_se3_exp_bwd_f32", dX, a, 6)
+
+
+# ------------------------------------------------------------------------------------------ config 3
+def svd3(E):
+    _req(E, "E")
+    assert tuple(E.shape[-2:]) == (3, 3)
+    n = E.numel() // 9
+    U = torch.empty_like(E)
+    V = torch.empty_like(E)
+    S = torch.empty(E.shape[:-2] + (3,), dtype=torch.float32, device=E.device)
+    dev, st = _ctx(E)
+    _lib.check(_lib.lib().rp_svd3_f32(_p(E), _p(U), _p(S), _p(V), n, dev, st), "rp_svd3")
+    _count()
+    return U, S, V
+
+
+def essential_to_rt(E):
+    _req(E, "E")
+    n = E.numel() // 9
+    R1 = torch.empty_like(E)
+    R2 = torch.empty_like(E)
+    t = torch.empty(E.shape[:-2] + (3,), dtype=torch.float32, device=E.device)
+    dev, st = _ctx(E)
+    _lib.check(_lib.lib().rp_essential_to_rt_f32(_p(E), _p(R1), _p(R2), _p(t), n, dev, st), "rp_essential_to_rt")
+    _count()
+    return R1, R2, t

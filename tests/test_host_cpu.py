@@ -1,0 +1,106 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the host mirror of
+the reference interface has the reference's state-dict layout, the SE3 shim's container behaviour,
+and the product path refuses to run without CUDA (no silent fallback)."""
+import argparse
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from rel_pose_b200 import _lib, ops, synthetic as S
+from rel_pose_b200.lietorch import SE3, install_as_lietorch
+from conftest import ROOT
+
+
+def _args(**kw):
+    d = dict(noess=False, pool_size=60, fc_hidden_size=512, fusion_transformer=True, transformer_depth=6,
+             cross_features=False, use_single_softmax=False, no_pos_encoding=False, l1_pos_encoding=False)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "relpose_b200.h")).read()
+    declared = set(re.findall(r"\b(rp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.exported_symbols())
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    L = _lib.lib()
+    assert L.rp_version() >= 100
+    # pure host queries (no GPU needed)
+    assert L.rp_linear_workspace_bytes(64, 512, 26880) > 0
+    assert L.rp_linear_workspace_bytes(73728, 576, 192) == 0
+    assert L.rp_essential_workspace_bytes(2) > 0
+
+
+def test_state_dict_layout_matches_reference_spec():
+    from rel_pose_b200 import ViTEss
+    m = ViTEss(_args())
+    sd = m.state_dict()
+    spec = S.state_dict_spec()
+    assert len(sd) == 227
+    assert list(sd.keys()) == [k for k, _, _ in spec]
+    for k, shape, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    # norm3 and downsample.1 are the same tensors (extractor.py:43-46)
+    assert m.extractor_final_conv.norm3 is m.extractor_final_conv.downsample[1]
+    res = m.load_state_dict(S.make_state_dict(0, "stress"), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    n_params = sum(p.numel() for p in m.parameters())
+    assert n_params == 29751950
+    for p in list(m.resnet.layer3.parameters()) + list(m.resnet.layer4.parameters()):
+        p.requires_grad = False                          # train.py:60-64
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 19258510
+
+
+def test_ablation_flags_are_rejected_loudly():
+    from rel_pose_b200 import ViTEss
+    for flag in ("noess", "cross_features", "use_single_softmax", "no_pos_encoding", "l1_pos_encoding"):
+        with pytest.raises(NotImplementedError):
+            ViTEss(_args(**{flag: True}))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-CUDA behaviour")
+def test_no_cpu_fallback():
+    from rel_pose_b200 import ViTEss
+    m = ViTEss(_args()).eval()
+    img = torch.zeros(1, 2, 3, 32, 32)
+    with pytest.raises(_lib.RelposeLibraryError):
+        m(img, SE3(torch.zeros(1, 2, 7)))
+    with pytest.raises(_lib.RelposeLibraryError):
+        ops.layernorm(torch.zeros(4, 192), torch.ones(192), torch.zeros(192))
+    with pytest.raises(_lib.RelposeLibraryError):
+        SE3(torch.zeros(3, 7)).inv()
+
+
+def test_se3_container_behaviour():
+    d = torch.arange(2 * 2 * 7, dtype=torch.float32).reshape(2, 2, 7)
+    G = SE3(d)
+    assert G.shape == (2, 2) and G[0][1].data.shape == (7,)
+    assert torch.equal(G[:, :1].data, d[:, :1])
+    jj = torch.tensor([1, 0])
+    assert torch.equal(G[:, jj].data, d[:, jj])
+    I = SE3.IdentityLike(G)
+    assert torch.equal(I.data[..., 6], torch.ones(2, 2)) and I.data[..., :6].abs().sum() == 0
+    G2 = SE3(torch.clone(G.data))
+    G2.data[:, :, 3:] = 0.5            # slice-assign like model.py:151
+    assert G2.data[0, 0, 3] == 0.5 and G.data[0, 0, 3] == 3.0
+    assert isinstance(G.detach(), SE3)
+    with pytest.raises(ValueError):
+        SE3(torch.zeros(3, 6))
+    mod = install_as_lietorch(force=True)
+    import lietorch
+    assert lietorch.SE3 is SE3 and mod.SE3 is SE3
+
+
+def test_synthetic_generators_are_stable():
+    u = S.hash_uniform(0, "abc", 5)
+    np.testing.assert_array_equal(u, S.hash_uniform(0, "abc", 5))
+    assert u.min() >= 0 and u.max() < 1
+    a = S.make_images_numpy(3, 1, 8, 8)
+    assert a.shape == (1, 2, 3, 8, 8) and a.dtype == np.float32 and a.max() <= 255 and np.all(a == np.floor(a))
+    assert float(a.sum()) == float(S.make_images_numpy(3, 1, 8, 8).sum())

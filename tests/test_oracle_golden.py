@@ -75,3 +75,20 @@ def test_forward_matches_reference(name):
     assert rot.max() < 1e-4, rot
     assert tr.max() < 1e-4, tr
     assert np.array_equal(poses[:, 0], Gs[:, 0])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_torch_port_matches_reference(name):
+    """The CPU-baseline port (oracle/torch_port.py) is pinned to the same golden vectors."""
+    import torch_port
+    g, seed, B, H, W, integer, profile, ikind = _load(name)
+    p = S.make_state_dict_numpy(seed, profile)
+    images = S.make_images_numpy(seed, B, H, W, integer)
+    intr = None if ikind is None else S.make_intrinsics_numpy(B, ikind, seed)
+    Gs = np.zeros((B, 2, 7), np.float32)
+    Gs[..., 6] = 1
+    poses = torch_port.forward_numpy(images, Gs, intr, p)
+    rot = O.rotation_error_rad(poses[:, 1, 3:], g["poses"][:, 1, 3:])
+    tr = O.translation_rel_error(poses[:, 1, :3], g["poses"][:, 1, :3])
+    assert rot.max() < 1e-4 and tr.max() < 1e-4, (rot, tr)
+    assert np.array_equal(poses[:, 0], Gs[:, 0])
