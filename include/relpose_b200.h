@@ -67,6 +67,30 @@ int rp_preprocess_u8(const uint8_t* images, float* out, int n_img, int H, int W,
  * pair 0 (the two conditions the reference asserts on).  flags must be zeroed by the caller. */
 int rp_intrinsics_prepare_f32(float* intrinsics, float* kxy, int* flags, int B, int H, int W, int device, void* stream);
 
+
+/* ---- A2/A3 CNN front end  src/model.py:127-134, src/modules/extractor.py:51-65 ----------------
+ * Activations are NHWC float32.  A convolution is an implicit GEMM (rows = output pixels,
+ * K = KH*KW*C with the channel innermost) whose epilogue applies the folded eval-mode BatchNorm:
+ *   y = act(conv(x,w)*scale[o] + shift[o] + res_pre) + res_post[row % res_post_rows]
+ * w is [O][KH][KW][C] (rp_permute_conv_weight_f32), C % 4 == 0; scale/shift/res_* may be NULL;
+ * res_post_rows = 0 means "same rows as y" (576 adds the [576,192] pos_embed to every image, A4).
+ * With O = 192 and a 24x24 output, y IS the token matrix [n_img,576,192] of src/model.py:136-141. */
+size_t rp_conv2d_workspace_bytes(int n_img, int H, int W, int C, int O, int KH, int KW, int stride, int pad);
+int rp_conv2d_nhwc_f32(const float* x, const float* w, const float* scale, const float* shift,
+                       const float* res_pre, const float* res_post, int res_post_rows, float* y,
+                       int n_img, int H, int W, int C, int O, int KH, int KW, int stride, int pad, int act,
+                       void* workspace, size_t workspace_bytes, int device, void* stream);
+/* A1 with NHWC output, channels padded 3 -> 4 (4th = 0): [n_img,3,H,W] BGR -> [n_img,224,224,4] */
+int rp_preprocess_nhwc4_f32(const float* images, float* out, int n_img, int H, int W, int device, void* stream);
+int rp_preprocess_nhwc4_u8(const uint8_t* images, float* out, int n_img, int H, int W, int device, void* stream);
+/* nn.MaxPool2d(3,2,1) on NHWC (torchvision resnet stem), C % 4 == 0; output [(H+1)/2... ] = floor((H-1)/2)+1 */
+int rp_maxpool3x3s2_nhwc_f32(const float* x, float* y, int n_img, int H, int W, int C, int device, void* stream);
+/* parameter preparation (once per weight version): [O][C][KH][KW] -> [O][KH][KW][Cp], zero padded */
+int rp_permute_conv_weight_f32(const float* w, float* out, int O, int C, int KH, int KW, int Cp, int device, void* stream);
+/* scale = gamma/sqrt(var+eps), shift = (conv_bias - mean)*scale + beta   (conv_bias may be NULL) */
+int rp_bn_fold_f32(const float* gamma, const float* beta, const float* mean, const float* var,
+                   const float* conv_bias, float eps, float* scale, float* shift, int C, int device, void* stream);
+
 /* ---- A4  src/model.py:136-141,172 ---------------------------------------------------------
  * fmap [n_img,192,576] (NCHW feature map, 24x24 flattened) -> x [n_img,576,192] + pos_embed[576,192] */
 int rp_tokens_posembed_f32(const float* fmap, const float* pos_embed, float* x, int n_img, int device, void* stream);

@@ -24,6 +24,13 @@ _SIGNATURES = {
     "rp_device_arch": (_c_int, [_c_int]),
     "rp_preprocess_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_preprocess_u8": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_conv2d_workspace_bytes": (_c_size, [_c_int] * 9),
+    "rp_conv2d_nhwc_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr] + [_c_int] * 10 + [_ptr, _c_size, _c_int, _ptr]),
+    "rp_preprocess_nhwc4_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_preprocess_nhwc4_u8": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_maxpool3x3s2_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_permute_conv_weight_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_bn_fold_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_intrinsics_prepare_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_tokens_posembed_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_layernorm_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_f32, _c_int, _ptr]),

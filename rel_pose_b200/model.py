@@ -147,20 +147,57 @@ class ViTEss(nn.Module):
             intrinsics.copy_(dev_k)                   # keep the caller-visible side effect
         return intrinsics, kxy, flags
 
-    def _cnn_front_end(self, x):
-        """A2+A3 (model.py:127-134, extractor.py:51-65).  Round 1: library convolutions (cuDNN through
-        torch, TF32 off so the 1e-4 parity bar holds); SURVEY.md 8(f) rank 1 replaces this."""
+    # ---- CNN front end (A2, A3): implicit-GEMM convolutions on NHWC activations -------------------
+    def _cnn_layers(self):
+        """(conv module, bn module) pairs of the layers the forward actually uses."""
         r, e = self.resnet, self.extractor_final_conv
-        ops._tbegin("cnn_front_end(cudnn)", 4.10e9 * x.shape[0], 0.0)     # 8.20 GFLOP / pair (BASELINE.md)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            x = r.maxpool(r.relu(r.bn1(r.conv1(x))))
-            x = r.layer2(r.layer1(x))
-            y = torch.relu(e.norm1(e.conv1(x)))
-            y = torch.relu(e.norm2(e.conv2(y)))
-            x = torch.relu(e.downsample(x) + y)
-        x = x.contiguous()
-        ops._tend()
-        return x
+        out = [("stem", r.conv1, r.bn1)]
+        for name, blk in (("l1.0", r.layer1[0]), ("l1.1", r.layer1[1]), ("l2.0", r.layer2[0]), ("l2.1", r.layer2[1])):
+            out += [(name + ".c1", blk.conv1, blk.bn1), (name + ".c2", blk.conv2, blk.bn2)]
+            if blk.downsample is not None:
+                out.append((name + ".ds", blk.downsample[0], blk.downsample[1]))
+        out += [("e.c1", e.conv1, e.norm1), ("e.c2", e.conv2, e.norm2), ("e.ds", e.downsample[0], e.norm3)]
+        return out
+
+    def _cnn_params(self):
+        """Weights re-laid out to [O][KH][KW][C] and BatchNorm folded to (scale, shift); rebuilt only
+        when a parameter / buffer changed (version counters) -- parameter preparation, not per-step work."""
+        layers = self._cnn_layers()
+        key = []
+        for _, conv, bn in layers:
+            for t in (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var):
+                if t is not None:
+                    key.append((t.data_ptr(), t._version))
+        key = tuple(key)
+        if getattr(self, "_cnn_cache_key", None) != key:
+            cache = {}
+            for name, conv, bn in layers:
+                w = ops.permute_conv_weight(conv.weight)
+                scale, shift = ops.bn_fold(bn, conv.bias)
+                cache[name] = (w, scale, shift, conv.stride[0], conv.padding[0])
+            self._cnn_cache, self._cnn_cache_key = cache, key
+        return self._cnn_cache
+
+    def _cnn_front_end(self, x):
+        """x [2B,224,224,4] NHWC -> tokens [2B,576,192] with pos_embed already added
+        (model.py:127-141,172; extractor.py:51-65).  BatchNorm in eval mode (running statistics)."""
+        P = self._cnn_params()
+
+        def conv(name, inp, act, res_pre=None, res_post=None, rows=0):
+            w, scale, shift, stride, pad = P[name]
+            return ops.conv2d_nhwc(inp, w, scale, shift, stride, pad, act, res_pre, res_post, rows)
+
+        R = ops.ACT_RELU
+        x = ops.maxpool3x3s2_nhwc(conv("stem", x, R))
+        for blk in ("l1.0", "l1.1"):
+            x = conv(blk + ".c2", conv(blk + ".c1", x, R), R, res_pre=x)
+        sc = conv("l2.0.ds", x, ops.ACT_NONE)
+        x = conv("l2.0.c2", conv("l2.0.c1", x, R), R, res_pre=sc)
+        x = conv("l2.1.c2", conv("l2.1.c1", x, R), R, res_pre=x)
+        y = conv("e.c2", conv("e.c1", x, R), R)
+        pos = self.fusion_transformer.pos_embed.reshape(576, 192)
+        tok = conv("e.ds", x, R, res_pre=y, res_post=pos, rows=576)      # relu(bn3(ds(x)) + y) + pos_embed
+        return tok.reshape(tok.shape[0], 576, 192)
 
     def _block(self, blk, x):
         """Block.forward (vision_transformer.py:349-354): 7 library calls, no 576x576 tensor in HBM."""
@@ -208,7 +245,7 @@ class ViTEss(nn.Module):
             images = images.contiguous()
             if images.dtype != torch.uint8:
                 images = images.float()
-            x = ops.preprocess(images)                                        # A1
+            x = ops.preprocess_nhwc4(images)                                  # A1 (NHWC, C padded to 4)
             kxy = flags = None
             if intrinsics is not None:
                 intrinsics, kxy, flags = self.update_intrinsics(images.shape, intrinsics)
@@ -217,12 +254,11 @@ class ViTEss(nn.Module):
                 flags_event = torch.cuda.Event()
                 flags_event.record()
             if stages is not None:
-                stages["preprocessed"] = x
-            fmap = self._cnn_front_end(x)                                     # A2, A3
+                stages["preprocessed"] = x[..., :3].permute(0, 3, 1, 2)
             vt = self.fusion_transformer
-            x = ops.tokens_posembed(fmap, vt.pos_embed)                       # A4
+            x = self._cnn_front_end(x)                                        # A2, A3, A4
             if stages is not None:
-                stages["tokens"] = fmap.reshape(fmap.shape[0], 192, 576).permute(0, 2, 1)
+                stages["tokens"] = x - vt.pos_embed
             for i in range(self.transformer_depth - 1):                       # A5
                 x = self._block(vt.blocks[i], x)
                 if stages is not None:

@@ -129,6 +129,90 @@ def intrinsics_prepare(intrinsics, H, W):
     return kxy, flags
 
 
+# ------------------------------------------------------------------------------------------ A2/A3
+def preprocess_nhwc4(images):
+    """[B,2,3,H,W] (float32 BGR 0..255, or uint8) -> [2B,224,224,4] float32 NHWC (4th channel 0)."""
+    if images.dtype == torch.uint8:
+        _req(images, "images", torch.uint8)
+        fn = _lib.lib().rp_preprocess_nhwc4_u8
+    else:
+        _req(images, "images")
+        fn = _lib.lib().rp_preprocess_nhwc4_f32
+    B, V, C, H, W = images.shape
+    assert C == 3
+    out = torch.empty((B * V, 224, 224, 4), dtype=torch.float32, device=images.device)
+    dev, st = _ctx(images)
+    _tbegin("preprocess", 0.0, float(images.numel() * images.element_size()) + 4.0 * B * V * 4 * 224 * 224)
+    _lib.check(fn(_p(images), _p(out), B * V, H, W, dev, st), "rp_preprocess_nhwc4")
+    _count()
+    return out
+
+
+def conv2d_nhwc(x, w, scale=None, shift=None, stride=1, pad=0, act=ACT_NONE, res_pre=None, res_post=None,
+                res_post_rows=0):
+    """x [n,H,W,C] NHWC, w [O,KH,KW,C] -> [n,Ho,Wo,O]; y = act(conv*scale+shift+res_pre)+res_post."""
+    _req(x, "x"); _req(w, "w")
+    n, H, W, C = x.shape
+    O, KH, KW, C2 = w.shape
+    assert C == C2, (x.shape, w.shape)
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    for t, nm in ((scale, "scale"), (shift, "shift"), (res_pre, "res_pre"), (res_post, "res_post")):
+        if t is not None:
+            _req(t, nm)
+    y = torch.empty((n, Ho, Wo, O), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws_bytes = L.rp_conv2d_workspace_bytes(n, H, W, C, O, KH, KW, stride, pad)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x.device) if ws_bytes else None
+    dev, st = _ctx(x)
+    M, K = n * Ho * Wo, KH * KW * C
+    _tbegin(f"conv[{O}x{KH}x{KW}x{C}/s{stride}]", 2.0 * M * O * K, 4.0 * (x.numel() + w.numel() + M * O))
+    _lib.check(L.rp_conv2d_nhwc_f32(_p(x), _p(w), _p(scale), _p(shift), _p(res_pre), _p(res_post), int(res_post_rows),
+                                    _p(y), n, H, W, C, O, KH, KW, stride, pad, int(act), _p(ws), ws_bytes, dev, st),
+               "rp_conv2d_nhwc")
+    _count(2 if ws_bytes else 1)
+    return y
+
+
+def maxpool3x3s2_nhwc(x):
+    _req(x, "x")
+    n, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((n, Ho, Wo, C), dtype=torch.float32, device=x.device)
+    dev, st = _ctx(x)
+    _tbegin("maxpool", 0.0, 4.0 * (x.numel() + y.numel()))
+    _lib.check(_lib.lib().rp_maxpool3x3s2_nhwc_f32(_p(x), _p(y), n, H, W, C, dev, st), "rp_maxpool3x3s2")
+    _count()
+    return y
+
+
+def permute_conv_weight(w, Cp=None):
+    """nn.Conv2d weight [O,C,KH,KW] -> [O,KH,KW,Cp] (zero padded channels); parameter preparation."""
+    w = _req(w.detach().contiguous(), "w")
+    O, C, KH, KW = w.shape
+    Cp = Cp or ((C + 3) // 4) * 4
+    out = torch.empty((O, KH, KW, Cp), dtype=torch.float32, device=w.device)
+    dev, st = _ctx(w)
+    _lib.check(_lib.lib().rp_permute_conv_weight_f32(_p(w), _p(out), O, C, KH, KW, Cp, dev, st), "rp_permute_conv_weight")
+    _count()
+    return out
+
+
+def bn_fold(bn, conv_bias=None):
+    """(scale, shift) of an eval-mode nn.BatchNorm2d folded with the preceding conv bias."""
+    g = _req(bn.weight.detach().contiguous(), "bn.weight")
+    C = g.numel()
+    scale = torch.empty((C,), dtype=torch.float32, device=g.device)
+    shift = torch.empty_like(scale)
+    cb = conv_bias.detach().contiguous() if conv_bias is not None else None
+    dev, st = _ctx(g)
+    _lib.check(_lib.lib().rp_bn_fold_f32(_p(g), _p(bn.bias.detach().contiguous()), _p(bn.running_mean.contiguous()),
+                                         _p(bn.running_var.contiguous()), _p(cb), float(bn.eps), _p(scale), _p(shift),
+                                         C, dev, st), "rp_bn_fold")
+    _count()
+    return scale, shift
+
+
 # ------------------------------------------------------------------------------------------ A4
 def tokens_posembed(fmap, pos_embed):
     """[n,192,24,24] -> [n,576,192] + pos_embed."""

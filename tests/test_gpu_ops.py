@@ -132,7 +132,8 @@ def test_self_attention(n, scale):
     q, k, v = O.split_qkv(qkv.astype(np.float64))
     p = O.softmax(q @ k.transpose(0, 1, 3, 2) * 0.125, -1)
     ref = (p @ v).transpose(0, 2, 1, 3).reshape(n, 576, 192)
-    report(f"self_attention n={n}", got, ref, atol=2e-5, rtol=1e-5)
+    # logits reach |S| ~ 40 at scale 3: one float32 ulp of S is already a 4e-6 relative change of exp(S)
+    report(f"self_attention n={n}", got, ref, atol=2e-5 * scale, rtol=1e-5 * scale)
 
 
 @pytest.mark.parametrize("B,scale", [(1, 1.0), (2, 2.5)])
@@ -149,11 +150,70 @@ def test_essential_module(B, scale):
     kxy = cu(np.stack([1 / (k[:, 0, 0] / k[:, 0, 2]), 1 / (k[:, 0, 1] / k[:, 0, 3])], -1).astype(np.float32))
     pos = ops.posenc(B, kxy, qkv.device)
     bil = ops.essential(qkv, pos)
-    report("bilinear1", bil[:, 0].cpu().numpy(), f1, atol=2e-6, rtol=2e-4)
-    report("bilinear2", bil[:, 1].cpu().numpy(), f2, atol=2e-6, rtol=2e-4)
+    # entries of one 70x70 form are sums with cancellation: tolerance relative to the form's scale
+    report("bilinear1", bil[:, 0].cpu().numpy(), f1, atol=1e-5 * np.abs(f1).max(), rtol=2e-4)
+    report("bilinear2", bil[:, 1].cpu().numpy(), f2, atol=1e-5 * np.abs(f2).max(), rtol=2e-4)
     out = ops.em_project(bil, cu(pw), cu(pb)).cpu().numpy().reshape(B, 2, 70, 192)
-    report("em_project slot0 (=Y2)", out[:, 0], y2, atol=2e-5, rtol=2e-4)
-    report("em_project slot1 (=Y1)", out[:, 1], y1, atol=2e-5, rtol=2e-4)
+    report("em_project slot0 (=Y2)", out[:, 0], y2, atol=1e-5 * np.abs(y2).max(), rtol=2e-4)
+    report("em_project slot1 (=Y1)", out[:, 1], y1, atol=1e-5 * np.abs(y1).max(), rtol=2e-4)
+
+
+class _BN:
+    def __init__(self, seed, C):
+        self.weight = cu(1 + 0.2 * rnd(seed, C)); self.bias = cu(0.1 * rnd(seed + 1, C))
+        self.running_mean = cu(0.2 * rnd(seed + 2, C)); self.running_var = cu(0.6 + np.abs(rnd(seed + 3, C)))
+        self.eps = 1e-5
+
+    def params(self, prefix):
+        return {prefix + ".weight": self.weight.cpu().numpy(), prefix + ".bias": self.bias.cpu().numpy(),
+                prefix + ".running_mean": self.running_mean.cpu().numpy(), prefix + ".running_var": self.running_var.cpu().numpy()}
+
+
+@pytest.mark.parametrize("n,H,W,C,O,k,stride,pad,bias,act,res", [
+    (2, 30, 34, 3, 64, 7, 2, 3, False, 2, "none"), (3, 20, 20, 64, 64, 3, 1, 1, False, 2, "pre"),
+    (2, 21, 19, 64, 128, 3, 2, 1, False, 2, "none"), (2, 21, 19, 64, 128, 1, 2, 0, False, 0, "none"),
+    (2, 28, 28, 128, 192, 5, 1, 0, True, 2, "pre+post"), (1, 28, 28, 192, 192, 5, 1, 0, True, 2, "none"),
+    (130, 6, 6, 8, 20, 3, 1, 1, True, 0, "none")])
+def test_conv2d_bn_act_residual(n, H, W, C, O, k, stride, pad, bias, act, res):
+    x = rnd(31, n, C, H, W)
+    w = rnd(32, O, C, k, k, scale=1.0 / np.sqrt(C * k * k))
+    b = rnd(33, O, scale=0.1) if bias else None
+    bn = _BN(40, O)
+    ref = O_conv(x, w, b, stride, pad, bn)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    rp = rnd(34, n, O, Ho, Wo) if "pre" in res else None
+    rq = rnd(35, Ho * Wo, O) if "post" in res else None
+    if rp is not None:
+        ref = ref + rp
+    if act == 2:
+        ref = np.maximum(ref, 0)
+    if rq is not None:
+        ref = ref + rq.reshape(Ho, Wo, O).transpose(2, 0, 1)[None]
+    Cp = (C + 3) // 4 * 4
+    xh = np.zeros((n, H, W, Cp), np.float32); xh[..., :C] = x.transpose(0, 2, 3, 1)
+    wp = ops.permute_conv_weight(cu(w))
+    assert tuple(wp.shape) == (O, k, k, Cp)
+    scale, shift = ops.bn_fold(bn, cu(b) if bias else None)
+    y = ops.conv2d_nhwc(cu(xh), wp, scale, shift, stride, pad, act,
+                        cu(rp.transpose(0, 2, 3, 1)) if rp is not None else None,
+                        cu(rq) if rq is not None else None, Ho * Wo if rq is not None else 0)
+    report(f"conv {k}x{k}/s{stride} {C}->{O}", y.cpu().numpy().transpose(0, 3, 1, 2), ref, atol=2e-5, rtol=2e-5)
+
+
+def O_conv(x, w, b, stride, pad, bn):
+    y = O.conv2d(x.astype(np.float64), w.astype(np.float64), None if b is None else b.astype(np.float64), stride, pad)
+    return O.batchnorm_eval(y, {k: v.astype(np.float64) for k, v in bn.params("bn").items()}, "bn")
+
+
+def test_maxpool_and_preprocess_nhwc4():
+    x = rnd(36, 3, 64, 23, 29)
+    got = ops.maxpool3x3s2_nhwc(cu(x.transpose(0, 2, 3, 1))).cpu().numpy().transpose(0, 3, 1, 2)
+    assert np.array_equal(got, O.maxpool3x3s2(x))
+    img = S.make_images_numpy(7, 2, 96, 128, True)
+    got = ops.preprocess_nhwc4(cu(img)).cpu().numpy()
+    assert np.array_equal(got[..., :3].transpose(0, 3, 1, 2), O.preprocess(img)) and np.all(got[..., 3] == 0)
+    got8 = ops.preprocess_nhwc4(cu(img.astype(np.uint8))).cpu().numpy()
+    assert np.array_equal(got8, got)
 
 
 def test_normalize_pose():
