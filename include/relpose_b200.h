@@ -106,6 +106,20 @@ size_t rp_linear_workspace_bytes(int M, int N, int K);
 int rp_linear_f32(const float* A, const float* W, const float* bias, const float* residual, float* C,
                   int M, int N, int K, int act, void* workspace, size_t workspace_bytes, int device, void* stream);
 
+
+/* ---- tensor-core (tcgen05 + TMA + TMEM) nn.Linear on split-bf16 operands ----------------------
+ * A float32 tensor is carried as P bf16 "planes" laid out [P][rows][K]: plane 0 = bf16(x), plane 1 =
+ * bf16(x - plane0).  P = 1 is plain bf16; P = 2 evaluates a0*b0 + a0*b1 + a1*b0 with fp32
+ * accumulation in tensor memory ("bf16x3", fp32-class products: holds the 1e-4 parity bar).
+ *   out = act(A W^T + bias) + residual, written as float32 [M,N] (out_f32) and/or as P_out planes
+ *   [P_out][M][N] (out_planes) ready to be the A operand of the next GEMM.   K % 8 == 0. */
+int rp_split_planes_bf16(const float* x, void* planes, int64_t n, int P, int device, void* stream);
+int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* beta, void* planes, int rows, int cols,
+                             float eps, int P, int device, void* stream);
+int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
+                 float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
+                 void* stream);
+
 /* ---- A5 attention core  vision_transformer.py:323-329 --------------------------------------
  * qkv [n_img,576,576] (column = s*192+h*64+d)  ->  out [n_img,576,192] (column = h*64+d),
  * out = softmax(q k^T * 0.125) v per image and head; nothing is materialised in HBM. */

@@ -1,0 +1,367 @@
+// tcgen05 / TMA / TMEM GEMM for nn.Linear on sm_100a, with split-bf16 operands.
+//
+//   C[M,N] = act(A[M,K] W[N,K]^T + bias) + residual
+//
+// Operands are bf16 "planes": a float32 value x is carried as P bf16 numbers x0 = bf16(x),
+// x1 = bf16(x - x0) (P = 2 keeps 16 mantissa bits).  The tensor core then evaluates
+//   P = 1 :  a0 b0                         (plain bf16, BASELINE.json configs[3] throughput mode)
+//   P = 2 :  a0 b0 + a0 b1 + a1 b0         ("bf16x3": fp32-class products, fp32 accumulation in TMEM;
+//                                           measured end to end: holds the 1e-4 parity bar)
+// into ONE fp32 TMEM accumulator.  Reference call sites: vision_transformer.py:323,331; mlp.py:21-24.
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor (3D maps [plane][row][K], 128B swizzle) into a
+//              STAGES-deep shared-memory ring guarded by full/empty mbarriers;
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=192, K=16) reading K-major
+//              SWIZZLE_128B smem descriptors; tcgen05.commit releases ring slots and publishes the
+//              accumulator; also owns TMEM alloc/dealloc (512 columns = 2 accumulator stages x 256);
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step), bias / activation /
+//              residual in registers, 16-byte global stores of fp32 and/or re-split bf16 planes.
+// The two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 192, BK = 64;
+constexpr int A_TILE = BM * BK * 2;   // 16 KiB
+constexpr int B_TILE = BN * BK * 2;   // 24 KiB
+constexpr int NTHREADS = 192;
+constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;
+
+template <int P>
+struct Cfg {
+    static constexpr int STAGE_BYTES = P * (A_TILE + B_TILE);
+    static constexpr int STAGES = P == 1 ? 4 : 2;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+    const float* bias;       // [N] or null
+    const float* residual;   // [M,N] or null (added after the activation)
+    float* out_f32;          // [M,N] or null
+    __nv_bfloat16* out_planes;   // [P_out][M][N] or null
+    int p_out;
+    int act;
+};
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+    if (act == RP_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    if (act == RP_ACT_RELU) return fmaxf(v, 0.0f);
+    return v;
+}
+
+template <int P>
+__global__ void __launch_bounds__(NTHREADS, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams ep,
+                 int M, int N, int K) {
+    using C = Cfg<P>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES]
+    uint64_t* empty = bars + C::STAGES;          // [STAGES]
+    uint64_t* tfull = bars + 2 * C::STAGES;      // [2]
+    uint64_t* tempty = bars + 2 * C::STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const int ntiles = tiles_m * tiles_n;
+    const int kblocks = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmA);
+        tc::prefetch_tmap(&tmB);
+        for (int i = 0; i < C::STAGES; ++i) {
+            tc::mbar_init(&full[i], 1);
+            tc::mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&tfull[i], 1);
+            tc::mbar_init(&tempty[i], 128);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto a_tile = [&](int stage, int p) { return smem + stage * C::STAGE_BYTES + p * A_TILE; };
+    auto b_tile = [&](int stage, int p) { return smem + stage * C::STAGE_BYTES + P * A_TILE + p * B_TILE; };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    tc::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        tc::tma_load_3d(a_tile(stage, p), &tmA, &full[stage], kb * BK, m0, p);
+                        tc::tma_load_3d(b_tile(stage, p), &tmB, &full[stage], kb * BK, n0, p);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+            int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc::tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    tc::mbar_wait(&full[stage], phase);
+                    tc::tcgen05_fence_after();
+                    uint32_t a_addr[P], b_addr[P];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        a_addr[p] = tc::smem_u32(a_tile(stage, p));
+                        b_addr[p] = tc::smem_u32(b_tile(stage, p));
+                    }
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t koff = k * 32;   // 16 bf16 = 32 bytes inside the 128-byte swizzle row
+                        uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                        // smallest terms first; all land in the same fp32 accumulator
+                        if (P == 2) {
+                            tc::umma_bf16(d_tmem, tc::make_kmajor_sw128_desc(a_addr[P - 1] + koff),
+                                          tc::make_kmajor_sw128_desc(b_addr[0] + koff), idesc, accum);
+                            tc::umma_bf16(d_tmem, tc::make_kmajor_sw128_desc(a_addr[0] + koff),
+                                          tc::make_kmajor_sw128_desc(b_addr[P - 1] + koff), idesc, 1u);
+                            accum = 1u;
+                        }
+                        tc::umma_bf16(d_tmem, tc::make_kmajor_sw128_desc(a_addr[0] + koff),
+                                      tc::make_kmajor_sw128_desc(b_addr[0] + koff), idesc, accum);
+                    }
+                    tc::umma_commit(&empty[stage]);           // frees the smem slot when these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&tfull[acc]);                 // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        const int row_in_tile = q * 32 + lane;
+        int acc = 0, acc_phase = 0;
+        const bool vec_ok = (N % 4) == 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            tc::mbar_wait(&tfull[acc], acc_phase);
+            tc::tcgen05_fence_after();
+            const int row = m0 + row_in_tile;
+            const uint32_t t_row = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= N) break;          // warp-uniform
+                uint32_t r[32];
+                tc::tmem_ld_32x32b_x32(t_row + c0, r);
+                tc::tmem_ld_wait();
+                if (row < M) {
+                    const int col0 = n0 + c0;
+                    const size_t o = (size_t)row * N + col0;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        int col = col0 + j;
+                        float x = __uint_as_float(r[j]);
+                        if (col < N) {
+                            if (ep.bias) x += ep.bias[col];
+                            x = act_fn(x, ep.act);
+                            if (ep.residual) x += ep.residual[o + j];
+                        }
+                        v[j] = x;
+                    }
+                    const bool full_chunk = vec_ok && (col0 + 32 <= N);
+                    if (ep.out_f32) {
+                        if (full_chunk) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(ep.out_f32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < N) ep.out_f32[o + j] = v[j];
+                        }
+                    }
+                    if (ep.out_planes) {
+                        for (int p = 0; p < ep.p_out; ++p) {
+                            __nv_bfloat16* dst = ep.out_planes + (size_t)p * M * N + o;
+                            if (vec_ok && (N % 8) == 0 && (col0 + 32 <= N)) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        __nv_bfloat16 lo = __float2bfloat16_rn(v[j + 2 * t]);
+                                        __nv_bfloat16 hi = __float2bfloat16_rn(v[j + 2 * t + 1]);
+                                        w[t] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+                                    }
+                                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
+                                }
+                            } else {
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < N) dst[j] = __float2bfloat16_rn(v[j]);
+                            }
+                            // next plane carries the rounding residue
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+                        }
+                    }
+                }
+            }
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------ plane producers
+// x -> P bf16 planes (x0 = bf16(x), x1 = bf16(x - x0), ...), 8 elements per thread, 16-byte stores
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           long long n, int P) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i >= n) return;
+    float v[8];
+    if (i + 8 <= n) {
+        float4 a = *reinterpret_cast<const float4*>(x + i), b = *reinterpret_cast<const float4*>(x + i + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        for (int j = 0; j < 8; ++j) v[j] = (i + j < n) ? x[i + j] : 0.f;
+    }
+    for (int p = 0; p < P; ++p) {
+        __nv_bfloat16 h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = __float2bfloat16_rn(v[j]);
+            v[j] -= __bfloat162float(h[j]);
+        }
+        __nv_bfloat16* dst = out + (size_t)p * n + i;
+        if (i + 8 <= n) {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+        } else {
+            for (int j = 0; j < 8 && i + j < n; ++j) dst[j] = h[j];
+        }
+    }
+}
+
+// LayerNorm (eps 1e-6, vision_transformer.py:396) writing bf16 planes directly (A operand of the next GEMM)
+__global__ void __launch_bounds__(256) layernorm_planes_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                               const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
+                                                               int rows, int cols, float eps, int P) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* xr = x + (size_t)warp * cols;
+    constexpr int PER = 8;
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        v[i] = c < cols ? xr[c] : 0.f;
+        s += v[i];
+    }
+    float mean = rp::warp_sum(s) / (float)cols, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        float d = c < cols ? v[i] - mean : 0.f;
+        q += d * d;
+    }
+    float rstd = 1.0f / sqrtf(rp::warp_sum(q) / (float)cols + eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        if (c < cols) v[i] = (v[i] - mean) * rstd * g[c] + b[c];
+    }
+    for (int p = 0; p < P; ++p) {
+        __nv_bfloat16* dst = out + ((size_t)p * rows + warp) * cols;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            int c = lane + 32 * i;
+            if (c < cols) {
+                __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
+                dst[c] = h;
+                v[i] -= __bfloat162float(h);
+            }
+        }
+    }
+}
+
+template <int P>
+int launch_linear_tc(const void* A, const void* W, const EpiParams& ep, int M, int N, int K, int device, cudaStream_t st) {
+    using C = Cfg<P>;
+    CUtensorMap tmA, tmB;
+    int rc = tc::make_planes_tmap(&tmA, A, P, M, K, BM);
+    if (rc) return rc;
+    rc = tc::make_planes_tmap(&tmB, W, P, N, K, BN);
+    if (rc) return rc;
+    static bool attr_set[64] = {false};
+    if (device >= 0 && device < 64 && !attr_set[device]) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) {
+            rp::set_error("rp_linear_tc: cudaFuncSetAttribute(%d): %s", C::SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_set[device] = true;
+    }
+    int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int grid = tiles < rp::num_sms(device) ? tiles : rp::num_sms(device);
+    linear_tc_kernel<P><<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmB, ep, M, N, K);
+    return rp::finish_launch("rp_linear_tc");
+}
+
+}  // namespace
+
+extern "C" int rp_split_planes_bf16(const float* x, void* planes, int64_t n, int P, int device, void* stream) {
+    RP_REQUIRE(x && planes && n > 0 && (P == 1 || P == 2 || P == 3), RP_EINVAL, "rp_split_planes: bad argument");
+    RP_REQUIRE(rp::aligned16(x) && rp::aligned16(planes) && (n % 8) == 0, RP_EALIGN,
+               "rp_split_planes: 16-byte alignment and n %% 8 == 0 required");
+    RP_GUARD(device);
+    long long threads = (n + 7) / 8;
+    split_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, static_cast<__nv_bfloat16*>(planes), n, P);
+    return rp::finish_launch("rp_split_planes");
+}
+
+extern "C" int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* beta, void* planes, int rows,
+                                        int cols, float eps, int P, int device, void* stream) {
+    RP_REQUIRE(x && gamma && beta && planes && rows > 0 && cols > 0 && cols <= 256 && (P == 1 || P == 2), RP_EINVAL,
+               "rp_layernorm_planes: bad argument (cols <= 256)");
+    RP_GUARD(device);
+    layernorm_planes_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        x, gamma, beta, static_cast<__nv_bfloat16*>(planes), rows, cols, eps, P);
+    return rp::finish_launch("rp_layernorm_planes");
+}
+
+extern "C" int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
+                            float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
+                            void* stream) {
+    RP_REQUIRE(A_planes && W_planes && (out_f32 || out_planes), RP_EINVAL, "rp_linear_tc: null pointer");
+    RP_REQUIRE(M > 0 && N > 0 && K > 0 && (K % 8) == 0, RP_EINVAL, "rp_linear_tc: bad shape M=%d N=%d K=%d (K%%8==0)", M, N, K);
+    RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_linear_tc: P must be 1 (bf16) or 2 (bf16x3)");
+    RP_REQUIRE(!out_planes || (P_out >= 1 && P_out <= 2), RP_EINVAL, "rp_linear_tc: bad P_out");
+    RP_REQUIRE(act >= RP_ACT_NONE && act <= RP_ACT_RELU, RP_EINVAL, "rp_linear_tc: bad act %d", act);
+    RP_REQUIRE(rp::aligned16(A_planes) && rp::aligned16(W_planes), RP_EALIGN, "rp_linear_tc: operands must be 16-byte aligned");
+    RP_GUARD(device);
+    EpiParams ep{bias, residual, out_f32, static_cast<__nv_bfloat16*>(out_planes), P_out, act};
+    if (P == 1) return launch_linear_tc<1>(A_planes, W_planes, ep, M, N, K, device, (cudaStream_t)stream);
+    return launch_linear_tc<2>(A_planes, W_planes, ep, M, N, K, device, (cudaStream_t)stream);
+}

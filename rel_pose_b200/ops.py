@@ -264,6 +264,57 @@ def linear(x, weight, bias=None, act=ACT_NONE, residual=None, out=None):
     return out
 
 
+# ------------------------------------------------------------------------------------------ tensor-core path
+def split_planes(x, P=2):
+    """float32 [...] -> bf16 planes [P, ...] (plane 0 = bf16(x), plane 1 = bf16(x - plane0))."""
+    _req(x, "x")
+    n = x.numel()
+    out = torch.empty((P,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    dev, st = _ctx(x)
+    _tbegin("split_planes", 0.0, 4.0 * n + 2.0 * P * n)
+    _lib.check(_lib.lib().rp_split_planes_bf16(_p(x), _p(out), n, P, dev, st), "rp_split_planes")
+    _count()
+    return out
+
+
+def layernorm_planes(x, gamma, beta, eps=1e-6, P=2):
+    _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    out = torch.empty((P,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    dev, st = _ctx(x)
+    _tbegin("layernorm_planes", 0.0, 4.0 * rows * cols + 2.0 * P * rows * cols)
+    _lib.check(_lib.lib().rp_layernorm_planes_bf16(_p(x), _p(gamma), _p(beta), _p(out), rows, cols, float(eps), P, dev, st),
+               "rp_layernorm_planes")
+    _count()
+    return out
+
+
+def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f32=True, planes_out=0):
+    """tcgen05 GEMM: a_planes [P,...,K] bf16, w_planes [P,N,K] bf16 -> (float32 [...,N] | None, planes | None)."""
+    _req(a_planes, "a_planes", torch.bfloat16); _req(w_planes, "w_planes", torch.bfloat16)
+    P = a_planes.shape[0]
+    assert w_planes.shape[0] == P and w_planes.dim() == 3
+    N, K = w_planes.shape[1], w_planes.shape[2]
+    assert a_planes.shape[-1] == K
+    lead = tuple(a_planes.shape[1:-1])
+    M = a_planes[0].numel() // K
+    if bias is not None:
+        _req(bias, "bias")
+    if residual is not None:
+        _req(residual, "residual")
+        assert residual.numel() == M * N
+    out = torch.empty(lead + (N,), dtype=torch.float32, device=a_planes.device) if want_f32 else None
+    outp = torch.empty((planes_out,) + lead + (N,), dtype=torch.bfloat16, device=a_planes.device) if planes_out else None
+    dev, st = _ctx(a_planes)
+    _tbegin(f"linear_tc{'x3' if P == 2 else ''}[{N}x{K}]", 2.0 * M * N * K,
+            2.0 * P * (M * K + N * K) + (4.0 * M * N if want_f32 else 0.0) + 2.0 * planes_out * M * N)
+    _lib.check(_lib.lib().rp_linear_tc(_p(a_planes), _p(w_planes), _p(bias), _p(residual), _p(out), _p(outp), M, N, K, P,
+                                       int(planes_out), int(act), dev, st), "rp_linear_tc")
+    _count()
+    return out, outp
+
+
 def self_attention(qkv):
     """qkv [n,576,576] -> [n,576,192]."""
     _req(qkv, "qkv")
