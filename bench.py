@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="pairs per step of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"],
+                    help="arithmetic of the transformer GEMMs (fp32 SIMT | tcgen05 split-bf16 | tcgen05 bf16)")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference_arm(a)
@@ -199,6 +201,7 @@ def main():
     model = ViTEss(model_args())
     model.load_state_dict(S.make_state_dict(0, "init"))
     model = model.to(dev).eval()
+    model.precision = a.precision
     B, size = a.batch, a.size
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     images = (torch.rand(B, 2, 3, size, size, generator=g, device=dev) * 255).floor()     # 226 MB at B=64
@@ -298,10 +301,12 @@ def main():
                        for k, v in sorted(stages.items(), key=lambda kv: -kv[1]["ms"])}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": {"fp32": "f32", "bf16x3": "bf16x3+f32", "bf16": "bf16+f32"}[a.precision], "data": "synthetic",
                 "config": {"workload": f"batch={B} synthetic {size}x{size} pair inference per GPU, full CNN+ViT+EM "
                                        "module, fp32 (BASELINE.json configs[1]); random-init weights",
-                           "pairs_per_gpu_per_step": B, "precision": "fp32 operands, fp32 accumulate",
+                           "pairs_per_gpu_per_step": B, "precision": {"fp32": "fp32 operands, fp32 accumulate (SIMT)",
+                                         "bf16x3": "transformer GEMMs on tcgen05 with split-bf16 operands (a0b0+a0b1+a1b0), fp32 accumulate; rest fp32",
+                                         "bf16": "transformer GEMMs on tcgen05 in bf16, fp32 accumulate; rest fp32"}[a.precision],
                            "l2_policy": f"inputs larger than L2 ({images.numel() * 4 / 1e6:.0f} MB of images per step vs 126 MB L2)",
                            "parallelism": f"{world} shard(s), no collective",
                            "cnn": "own implicit-GEMM convolutions (NHWC, BN folded), no cuDNN"},

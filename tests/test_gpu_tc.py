@@ -74,7 +74,9 @@ def test_linear_tc(P, M, N, K, act, res, pout):
     if res:
         y = y + r
     got = out.cpu().numpy().astype(np.float64)
-    tol = (3e-5 if P == 2 else 2e-2) * np.abs(y).max()
+    # tcgen05 accumulates in fp32 with truncation: the error grows with the number of chained MMAs (K/16),
+    # which is why the K=26880 regressor layer stays on the fp32 SIMT path in the model
+    tol = (3e-5 if P == 2 else 2e-2) * np.abs(y).max() * max(1.0, (K / 192.0) ** 0.5)
     err = np.abs(got - y).max()
     print(f"[parity] linear_tc P={P} {M}x{N}x{K} act={act}: max_abs_err={err:.3e} max_ref={np.abs(y).max():.3e} ratio={err / tol:.3f}")
     if not err <= tol:
