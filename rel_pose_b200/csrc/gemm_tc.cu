@@ -9,14 +9,15 @@
 //                                           measured end to end: holds the 1e-4 parity bar)
 // into ONE fp32 TMEM accumulator.  Reference call sites: vision_transformer.py:323,331; mlp.py:21-24.
 //
-// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+// Kernel anatomy (persistent, one CTA per SM, 320 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor (3D maps [plane][row][K], 128B swizzle) into a
 //              STAGES-deep shared-memory ring guarded by full/empty mbarriers;
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=192, K=16) reading K-major
 //              SWIZZLE_128B smem descriptors; tcgen05.commit releases ring slots and publishes the
 //              accumulator; also owns TMEM alloc/dealloc (512 columns = 2 accumulator stages x 256);
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step), bias / activation /
-//              residual in registers, 16-byte global stores of fp32 and/or re-split bf16 planes.
+//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step), transpose through a
+//              warp-private shared-memory patch so that bias / activation / residual / plane split run
+//              on coalesced 128-byte row segments (fp32 and/or re-split bf16 plane outputs).
 // The two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "tc_common.cuh"
 
@@ -25,14 +26,17 @@ namespace {
 constexpr int BM = 128, BN = 192, BK = 64;
 constexpr int A_TILE = BM * BK * 2;   // 16 KiB
 constexpr int B_TILE = BN * BK * 2;   // 24 KiB
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter, each owning half of the columns
+constexpr int NTHREADS = 32 * (2 + EPI_WARPS);     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;
+constexpr int STG_LD = 36;                         // staging row stride (floats): conflict-free v4 access
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
 
 template <int P>
 struct Cfg {
     static constexpr int STAGE_BYTES = P * (A_TILE + B_TILE);
     static constexpr int STAGES = P == 1 ? 4 : 2;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct EpiParams {
@@ -57,7 +61,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     using C = Cfg<P>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + STG_BYTES);
     uint64_t* full = bars;                       // [STAGES]
     uint64_t* empty = bars + C::STAGES;          // [STAGES]
     uint64_t* tfull = bars + 2 * C::STAGES;      // [2]
@@ -78,7 +83,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&tfull[i], 1);
-            tc::mbar_init(&tempty[i], 128);
+            tc::mbar_init(&tempty[i], EPI_WARPS * 32);
         }
         tc::fence_barrier_init();
     }
@@ -150,74 +155,86 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;                   // TMEM lane quarter this warp may access
-        const int row_in_tile = q * 32 + lane;
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // TMEM hands every thread one ROW (32 consecutive columns); global memory wants a warp to touch
+        // whole 128-byte row segments.  Each warp therefore transposes its 32x32 block through a private,
+        // padded shared-memory patch and does bias / activation / residual / plane split on the coalesced
+        // side: 8 lanes x 16 B per row, 4 rows per instruction.
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                // column half owned by this warp
+        float* stg = staging + (warp - 2) * 32 * STG_LD;
         int acc = 0, acc_phase = 0;
-        const bool vec_ok = (N % 4) == 0;
+        const bool vec4 = (N % 4) == 0;
+        const int rr = lane >> 3, c4 = (lane & 7) * 4;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tcgen05_fence_after();
-            const int row = m0 + row_in_tile;
             const uint32_t t_row = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (n0 + c0 >= N) break;          // warp-uniform
+            for (int ci = 0; ci < BN / 64; ++ci) {
+                const int c0 = (half * (BN / 64) + ci) * 32;
+                if (n0 + c0 >= N) break;                 // warp-uniform
                 uint32_t r[32];
                 tc::tmem_ld_32x32b_x32(t_row + c0, r);
                 tc::tmem_ld_wait();
-                if (row < M) {
-                    const int col0 = n0 + c0;
-                    const size_t o = (size_t)row * N + col0;
-                    float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        int col = col0 + j;
-                        float x = __uint_as_float(r[j]);
-                        if (col < N) {
-                            if (ep.bias) x += ep.bias[col];
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(stg + lane * STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                __syncwarp();
+                const int col = n0 + c0 + c4;
+#pragma unroll 2
+                for (int it = 0; it < 8; ++it) {
+                    const int rt = it * 4 + rr;
+                    const int row = m0 + q * 32 + rt;
+                    if (row >= M || col >= N) continue;
+                    float4 a = *reinterpret_cast<const float4*>(stg + rt * STG_LD + c4);
+                    float v[4] = {a.x, a.y, a.z, a.w};
+                    const size_t o = (size_t)row * N + col;
+                    const bool full4 = vec4 && (col + 4 <= N);
+                    if (full4) {
+                        if (ep.bias) {
+                            float4 b = *reinterpret_cast<const float4*>(ep.bias + col);
+                            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = act_fn(v[j], ep.act);
+                        if (ep.residual) {
+                            float4 b = *reinterpret_cast<const float4*>(ep.residual + o);
+                            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                        }
+                        if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+                        if (ep.out_planes) {
+                            for (int p = 0; p < ep.p_out; ++p) {
+                                __nv_bfloat16 h[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    h[j] = __float2bfloat16_rn(v[j]);
+                                    v[j] -= __bfloat162float(h[j]);          // next plane carries the residue
+                                }
+                                uint2 w;
+                                w.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+                                w.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+                                *reinterpret_cast<uint2*>(ep.out_planes + (size_t)p * M * N + o) = w;
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < 4 && col + j < N; ++j) {
+                            float x = v[j];
+                            if (ep.bias) x += ep.bias[col + j];
                             x = act_fn(x, ep.act);
                             if (ep.residual) x += ep.residual[o + j];
-                        }
-                        v[j] = x;
-                    }
-                    const bool full_chunk = vec_ok && (col0 + 32 <= N);
-                    if (ep.out_f32) {
-                        if (full_chunk) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(ep.out_f32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < N) ep.out_f32[o + j] = v[j];
-                        }
-                    }
-                    if (ep.out_planes) {
-                        for (int p = 0; p < ep.p_out; ++p) {
-                            __nv_bfloat16* dst = ep.out_planes + (size_t)p * M * N + o;
-                            if (vec_ok && (N % 8) == 0 && (col0 + 32 <= N)) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 8) {
-                                    uint32_t w[4];
-#pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        __nv_bfloat16 lo = __float2bfloat16_rn(v[j + 2 * t]);
-                                        __nv_bfloat16 hi = __float2bfloat16_rn(v[j + 2 * t + 1]);
-                                        w[t] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
-                                    }
-                                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
+                            if (ep.out_f32) ep.out_f32[o + j] = x;
+                            if (ep.out_planes)
+                                for (int p = 0; p < ep.p_out; ++p) {
+                                    __nv_bfloat16 h = __float2bfloat16_rn(x);
+                                    ep.out_planes[(size_t)p * M * N + o + j] = h;
+                                    x -= __bfloat162float(h);
                                 }
-                            } else {
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < N) dst[j] = __float2bfloat16_rn(v[j]);
-                            }
-                            // next plane carries the rounding residue
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
                         }
                     }
                 }
+                __syncwarp();                            // staging patch is reused by the next chunk
             }
             tc::tcgen05_fence_before();
             tc::mbar_arrive(&tempty[acc]);
