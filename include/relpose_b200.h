@@ -119,6 +119,17 @@ int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* be
 int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
                  float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
                  void* stream);
+/* Tensor-core convolution (A2/A3), same epilogue contract as rp_conv2d_nhwc_f32.  x_planes is the NHWC
+ * activation as bf16 planes [P][n_img][H][W][C] (C % 64 == 0), w_planes [P][O][KH*KW*C] is the split of
+ * the [O][KH][KW][C] weight, O in {64,128,192}, stride 1 or 2.  Every (tap, 64-channel block) K step is
+ * one 5-D TMA box; padding is TMA zero fill.  Outputs: float32 [n,Ho,Wo,O] and/or P_out planes. */
+int rp_conv2d_tc(const void* x_planes, const void* w_planes, const float* scale, const float* shift,
+                 const float* res_pre, const float* res_post, int res_post_rows, float* out_f32, void* out_planes,
+                 int n_img, int H, int W, int C, int O, int KH, int KW, int stride, int pad, int P, int P_out, int act,
+                 int device, void* stream);
+/* nn.MaxPool2d(3,2,1) on NHWC float32 writing float32 (y_f32, may be NULL) and/or P bf16 planes */
+int rp_maxpool3x3s2_planes(const float* x, float* y_f32, void* y_planes, int P, int n_img, int H, int W, int C,
+                           int device, void* stream);
 
 /* ---- A5 attention core  vision_transformer.py:323-329 --------------------------------------
  * qkv [n_img,576,576] (column = s*192+h*64+d)  ->  out [n_img,576,192] (column = h*64+d),

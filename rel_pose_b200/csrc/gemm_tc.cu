@@ -1,47 +1,65 @@
-// tcgen05 / TMA / TMEM GEMM for nn.Linear on sm_100a, with split-bf16 operands.
-//
-//   C[M,N] = act(A[M,K] W[N,K]^T + bias) + residual
+// tcgen05 / TMA / TMEM GEMM engine on sm_100a with split-bf16 operands, two front ends:
+//   * nn.Linear          C[M,N] = act(A[M,K] W[N,K]^T * scale + shift + res_pre) + res_post     (rp_linear_tc)
+//   * nn.Conv2d (NHWC)   implicit GEMM: the A tile of every (filter tap, 64-channel block) K step is ONE
+//                        5-D TMA box of the activation tensor [plane][image][H][W][C]; zero padding and
+//                        image borders are TMA out-of-bounds zero fill, stride-2 is the map's element
+//                        stride.  Eval-mode BatchNorm is the scale/shift epilogue            (rp_conv2d_tc)
 //
 // Operands are bf16 "planes": a float32 value x is carried as P bf16 numbers x0 = bf16(x),
 // x1 = bf16(x - x0) (P = 2 keeps 16 mantissa bits).  The tensor core then evaluates
 //   P = 1 :  a0 b0                         (plain bf16, BASELINE.json configs[3] throughput mode)
 //   P = 2 :  a0 b0 + a0 b1 + a1 b0         ("bf16x3": fp32-class products, fp32 accumulation in TMEM;
 //                                           measured end to end: holds the 1e-4 parity bar)
-// into ONE fp32 TMEM accumulator.  Reference call sites: vision_transformer.py:323,331; mlp.py:21-24.
+// into ONE fp32 TMEM accumulator.  Reference call sites: vision_transformer.py:323,331; mlp.py:21-24;
+// src/model.py:127-134; extractor.py:51-65.
 //
 // Kernel anatomy (persistent, one CTA per SM, 320 threads):
-//   warp 0     TMA producer: cp.async.bulk.tensor (3D maps [plane][row][K], 128B swizzle) into a
-//              STAGES-deep shared-memory ring guarded by full/empty mbarriers;
-//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=192, K=16) reading K-major
+//   warp 0     TMA producer: cp.async.bulk.tensor (128B swizzle) into a STAGES-deep shared-memory ring
+//              guarded by full/empty mbarriers;
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) reading K-major
 //              SWIZZLE_128B smem descriptors; tcgen05.commit releases ring slots and publishes the
 //              accumulator; also owns TMEM alloc/dealloc (512 columns = 2 accumulator stages x 256);
 //   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step), transpose through a
-//              warp-private shared-memory patch so that bias / activation / residual / plane split run
-//              on coalesced 128-byte row segments (fp32 and/or re-split bf16 plane outputs).
+//              warp-private shared-memory patch so that scale / shift / activation / residual / plane
+//              split run on coalesced 128-byte row segments (fp32 and/or re-split bf16 plane outputs).
 // The two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// Convolution tiles are R whole output rows of one image (R*Wo <= 128 pixels) so that the pixels of a
+// tile are one rectangular TMA box for every filter tap; unused accumulator rows are never stored.
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 192, BK = 64;
+constexpr int BM = 128, BK = 64;
 constexpr int A_TILE = BM * BK * 2;   // 16 KiB
-constexpr int B_TILE = BN * BK * 2;   // 24 KiB
 constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter, each owning half of the columns
 constexpr int NTHREADS = 32 * (2 + EPI_WARPS);     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;
 constexpr int STG_LD = 36;                         // staging row stride (floats): conflict-free v4 access
 constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+constexpr int SMEM_BUDGET = 200 * 1024;
 
-template <int P>
+template <int P, int BN>
 struct Cfg {
+    static constexpr int B_TILE = BN * BK * 2;
     static constexpr int STAGE_BYTES = P * (A_TILE + B_TILE);
-    static constexpr int STAGES = P == 1 ? 4 : 2;
+    static constexpr int STAGES_RAW = (SMEM_BUDGET - STG_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 2, "pipeline too shallow");
+};
+
+struct Geom {
+    int M, N, K;          // GEMM view: output rows (pixels), output columns, reduction length
+    // convolution only
+    int Ho, Wo, R, tiles_per_img, C, KW, stride, pad, cblocks, taps;
 };
 
 struct EpiParams {
-    const float* bias;       // [N] or null
-    const float* residual;   // [M,N] or null (added after the activation)
+    const float* scale;      // [N] or null
+    const float* shift;      // [N] or null (nn.Linear bias / folded BN shift)
+    const float* res_pre;    // [M,N] or null: added before the activation
+    const float* res_post;   // added after the activation, row index modulo res_post_rows (0: same rows)
+    int res_post_rows;
     float* out_f32;          // [M,N] or null
     __nv_bfloat16* out_planes;   // [P_out][M][N] or null
     int p_out;
@@ -54,11 +72,10 @@ __device__ __forceinline__ float act_fn(float v, int act) {
     return v;
 }
 
-template <int P>
+template <int P, int BN, bool CONV>
 __global__ void __launch_bounds__(NTHREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams ep,
-                 int M, int N, int K) {
-    using C = Cfg<P>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams ep, Geom g) {
+    using C = Cfg<P, BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -70,9 +87,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const int M = g.M, N = g.N;
+    const int tiles_n = CONV ? 1 : (N + BN - 1) / BN;
+    const int tiles_m = CONV ? (g.M / (g.Ho * g.Wo)) * g.tiles_per_img : (M + BM - 1) / BM;
     const int ntiles = tiles_m * tiles_n;
-    const int kblocks = (K + BK - 1) / BK;
+    const int ksteps = CONV ? g.taps * g.cblocks : (g.K + BK - 1) / BK;
+    // bytes one stage receives from TMA: full boxes, zero-filled where out of bounds
+    const uint32_t stage_tx = CONV ? (uint32_t)(P * (g.R * g.Wo * 128 + C::B_TILE)) : (uint32_t)C::STAGE_BYTES;
 
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmA);
@@ -94,21 +115,34 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     auto a_tile = [&](int stage, int p) { return smem + stage * C::STAGE_BYTES + p * A_TILE; };
-    auto b_tile = [&](int stage, int p) { return smem + stage * C::STAGE_BYTES + P * A_TILE + p * B_TILE; };
+    auto b_tile = [&](int stage, int p) { return smem + stage * C::STAGE_BYTES + P * A_TILE + p * C::B_TILE; };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+                const int img = CONV ? tm / g.tiles_per_img : 0;
+                const int oy0 = CONV ? (tm % g.tiles_per_img) * g.R : 0;
+                for (int ks = 0; ks < ksteps; ++ks) {
                     tc::mbar_wait(&empty[stage], phase ^ 1);
-                    tc::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    tc::mbar_expect_tx(&full[stage], stage_tx);
+                    if (CONV) {
+                        const int tap = ks / g.cblocks, cb = ks - tap * g.cblocks;
+                        const int ky = tap / g.KW, kx = tap - ky * g.KW;
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        tc::tma_load_3d(a_tile(stage, p), &tmA, &full[stage], kb * BK, m0, p);
-                        tc::tma_load_3d(b_tile(stage, p), &tmB, &full[stage], kb * BK, n0, p);
+                        for (int p = 0; p < P; ++p) {
+                            tc::tma_load_5d(a_tile(stage, p), &tmA, &full[stage], cb * 64, kx - g.pad,
+                                            oy0 * g.stride + ky - g.pad, img, p);
+                            tc::tma_load_3d(b_tile(stage, p), &tmB, &full[stage], tap * g.C + cb * 64, n0, p);
+                        }
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            tc::tma_load_3d(a_tile(stage, p), &tmA, &full[stage], ks * BK, tm * BM, p);
+                            tc::tma_load_3d(b_tile(stage, p), &tmB, &full[stage], ks * BK, n0, p);
+                        }
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -123,7 +157,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc::tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int ks = 0; ks < ksteps; ++ks) {
                     tc::mbar_wait(&full[stage], phase);
                     tc::tcgen05_fence_after();
                     uint32_t a_addr[P], b_addr[P];
@@ -135,7 +169,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint32_t koff = k * 32;   // 16 bf16 = 32 bytes inside the 128-byte swizzle row
-                        uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                        uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
                         // smallest terms first; all land in the same fp32 accumulator
                         if (P == 2) {
                             tc::umma_bf16(d_tmem, tc::make_kmajor_sw128_desc(a_addr[P - 1] + koff),
@@ -158,22 +192,35 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ------------------------------------------------------------------ epilogue (warps 2..9)
         // TMEM hands every thread one ROW (32 consecutive columns); global memory wants a warp to touch
         // whole 128-byte row segments.  Each warp therefore transposes its 32x32 block through a private,
-        // padded shared-memory patch and does bias / activation / residual / plane split on the coalesced
-        // side: 8 lanes x 16 B per row, 4 rows per instruction.
+        // padded shared-memory patch and does the epilogue arithmetic on the coalesced side:
+        // 8 lanes x 16 B per row, 4 rows per instruction.
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                // column half owned by this warp
         float* stg = staging + (warp - 2) * 32 * STG_LD;
         int acc = 0, acc_phase = 0;
         const bool vec4 = (N % 4) == 0;
         const int rr = lane >> 3, c4 = (lane & 7) * 4;
+        constexpr int NCHUNK = BN / 32;                  // 32-column chunks per tile (2, 4 or 6)
+        constexpr int CH_PER_HALF = (NCHUNK + 1) / 2;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+            int row_base, valid_rows;                    // global row of tile row 0; rows of the tile that exist
+            if (CONV) {
+                const int img = tm / g.tiles_per_img, oy0 = (tm % g.tiles_per_img) * g.R;
+                row_base = (img * g.Ho + oy0) * g.Wo;
+                valid_rows = min(g.R, g.Ho - oy0) * g.Wo;
+            } else {
+                row_base = tm * BM;
+                valid_rows = min(BM, M - row_base);
+            }
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int ci = 0; ci < BN / 64; ++ci) {
-                const int c0 = (half * (BN / 64) + ci) * 32;
+            for (int ci = 0; ci < CH_PER_HALF; ++ci) {
+                const int chunk = half * CH_PER_HALF + ci;
+                if (chunk >= NCHUNK) break;
+                const int c0 = chunk * 32;
                 if (n0 + c0 >= N) break;                 // warp-uniform
                 uint32_t r[32];
                 tc::tmem_ld_32x32b_x32(t_row + c0, r);
@@ -185,22 +232,31 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int col = n0 + c0 + c4;
 #pragma unroll 2
                 for (int it = 0; it < 8; ++it) {
-                    const int rt = it * 4 + rr;
-                    const int row = m0 + q * 32 + rt;
-                    if (row >= M || col >= N) continue;
-                    float4 a = *reinterpret_cast<const float4*>(stg + rt * STG_LD + c4);
+                    const int rt = q * 32 + it * 4 + rr;         // row inside the tile
+                    if (rt >= valid_rows || col >= N) continue;
+                    const int row = row_base + rt;
+                    float4 a = *reinterpret_cast<const float4*>(stg + (it * 4 + rr) * STG_LD + c4);
                     float v[4] = {a.x, a.y, a.z, a.w};
                     const size_t o = (size_t)row * N + col;
-                    const bool full4 = vec4 && (col + 4 <= N);
-                    if (full4) {
-                        if (ep.bias) {
-                            float4 b = *reinterpret_cast<const float4*>(ep.bias + col);
+                    const int nvalid = (vec4 && col + 4 <= N) ? 4 : min(4, N - col);
+                    if (nvalid == 4 && vec4) {
+                        if (ep.scale) {
+                            float4 b = *reinterpret_cast<const float4*>(ep.scale + col);
+                            v[0] *= b.x; v[1] *= b.y; v[2] *= b.z; v[3] *= b.w;
+                        }
+                        if (ep.shift) {
+                            float4 b = *reinterpret_cast<const float4*>(ep.shift + col);
+                            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                        }
+                        if (ep.res_pre) {
+                            float4 b = *reinterpret_cast<const float4*>(ep.res_pre + o);
                             v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) v[j] = act_fn(v[j], ep.act);
-                        if (ep.residual) {
-                            float4 b = *reinterpret_cast<const float4*>(ep.residual + o);
+                        if (ep.res_post) {
+                            const int rq = ep.res_post_rows > 0 ? row % ep.res_post_rows : row;
+                            float4 b = *reinterpret_cast<const float4*>(ep.res_post + (size_t)rq * N + col);
                             v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
                         }
                         if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -219,11 +275,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         }
                     } else {
-                        for (int j = 0; j < 4 && col + j < N; ++j) {
+                        for (int j = 0; j < nvalid; ++j) {
                             float x = v[j];
-                            if (ep.bias) x += ep.bias[col + j];
+                            if (ep.scale) x *= ep.scale[col + j];
+                            if (ep.shift) x += ep.shift[col + j];
+                            if (ep.res_pre) x += ep.res_pre[o + j];
                             x = act_fn(x, ep.act);
-                            if (ep.residual) x += ep.residual[o + j];
+                            if (ep.res_post) {
+                                const int rq = ep.res_post_rows > 0 ? row % ep.res_post_rows : row;
+                                x += ep.res_post[(size_t)rq * N + col + j];
+                            }
                             if (ep.out_f32) ep.out_f32[o + j] = x;
                             if (ep.out_planes)
                                 for (int p = 0; p < ep.p_out; ++p) {
@@ -322,27 +383,64 @@ __global__ void __launch_bounds__(256) layernorm_planes_kernel(const float* __re
     }
 }
 
-template <int P>
-int launch_linear_tc(const void* A, const void* W, const EpiParams& ep, int M, int N, int K, int device, cudaStream_t st) {
-    using C = Cfg<P>;
-    CUtensorMap tmA, tmB;
-    int rc = tc::make_planes_tmap(&tmA, A, P, M, K, BM);
-    if (rc) return rc;
-    rc = tc::make_planes_tmap(&tmB, W, P, N, K, BN);
-    if (rc) return rc;
+// nn.MaxPool2d(3,2,1) on NHWC float32 -> float32 and/or bf16 planes (input of the first tensor-core conv)
+__global__ void __launch_bounds__(256) maxpool_planes_kernel(const float4* __restrict__ x, float4* __restrict__ y,
+                                                             __nv_bfloat16* __restrict__ yp, int P, int n_img, int H, int W,
+                                                             int C4, int Ho, int Wo) {
+    long long total = (long long)n_img * Ho * Wo * C4;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C4);
+        long long pix = idx / C4;
+        int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            int iy = oy * 2 - 1 + dy;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                int ix = ox * 2 - 1 + dx;
+                if (ix < 0 || ix >= W) continue;
+                float4 v = x[(((long long)n * H + iy) * W + ix) * C4 + c];
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        if (y) y[idx] = m;
+        if (yp) {
+            float v[4] = {m.x, m.y, m.z, m.w};
+            for (int p = 0; p < P; ++p) {
+                __nv_bfloat16 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    h[j] = __float2bfloat16_rn(v[j]);
+                    v[j] -= __bfloat162float(h[j]);
+                }
+                uint2 w;
+                w.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+                w.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+                *reinterpret_cast<uint2*>(yp + ((size_t)p * total + idx) * 4) = w;
+            }
+        }
+    }
+}
+
+template <int P, int BN, bool CONV>
+int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, const Geom& g, int ntiles,
+                   int device, cudaStream_t st, const char* what) {
+    using C = Cfg<P, BN>;
     static bool attr_set[64] = {false};
     if (device >= 0 && device < 64 && !attr_set[device]) {
-        cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<P, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
-            rp::set_error("rp_linear_tc: cudaFuncSetAttribute(%d): %s", C::SMEM, cudaGetErrorString(e));
+            rp::set_error("%s: cudaFuncSetAttribute(%d): %s", what, C::SMEM, cudaGetErrorString(e));
             return (int)e;
         }
         attr_set[device] = true;
     }
-    int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    int grid = tiles < rp::num_sms(device) ? tiles : rp::num_sms(device);
-    linear_tc_kernel<P><<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmB, ep, M, N, K);
-    return rp::finish_launch("rp_linear_tc");
+    int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
+    gemm_tc_kernel<P, BN, CONV><<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmB, ep, g);
+    return rp::finish_launch(what);
 }
 
 }  // namespace
@@ -368,6 +466,22 @@ extern "C" int rp_layernorm_planes_bf16(const float* x, const float* gamma, cons
     return rp::finish_launch("rp_layernorm_planes");
 }
 
+extern "C" int rp_maxpool3x3s2_planes(const float* x, float* y_f32, void* y_planes, int P, int n_img, int H, int W, int C,
+                                      int device, void* stream) {
+    RP_REQUIRE(x && (y_f32 || y_planes) && n_img > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0 && (P == 1 || P == 2),
+               RP_EINVAL, "rp_maxpool3x3s2_planes: bad argument");
+    RP_REQUIRE(rp::aligned16(x) && rp::aligned16(y_f32) && rp::aligned16(y_planes), RP_EALIGN, "rp_maxpool3x3s2_planes: alignment");
+    RP_GUARD(device);
+    int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    long long total = (long long)n_img * Ho * Wo * (C / 4);
+    long long blocks = (total + 255) / 256;
+    long long cap = (long long)rp::num_sms(device) * 16;
+    maxpool_planes_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y_f32), static_cast<__nv_bfloat16*>(y_planes), P,
+        n_img, H, W, C / 4, Ho, Wo);
+    return rp::finish_launch("rp_maxpool3x3s2_planes");
+}
+
 extern "C" int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
                             float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
                             void* stream) {
@@ -378,7 +492,75 @@ extern "C" int rp_linear_tc(const void* A_planes, const void* W_planes, const fl
     RP_REQUIRE(act >= RP_ACT_NONE && act <= RP_ACT_RELU, RP_EINVAL, "rp_linear_tc: bad act %d", act);
     RP_REQUIRE(rp::aligned16(A_planes) && rp::aligned16(W_planes), RP_EALIGN, "rp_linear_tc: operands must be 16-byte aligned");
     RP_GUARD(device);
-    EpiParams ep{bias, residual, out_f32, static_cast<__nv_bfloat16*>(out_planes), P_out, act};
-    if (P == 1) return launch_linear_tc<1>(A_planes, W_planes, ep, M, N, K, device, (cudaStream_t)stream);
-    return launch_linear_tc<2>(A_planes, W_planes, ep, M, N, K, device, (cudaStream_t)stream);
+    constexpr int BN = 192;
+    CUtensorMap tmA, tmB;
+    int rc = tc::make_planes_tmap(&tmA, A_planes, P, M, K, BM);
+    if (rc) return rc;
+    rc = tc::make_planes_tmap(&tmB, W_planes, P, N, K, BN);
+    if (rc) return rc;
+    EpiParams ep{nullptr, bias, nullptr, residual, 0, out_f32, static_cast<__nv_bfloat16*>(out_planes), P_out, act};
+    Geom g{};
+    g.M = M; g.N = N; g.K = K;
+    int ntiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P == 1) return launch_gemm_tc<1, BN, false>(tmA, tmB, ep, g, ntiles, device, st, "rp_linear_tc");
+    return launch_gemm_tc<2, BN, false>(tmA, tmB, ep, g, ntiles, device, st, "rp_linear_tc");
+}
+
+extern "C" int rp_conv2d_tc(const void* x_planes, const void* w_planes, const float* scale, const float* shift,
+                            const float* res_pre, const float* res_post, int res_post_rows, float* out_f32,
+                            void* out_planes, int n_img, int H, int W, int C, int O, int KH, int KW, int stride, int pad,
+                            int P, int P_out, int act, int device, void* stream) {
+    RP_REQUIRE(x_planes && w_planes && (out_f32 || out_planes), RP_EINVAL, "rp_conv2d_tc: null pointer");
+    RP_REQUIRE(n_img > 0 && H > 0 && W > 0 && C > 0 && (C % 64) == 0 && KH > 0 && KW > 0 && (stride == 1 || stride == 2) && pad >= 0,
+               RP_EINVAL, "rp_conv2d_tc: bad shape n=%d H=%d W=%d C=%d (C%%64==0) k=%dx%d s=%d p=%d", n_img, H, W, C, KH, KW, stride, pad);
+    RP_REQUIRE(O == 64 || O == 128 || O == 192, RP_EINVAL, "rp_conv2d_tc: O must be 64, 128 or 192 (got %d)", O);
+    RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_conv2d_tc: P must be 1 or 2");
+    RP_REQUIRE(!out_planes || (P_out >= 1 && P_out <= 2), RP_EINVAL, "rp_conv2d_tc: bad P_out");
+    RP_REQUIRE(act >= RP_ACT_NONE && act <= RP_ACT_RELU, RP_EINVAL, "rp_conv2d_tc: bad act %d", act);
+    RP_REQUIRE(rp::aligned16(x_planes) && rp::aligned16(w_planes), RP_EALIGN, "rp_conv2d_tc: 16-byte alignment");
+    Geom g{};
+    g.Ho = (H + 2 * pad - KH) / stride + 1;
+    g.Wo = (W + 2 * pad - KW) / stride + 1;
+    RP_REQUIRE(g.Ho > 0 && g.Wo > 0 && g.Wo <= 128 && g.Wo * stride <= 256, RP_EINVAL, "rp_conv2d_tc: unsupported output width %d", g.Wo);
+    g.R = 128 / g.Wo;
+    if (g.R > g.Ho) g.R = g.Ho;
+    if (g.R * stride > 256) g.R = 256 / stride;
+    g.tiles_per_img = (g.Ho + g.R - 1) / g.R;
+    g.C = C; g.KW = KW; g.stride = stride; g.pad = pad; g.cblocks = C / 64; g.taps = KH * KW;
+    long long M = (long long)n_img * g.Ho * g.Wo;
+    RP_REQUIRE(M < (1ll << 31), RP_EINVAL, "rp_conv2d_tc: too many output pixels");
+    g.M = (int)M; g.N = O; g.K = KH * KW * C;
+    RP_GUARD(device);
+    // activation map: [plane][image][H][W][C], box = [1][1][R*stride][Wo*stride][64] traversed with the conv stride
+    tc::EncodeTiledFn fn = tc::get_encode_fn();
+    RP_REQUIRE(fn != nullptr, RP_EINVAL, "rp_conv2d_tc: cuTensorMapEncodeTiled entry point unavailable");
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img, (cuuint64_t)P};
+        cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                              (cuuint64_t)n_img * H * W * C * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)(g.Wo * stride), (cuuint32_t)(g.R * stride), 1, 1};
+        cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+        CUresult r = fn(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_planes), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RP_REQUIRE(r == CUDA_SUCCESS, RP_EINVAL, "rp_conv2d_tc: activation tensor map failed (CUresult %d)", (int)r);
+    }
+    int rc = tc::make_planes_tmap(&tmB, w_planes, P, O, g.K, O);
+    if (rc) return rc;
+    EpiParams ep{scale, shift, res_pre, res_post, res_post_rows, out_f32, static_cast<__nv_bfloat16*>(out_planes), P_out, act};
+    int ntiles = n_img * g.tiles_per_img;
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* what = "rp_conv2d_tc";
+#define RP_CONV_DISPATCH(PP, NN) return launch_gemm_tc<PP, NN, true>(tmA, tmB, ep, g, ntiles, device, st, what)
+    if (P == 1) {
+        if (O == 64) RP_CONV_DISPATCH(1, 64);
+        if (O == 128) RP_CONV_DISPATCH(1, 128);
+        RP_CONV_DISPATCH(1, 192);
+    }
+    if (O == 64) RP_CONV_DISPATCH(2, 64);
+    if (O == 128) RP_CONV_DISPATCH(2, 128);
+    RP_CONV_DISPATCH(2, 192);
+#undef RP_CONV_DISPATCH
 }

@@ -164,10 +164,12 @@ class ViTEss(nn.Module):
         return out
 
     def _cnn_params(self):
-        """Weights re-laid out to [O][KH][KW][C] and BatchNorm folded to (scale, shift); rebuilt only
-        when a parameter / buffer changed (version counters) -- parameter preparation, not per-step work."""
+        """Weights re-laid out to [O][KH][KW][C] (+ bf16 planes for the tensor-core engine) and BatchNorm
+        folded to (scale, shift); rebuilt only when a parameter / buffer changed (version counters) --
+        parameter preparation, not per-step work."""
         layers = self._cnn_layers()
-        key = []
+        P = self._tc_planes()
+        key = [P]
         for _, conv, bn in layers:
             for t in (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var):
                 if t is not None:
@@ -178,29 +180,54 @@ class ViTEss(nn.Module):
             for name, conv, bn in layers:
                 w = ops.permute_conv_weight(conv.weight)
                 scale, shift = ops.bn_fold(bn, conv.bias)
-                cache[name] = (w, scale, shift, conv.stride[0], conv.padding[0])
+                wp = ops.split_planes(w.reshape(w.shape[0], -1), P) if (P and name != "stem") else None
+                cache[name] = (w, scale, shift, conv.stride[0], conv.padding[0], wp, conv.kernel_size[0])
             self._cnn_cache, self._cnn_cache_key = cache, key
         return self._cnn_cache
 
     def _cnn_front_end(self, x):
         """x [2B,224,224,4] NHWC -> tokens [2B,576,192] with pos_embed already added
         (model.py:127-141,172; extractor.py:51-65).  BatchNorm in eval mode (running statistics)."""
-        P = self._cnn_params()
+        prm = self._cnn_params()
+        P = self._tc_planes()
+        R, NONE = ops.ACT_RELU, ops.ACT_NONE
+        pos = self.fusion_transformer.pos_embed.reshape(576, 192)
 
         def conv(name, inp, act, res_pre=None, res_post=None, rows=0):
-            w, scale, shift, stride, pad = P[name]
+            w, scale, shift, stride, pad = prm[name][:5]
             return ops.conv2d_nhwc(inp, w, scale, shift, stride, pad, act, res_pre, res_post, rows)
 
-        R = ops.ACT_RELU
-        x = ops.maxpool3x3s2_nhwc(conv("stem", x, R))
+        stem = conv("stem", x, R)                                     # 7x7/2 on 4 input channels: SIMT engine
+        if P == 0:
+            x = ops.maxpool3x3s2_nhwc(stem)
+            for blk in ("l1.0", "l1.1"):
+                x = conv(blk + ".c2", conv(blk + ".c1", x, R), R, res_pre=x)
+            sc = conv("l2.0.ds", x, NONE)
+            x = conv("l2.0.c2", conv("l2.0.c1", x, R), R, res_pre=sc)
+            x = conv("l2.1.c2", conv("l2.1.c1", x, R), R, res_pre=x)
+            y = conv("e.c2", conv("e.c1", x, R), R)
+            tok = conv("e.ds", x, R, res_pre=y, res_post=pos, rows=576)      # relu(bn3(ds(x)) + y) + pos_embed
+            return tok.reshape(tok.shape[0], 576, 192)
+
+        # tensor-core engine: activations travel as bf16 planes; an fp32 copy is written only where a
+        # later layer needs it as the residual identity
+        def tconv(name, xp, act, res_pre=None, res_post=None, rows=0, f32=False, planes=True):
+            _, scale, shift, stride, pad, wp, k = prm[name]
+            return ops.conv2d_tc(xp, wp, k, k, scale, shift, stride, pad, act, res_pre, res_post, rows,
+                                 want_f32=f32, planes_out=P if planes else 0)
+
+        xf, xp = ops.maxpool3x3s2_planes(stem, P)
         for blk in ("l1.0", "l1.1"):
-            x = conv(blk + ".c2", conv(blk + ".c1", x, R), R, res_pre=x)
-        sc = conv("l2.0.ds", x, ops.ACT_NONE)
-        x = conv("l2.0.c2", conv("l2.0.c1", x, R), R, res_pre=sc)
-        x = conv("l2.1.c2", conv("l2.1.c1", x, R), R, res_pre=x)
-        y = conv("e.c2", conv("e.c1", x, R), R)
-        pos = self.fusion_transformer.pos_embed.reshape(576, 192)
-        tok = conv("e.ds", x, R, res_pre=y, res_post=pos, rows=576)      # relu(bn3(ds(x)) + y) + pos_embed
+            _, yp = tconv(blk + ".c1", xp, R)
+            xf, xp = tconv(blk + ".c2", yp, R, res_pre=xf, f32=True)
+        sc, _ = tconv("l2.0.ds", xp, NONE, f32=True, planes=False)
+        _, yp = tconv("l2.0.c1", xp, R)
+        xf, xp = tconv("l2.0.c2", yp, R, res_pre=sc, f32=True)
+        _, yp = tconv("l2.1.c1", xp, R)
+        _, xp = tconv("l2.1.c2", yp, R, res_pre=xf)
+        _, yp = tconv("e.c1", xp, R)
+        y, _ = tconv("e.c2", yp, R, f32=True, planes=False)
+        tok, _ = tconv("e.ds", xp, R, res_pre=y, res_post=pos, rows=576, f32=True, planes=False)
         return tok.reshape(tok.shape[0], 576, 192)
 
     # ---- transformer blocks --------------------------------------------------------------------

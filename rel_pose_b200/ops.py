@@ -315,6 +315,45 @@ def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f
     return out, outp
 
 
+def conv2d_tc(x_planes, w_planes, KH, KW, scale=None, shift=None, stride=1, pad=0, act=ACT_NONE, res_pre=None,
+              res_post=None, res_post_rows=0, want_f32=True, planes_out=0):
+    """Tensor-core conv: x_planes [P,n,H,W,C] bf16, w_planes [P,O,KH*KW*C] bf16 -> (f32 [n,Ho,Wo,O] | None, planes | None)."""
+    _req(x_planes, "x_planes", torch.bfloat16); _req(w_planes, "w_planes", torch.bfloat16)
+    P, n, H, W, C = x_planes.shape
+    O = w_planes.shape[1]
+    assert w_planes.shape[0] == P and w_planes.shape[2] == KH * KW * C
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    for t, nm in ((scale, "scale"), (shift, "shift"), (res_pre, "res_pre"), (res_post, "res_post")):
+        if t is not None:
+            _req(t, nm)
+    out = torch.empty((n, Ho, Wo, O), dtype=torch.float32, device=x_planes.device) if want_f32 else None
+    outp = torch.empty((planes_out, n, Ho, Wo, O), dtype=torch.bfloat16, device=x_planes.device) if planes_out else None
+    dev, st = _ctx(x_planes)
+    M, K = n * Ho * Wo, KH * KW * C
+    _tbegin(f"conv_tc{'x3' if P == 2 else ''}[{O}x{KH}x{KW}x{C}/s{stride}]", 2.0 * M * O * K,
+            2.0 * P * (x_planes[0].numel() + O * K) + (4.0 * M * O if want_f32 else 0.0) + 2.0 * planes_out * M * O)
+    _lib.check(_lib.lib().rp_conv2d_tc(_p(x_planes), _p(w_planes), _p(scale), _p(shift), _p(res_pre), _p(res_post),
+                                       int(res_post_rows), _p(out), _p(outp), n, H, W, C, O, KH, KW, stride, pad, P,
+                                       int(planes_out), int(act), dev, st), "rp_conv2d_tc")
+    _count()
+    return out, outp
+
+
+def maxpool3x3s2_planes(x, P, want_f32=True):
+    """NHWC float32 -> (float32 | None, bf16 planes [P,n,Ho,Wo,C])."""
+    _req(x, "x")
+    n, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((n, Ho, Wo, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    yp = torch.empty((P, n, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    dev, st = _ctx(x)
+    _tbegin("maxpool", 0.0, 4.0 * x.numel() + (4.0 if want_f32 else 0.0) * n * Ho * Wo * C + 2.0 * P * n * Ho * Wo * C)
+    _lib.check(_lib.lib().rp_maxpool3x3s2_planes(_p(x), _p(y), _p(yp), P, n, H, W, C, dev, st), "rp_maxpool3x3s2_planes")
+    _count()
+    return y, yp
+
+
 def self_attention(qkv):
     """qkv [n,576,576] -> [n,576,192]."""
     _req(qkv, "qkv")

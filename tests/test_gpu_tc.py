@@ -94,3 +94,72 @@ def test_linear_tc_only_planes_output():
     assert out is None
     y = O.gelu(a.astype(np.float64) @ w.astype(np.float64).T)
     assert np.abs(planes_to_f64(outp) - y).max() < 5e-5 * np.abs(y).max()
+
+
+# ------------------------------------------------------------------------------------------ conv on tcgen05
+class _BN:
+    def __init__(self, seed, C):
+        self.weight = cu(1 + 0.2 * rnd(seed, C)); self.bias = cu(0.1 * rnd(seed + 1, C))
+        self.running_mean = cu(0.2 * rnd(seed + 2, C)); self.running_var = cu(0.6 + np.abs(rnd(seed + 3, C)))
+        self.eps = 1e-5
+
+    def params(self, prefix):
+        return {prefix + ".weight": self.weight.cpu().numpy(), prefix + ".bias": self.bias.cpu().numpy(),
+                prefix + ".running_mean": self.running_mean.cpu().numpy(), prefix + ".running_var": self.running_var.cpu().numpy()}
+
+
+@pytest.mark.parametrize("P", [2, 1])
+@pytest.mark.parametrize("n,H,W,C,Oc,k,stride,pad,bias,act,res", [
+    (2, 20, 20, 64, 64, 3, 1, 1, False, 2, "pre"), (3, 56, 56, 64, 64, 3, 1, 1, False, 2, "none"),
+    (2, 21, 19, 64, 128, 3, 2, 1, False, 2, "none"), (2, 56, 56, 64, 128, 1, 2, 0, False, 0, "none"),
+    (2, 28, 28, 128, 128, 3, 1, 1, False, 2, "pre"), (2, 28, 28, 128, 192, 5, 1, 0, True, 2, "pre+post"),
+    (1, 28, 28, 192, 192, 5, 1, 0, True, 2, "none"), (5, 9, 130, 64, 64, 3, 1, 1, True, 0, "none")])
+def test_conv2d_tc(P, n, H, W, C, Oc, k, stride, pad, bias, act, res):
+    if W > 128 and stride == 1 and (W + 2 * pad - k) // stride + 1 > 128:
+        pytest.skip("output rows wider than 128 pixels are outside the tile scheme (not used by the model)")
+    x = rnd(31, n, C, H, W)
+    w = rnd(32, Oc, C, k, k, scale=1.0 / np.sqrt(C * k * k))
+    b = rnd(33, Oc, scale=0.1) if bias else None
+    bn = _BN(40, Oc)
+    y = O.conv2d(x.astype(np.float64), w.astype(np.float64), None if b is None else b.astype(np.float64), stride, pad)
+    ref = O.batchnorm_eval(y, {kk: v.astype(np.float64) for kk, v in bn.params("bn").items()}, "bn")
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    rp = rnd(34, n, Oc, Ho, Wo) if "pre" in res else None
+    rq = rnd(35, Ho * Wo, Oc) if "post" in res else None
+    if rp is not None:
+        ref = ref + rp
+    if act == 2:
+        ref = np.maximum(ref, 0)
+    if rq is not None:
+        ref = ref + rq.reshape(Ho, Wo, Oc).transpose(2, 0, 1)[None]
+    xp = ops.split_planes(cu(x.transpose(0, 2, 3, 1)), P)
+    wperm = ops.permute_conv_weight(cu(w))
+    wp = ops.split_planes(wperm.reshape(Oc, -1), P)
+    scale, shift = ops.bn_fold(bn, cu(b) if bias else None)
+    out, outp = ops.conv2d_tc(xp, wp, k, k, scale, shift, stride, pad, act,
+                              cu(rp.transpose(0, 2, 3, 1)) if rp is not None else None,
+                              cu(rq) if rq is not None else None, Ho * Wo if rq is not None else 0,
+                              want_f32=True, planes_out=P)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().transpose(0, 3, 1, 2).astype(np.float64)
+    tol = (4e-5 if P == 2 else 3e-2) * np.abs(ref).max()
+    err = np.abs(got - ref).max()
+    print(f"[parity] conv_tc P={P} {k}x{k}/s{stride} {C}->{Oc} {H}x{W}: max_abs_err={err:.3e} max_ref={np.abs(ref).max():.3e} ratio={err / tol:.3f}")
+    if not err <= tol:
+        e = np.abs(got - ref)
+        bad = np.argwhere(e > tol)
+        print(f"[tc-diag] {len(bad)} bad of {e.size}; first (n,o,y,x): {bad[:12].tolist()}")
+        print(f"[tc-diag] err by y: {e.max(axis=(0, 1, 3))[:30]}")
+        print(f"[tc-diag] err by x: {e.max(axis=(0, 1, 2))[:30]}")
+        print(f"[tc-diag] err by n: {e.max(axis=(1, 2, 3))}")
+    assert np.isfinite(got).all() and err <= tol
+    gp = planes_to_f64(outp).transpose(0, 3, 1, 2)
+    assert np.abs(gp - got).max() <= (2.0 ** -15 if P == 2 else 2.0 ** -7) * np.abs(got).max()
+
+
+def test_maxpool_planes():
+    x = rnd(36, 3, 64, 23, 29)
+    y, yp = ops.maxpool3x3s2_planes(cu(x.transpose(0, 2, 3, 1)), 2)
+    ref = O.maxpool3x3s2(x)
+    assert np.array_equal(y.cpu().numpy().transpose(0, 3, 1, 2), ref)
+    assert np.abs(planes_to_f64(yp).transpose(0, 3, 1, 2) - ref).max() <= 2.0 ** -16 * np.abs(ref).max()

@@ -1,8 +1,8 @@
 #!/bin/bash
 set -u
 OUT=gpurun_out; mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -q -rA -p no:cacheprovider > $OUT/pytest_tc.log 2>&1; echo "rc=$?" | tee -a $OUT/pytest_tc.log
-grep -E "tc-diag|FAILED|passed|failed|Error" $OUT/pytest_tc.log | head -20
+timeout 900 python -m pytest tests/test_gpu_tc.py -m gpu -q -rA -p no:cacheprovider > $OUT/pytest_tc.log 2>&1; echo "rc=$?" | tee -a $OUT/pytest_tc.log
+grep -E "conv_tc|tc-diag|FAILED|passed|failed|Error" $OUT/pytest_tc.log | head -60
 timeout 900 python -m pytest tests/test_gpu_forward.py -m gpu -q -rA -p no:cacheprovider -k "tensor_core" > $OUT/pytest_fwd_tc.log 2>&1; echo "rc=$?"
 grep -E "parity\].*precision|FAILED|passed|failed|Error" $OUT/pytest_fwd_tc.log | head -30
 for prec in bf16x3 bf16; do
