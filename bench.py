@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="pairs per step of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="arithmetic of the transformer GEMMs (fp32 SIMT | tcgen05 split-bf16 | tcgen05 bf16)")
     a = ap.parse_args()
@@ -262,17 +263,17 @@ def main():
             res = model(dimg, G, intrinsics=k)
             return res[0].data.cpu()                      # D2H read of the step's result (syncs)
 
-        for _ in range(2):
+        for _ in range(0 if a.no_e2e else 2):
             e2e_step()
         barrier()
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(a.steps):
+        for _ in range(0 if a.no_e2e else a.steps):
             e2e_step()
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
-        ms_e2e = max(e0.elapsed_time(e1), 0.0)
+        ms_e2e = max(e0.elapsed_time(e1), 1e-9)
         t = torch.tensor([ms_e2e, wall], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -135,6 +135,12 @@ int rp_maxpool3x3s2_planes(const float* x, float* y_f32, void* y_planes, int P, 
  * qkv [n_img,576,576] (column = s*192+h*64+d)  ->  out [n_img,576,192] (column = h*64+d),
  * out = softmax(q k^T * 0.125) v per image and head; nothing is materialised in HBM. */
 int rp_self_attention_f32(const float* qkv, float* out, int n_img, int device, void* stream);
+/* Same contract on tcgen05 tensor cores (flash style: QK^T -> online softmax -> PV inside one kernel, S and
+ * O accumulators in tensor memory, operands by TMA).  qkv_planes = bf16 planes [P][n_img][576][576] as
+ * written by rp_linear_tc (P = 1 bf16, P = 2 split bf16 = fp32-class); outputs float32 [n_img,576,192]
+ * (out_f32, may be NULL) and/or P_out bf16 planes [P_out][n_img][576][192] (A operand of attn.proj). */
+int rp_self_attention_tc(const void* qkv_planes, float* out_f32, void* out_planes, int n_img, int P, int P_out,
+                         int device, void* stream);
 
 /* ---- A6  vision_transformer.py:90-158 ------------------------------------------------------
  * pos [B,576,6] = [p3^2,p4^2,p3*p4,p3,p4,1], p3 = ys[i%24]*ky, p4 = xs[i/24]*kx (transposed grid).

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "rp_conv2d_tc": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr] + [_c_int] * 13 + [_ptr]),
     "rp_maxpool3x3s2_planes": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_self_attention_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_self_attention_tc": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_posenc_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_essential_workspace_bytes": (_c_size, [_c_int]),
     "rp_essential_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _ptr, _c_size, _c_int, _ptr]),

@@ -1,0 +1,390 @@
+// Fused self-attention (A5: vision_transformer.py:321-329) on tcgen05 tensor cores, flash style: nothing of
+// size 576x576 ever leaves the SM.  softmax(q k^T * 0.125) v for every (image, head), N = 576 tokens, d = 64.
+//
+// Operands are the bf16 "planes" the QKV GEMM epilogue wrote (gemm_tc.cu): P = 1 plain bf16, P = 2 split bf16
+// (x = x0 + x1; every product is evaluated as a0 b0 + a0 b1 + a1 b0 into one fp32 TMEM accumulator, fp32 class).
+//
+// Work item = (image, head, 128-query tile); 576 = 4.5 tiles, the 5th tile is half empty (TMA zero fill, rows
+// never stored).  Keys/values stream in 6 blocks of 96.  Persistent CTAs (one per SM), 192 threads:
+//   warp 0      TMA producer: Q tile (once per item), K and V blocks through two independent 2-stage rings
+//   warp 1      MMA issuer (one lane) + TMEM owner:
+//                 S_j  = Q K_j^T      M=128 N=96 K=64   A,B K-major SWIZZLE_128B            -> TMEM S[j&1]
+//                 O_j  = P_j V_j      M=128 N=64 K=96   A = P_j (smem, K-major), B = V_j as loaded by TMA
+//                                                       ([key][d] rows = MN-major SWIZZLE_128B) -> TMEM O
+//   warps 2-5   softmax: thread = query row (TMEM lane).  tcgen05.ld S_j, online max / sum, p = 2^((s-m) c),
+//               P_j re-split into bf16 planes and written to shared memory in the UMMA K-major swizzle,
+//               fence.proxy.async, mbarrier arrive.  The un-normalised output is carried in registers:
+//               o = o * alpha + O_j (tcgen05.ld of the per-block product), so TMEM is never rescaled.
+// S is double buffered in TMEM (S_{j+1} is issued before P_j is consumed), O and P are single buffers:
+// P_j may only be overwritten / O_j only be replaced after the softmax threads have seen pv_done(j-1),
+// and the issuer starts PV_j only after p_ready(j), which each softmax thread signals after reading O_{j-1}.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int NTOK = RP_NTOK, HD = RP_HDIM, EMB = RP_EMBED, HEADS = RP_HEADS;
+constexpr int BM = 128, BKV = 96, NBLK = NTOK / BKV, QTILES = (NTOK + BM - 1) / BM;   // 6 key blocks, 5 query tiles
+constexpr int Q_TILE = BM * 128;          // bytes of one [128 x 64] bf16 tile
+constexpr int KV_TILE = BKV * 128;        // bytes of one [96 x 64] bf16 tile
+constexpr int P_SUB = BM * 128;           // P_j is [128 x 96] = one full and one half-used 64-wide K-major sub-tile
+constexpr int KV_STAGES = 2;
+constexpr int ATT_THREADS = 192;
+constexpr int TMEM_COLS_ATT = 256;        // S[0] 0..95, S[1] 96..191, O 192..255
+constexpr int S_COL = 0, O_COL = 2 * BKV;
+static_assert(NTOK % BKV == 0 && BKV % 16 == 0 && (NBLK % 2) == 0, "key blocking");
+
+template <int P>
+struct ACfg {
+    static constexpr int Q_BYTES = P * Q_TILE;
+    static constexpr int KV_BYTES = P * KV_TILE;
+    static constexpr int P_BYTES = P * 2 * P_SUB;
+    static constexpr int OFF_K = Q_BYTES;
+    static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
+    static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;
+    static constexpr int OFF_BAR = OFF_P + P_BYTES;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int P>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_planes, int p_out, int n_img,
+                         float scale_log2) {
+    using C = ACfg<P>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_free = bars + 1;
+    uint64_t* k_full = bars + 2;     // [2]
+    uint64_t* k_free = bars + 4;     // [2]
+    uint64_t* v_full = bars + 6;     // [2]
+    uint64_t* v_free = bars + 8;     // [2]
+    uint64_t* s_full = bars + 10;    // [2]
+    uint64_t* p_ready = bars + 12;
+    uint64_t* pv_done = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = n_img * HEADS * QTILES;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmQ);
+        tc::prefetch_tmap(&tmKV);
+        tc::mbar_init(q_full, 1);
+        tc::mbar_init(q_free, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&k_full[i], 1);
+            tc::mbar_init(&k_free[i], 1);
+            tc::mbar_init(&v_full[i], 1);
+            tc::mbar_init(&v_free[i], 1);
+            tc::mbar_init(&s_full[i], 1);
+        }
+        tc::mbar_init(p_ready, 128);
+        tc::mbar_init(pv_done, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS_ATT);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto q_tile = [&](int p) { return smem + p * Q_TILE; };
+    auto k_tile = [&](int st, int p) { return smem + C::OFF_K + st * C::KV_BYTES + p * KV_TILE; };
+    auto v_tile = [&](int st, int p) { return smem + C::OFF_V + st * C::KV_BYTES + p * KV_TILE; };
+    auto p_tile = [&](int p) { return smem + C::OFF_P + p * 2 * P_SUB; };
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            int ks = 0, kph = 0, vs = 0, vph = 0, it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int qt = tile % QTILES, h = (tile / QTILES) % HEADS, img = tile / (QTILES * HEADS);
+                tc::mbar_wait(q_free, (it & 1) ^ 1);
+                tc::mbar_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+                for (int p = 0; p < P; ++p) tc::tma_load_4d(q_tile(p), &tmQ, q_full, h * HD, qt * BM, img, p);
+                for (int j = 0; j < NBLK; ++j) {
+                    tc::mbar_wait(&k_free[ks], kph ^ 1);
+                    tc::mbar_expect_tx(&k_full[ks], C::KV_BYTES);
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        tc::tma_load_4d(k_tile(ks, p), &tmKV, &k_full[ks], EMB + h * HD, j * BKV, img, p);
+                    if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+                    tc::mbar_wait(&v_free[vs], vph ^ 1);
+                    tc::mbar_expect_tx(&v_full[vs], C::KV_BYTES);
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        tc::tma_load_4d(v_tile(vs, p), &tmKV, &v_full[vs], 2 * EMB + h * HD, j * BKV, img, p);
+                    if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = tc::make_idesc_bf16(BM, BKV);
+            constexpr uint32_t idesc_o = tc::make_idesc_bf16(BM, HD) | tc::IDESC_B_MN;
+            int ks = 0, kph = 0, vs = 0, vph = 0, it = 0;
+            uint32_t g = 0;     // global key-block counter of this CTA
+            auto issue_s = [&](uint32_t gb) {
+                tc::mbar_wait(&k_full[ks], kph);
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + S_COL + (gb & 1) * BKV;
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint32_t koff = k * 32;
+                    uint32_t accum = k > 0 ? 1u : 0u;
+                    if (P == 2) {
+                        tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(P - 1)) + koff),
+                                      tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)) + koff), idesc_s, accum);
+                        tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(0)) + koff),
+                                      tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, P - 1)) + koff), idesc_s, 1u);
+                        accum = 1u;
+                    }
+                    tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(0)) + koff),
+                                  tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)) + koff), idesc_s, accum);
+                }
+                tc::umma_commit(&k_free[ks]);
+                tc::umma_commit(&s_full[gb & 1]);
+                if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+            };
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                tc::mbar_wait(q_full, it & 1);
+                tc::tcgen05_fence_after();
+                issue_s(g);
+                for (int j = 0; j < NBLK; ++j, ++g) {
+                    if (j + 1 < NBLK) {
+                        issue_s(g + 1);
+                        if (j + 2 == NBLK) tc::umma_commit(q_free);    // last S of this item is in flight
+                    }
+                    tc::mbar_wait(p_ready, g & 1);
+                    tc::mbar_wait(&v_full[vs], vph);
+                    tc::tcgen05_fence_after();
+                    const uint32_t d = tmem_base + O_COL;
+#pragma unroll
+                    for (int kk = 0; kk < BKV / 16; ++kk) {
+                        const uint32_t a_off = (kk >> 2) * P_SUB + (kk & 3) * 32;   // K-major: 16 keys = 32 B in the row
+                        const uint32_t b_off = kk * 16 * 128;                       // MN-major: 16 keys = 16 rows
+                        uint32_t accum = kk > 0 ? 1u : 0u;
+                        if (P == 2) {
+                            tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(P - 1)) + a_off),
+                                          tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)) + b_off, 0), idesc_o, accum);
+                            tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(0)) + a_off),
+                                          tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, P - 1)) + b_off, 0), idesc_o, 1u);
+                            accum = 1u;
+                        }
+                        tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(0)) + a_off),
+                                      tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)) + b_off, 0), idesc_o, accum);
+                    }
+                    tc::umma_commit(&v_free[vs]);
+                    tc::umma_commit(pv_done);
+                    if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------------- softmax warps
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+        const int r = quarter * 32 + lane;                 // query row inside the tile
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // byte offset of 16-byte chunk c (8 keys) of row r inside a K-major SWIZZLE_128B tile
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
+        const uint32_t sw = (uint32_t)(r & 7);
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int qt = tile % QTILES, h = (tile / QTILES) % HEADS, img = tile / (QTILES * HEADS);
+            float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+            float o[HD];
+#pragma unroll
+            for (int i = 0; i < HD; ++i) o[i] = 0.f;
+            for (int j = 0; j < NBLK; ++j, ++g) {
+                tc::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+                tc::tcgen05_fence_after();
+                uint32_t s[BKV];
+                {
+                    uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+                    uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+                    uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+                    const uint32_t t_s = t_lane + S_COL + (g & 1) * BKV;
+                    tc::tmem_ld_32x32b_x32(t_s, s0);
+                    tc::tmem_ld_32x32b_x32(t_s + 32, s1);
+                    tc::tmem_ld_32x32b_x32(t_s + 64, s2);
+                    tc::tmem_ld_wait();
+                }
+                float bmax = __uint_as_float(s[0]);
+#pragma unroll
+                for (int i = 1; i < BKV; ++i) bmax = fmaxf(bmax, __uint_as_float(s[i]));
+                const float m_new = fmaxf(m, bmax);
+                const float alpha = tc::fast_exp2((m - m_new) * scale_log2);      // 0 on the first block
+                const float ms = m_new * scale_log2;
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < BKV; ++i) {
+                    float p = tc::fast_exp2(fmaf(__uint_as_float(s[i]), scale_log2, -ms));
+                    sum += p;
+                    s[i] = __float_as_uint(p);
+                }
+                l = l * alpha + sum;
+                m = m_new;
+                if (j > 0) {
+                    // O_{j-1} is complete: fold it into the register accumulator; P may now be overwritten
+                    tc::mbar_wait(pv_done, (g - 1) & 1);
+                    tc::tcgen05_fence_after();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t t[32];
+                        tc::tmem_ld_32x32b_x32(t_lane + O_COL + half * 32, t);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[half * 32 + i] = fmaf(o[half * 32 + i], alpha_prev, __uint_as_float(t[i]));
+                    }
+                }
+                alpha_prev = alpha;
+                // P_j -> bf16 planes in shared memory (A operand of the PV product)
+#pragma unroll
+                for (int c = 0; c < BKV / 8; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(s[c * 8 + i]);
+                    const uint32_t off = (uint32_t)(c >> 3) * P_SUB + row_off + ((((uint32_t)c & 7) ^ sw) << 4);
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        uint4 w;
+                        w.x = pack_bf16x2(v[0], v[1]);
+                        w.y = pack_bf16x2(v[2], v[3]);
+                        w.z = pack_bf16x2(v[4], v[5]);
+                        w.w = pack_bf16x2(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(p_tile(p) + off) = w;
+                        if (p + 1 < P) {
+                            v[0] -= __uint_as_float(w.x << 16); v[1] -= __uint_as_float(w.x & 0xffff0000u);
+                            v[2] -= __uint_as_float(w.y << 16); v[3] -= __uint_as_float(w.y & 0xffff0000u);
+                            v[4] -= __uint_as_float(w.z << 16); v[5] -= __uint_as_float(w.z & 0xffff0000u);
+                            v[6] -= __uint_as_float(w.w << 16); v[7] -= __uint_as_float(w.w & 0xffff0000u);
+                        }
+                    }
+                }
+                tc::fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+                tc::tcgen05_fence_before();
+                tc::mbar_arrive(p_ready);
+            }
+            // last product of the item
+            tc::mbar_wait(pv_done, (g - 1) & 1);
+            tc::tcgen05_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t t[32];
+                tc::tmem_ld_32x32b_x32(t_lane + O_COL + half * 32, t);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[half * 32 + i] = fmaf(o[half * 32 + i], alpha_prev, __uint_as_float(t[i]));
+            }
+            const float inv = 1.0f / l;
+            const int row = qt * BM + r;
+            if (row < NTOK) {
+                // out[n, row, h*64 + d]  ((attn @ v).transpose(1,2).reshape(B,N,C), vision_transformer.py:329)
+                const size_t o_idx = ((size_t)img * NTOK + row) * EMB + h * HD;
+#pragma unroll
+                for (int i = 0; i < HD; ++i) o[i] *= inv;
+                if (out_f32) {
+#pragma unroll
+                    for (int i = 0; i < HD; i += 4)
+                        *reinterpret_cast<float4*>(out_f32 + o_idx + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                }
+                if (out_planes) {
+                    const size_t plane = (size_t)n_img * NTOK * EMB;
+                    for (int p = 0; p < p_out; ++p) {
+#pragma unroll
+                        for (int i = 0; i < HD; i += 8) {
+                            uint4 w;
+                            w.x = pack_bf16x2(o[i], o[i + 1]);
+                            w.y = pack_bf16x2(o[i + 2], o[i + 3]);
+                            w.z = pack_bf16x2(o[i + 4], o[i + 5]);
+                            w.w = pack_bf16x2(o[i + 6], o[i + 7]);
+                            *reinterpret_cast<uint4*>(out_planes + p * plane + o_idx + i) = w;
+                            o[i] -= __uint_as_float(w.x << 16); o[i + 1] -= __uint_as_float(w.x & 0xffff0000u);
+                            o[i + 2] -= __uint_as_float(w.y << 16); o[i + 3] -= __uint_as_float(w.y & 0xffff0000u);
+                            o[i + 4] -= __uint_as_float(w.z << 16); o[i + 5] -= __uint_as_float(w.z & 0xffff0000u);
+                            o[i + 6] -= __uint_as_float(w.w << 16); o[i + 7] -= __uint_as_float(w.w & 0xffff0000u);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS_ATT);
+    }
+}
+
+// bf16 [P][n_img][576][576] qkv planes, box = [1][1][box_rows][64 columns], 128-byte swizzle, OOB rows -> 0
+int make_qkv_tmap(CUtensorMap* out, const void* base, int P, int n_img, int box_rows) {
+    tc::EncodeTiledFn fn = tc::get_encode_fn();
+    if (!fn) {
+        rp::set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return RP_EINVAL;
+    }
+    const cuuint64_t ld = 3 * EMB;
+    cuuint64_t gdim[4] = {ld, (cuuint64_t)NTOK, (cuuint64_t)n_img, (cuuint64_t)P};
+    cuuint64_t gstr[3] = {ld * 2, ld * NTOK * 2, ld * NTOK * 2 * (cuuint64_t)n_img};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rp::set_error("qkv tensor map failed (CUresult %d) n_img=%d box_rows=%d", (int)r, n_img, box_rows);
+        return RP_EINVAL;
+    }
+    return RP_OK;
+}
+
+template <int P>
+int launch_attention(const void* qkv_planes, float* out_f32, void* out_planes, int p_out, int n_img, int device,
+                     cudaStream_t st) {
+    using C = ACfg<P>;
+    CUtensorMap tmQ, tmKV;
+    int rc = make_qkv_tmap(&tmQ, qkv_planes, P, n_img, BM);
+    if (rc) return rc;
+    rc = make_qkv_tmap(&tmKV, qkv_planes, P, n_img, BKV);
+    if (rc) return rc;
+    static bool attr_set[64] = {false};
+    if (device >= 0 && device < 64 && !attr_set[device]) {
+        cudaError_t e = cudaFuncSetAttribute(self_attention_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) {
+            rp::set_error("rp_self_attention_tc: cudaFuncSetAttribute(%d): %s", C::SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_set[device] = true;
+    }
+    const int ntiles = n_img * HEADS * QTILES;
+    const int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
+    const float scale_log2 = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
+    self_attention_tc_kernel<P><<<grid, ATT_THREADS, C::SMEM, st>>>(tmQ, tmKV, out_f32, static_cast<__nv_bfloat16*>(out_planes),
+                                                                  p_out, n_img, scale_log2);
+    return rp::finish_launch("rp_self_attention_tc");
+}
+
+}  // namespace
+
+extern "C" int rp_self_attention_tc(const void* qkv_planes, float* out_f32, void* out_planes, int n_img, int P, int P_out,
+                                    int device, void* stream) {
+    RP_REQUIRE(qkv_planes && (out_f32 || out_planes) && n_img > 0, RP_EINVAL, "rp_self_attention_tc: bad argument");
+    RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_self_attention_tc: P must be 1 (bf16) or 2 (bf16x3)");
+    RP_REQUIRE(!out_planes || (P_out >= 1 && P_out <= 2), RP_EINVAL, "rp_self_attention_tc: bad P_out");
+    RP_REQUIRE(rp::aligned16(qkv_planes) && rp::aligned16(out_f32) && rp::aligned16(out_planes), RP_EALIGN,
+               "rp_self_attention_tc: 16-byte alignment");
+    RP_GUARD(device);
+    if (P == 1) return launch_attention<1>(qkv_planes, out_f32, out_planes, P_out, n_img, device, (cudaStream_t)stream);
+    return launch_attention<2>(qkv_planes, out_f32, out_planes, P_out, n_img, device, (cudaStream_t)stream);
+}

@@ -112,6 +112,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 2^x, 2 ulp (ex2.approx): the softmax exponentials
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // ------------------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 bytes (64 bf16) with the
@@ -125,6 +141,20 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= 2ull << 61;
     return d;
 }
+// Shared-memory matrix descriptor, MN-major operand (the MN index is the contiguous one): a tile stored as
+// K rows of 128 bytes (64 bf16 along MN) with the 128-byte swizzle -- exactly what a TMA box {64, K} produces.
+// Canonical form (cute/atom/mma_traits_sm100.hpp, units of 16 B): ((8,n),(8,k)):((1,LBO),(8,SBO)): 8 K rows are
+// 128 B apart, groups of 8 K rows SBO = 1024 B apart; LBO (next 64-wide MN span) is unused when MN == 64.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+constexpr uint32_t IDESC_A_MN = 1u << 15, IDESC_B_MN = 1u << 16;   // operand is MN-major instead of K-major
+
 // Instruction descriptor, kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {

@@ -259,8 +259,8 @@ class ViTEss(nn.Module):
             return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=x)
         # tensor-core engine: LayerNorm and the GEMM epilogues emit the bf16 planes the next GEMM reads
         h = ops.layernorm_planes(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, P)
-        qkv, _ = ops.linear_tc(h, self._planes(blk.attn.qkv.weight, P), blk.attn.qkv.bias)
-        a = ops.split_planes(ops.self_attention(qkv), P)
+        _, qkv = ops.linear_tc(h, self._planes(blk.attn.qkv.weight, P), blk.attn.qkv.bias, want_f32=False, planes_out=P)
+        _, a = ops.self_attention_tc(qkv, planes_out=P)
         x, _ = ops.linear_tc(a, self._planes(blk.attn.proj.weight, P), blk.attn.proj.bias, residual=x)
         h = ops.layernorm_planes(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, P)
         _, h = ops.linear_tc(h, self._planes(blk.mlp.fc1.weight, P), blk.mlp.fc1.bias, act=ops.ACT_GELU,

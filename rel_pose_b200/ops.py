@@ -367,6 +367,23 @@ def self_attention(qkv):
     return out
 
 
+def self_attention_tc(qkv_planes, want_f32=False, planes_out=0):
+    """qkv_planes bf16 [P,n,576,576] -> (float32 [n,576,192] | None, bf16 planes [planes_out,n,576,192] | None)."""
+    _req(qkv_planes, "qkv_planes", torch.bfloat16)
+    P, n = qkv_planes.shape[0], qkv_planes.shape[1]
+    assert tuple(qkv_planes.shape[2:]) == (NTOK, 3 * EMBED)
+    assert want_f32 or planes_out
+    out = torch.empty((n, NTOK, EMBED), dtype=torch.float32, device=qkv_planes.device) if want_f32 else None
+    outp = torch.empty((planes_out, n, NTOK, EMBED), dtype=torch.bfloat16, device=qkv_planes.device) if planes_out else None
+    dev, st = _ctx(qkv_planes)
+    _tbegin(f"self_attention_tc{'x3' if P == 2 else ''}", 4.0 * n * HEADS * NTOK * NTOK * HDIM,
+            2.0 * P * n * NTOK * 3 * EMBED + (4.0 if want_f32 else 0.0) * n * NTOK * EMBED + 2.0 * planes_out * n * NTOK * EMBED)
+    _lib.check(_lib.lib().rp_self_attention_tc(_p(qkv_planes), _p(out), _p(outp), n, P, int(planes_out), dev, st),
+               "rp_self_attention_tc")
+    _count()
+    return out, outp
+
+
 _LIN24 = None
 
 

@@ -163,3 +163,44 @@ def test_maxpool_planes():
     ref = O.maxpool3x3s2(x)
     assert np.array_equal(y.cpu().numpy().transpose(0, 3, 1, 2), ref)
     assert np.abs(planes_to_f64(yp).transpose(0, 3, 1, 2) - ref).max() <= 2.0 ** -16 * np.abs(ref).max()
+
+
+def _attention_ref(qkv):
+    """float64 softmax(q k^T / 8) v per image and head; qkv [n,576,576] (column = s*192+h*64+d)."""
+    n = qkv.shape[0]
+    q = qkv.astype(np.float64).reshape(n, 576, 3, 3, 64)
+    out = np.empty((n, 576, 192))
+    for h in range(3):
+        s = np.einsum("nid,njd->nij", q[:, :, 0, h], q[:, :, 1, h]) * 0.125
+        s -= s.max(-1, keepdims=True)
+        p = np.exp(s)
+        p /= p.sum(-1, keepdims=True)
+        out[:, :, h * 64:(h + 1) * 64] = np.einsum("nij,njd->nid", p, q[:, :, 2, h])
+    return out
+
+
+@pytest.mark.parametrize("P", [2, 1])
+@pytest.mark.parametrize("n,scale", [(1, 1.0), (3, 2.5), (40, 1.0)])
+def test_self_attention_tc(P, n, scale):
+    qkv = rnd(21 + n, n, 576, 576, scale=scale)
+    qkv[:, :, 384:] += 0.25                          # non-zero-mean values
+    ref = _attention_ref(qkv)
+    qp = ops.split_planes(cu(qkv), P)
+    out, outp = ops.self_attention_tc(qp, want_f32=True, planes_out=P)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float64)
+    gotp = planes_to_f64(outp)
+    scale_ref = np.abs(ref).max()
+    err = np.abs(got - ref).max()
+    print(f"[parity] self_attention_tc P={P} n={n} scale={scale}: max_abs_err={err:.3e} max_ref={scale_ref:.3e}")
+    # split-bf16 logits carry ~2^-17 relative error per product; with |logit| ~ 6 (scale 2.5: a far peakier
+    # softmax than the model ever produces) that is ~5e-5 relative on the output
+    tol = ((2e-5 if scale <= 1.0 else 1e-4) if P == 2 else 2e-2) * scale_ref
+    if err > tol:
+        for h in range(3):
+            _diagnose(f"attn n0 head{h}", got[0][:, h * 64:(h + 1) * 64], ref[0][:, h * 64:(h + 1) * 64])
+    assert err <= tol
+    assert np.abs(gotp - got).max() <= (2.0 ** -15 if P == 2 else 2.0 ** -7) * scale_ref
+    # agreement with the fp32 SIMT kernel of the same op
+    simt = ops.self_attention(cu(qkv)).cpu().numpy().astype(np.float64)
+    assert np.abs(simt - ref).max() < 1e-5 * scale_ref
