@@ -127,6 +127,18 @@ int rp_conv2d_tc(const void* x_planes, const void* w_planes, const float* scale,
                  const float* res_pre, const float* res_post, int res_post_rows, float* out_f32, void* out_planes,
                  int n_img, int H, int W, int C, int O, int KH, int KW, int stride, int pad, int P, int P_out, int act,
                  int device, void* stream);
+/* Stem on tensor cores: resnet.conv1 (7x7/2, pad 3; src/model.py:127) as a 4x4 stride-1 convolution over
+ * the 2x2 space-to-depth image.  rp_preprocess_stem_windows_* is A1 (src/model.py:114-125: BGR->RGB, /255,
+ * mean/std, legacy-nearest resize to 224) fused with that layout: it writes bf16 planes
+ * [P][n_img][115][112][64] where [yp][ox][b*16 + (dy*2+dx)*3 + c] = pixel (2(yp-2)+dy, 2(ox-2+b)+dx) channel c
+ * of the normalised 224x224 image (0 outside, channels 12..15 of each group 0).  rp_stem_weight_windows_f32
+ * re-lays conv1.weight [O][3][7][7] as [O][4][64] to match; the convolution itself is
+ * rp_conv2d_tc(H=115, W=112, C=64, KH=4, KW=1, stride 1, pad 0). */
+int rp_preprocess_stem_windows_f32(const float* images, void* planes, int n_img, int H, int W, int P, int device,
+                                   void* stream);
+int rp_preprocess_stem_windows_u8(const uint8_t* images, void* planes, int n_img, int H, int W, int P, int device,
+                                  void* stream);
+int rp_stem_weight_windows_f32(const float* w, float* out, int O, int device, void* stream);
 /* nn.MaxPool2d(3,2,1) on NHWC float32 writing float32 (y_f32, may be NULL) and/or P bf16 planes */
 int rp_maxpool3x3s2_planes(const float* x, float* y_f32, void* y_planes, int P, int n_img, int H, int W, int C,
                            int device, void* stream);

@@ -28,6 +28,9 @@ _SIGNATURES = {
     "rp_conv2d_nhwc_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr] + [_c_int] * 10 + [_ptr, _c_size, _c_int, _ptr]),
     "rp_preprocess_nhwc4_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_preprocess_nhwc4_u8": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_preprocess_stem_windows_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_preprocess_stem_windows_u8": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_stem_weight_windows_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_maxpool3x3s2_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_permute_conv_weight_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_bn_fold_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _c_int, _c_int, _ptr]),

@@ -180,13 +180,18 @@ class ViTEss(nn.Module):
             for name, conv, bn in layers:
                 w = ops.permute_conv_weight(conv.weight)
                 scale, shift = ops.bn_fold(bn, conv.bias)
-                wp = ops.split_planes(w.reshape(w.shape[0], -1), P) if (P and name != "stem") else None
+                if P and name == "stem":
+                    # 7x7/2 as a 4x4 convolution over the space-to-depth windows (conv_aux.cu)
+                    wp = ops.split_planes(ops.stem_weight_windows(conv.weight).reshape(w.shape[0], -1), P)
+                else:
+                    wp = ops.split_planes(w.reshape(w.shape[0], -1), P) if P else None
                 cache[name] = (w, scale, shift, conv.stride[0], conv.padding[0], wp, conv.kernel_size[0])
             self._cnn_cache, self._cnn_cache_key = cache, key
         return self._cnn_cache
 
     def _cnn_front_end(self, x):
-        """x [2B,224,224,4] NHWC -> tokens [2B,576,192] with pos_embed already added
+        """x = A1 output: [2B,224,224,4] NHWC float32 (fp32 engine) or the stem's bf16 window planes
+        [P,2B,115,112,64] (tensor-core engine) -> tokens [2B,576,192] with pos_embed already added
         (model.py:127-141,172; extractor.py:51-65).  BatchNorm in eval mode (running statistics)."""
         prm = self._cnn_params()
         P = self._tc_planes()
@@ -197,8 +202,8 @@ class ViTEss(nn.Module):
             w, scale, shift, stride, pad = prm[name][:5]
             return ops.conv2d_nhwc(inp, w, scale, shift, stride, pad, act, res_pre, res_post, rows)
 
-        stem = conv("stem", x, R)                                     # 7x7/2 on 4 input channels: SIMT engine
         if P == 0:
+            stem = conv("stem", x, R)                                 # 7x7/2 on 4 input channels: SIMT engine
             x = ops.maxpool3x3s2_nhwc(stem)
             for blk in ("l1.0", "l1.1"):
                 x = conv(blk + ".c2", conv(blk + ".c1", x, R), R, res_pre=x)
@@ -216,6 +221,8 @@ class ViTEss(nn.Module):
             return ops.conv2d_tc(xp, wp, k, k, scale, shift, stride, pad, act, res_pre, res_post, rows,
                                  want_f32=f32, planes_out=P if planes else 0)
 
+        _, scale, shift, _, _, wp, _ = prm["stem"]
+        stem, _ = ops.conv2d_tc(x, wp, 4, 1, scale, shift, 1, 0, R, want_f32=True, planes_out=0)
         xf, xp = ops.maxpool3x3s2_planes(stem, P)
         for blk in ("l1.0", "l1.1"):
             _, yp = tconv(blk + ".c1", xp, R)
@@ -316,7 +323,12 @@ class ViTEss(nn.Module):
             images = images.contiguous()
             if images.dtype != torch.uint8:
                 images = images.float()
-            x = ops.preprocess_nhwc4(images)                                  # A1 (NHWC, C padded to 4)
+            if self._tc_planes() == 0 or stages is not None:
+                x = ops.preprocess_nhwc4(images)                              # A1 (NHWC, C padded to 4)
+                if stages is not None:
+                    stages["preprocessed"] = x[..., :3].permute(0, 3, 1, 2)
+            if self._tc_planes():
+                x = ops.preprocess_stem_windows(images, self._tc_planes())    # A1 in the stem's window layout
             kxy = flags = None
             if intrinsics is not None:
                 intrinsics, kxy, flags = self.update_intrinsics(images.shape, intrinsics)
@@ -324,8 +336,6 @@ class ViTEss(nn.Module):
                 flags_host.copy_(flags, non_blocking=True)
                 flags_event = torch.cuda.Event()
                 flags_event.record()
-            if stages is not None:
-                stages["preprocessed"] = x[..., :3].permute(0, 3, 1, 2)
             vt = self.fusion_transformer
             x = self._cnn_front_end(x)                                        # A2, A3, A4
             if stages is not None:

@@ -148,6 +148,36 @@ def preprocess_nhwc4(images):
     return out
 
 
+def preprocess_stem_windows(images, P):
+    """A1 fused with the stem's space-to-depth window layout: [B,2,3,H,W] -> bf16 planes [P,2B,115,112,64]."""
+    if images.dtype == torch.uint8:
+        _req(images, "images", torch.uint8)
+        fn = _lib.lib().rp_preprocess_stem_windows_u8
+    else:
+        _req(images, "images")
+        fn = _lib.lib().rp_preprocess_stem_windows_f32
+    B, V, C, H, W = images.shape
+    assert C == 3
+    out = torch.empty((P, B * V, 115, 112, 64), dtype=torch.bfloat16, device=images.device)
+    dev, st = _ctx(images)
+    _tbegin("preprocess_stem_windows", 0.0, float(images.numel() * images.element_size()) + 2.0 * out.numel())
+    _lib.check(fn(_p(images), _p(out), B * V, H, W, P, dev, st), "rp_preprocess_stem_windows")
+    _count()
+    return out
+
+
+def stem_weight_windows(w):
+    """conv1.weight [O,3,7,7] -> [O,4,1,64] (the 4x4 space-to-depth kernel, KW folded into C); parameter preparation."""
+    w = _req(w.detach().contiguous(), "w")
+    O = w.shape[0]
+    assert tuple(w.shape[1:]) == (3, 7, 7)
+    out = torch.empty((O, 4, 1, 64), dtype=torch.float32, device=w.device)
+    dev, st = _ctx(w)
+    _lib.check(_lib.lib().rp_stem_weight_windows_f32(_p(w), _p(out), O, dev, st), "rp_stem_weight_windows")
+    _count()
+    return out
+
+
 def conv2d_nhwc(x, w, scale=None, shift=None, stride=1, pad=0, act=ACT_NONE, res_pre=None, res_post=None,
                 res_post_rows=0):
     """x [n,H,W,C] NHWC, w [O,KH,KW,C] -> [n,Ho,Wo,O]; y = act(conv*scale+shift+res_pre)+res_post."""

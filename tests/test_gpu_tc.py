@@ -204,3 +204,38 @@ def test_self_attention_tc(P, n, scale):
     # agreement with the fp32 SIMT kernel of the same op
     simt = ops.self_attention(cu(qkv)).cpu().numpy().astype(np.float64)
     assert np.abs(simt - ref).max() < 1e-5 * scale_ref
+
+
+@pytest.mark.parametrize("P", [2, 1])
+@pytest.mark.parametrize("B,H,W,u8", [(1, 96, 128, False), (2, 384, 384, False), (1, 480, 640, True)])
+def test_stem_windows_conv(P, B, H, W, u8):
+    """A1 + resnet.conv1 + bn1 + relu through the space-to-depth window layout vs the oracle's 7x7/2 conv."""
+    img = S.make_images_numpy(3, B, H, W)
+    w = rnd(51, 64, 3, 7, 7, scale=1.0 / np.sqrt(147.0))
+    bn = _BN(52, 64)
+    x = O.preprocess(img, np.float32).astype(np.float64)                     # [2B,3,224,224]
+    y = O.conv2d(x, w.astype(np.float64), None, 2, 3)
+    ref = np.maximum(O.batchnorm_eval(y, {kk: v.astype(np.float64) for kk, v in bn.params("bn").items()}, "bn"), 0)
+    src = cu(img.astype(np.uint8)) if u8 else cu(img)
+    if u8:
+        assert np.array_equal(img, np.floor(img))
+    win = ops.preprocess_stem_windows(src, P)
+    assert tuple(win.shape) == (P, 2 * B, 115, 112, 64)
+    # bit-exact indexing of the windows: window (yp, ox), group b is s2d pixel (yp-2, ox-2+b)
+    wf = win.float().sum(0).cpu().numpy().reshape(2 * B, 115, 112, 4, 16)
+    z = np.zeros((2 * B, 116, 116, 16))
+    z[:, 2:114, 2:114, :12] = x.reshape(2 * B, 3, 112, 2, 112, 2).transpose(0, 2, 4, 3, 5, 1).reshape(2 * B, 112, 112, 12)
+    exp = np.stack([z[:, :115, b:b + 112] for b in range(4)], axis=3)
+    assert np.abs(wf - exp).max() <= (2.0 ** -16 if P == 2 else 2.0 ** -8) * np.abs(x).max()
+    assert np.array_equal(wf == 0, exp == 0)
+    w2 = ops.stem_weight_windows(cu(w))
+    wp = ops.split_planes(w2.reshape(64, 256), P)
+    scale, shift = ops.bn_fold(bn, None)
+    out, _ = ops.conv2d_tc(win, wp, 4, 1, scale, shift, 1, 0, ops.ACT_RELU, want_f32=True, planes_out=0)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().transpose(0, 3, 1, 2).astype(np.float64)
+    assert got.shape == ref.shape
+    err = np.abs(got - ref).max()
+    tol = (4e-5 if P == 2 else 3e-2) * np.abs(ref).max()
+    print(f"[parity] stem_windows P={P} {H}x{W} u8={u8}: max_abs_err={err:.3e} max_ref={np.abs(ref).max():.3e} ratio={err / tol:.3f}")
+    assert err <= tol
