@@ -169,6 +169,14 @@ int rp_posenc_f32(const float* kxy, const float* host_lin24, float* pos, int B, 
 size_t rp_essential_workspace_bytes(int B);
 int rp_essential_f32(const float* qkv, const float* pos, float* bil, int B, void* workspace,
                      size_t workspace_bytes, int device, void* stream);
+/* Same contract on tcgen05 tensor cores.  qkv_planes = bf16 planes [P][2B][576][576] of the cross block's QKV GEMM
+ * (P = 1 bf16, P = 2 split bf16 = fp32 class).  Two kernels: row/column log-sum-exp of S, then the fused
+ * dual-softmax -> A [v|pos] -> [v|pos]^T T accumulation with F resident in tensor memory (no partials, no
+ * atomics, bit-reproducible).  workspace: rp_essential_tc_workspace_bytes(B, P). */
+size_t rp_essential_tc_workspace_bytes(int B, int P);
+int rp_essential_tc(const void* qkv_planes, const float* pos, float* bil, int B, int P, void* workspace,
+                    size_t workspace_bytes, int device, void* stream);
+
 
 /* ---- A7 tail  vision_transformer.py:229-238 + :292-294 --------------------------------------
  * Z[b,c,h*70+a] = bil[b,dir,h,a,c];  Y = Z W^T + bias (proj_fundamental, W [192,210]);

@@ -137,19 +137,26 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 tc::mbar_wait(&k_full[ks], kph);
                 tc::tcgen05_fence_after();
                 const uint32_t d = tmem_base + S_COL + (gb & 1) * BKV;
+                // tcgen05 accumulates with truncation (bias ~ chain length x 2^-25): the small correction terms of
+                // ALL K steps go first, the main terms last, so the full-magnitude chain is K/16 long, not 3K/16
+                uint32_t accum = 0u;
+                if (P == 2) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    const uint32_t koff = k * 32;
-                    uint32_t accum = k > 0 ? 1u : 0u;
-                    if (P == 2) {
+                    for (int k = 0; k < HD / 16; ++k) {
+                        const uint32_t koff = k * 32;
                         tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(P - 1)) + koff),
                                       tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)) + koff), idesc_s, accum);
                         tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(0)) + koff),
                                       tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, P - 1)) + koff), idesc_s, 1u);
                         accum = 1u;
                     }
+                }
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint32_t koff = k * 32;
                     tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(0)) + koff),
                                   tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)) + koff), idesc_s, accum);
+                    accum = 1u;
                 }
                 tc::umma_commit(&k_free[ks]);
                 tc::umma_commit(&s_full[gb & 1]);
@@ -168,20 +175,26 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     tc::mbar_wait(&v_full[vs], vph);
                     tc::tcgen05_fence_after();
                     const uint32_t d = tmem_base + O_COL;
+                    uint32_t accum = 0u;
+                    if (P == 2) {
 #pragma unroll
-                    for (int kk = 0; kk < BKV / 16; ++kk) {
-                        const uint32_t a_off = (kk >> 2) * P_SUB + (kk & 3) * 32;   // K-major: 16 keys = 32 B in the row
-                        const uint32_t b_off = kk * 16 * 128;                       // MN-major: 16 keys = 16 rows
-                        uint32_t accum = kk > 0 ? 1u : 0u;
-                        if (P == 2) {
+                        for (int kk = 0; kk < BKV / 16; ++kk) {
+                            const uint32_t a_off = (kk >> 2) * P_SUB + (kk & 3) * 32;   // K-major: 16 keys = 32 B in the row
+                            const uint32_t b_off = kk * 16 * 128;                       // MN-major: 16 keys = 16 rows
                             tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(P - 1)) + a_off),
                                           tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)) + b_off, 0), idesc_o, accum);
                             tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(0)) + a_off),
                                           tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, P - 1)) + b_off, 0), idesc_o, 1u);
                             accum = 1u;
                         }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < BKV / 16; ++kk) {
+                        const uint32_t a_off = (kk >> 2) * P_SUB + (kk & 3) * 32;
+                        const uint32_t b_off = kk * 16 * 128;
                         tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(0)) + a_off),
                                       tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)) + b_off, 0), idesc_o, accum);
+                        accum = 1u;
                     }
                     tc::umma_commit(&v_free[vs]);
                     tc::umma_commit(pv_done);

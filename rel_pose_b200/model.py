@@ -285,9 +285,9 @@ class ViTEss(nn.Module):
             qkv = ops.linear(h, ca.qkv.weight, ca.qkv.bias)
         else:
             h = ops.layernorm_planes(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, P)
-            qkv, _ = ops.linear_tc(h, self._planes(ca.qkv.weight, P), ca.qkv.bias)
+            _, qkv = ops.linear_tc(h, self._planes(ca.qkv.weight, P), ca.qkv.bias, want_f32=False, planes_out=P)
         pos = ops.posenc(B, kxy, x.device)
-        bil = ops.essential(qkv, pos)
+        bil = ops.essential(qkv, pos) if P == 0 else ops.essential_tc(qkv, pos)
         if stages is not None:
             stages["bilinear1"], stages["bilinear2"] = bil[:, 0], bil[:, 1]
         f = ops.em_project(bil, ca.proj_fundamental.weight, ca.proj_fundamental.bias)

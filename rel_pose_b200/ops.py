@@ -460,6 +460,29 @@ def essential(qkv, pos):
     return bil
 
 
+def essential_tc(qkv_planes, pos):
+    """qkv_planes bf16 [P,2B,576,576], pos [B,576,6] or None -> bilinear forms [B,2,3,W,W] (tensor cores)."""
+    _req(qkv_planes, "qkv_planes", torch.bfloat16)
+    P, n = qkv_planes.shape[0], qkv_planes.shape[1]
+    B = n // 2
+    assert n == 2 * B and tuple(qkv_planes.shape[2:]) == (NTOK, 3 * EMBED)
+    width = EMW if pos is not None else HDIM
+    if pos is not None:
+        _req(pos, "pos")
+        assert tuple(pos.shape) == (B, NTOK, NPOS)
+    bil = torch.empty((B, 2, HEADS, width, width), dtype=torch.float32, device=qkv_planes.device)
+    L = _lib.lib()
+    ws_bytes = L.rp_essential_tc_workspace_bytes(B, P)
+    ws = torch.empty((ws_bytes // 4 + 4,), dtype=torch.float32, device=qkv_planes.device)
+    dev, st = _ctx(qkv_planes)
+    _tbegin(f"essential_tc{'x3' if P == 2 else ''}",
+            B * 2.0 * HEADS * (3 * 2.0 * NTOK * NTOK * HDIM + 2.0 * NTOK * NTOK * width + 2.0 * NTOK * width * width),
+            2.0 * P * n * NTOK * 3 * EMBED + 4.0 * B * 2 * HEADS * width * width)
+    _lib.check(L.rp_essential_tc(_p(qkv_planes), _p(pos), _p(bil), B, P, _p(ws), ws_bytes, dev, st), "rp_essential_tc")
+    _count(3 if pos is not None else 2)
+    return bil
+
+
 def em_project(bil, weight, bias):
     """bil [B,2,3,70,70] -> [2B,70,192] (proj_fundamental + the reference's output flip)."""
     _req(bil, "bil"); _req(weight, "weight"); _req(bias, "bias")

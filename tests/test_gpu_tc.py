@@ -239,3 +239,69 @@ def test_stem_windows_conv(P, B, H, W, u8):
     tol = (4e-5 if P == 2 else 3e-2) * np.abs(ref).max()
     print(f"[parity] stem_windows P={P} {H}x{W} u8={u8}: max_abs_err={err:.3e} max_ref={np.abs(ref).max():.3e} ratio={err / tol:.3f}")
     assert err <= tol
+
+
+@pytest.mark.parametrize("P", [2, 1])
+@pytest.mark.parametrize("B,scale,use_pos", [(1, 1.0, True), (2, 3.0, True), (2, 1.0, False), (30, 1.0, True)])
+def test_essential_tc(P, B, scale, use_pos):
+    """Essential Matrix Module core on tensor cores vs the float64 oracle (and vs the fp32 SIMT kernels)."""
+    x = rnd(12, 2 * B, 576, 192)
+    w = rnd(13, 576, 192, scale=scale / np.sqrt(192)); bq = rnd(14, 576, scale=0.1)
+    pw = rnd(15, 192, 210, scale=1 / np.sqrt(210)); pb = rnd(16, 192, scale=0.1)
+    k = O.update_intrinsics(S.make_intrinsics_numpy(B, "varied", 3), 384, 512)
+    qkv = ops.linear(cu(x), cu(w), cu(bq))
+    kxy = cu(np.stack([1 / (k[:, 0, 0] / k[:, 0, 2]), 1 / (k[:, 0, 1] / k[:, 0, 3])], -1).astype(np.float32))
+    pos = ops.posenc(B, kxy, qkv.device) if use_pos else None
+    simt = ops.essential(qkv, pos).cpu().numpy().astype(np.float64)
+    qp = ops.split_planes(qkv, P)
+    bil = ops.essential_tc(qp, pos)
+    again = ops.essential_tc(qp, pos)
+    torch.cuda.synchronize()
+    assert torch.equal(bil, again)                       # no atomics: bit-reproducible
+    got = bil.cpu().numpy().astype(np.float64)
+    if use_pos:
+        p = {"c.qkv.weight": w.astype(np.float64), "c.qkv.bias": bq.astype(np.float64),
+             "c.proj_fundamental.weight": pw.astype(np.float64), "c.proj_fundamental.bias": pb.astype(np.float64)}
+        x64 = x.astype(np.float64).reshape(B, 2, 576, 192)
+        _, (f1, f2) = O.essential_matrix_module(x64[:, 0], x64[:, 1], p, "c", k, return_bilinear=True)
+        ref = np.stack([f1, f2], 1)
+    else:
+        ref = simt
+    assert got.shape == ref.shape
+    if use_pos:
+        # same oracle fed with the 16-bit-mantissa qkv the kernel actually reads: separates operand rounding
+        # (inherent to the split-bf16 format) from arithmetic error inside the kernels
+        qr = qp.float().double().sum(0).cpu().numpy().reshape(B, 2, 576, 3, 3, 64)
+        posd = pos.double().cpu().numpy()
+        f_r = []
+        for d_ in range(2):
+            qi, ki = 1 - d_, d_
+            q_ = qr[:, qi, :, 0].transpose(0, 2, 1, 3); k_ = qr[:, ki, :, 1].transpose(0, 2, 1, 3); v_ = qr[:, ki, :, 2].transpose(0, 2, 1, 3)
+            s_ = q_ @ k_.transpose(0, 1, 3, 2) * 0.125
+            a_ = O.softmax(s_, -1) * O.softmax(s_, -2)
+            V_ = np.concatenate([v_, np.broadcast_to(posd[:, None], (B, 3, 576, 6))], 3)
+            f_r.append(V_.transpose(0, 1, 3, 2) @ a_ @ V_)
+        ref_r = np.stack(f_r, 1)
+    else:
+        ref_r = ref
+    for d in range(2):
+        sc = np.abs(ref[:, d]).max()
+        e = np.abs(got[:, d] - ref[:, d])
+        er = np.abs(got[:, d] - ref_r[:, d])
+        es_ = np.abs(simt[:, d] - ref[:, d])
+        es = es_.max()
+        def blk(x):
+            return {"vv": x[..., :64, :64], "vp": x[..., :64, 64:], "pv": x[..., 64:, :64], "pp": x[..., 64:, 64:]} if use_pos else {"vv": x}
+        blocks = {kk: float(f"{v.max():.2e}") for kk, v in blk(e).items()}
+        rel = {kk: float(f"{(blk(e)[kk].max() / np.abs(v).max()):.2e}") for kk, v in blk(ref[:, d]).items()}
+        rel_r = {kk: float(f"{(blk(er)[kk].max() / np.abs(v).max()):.2e}") for kk, v in blk(ref[:, d]).items()}
+        rel_s = {kk: float(f"{(blk(es_)[kk].max() / np.abs(v).max()):.2e}") for kk, v in blk(ref[:, d]).items()}
+        print(f"[parity] em_tc P={P} B={B} scale={scale} pos={use_pos} dir{d}: max_abs_err={e.max():.3e} max_ref={sc:.3e} "
+              f"simt_err={es:.3e} abs={blocks} rel_to_block={rel} rel_vs_rounded_inputs={rel_r} simt_rel={rel_s}")
+        tol = (5e-5 if P == 2 else 3e-2) * sc
+        if e.max() > tol:
+            bad = np.argwhere(e > tol)
+            print(f"[tc-diag] {len(bad)} bad of {e.size}; first (b,h,a,c): {bad[:10].tolist()}")
+            print(f"[tc-diag] err by a: {e.max(axis=(0, 1, 3))}")
+            print(f"[tc-diag] err by c: {e.max(axis=(0, 1, 2))}")
+        assert np.isfinite(got).all() and e.max() <= tol
