@@ -14,6 +14,7 @@ Parameter containers mirror the reference's module tree only so that `state_dict
   pose_regressor.{0,2,4}.*    26880->512->512->14
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -132,7 +133,7 @@ class ViTEss(nn.Module):
             nn.Unflatten(1, (self.num_images, self.pose_size)))
         # arithmetic of the transformer GEMMs: "fp32" (SIMT FFMA), "bf16x3" (tcgen05, split-bf16 operands,
         # fp32-class: holds the 1e-4 parity bar), "bf16" (tcgen05 single pass: throughput mode, ~1e-2)
-        self.precision = getattr(args, "precision", None) or "fp32"
+        self.precision = getattr(args, "precision", None) or os.environ.get("RELPOSE_PRECISION", "bf16x3")
         assert self.precision in ("fp32", "bf16x3", "bf16")
         self.check_intrinsics = True      # reproduce the reference's assert on per-view intrinsics
         self.last_stages = None           # filled when `capture_stages` is set (parity tests)
@@ -332,7 +333,9 @@ class ViTEss(nn.Module):
             kxy = flags = None
             if intrinsics is not None:
                 intrinsics, kxy, flags = self.update_intrinsics(images.shape, intrinsics)
-                flags_host = torch.empty((1,), dtype=torch.int32, pin_memory=True)
+                flags_host = self.__dict__.get("_flags_host")
+                if flags_host is None:
+                    flags_host = self.__dict__["_flags_host"] = torch.empty((1,), dtype=torch.int32, pin_memory=True)
                 flags_host.copy_(flags, non_blocking=True)
                 flags_event = torch.cuda.Event()
                 flags_event.record()

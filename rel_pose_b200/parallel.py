@@ -1,0 +1,117 @@
+"""Sharded and streamed inference over independent image pairs.
+
+Every pair is independent in the forward pass (self-attention is per image, the Essential Matrix Module is
+per pair, BatchNorm uses running statistics), so N GPUs run N shards with NO data-path collective; the two
+images of a pair always stay on the same rank (CrossBlock relies on their adjacency, vision_transformer.py:287).
+This module is host logic only: shard arithmetic, an optional gather of the [B,2,7] results, and a
+double-buffered host->device pipeline that overlaps the copy of micro-batch k+1 with the kernels of
+micro-batch k (the reference's callers do `images.cuda()` synchronously, demo.py:76 / train.py:143).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_pairs, world_size, rank):
+    """Contiguous [lo, hi) of pair indices owned by `rank`; sizes differ by at most one."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank {rank} / world_size {world_size}")
+    base, rem = divmod(int(n_pairs), world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def micro_batches(lo, hi, size):
+    """[(a, b)] covering [lo, hi) in chunks of at most `size` pairs."""
+    if size <= 0:
+        raise ValueError("micro-batch size must be positive")
+    return [(a, min(a + size, hi)) for a in range(lo, hi, size)]
+
+
+def gather_poses(local_poses, n_pairs, group=None):
+    """All ranks receive the full [n_pairs,2,7] tensor (shards in rank order).  Works with gloo (CPU
+    tensors) and nccl (CUDA tensors); shards may be ragged."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local_poses
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_range(n_pairs, world, rank)
+    if local_poses.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} holds {local_poses.shape[0]} pairs, expected {hi - lo}")
+    cap = -(-n_pairs // world)
+    pad = torch.zeros((cap,) + tuple(local_poses.shape[1:]), dtype=local_poses.dtype, device=local_poses.device)
+    pad[: hi - lo] = local_poses
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = []
+    for r, p in enumerate(parts):
+        a, b = shard_range(n_pairs, world, r)
+        out.append(p[: b - a])
+    return torch.cat(out, 0)
+
+
+class StreamedInference:
+    """Double-buffered inference from PINNED host batches.
+
+        runner = StreamedInference(model)
+        for poses in runner.run(batches):      # batches: iterable of (images, Gs_data, intrinsics) host tensors
+            ...                                # poses: host tensor [b,2,7] of the corresponding batch
+
+    The H2D copy of batch k+1 is issued on a side stream while batch k computes; results come back through
+    pinned staging buffers.  Order is preserved; nothing is dropped."""
+
+    def __init__(self, model, device=None):
+        self.model = model
+        self.device = device if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("StreamedInference needs the model on a CUDA device (no CPU path)")
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._bufs = [None, None]
+
+    def _stage(self, slot, batch):
+        images, gs, intr = batch
+        with torch.cuda.stream(self.copy_stream):
+            d_img = images.to(self.device, non_blocking=True)
+            d_gs = gs.to(self.device, non_blocking=True)
+            d_k = intr.to(self.device, non_blocking=True) if intr is not None else None
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._bufs[slot] = (d_img, d_gs, d_k, ev)
+
+    def run(self, batches):
+        from .lietorch import SE3
+        it = iter(batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        self._stage(0, nxt)
+        slot = 0
+        pending = None                       # (host result, event) of the previous batch
+        compute = torch.cuda.current_stream(self.device)
+        while True:
+            d_img, d_gs, d_k, ev = self._bufs[slot]
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            if nxt is not None:
+                self._stage(slot ^ 1, nxt)   # overlaps with the kernels launched below
+            compute.wait_event(ev)
+            with torch.no_grad():
+                out = self.model(d_img, SE3(d_gs), intrinsics=d_k)[0].data
+            for t in (d_img, d_gs, d_k):     # the copy stream allocated them, the compute stream used them
+                if t is not None:
+                    t.record_stream(compute)
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(compute)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = (host, done)
+            if nxt is None:
+                break
+            slot ^= 1
+        pending[1].synchronize()
+        yield pending[0]
