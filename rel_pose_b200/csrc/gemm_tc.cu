@@ -31,10 +31,10 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE = BM * BK * 2;   // 16 KiB
-constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter, each owning half of the columns
-constexpr int NTHREADS = 32 * (2 + EPI_WARPS);     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_WARPS = 16;                      // four per TMEM lane quarter, each owning a quarter of the columns
+constexpr int NTHREADS = 32 * (2 + EPI_WARPS);     // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;
-constexpr int STG_LD = 36;                         // staging row stride (floats): conflict-free v4 access
+constexpr int STG_LD = 16;                         // staging patch: 32 rows x 16 floats, 16-byte chunks XOR-swizzled
 constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
@@ -65,6 +65,22 @@ struct EpiParams {
     int p_out;
     int act;
 };
+
+// erf(x) to ~3e-7 absolute (Abramowitz & Stegun 7.1.26: 1 - (a1 t + .. + a5 t^5) exp(-x^2), t = 1/(1 + p|x|)):
+// two MUFU ops and seven FMAs, branch free.  The GELU epilogue is instruction bound, and its output is
+// re-split to 16 mantissa bits right away, so libdevice's 1-ulp erff (about 3x the instructions) buys nothing.
+__device__ __forceinline__ float fast_erf(float x) {
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    const float e = tc::fast_exp2(-1.4426950408889634f * ax * ax);
+    return copysignf(fmaf(-p, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_fast(float v) { return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ float act_fn(float v, int act) {
     if (act == RP_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
@@ -189,19 +205,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..9)
-        // TMEM hands every thread one ROW (32 consecutive columns); global memory wants a warp to touch
-        // whole 128-byte row segments.  Each warp therefore transposes its 32x32 block through a private,
-        // padded shared-memory patch and does the epilogue arithmetic on the coalesced side:
-        // 8 lanes x 16 B per row, 4 rows per instruction.
+        // ------------------------------------------------------------------ epilogue (warps 2..17)
+        // TMEM hands every thread one ROW; global memory wants a warp to touch whole row segments.  Each warp
+        // owns a 32-row x (BN/4)-column slab of the tile and walks it in 16-column chunks: tcgen05.ld (x16),
+        // transpose through a private 2 KiB shared-memory patch (16-byte chunks XOR-swizzled by row pair:
+        // conflict free both ways), then the epilogue arithmetic on the coalesced side -- 4 lanes x 16 B per row,
+        // 8 rows per instruction.  ncu showed the 8-warp version issue bound at ~0.25 IPC per scheduler with the
+        // per-column constants and residual loads exposed: 16 warps double the latency hiding, the constants are
+        // requested before the TMEM load and all residual loads of a chunk are in flight before the first store.
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                // column half owned by this warp
+        const int part = (warp - 2) >> 2;                // column quarter owned by this warp
         float* stg = staging + (warp - 2) * 32 * STG_LD;
         int acc = 0, acc_phase = 0;
         const bool vec4 = (N % 4) == 0;
-        const int rr = lane >> 3, c4 = (lane & 7) * 4;
-        constexpr int NCHUNK = BN / 32;                  // 32-column chunks per tile (2, 4 or 6)
-        constexpr int CH_PER_HALF = (NCHUNK + 1) / 2;
+        const int rr = lane >> 2, cq = lane & 3;         // read side: row inside an 8-row group, 16-byte chunk
+        constexpr int NCHUNK = BN / 16;                  // 16-column chunks per tile (4, 8 or 12)
+        constexpr int CH_PER_PART = NCHUNK / 4;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
             int row_base, valid_rows;                    // global row of tile row 0; rows of the tile that exist
@@ -217,30 +236,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int ci = 0; ci < CH_PER_HALF; ++ci) {
-                const int chunk = half * CH_PER_HALF + ci;
-                if (chunk >= NCHUNK) break;
-                const int c0 = chunk * 32;
+            for (int ci = 0; ci < CH_PER_PART; ++ci) {
+                const int c0 = (part * CH_PER_PART + ci) * 16;
                 if (n0 + c0 >= N) break;                 // warp-uniform
-                uint32_t r[32];
-                tc::tmem_ld_32x32b_x32(t_row + c0, r);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<uint4*>(stg + lane * STG_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                __syncwarp();
-                const int col = n0 + c0 + c4;            // the lane's 4 columns: the same for all 8 row groups
+                const int col = n0 + c0 + cq * 4;        // the lane's 4 columns: the same for all row groups
+                const bool colv = vec4 && col < N;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (colv && ep.scale) sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col));
+                if (colv && ep.shift) sh = __ldg(reinterpret_cast<const float4*>(ep.shift + col));
+                float4 rpre[4], rpost[4];
                 if (vec4) {
-                    // Two phases so that no global load sits behind a global store of the previous row group
-                    // (ncu: the scalar version spent ~50% of its samples on the exposed bias / residual loads).
-                    const bool colv = col < N;
-                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (colv && ep.scale) sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col));
-                    if (colv && ep.shift) sh = __ldg(reinterpret_cast<const float4*>(ep.shift + col));
-                    float4 rpre[8], rpost[8];
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rt = q * 32 + it * 4 + rr;
+                    for (int it = 0; it < 4; ++it) {
+                        const int rt = q * 32 + it * 8 + rr;
                         const bool ok = colv && rt < valid_rows;
                         const int row = row_base + rt;
                         rpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -251,17 +259,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             rpost[it] = __ldg(reinterpret_cast<const float4*>(ep.res_post + (size_t)rq * N + col));
                         }
                     }
+                }
+                uint32_t r[16];
+                tc::tmem_ld_32x32b_x16(t_row + c0, r);
+                tc::tmem_ld_wait();
+                __syncwarp();                            // the previous chunk's readers are done with the patch
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rt = q * 32 + it * 4 + rr;
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(stg + lane * STG_LD + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                if (vec4) {
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int rl = it * 8 + rr;                  // row inside the warp's 32-row slab
+                        const int rt = q * 32 + rl;
                         if (!colv || rt >= valid_rows) continue;
                         const size_t o = (size_t)(row_base + rt) * N + col;
-                        const float4 a = *reinterpret_cast<const float4*>(stg + (it * 4 + rr) * STG_LD + c4);
+                        const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2));
                         float v0 = fmaf(a.x, sc.x, sh.x) + rpre[it].x, v1 = fmaf(a.y, sc.y, sh.y) + rpre[it].y;
                         float v2 = fmaf(a.z, sc.z, sh.z) + rpre[it].z, v3 = fmaf(a.w, sc.w, sh.w) + rpre[it].w;
                         if (ep.act == RP_ACT_GELU) {
-                            v0 = act_fn(v0, RP_ACT_GELU); v1 = act_fn(v1, RP_ACT_GELU);
-                            v2 = act_fn(v2, RP_ACT_GELU); v3 = act_fn(v3, RP_ACT_GELU);
+                            v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3);
                         } else if (ep.act == RP_ACT_RELU) {
                             v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
                         }
@@ -281,21 +300,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else {
 #pragma unroll 1
-                    for (int it = 0; it < 8; ++it) {
-                        const int rt = q * 32 + it * 4 + rr;         // row inside the tile
-                        if (rt >= valid_rows || col >= N) continue;
+                    for (int it = 0; it < 4; ++it) {
+                        const int rl = it * 8 + rr;
+                        const int rt = q * 32 + rl;
+                        const int colx = n0 + c0 + cq * 4;
+                        if (rt >= valid_rows || colx >= N) continue;
                         const int row = row_base + rt;
-                        const size_t o = (size_t)row * N + col;
-                        const int nvalid = min(4, N - col);
+                        const size_t o = (size_t)row * N + colx;
+                        const int nvalid = min(4, N - colx);
                         for (int j = 0; j < nvalid; ++j) {
-                            float x = stg[(it * 4 + rr) * STG_LD + c4 + j];
-                            if (ep.scale) x *= ep.scale[col + j];
-                            if (ep.shift) x += ep.shift[col + j];
+                            float x = stg[rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2) + j];
+                            if (ep.scale) x *= ep.scale[colx + j];
+                            if (ep.shift) x += ep.shift[colx + j];
                             if (ep.res_pre) x += ep.res_pre[o + j];
                             x = act_fn(x, ep.act);
                             if (ep.res_post) {
                                 const int rq = ep.res_post_rows > 0 ? row % ep.res_post_rows : row;
-                                x += ep.res_post[(size_t)rq * N + col + j];
+                                x += ep.res_post[(size_t)rq * N + colx + j];
                             }
                             if (ep.out_f32) ep.out_f32[o + j] = x;
                             if (ep.out_planes)
@@ -307,7 +328,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                __syncwarp();                            // staging patch is reused by the next chunk
             }
             tc::tcgen05_fence_before();
             tc::mbar_arrive(&tempty[acc]);
