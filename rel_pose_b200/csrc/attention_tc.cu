@@ -28,7 +28,8 @@ constexpr int Q_TILE = BM * 128;          // bytes of one [128 x 64] bf16 tile
 constexpr int KV_TILE = BKV * 128;        // bytes of one [96 x 64] bf16 tile
 constexpr int P_SUB = BM * 128;           // P_j is [128 x 96] = one full and one half-used 64-wide K-major sub-tile
 constexpr int KV_STAGES = 2;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quarter)
+constexpr int HB = BKV / 2, HO = HD / 2;  // key columns / output columns per softmax thread
 constexpr int TMEM_COLS_ATT = 256;        // S[0] 0..95, S[1] 96..191, O 192..255
 constexpr int S_COL = 0, O_COL = 2 * BKV;
 static_assert(NTOK % BKV == 0 && BKV % 16 == 0 && (NBLK % 2) == 0, "key blocking");
@@ -41,7 +42,8 @@ struct ACfg {
     static constexpr int OFF_K = Q_BYTES;
     static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
     static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;
-    static constexpr int OFF_BAR = OFF_P + P_BYTES;
+    static constexpr int OFF_XCH = OFF_P + P_BYTES;          // float [2 parity][2 halves][128 rows]: row-max exchange
+    static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * BM * 4;
     static constexpr int SMEM = OFF_BAR + 256 + 1024 /*align slack*/;
 };
 
@@ -85,7 +87,7 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc::mbar_init(&v_free[i], 1);
             tc::mbar_init(&s_full[i], 1);
         }
-        tc::mbar_init(p_ready, 128);
+        tc::mbar_init(p_ready, 256);
         tc::mbar_init(pv_done, 1);
         tc::fence_barrier_init();
     }
@@ -101,171 +103,199 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     auto p_tile = [&](int p) { return smem + C::OFF_P + p * 2 * P_SUB; };
 
     if (warp == 0) {
-        // ---------------------------------------------------------------------------- TMA producer
-        if (lane == 0) {
-            int ks = 0, kph = 0, vs = 0, vph = 0, it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int qt = tile % QTILES, h = (tile / QTILES) % HEADS, img = tile / (QTILES * HEADS);
-                tc::mbar_wait(q_free, (it & 1) ^ 1);
+        // ---------------------------------------------------------------------------- TMA producer (convergent warp)
+        int ks = 0, kph = 0, vs = 0, vph = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int qt = tile % QTILES, h = (tile / QTILES) % HEADS, img = tile / (QTILES * HEADS);
+            tc::mbar_wait(q_free, (it & 1) ^ 1);
+            if (tc::elect_one_sync()) {
                 tc::mbar_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
                 for (int p = 0; p < P; ++p) tc::tma_load_4d(q_tile(p), &tmQ, q_full, h * HD, qt * BM, img, p);
-                for (int j = 0; j < NBLK; ++j) {
-                    tc::mbar_wait(&k_free[ks], kph ^ 1);
+            }
+            __syncwarp();
+            for (int j = 0; j < NBLK; ++j) {
+                tc::mbar_wait(&k_free[ks], kph ^ 1);
+                if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(&k_full[ks], C::KV_BYTES);
 #pragma unroll
                     for (int p = 0; p < P; ++p)
                         tc::tma_load_4d(k_tile(ks, p), &tmKV, &k_full[ks], EMB + h * HD, j * BKV, img, p);
-                    if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
-                    tc::mbar_wait(&v_free[vs], vph ^ 1);
+                }
+                __syncwarp();
+                if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+                tc::mbar_wait(&v_free[vs], vph ^ 1);
+                if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(&v_full[vs], C::KV_BYTES);
 #pragma unroll
                     for (int p = 0; p < P; ++p)
                         tc::tma_load_4d(v_tile(vs, p), &tmKV, &v_full[vs], 2 * EMB + h * HD, j * BKV, img, p);
-                    if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
                 }
+                __syncwarp();
+                if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = tc::make_idesc_bf16(BM, BKV);
-            constexpr uint32_t idesc_o = tc::make_idesc_bf16(BM, HD) | tc::IDESC_B_MN;
-            int ks = 0, kph = 0, vs = 0, vph = 0, it = 0;
-            uint32_t g = 0;     // global key-block counter of this CTA
-            auto issue_s = [&](uint32_t gb) {
-                tc::mbar_wait(&k_full[ks], kph);
-                tc::tcgen05_fence_after();
-                const uint32_t d = tmem_base + S_COL + (gb & 1) * BKV;
+        // ---------------------------------------------------------------------------- MMA issuer (convergent warp)
+        // All 32 lanes run the control flow and the barrier waits; one elected lane issues.  Descriptors are
+        // built once per tile and advanced by adding to their address field (16-byte units).
+        constexpr uint32_t idesc_s = tc::make_idesc_bf16(BM, BKV);
+        constexpr uint32_t idesc_o = tc::make_idesc_bf16(BM, HD) | tc::IDESC_B_MN;
+        int ks = 0, kph = 0, vs = 0, vph = 0, it = 0;
+        uint32_t g = 0;     // global key-block counter of this CTA
+        const uint64_t dq0 = tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(0)));
+        const uint64_t dq1 = tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(P - 1)));
+        const uint64_t dp0 = tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(0)));
+        const uint64_t dp1 = tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(P - 1)));
+        auto issue_s = [&](uint32_t gb) {
+            tc::mbar_wait(&k_full[ks], kph);
+            tc::tcgen05_fence_after();
+            const uint32_t d = tmem_base + S_COL + (gb & 1) * BKV;
+            const uint64_t dk0 = tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)));
+            const uint64_t dk1 = tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, P - 1)));
+            if (tc::elect_one_sync()) {
                 // tcgen05 accumulates with truncation (bias ~ chain length x 2^-25): the small correction terms of
                 // ALL K steps go first, the main terms last, so the full-magnitude chain is K/16 long, not 3K/16
                 uint32_t accum = 0u;
                 if (P == 2) {
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {
-                        const uint32_t koff = k * 32;
-                        tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(P - 1)) + koff),
-                                      tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)) + koff), idesc_s, accum);
-                        tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(0)) + koff),
-                                      tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, P - 1)) + koff), idesc_s, 1u);
+                    for (int k = 0; k < HD / 16; ++k) {          // 16 bf16 = 32 B inside the swizzle row = +2
+                        tc::umma_bf16(d, dq1 + 2 * k, dk0 + 2 * k, idesc_s, accum);
+                        tc::umma_bf16(d, dq0 + 2 * k, dk1 + 2 * k, idesc_s, 1u);
                         accum = 1u;
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) {
-                    const uint32_t koff = k * 32;
-                    tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(0)) + koff),
-                                  tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)) + koff), idesc_s, accum);
+                    tc::umma_bf16(d, dq0 + 2 * k, dk0 + 2 * k, idesc_s, accum);
                     accum = 1u;
                 }
                 tc::umma_commit(&k_free[ks]);
                 tc::umma_commit(&s_full[gb & 1]);
-                if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
-            };
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                tc::mbar_wait(q_full, it & 1);
-                tc::tcgen05_fence_after();
-                issue_s(g);
-                for (int j = 0; j < NBLK; ++j, ++g) {
-                    if (j + 1 < NBLK) {
-                        issue_s(g + 1);
-                        if (j + 2 == NBLK) tc::umma_commit(q_free);    // last S of this item is in flight
+            }
+            __syncwarp();
+            if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+        };
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            tc::mbar_wait(q_full, it & 1);
+            tc::tcgen05_fence_after();
+            issue_s(g);
+            for (int j = 0; j < NBLK; ++j, ++g) {
+                if (j + 1 < NBLK) {
+                    issue_s(g + 1);
+                    if (j + 2 == NBLK) {
+                        if (tc::elect_one_sync()) tc::umma_commit(q_free);    // last S of this item is in flight
+                        __syncwarp();
                     }
-                    tc::mbar_wait(p_ready, g & 1);
-                    tc::mbar_wait(&v_full[vs], vph);
-                    tc::tcgen05_fence_after();
-                    const uint32_t d = tmem_base + O_COL;
+                }
+                tc::mbar_wait(p_ready, g & 1);
+                tc::mbar_wait(&v_full[vs], vph);
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + O_COL;
+                const uint64_t dv0 = tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)), 0);
+                const uint64_t dv1 = tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, P - 1)), 0);
+                if (tc::elect_one_sync()) {
                     uint32_t accum = 0u;
                     if (P == 2) {
 #pragma unroll
                         for (int kk = 0; kk < BKV / 16; ++kk) {
-                            const uint32_t a_off = (kk >> 2) * P_SUB + (kk & 3) * 32;   // K-major: 16 keys = 32 B in the row
-                            const uint32_t b_off = kk * 16 * 128;                       // MN-major: 16 keys = 16 rows
-                            tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(P - 1)) + a_off),
-                                          tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)) + b_off, 0), idesc_o, accum);
-                            tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(0)) + a_off),
-                                          tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, P - 1)) + b_off, 0), idesc_o, 1u);
+                            const uint32_t a_off = ((kk >> 2) * P_SUB + (kk & 3) * 32) >> 4;   // K-major: 16 keys = 32 B in the row
+                            const uint32_t b_off = (kk * 16 * 128) >> 4;                       // MN-major: 16 keys = 16 rows
+                            tc::umma_bf16(d, dp1 + a_off, dv0 + b_off, idesc_o, accum);
+                            tc::umma_bf16(d, dp0 + a_off, dv1 + b_off, idesc_o, 1u);
                             accum = 1u;
                         }
                     }
 #pragma unroll
                     for (int kk = 0; kk < BKV / 16; ++kk) {
-                        const uint32_t a_off = (kk >> 2) * P_SUB + (kk & 3) * 32;
-                        const uint32_t b_off = kk * 16 * 128;
-                        tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(0)) + a_off),
-                                      tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)) + b_off, 0), idesc_o, accum);
+                        const uint32_t a_off = ((kk >> 2) * P_SUB + (kk & 3) * 32) >> 4;
+                        const uint32_t b_off = (kk * 16 * 128) >> 4;
+                        tc::umma_bf16(d, dp0 + a_off, dv0 + b_off, idesc_o, accum);
                         accum = 1u;
                     }
                     tc::umma_commit(&v_free[vs]);
                     tc::umma_commit(pv_done);
-                    if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
                 }
+                __syncwarp();
+                if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
             }
         }
     } else {
         // ---------------------------------------------------------------------------- softmax warps
+        // Two threads per query row: warps w and w+4 share a TMEM lane quarter, thread `hsel` owns key columns
+        // [48 hsel, 48 hsel + 48) of every block and output columns [32 hsel, 32 hsel + 32).  The pair agrees on
+        // the running maximum through a double-buffered shared-memory slot and a 64-thread named barrier per
+        // block; the partial sums are only combined at the end.  (ncu on the one-thread-per-row version: one
+        // softmax warp per scheduler at 0.22 IPC, MUFU / F2FP bound with nothing to overlap.)
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+        const int hsel = (warp - 2) >> 2;                  // which half of the columns
         const int r = quarter * 32 + lane;                 // query row inside the tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         // byte offset of 16-byte chunk c (8 keys) of row r inside a K-major SWIZZLE_128B tile
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
         const uint32_t sw = (uint32_t)(r & 7);
+        float* xch = reinterpret_cast<float*>(smem + C::OFF_XCH);
+        const int bar_id = 1 + quarter;
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int qt = tile % QTILES, h = (tile / QTILES) % HEADS, img = tile / (QTILES * HEADS);
             float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-            float o[HD];
+            float o[HO];
 #pragma unroll
-            for (int i = 0; i < HD; ++i) o[i] = 0.f;
+            for (int i = 0; i < HO; ++i) o[i] = 0.f;
+            auto fold_o = [&]() {                           // o = o * alpha_prev + O_j (this thread's 32 columns)
+                uint32_t t[32];
+                tc::tmem_ld_32x32b_x32(t_lane + O_COL + hsel * HO, t);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < HO; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(t[i]));
+            };
             for (int j = 0; j < NBLK; ++j, ++g) {
                 tc::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
                 tc::tcgen05_fence_after();
-                uint32_t s[BKV];
+                uint32_t s[HB];
                 {
                     uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-                    uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                    uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-                    const uint32_t t_s = t_lane + S_COL + (g & 1) * BKV;
+                    uint32_t(&s1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&s[32]);
+                    const uint32_t t_s = t_lane + S_COL + (g & 1) * BKV + hsel * HB;
                     tc::tmem_ld_32x32b_x32(t_s, s0);
-                    tc::tmem_ld_32x32b_x32(t_s + 32, s1);
-                    tc::tmem_ld_32x32b_x32(t_s + 64, s2);
+                    tc::tmem_ld_32x32b_x16(t_s + 32, s1);
                     tc::tmem_ld_wait();
                 }
                 float bmax = __uint_as_float(s[0]);
 #pragma unroll
-                for (int i = 1; i < BKV; ++i) bmax = fmaxf(bmax, __uint_as_float(s[i]));
+                for (int i = 1; i < HB; ++i) bmax = fmaxf(bmax, __uint_as_float(s[i]));
+                float* slot = xch + (g & 1) * 2 * BM;
+                slot[hsel * BM + r] = bmax;
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                bmax = fmaxf(bmax, slot[(hsel ^ 1) * BM + r]);
                 const float m_new = fmaxf(m, bmax);
                 const float alpha = tc::fast_exp2((m - m_new) * scale_log2);      // 0 on the first block
                 const float ms = m_new * scale_log2;
-                float sum = 0.f;
+                float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < BKV; ++i) {
-                    float p = tc::fast_exp2(fmaf(__uint_as_float(s[i]), scale_log2, -ms));
-                    sum += p;
-                    s[i] = __float_as_uint(p);
+                for (int i = 0; i < HB; i += 2) {
+                    const float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[i]), scale_log2, -ms));
+                    const float p1 = tc::fast_exp2(fmaf(__uint_as_float(s[i + 1]), scale_log2, -ms));
+                    sum0 += p0; sum1 += p1;
+                    s[i] = __float_as_uint(p0); s[i + 1] = __float_as_uint(p1);
                 }
-                l = l * alpha + sum;
+                l = l * alpha + (sum0 + sum1);
                 m = m_new;
                 if (j > 0) {
                     // O_{j-1} is complete: fold it into the register accumulator; P may now be overwritten
                     tc::mbar_wait(pv_done, (g - 1) & 1);
                     tc::tcgen05_fence_after();
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t t[32];
-                        tc::tmem_ld_32x32b_x32(t_lane + O_COL + half * 32, t);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[half * 32 + i] = fmaf(o[half * 32 + i], alpha_prev, __uint_as_float(t[i]));
-                    }
+                    fold_o();
                 }
                 alpha_prev = alpha;
                 // P_j -> bf16 planes in shared memory (A operand of the PV product)
 #pragma unroll
-                for (int c = 0; c < BKV / 8; ++c) {
+                for (int ci = 0; ci < HB / 8; ++ci) {
+                    const int c = hsel * (HB / 8) + ci;
                     float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(s[c * 8 + i]);
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(s[ci * 8 + i]);
                     const uint32_t off = (uint32_t)(c >> 3) * P_SUB + row_off + ((((uint32_t)c & 7) ^ sw) << 4);
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
@@ -290,31 +320,29 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             // last product of the item
             tc::mbar_wait(pv_done, (g - 1) & 1);
             tc::tcgen05_fence_after();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t t[32];
-                tc::tmem_ld_32x32b_x32(t_lane + O_COL + half * 32, t);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[half * 32 + i] = fmaf(o[half * 32 + i], alpha_prev, __uint_as_float(t[i]));
-            }
-            const float inv = 1.0f / l;
+            fold_o();
+            // combine the two partial sums of the row (same slot discipline as the maxima: one more barrier)
+            float* slot = xch + (g & 1) * 2 * BM;
+            slot[hsel * BM + r] = l;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            const float inv = 1.0f / (l + slot[(hsel ^ 1) * BM + r]);
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // slot parity g&1 is reused by the next tile's block 0
             const int row = qt * BM + r;
             if (row < NTOK) {
                 // out[n, row, h*64 + d]  ((attn @ v).transpose(1,2).reshape(B,N,C), vision_transformer.py:329)
-                const size_t o_idx = ((size_t)img * NTOK + row) * EMB + h * HD;
+                const size_t o_idx = ((size_t)img * NTOK + row) * EMB + h * HD + hsel * HO;
 #pragma unroll
-                for (int i = 0; i < HD; ++i) o[i] *= inv;
+                for (int i = 0; i < HO; ++i) o[i] *= inv;
                 if (out_f32) {
 #pragma unroll
-                    for (int i = 0; i < HD; i += 4)
+                    for (int i = 0; i < HO; i += 4)
                         *reinterpret_cast<float4*>(out_f32 + o_idx + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
                 }
                 if (out_planes) {
                     const size_t plane = (size_t)n_img * NTOK * EMB;
                     for (int p = 0; p < p_out; ++p) {
 #pragma unroll
-                        for (int i = 0; i < HD; i += 8) {
+                        for (int i = 0; i < HO; i += 8) {
                             uint4 w;
                             w.x = pack_bf16x2(o[i], o[i + 1]);
                             w.y = pack_bf16x2(o[i + 2], o[i + 3]);

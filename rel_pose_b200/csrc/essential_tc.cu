@@ -96,63 +96,69 @@ em_stats_tc_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            int cs = 0, cph = 0, it = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-                int tile, h, which, dir, b;
-                decode(item, tile, h, which, dir, b);
-                const int q_img = 2 * b + (1 - dir), kv_img = 2 * b + dir;
-                const int r_img = which == 0 ? q_img : kv_img, r_col = (which == 0 ? 0 : EMB) + h * HD;
-                const int c_img = which == 0 ? kv_img : q_img, c_col = (which == 0 ? EMB : 0) + h * HD;
-                tc::mbar_wait(r_free, (it & 1) ^ 1);
+        // TMA producer (convergent warp, one elected lane issues)
+        int cs = 0, cph = 0, it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+            int tile, h, which, dir, b;
+            decode(item, tile, h, which, dir, b);
+            const int q_img = 2 * b + (1 - dir), kv_img = 2 * b + dir;
+            const int r_img = which == 0 ? q_img : kv_img, r_col = (which == 0 ? 0 : EMB) + h * HD;
+            const int c_img = which == 0 ? kv_img : q_img, c_col = (which == 0 ? EMB : 0) + h * HD;
+            tc::mbar_wait(r_free, (it & 1) ^ 1);
+            if (tc::elect_one_sync()) {
                 tc::mbar_expect_tx(r_full, C::R_BYTES);
 #pragma unroll
                 for (int p = 0; p < P; ++p) tc::tma_load_4d(r_tile(p), &tmR, r_full, r_col, tile * BM, r_img, p);
-                for (int j = 0; j < NBLK; ++j) {
-                    tc::mbar_wait(&c_free[cs], cph ^ 1);
+            }
+            __syncwarp();
+            for (int j = 0; j < NBLK; ++j) {
+                tc::mbar_wait(&c_free[cs], cph ^ 1);
+                if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(&c_full[cs], C::C_BYTES);
 #pragma unroll
                     for (int p = 0; p < P; ++p) tc::tma_load_4d(c_tile(cs, p), &tmC, &c_full[cs], c_col, j * BKV, c_img, p);
-                    if (++cs == 2) { cs = 0; cph ^= 1; }
                 }
+                __syncwarp();
+                if (++cs == 2) { cs = 0; cph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = tc::make_idesc_bf16(BM, BKV);
-            int cs = 0, cph = 0, it = 0;
-            uint32_t g = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-                tc::mbar_wait(r_full, it & 1);
-                for (int j = 0; j < NBLK; ++j, ++g) {
-                    tc::mbar_wait(&s_free[g & 1], ((g >> 1) & 1) ^ 1);
-                    tc::mbar_wait(&c_full[cs], cph);
-                    tc::tcgen05_fence_after();
-                    const uint32_t d = tmem_base + (g & 1) * BKV;
+        // MMA issuer (convergent warp)
+        constexpr uint32_t idesc_s = tc::make_idesc_bf16(BM, BKV);
+        int cs = 0, cph = 0, it = 0;
+        uint32_t g = 0;
+        const uint64_t dr0 = tc::make_kmajor_sw128_desc(tc::smem_u32(r_tile(0)));
+        const uint64_t dr1 = tc::make_kmajor_sw128_desc(tc::smem_u32(r_tile(P - 1)));
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+            tc::mbar_wait(r_full, it & 1);
+            for (int j = 0; j < NBLK; ++j, ++g) {
+                tc::mbar_wait(&s_free[g & 1], ((g >> 1) & 1) ^ 1);
+                tc::mbar_wait(&c_full[cs], cph);
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + (g & 1) * BKV;
+                const uint64_t dc0 = tc::make_kmajor_sw128_desc(tc::smem_u32(c_tile(cs, 0)));
+                const uint64_t dc1 = tc::make_kmajor_sw128_desc(tc::smem_u32(c_tile(cs, P - 1)));
+                if (tc::elect_one_sync()) {
                     uint32_t accum = 0u;
                     if (P == 2) {                          // small correction terms first (see em_accum_tc_kernel)
 #pragma unroll
                         for (int k = 0; k < HD / 16; ++k) {
-                            const uint32_t koff = k * 32;
-                            tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(r_tile(P - 1)) + koff),
-                                          tc::make_kmajor_sw128_desc(tc::smem_u32(c_tile(cs, 0)) + koff), idesc_s, accum);
-                            tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(r_tile(0)) + koff),
-                                          tc::make_kmajor_sw128_desc(tc::smem_u32(c_tile(cs, P - 1)) + koff), idesc_s, 1u);
+                            tc::umma_bf16(d, dr1 + 2 * k, dc0 + 2 * k, idesc_s, accum);
+                            tc::umma_bf16(d, dr0 + 2 * k, dc1 + 2 * k, idesc_s, 1u);
                             accum = 1u;
                         }
                     }
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k) {
-                        const uint32_t koff = k * 32;
-                        tc::umma_bf16(d, tc::make_kmajor_sw128_desc(tc::smem_u32(r_tile(0)) + koff),
-                                      tc::make_kmajor_sw128_desc(tc::smem_u32(c_tile(cs, 0)) + koff), idesc_s, accum);
+                        tc::umma_bf16(d, dr0 + 2 * k, dc0 + 2 * k, idesc_s, accum);
                         accum = 1u;
                     }
                     tc::umma_commit(&c_free[cs]);
                     tc::umma_commit(&s_full[g & 1]);
                     if (j + 1 == NBLK) tc::umma_commit(r_free);
-                    if (++cs == 2) { cs = 0; cph ^= 1; }
                 }
+                __syncwarp();
+                if (++cs == 2) { cs = 0; cph ^= 1; }
             }
         }
     } else {
@@ -292,23 +298,26 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto a_tile = [&](int p) { return smem + C::OFF_A + p * 2 * P_SUB; };
 
     if (warp == 0) {
-        // ---------------------------------------------------------------------------- TMA producer
-        if (lane == 0) {
-            int rs = 0, rph = 0;
-            uint32_t tt = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int h = item % HEADS, dir = (item / HEADS) & 1, b = item / (2 * HEADS);
-                const int q_img = 2 * b + (1 - dir), kv_img = 2 * b + dir;
-                auto load_k = [&](int j) {
-                    tc::mbar_wait(&ring_free[rs], rph ^ 1);
+        // ---------------------------------------------------------------------------- TMA producer (convergent warp)
+        int rs = 0, rph = 0;
+        uint32_t tt = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int h = item % HEADS, dir = (item / HEADS) & 1, b = item / (2 * HEADS);
+            const int q_img = 2 * b + (1 - dir), kv_img = 2 * b + dir;
+            auto load_k = [&](int j) {
+                tc::mbar_wait(&ring_free[rs], rph ^ 1);
+                if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(&ring_full[rs], C::SLOT_BYTES);
 #pragma unroll
                     for (int p = 0; p < P; ++p)
                         tc::tma_load_4d(ring_tile(rs, p), &tmKV, &ring_full[rs], EMB + h * HD, j * BKV, kv_img, p);
-                    if (++rs == RING) { rs = 0; rph ^= 1; }
-                };
-                auto load_v = [&](int j) {
-                    tc::mbar_wait(&ring_free[rs], rph ^ 1);
+                }
+                __syncwarp();
+                if (++rs == RING) { rs = 0; rph ^= 1; }
+            };
+            auto load_v = [&](int j) {
+                tc::mbar_wait(&ring_free[rs], rph ^ 1);
+                if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(&ring_full[rs], C::SLOT_BYTES + (has_pos ? C::POSJ_BYTES : 0));
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
@@ -318,21 +327,27 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             tc::tma_load_4d(posj_tile(rs, p) + POS_SUB, &tmPos, &ring_full[rs], j * BKV + 64, 0, b, p);
                         }
                     }
-                    if (++rs == RING) { rs = 0; rph ^= 1; }
-                };
-                for (int tile = 0; tile < RTILES; ++tile, ++tt) {
-                    tc::mbar_wait(q_free, (tt & 1) ^ 1);
+                }
+                __syncwarp();
+                if (++rs == RING) { rs = 0; rph ^= 1; }
+            };
+            for (int tile = 0; tile < RTILES; ++tile, ++tt) {
+                tc::mbar_wait(q_free, (tt & 1) ^ 1);
+                if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(q_full, P * R_TILE);
 #pragma unroll
                     for (int p = 0; p < P; ++p) tc::tma_load_4d(q_tile(p), &tmQ, q_full, h * HD, tile * BM, q_img, p);
-                    // same order as the issuer consumes: K0, then (K_{j+1}), V_j
-                    load_k(0);
-                    for (int j = 0; j < NBLK; ++j) {
-                        if (j + 1 < NBLK) load_k(j + 1);
-                        load_v(j);
-                        if (j == 0) {
-                            // left factor of F for this row tile (needed only after the 6 blocks)
-                            tc::mbar_wait(vi_free, (tt & 1) ^ 1);
+                }
+                __syncwarp();
+                // same order as the issuer consumes: K0, then (K_{j+1}), V_j
+                load_k(0);
+                for (int j = 0; j < NBLK; ++j) {
+                    if (j + 1 < NBLK) load_k(j + 1);
+                    load_v(j);
+                    if (j == 0) {
+                        // left factor of F for this row tile (needed only after the 6 blocks)
+                        tc::mbar_wait(vi_free, (tt & 1) ^ 1);
+                        if (tc::elect_one_sync()) {
                             tc::mbar_expect_tx(vi_full, P * R_TILE + (has_pos ? P * 2 * POS_SUB : 0));
 #pragma unroll
                             for (int p = 0; p < P; ++p) {
@@ -343,114 +358,133 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 }
                             }
                         }
+                        __syncwarp();
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------------------- MMA issuer
+        // ---------------------------------------------------------------------------- MMA issuer (convergent warp)
         // tcgen05 accumulates in fp32 with truncation: a chain of n accumulations carries a bias of ~n 2^-25.
         // Every product group therefore issues its small correction terms (a1 b0, a0 b1) for ALL K steps first
         // and the main terms (a0 b0) last, and no TMEM accumulator lives longer than one key block / row tile:
         // T_j and F_t are folded in fp32 (round to nearest) by the softmax threads.
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = tc::make_idesc_bf16(BM, BKV);
-            constexpr uint32_t idesc_tv = tc::make_idesc_bf16(BM, HD) | tc::IDESC_B_MN;
-            constexpr uint32_t idesc_tp = tc::make_idesc_bf16(BM, 16);
-            constexpr uint32_t idesc_fvv = tc::make_idesc_bf16(BM, HD) | tc::IDESC_A_MN | tc::IDESC_B_MN;
-            constexpr uint32_t idesc_fvp = tc::make_idesc_bf16(BM, 16) | tc::IDESC_A_MN | tc::IDESC_B_MN;
-            constexpr uint32_t idesc_g = tc::make_idesc_bf16(BM, 16) | tc::IDESC_A_MN;
-            int rs = 0, rph = 0;
-            uint32_t g = 0, tt = 0;
-            auto kdesc = [&](const uint8_t* base, uint32_t off) { return tc::make_kmajor_sw128_desc(tc::smem_u32(base) + off); };
-            auto mdesc = [&](const uint8_t* base, uint32_t off, uint32_t lbo) {
-                return tc::make_mnmajor_sw128_desc(tc::smem_u32(base) + off, lbo);
-            };
-            auto issue_s = [&](uint32_t gb) {
-                tc::mbar_wait(&ring_full[rs], rph);
-                tc::tcgen05_fence_after();
-                const uint32_t d = tmem_base + T_S + (gb & 1) * BKV;
+        // All 32 lanes run the control flow; one elected lane issues (see tc::elect_one_sync).
+        constexpr uint32_t idesc_s = tc::make_idesc_bf16(BM, BKV);
+        constexpr uint32_t idesc_tv = tc::make_idesc_bf16(BM, HD) | tc::IDESC_B_MN;
+        constexpr uint32_t idesc_tp = tc::make_idesc_bf16(BM, 16);
+        constexpr uint32_t idesc_fvv = tc::make_idesc_bf16(BM, HD) | tc::IDESC_A_MN | tc::IDESC_B_MN;
+        constexpr uint32_t idesc_fvp = tc::make_idesc_bf16(BM, 16) | tc::IDESC_A_MN | tc::IDESC_B_MN;
+        constexpr uint32_t idesc_g = tc::make_idesc_bf16(BM, 16) | tc::IDESC_A_MN;
+        int rs = 0, rph = 0;
+        uint32_t g = 0, tt = 0;
+        auto kdesc = [&](const uint8_t* base, uint32_t off) { return tc::make_kmajor_sw128_desc(tc::smem_u32(base) + off); };
+        auto mdesc = [&](const uint8_t* base, uint32_t off, uint32_t lbo) {
+            return tc::make_mnmajor_sw128_desc(tc::smem_u32(base) + off, lbo);
+        };
+        const uint64_t dq0 = kdesc(q_tile(0), 0), dq1 = kdesc(q_tile(P - 1), 0);
+        const uint64_t da0 = kdesc(a_tile(0), 0), da1 = kdesc(a_tile(P - 1), 0);          // A planes as K-major A operand
+        const uint64_t dvi0 = mdesc(vi_tile(0), 0, 0), dvi1 = mdesc(vi_tile(P - 1), 0, 0);
+        const uint64_t dt0 = mdesc(a_tile(0), 0, 0), dt1 = mdesc(a_tile(P - 1), 0, 0);    // T_v: MN-major B operand
+        const uint64_t dtp0 = mdesc(a_tile(0) + P_SUB, 0, 0), dtp1 = mdesc(a_tile(P - 1) + P_SUB, 0, 0);   // T_pos atom
+        const uint64_t dta0 = mdesc(a_tile(0), 0, P_SUB), dta1 = mdesc(a_tile(P - 1), 0, P_SUB);          // [T_v|T_pos] as A
+        const uint64_t dpi0 = kdesc(posi_tile(0), 0), dpi1 = kdesc(posi_tile(P - 1), 0);
+        auto issue_s = [&](uint32_t gb) {
+            tc::mbar_wait(&ring_full[rs], rph);
+            tc::tcgen05_fence_after();
+            const uint32_t d = tmem_base + T_S + (gb & 1) * BKV;
+            const uint64_t dk0 = kdesc(ring_tile(rs, 0), 0), dk1 = kdesc(ring_tile(rs, P - 1), 0);
+            if (tc::elect_one_sync()) {
                 uint32_t acc = 0;
                 if (P == 2) {
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k) {
-                        tc::umma_bf16(d, kdesc(q_tile(P - 1), k * 32), kdesc(ring_tile(rs, 0), k * 32), idesc_s, acc);
-                        tc::umma_bf16(d, kdesc(q_tile(0), k * 32), kdesc(ring_tile(rs, P - 1), k * 32), idesc_s, 1u);
+                        tc::umma_bf16(d, dq1 + 2 * k, dk0 + 2 * k, idesc_s, acc);
+                        tc::umma_bf16(d, dq0 + 2 * k, dk1 + 2 * k, idesc_s, 1u);
                         acc = 1u;
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) {
-                    tc::umma_bf16(d, kdesc(q_tile(0), k * 32), kdesc(ring_tile(rs, 0), k * 32), idesc_s, acc);
+                    tc::umma_bf16(d, dq0 + 2 * k, dk0 + 2 * k, idesc_s, acc);
                     acc = 1u;
                 }
                 tc::umma_commit(&ring_free[rs]);
                 tc::umma_commit(&s_full[gb & 1]);
-                if (++rs == RING) { rs = 0; rph ^= 1; }
-            };
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                for (int tile = 0; tile < RTILES; ++tile, ++tt) {
-                    tc::mbar_wait(q_full, tt & 1);
-                    tc::tcgen05_fence_after();
-                    issue_s(g);
-                    for (int j = 0; j < NBLK; ++j, ++g) {
-                        if (j + 1 < NBLK) {
-                            issue_s(g + 1);
-                            if (j + 2 == NBLK) tc::umma_commit(q_free);
+            }
+            __syncwarp();
+            if (++rs == RING) { rs = 0; rph ^= 1; }
+        };
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (int tile = 0; tile < RTILES; ++tile, ++tt) {
+                tc::mbar_wait(q_full, tt & 1);
+                tc::tcgen05_fence_after();
+                issue_s(g);
+                for (int j = 0; j < NBLK; ++j, ++g) {
+                    if (j + 1 < NBLK) {
+                        issue_s(g + 1);
+                        if (j + 2 == NBLK) {
+                            if (tc::elect_one_sync()) tc::umma_commit(q_free);
+                            __syncwarp();
                         }
-                        tc::mbar_wait(p_ready, g & 1);
-                        tc::mbar_wait(&ring_full[rs], rph);
-                        tc::tcgen05_fence_after();
+                    }
+                    tc::mbar_wait(p_ready, g & 1);
+                    tc::mbar_wait(&ring_full[rs], rph);
+                    tc::tcgen05_fence_after();
+                    const uint64_t dv0 = mdesc(ring_tile(rs, 0), 0, 0), dv1 = mdesc(ring_tile(rs, P - 1), 0, 0);
+                    const uint64_t dpj0 = kdesc(posj_tile(rs, 0), 0), dpj1 = kdesc(posj_tile(rs, P - 1), 0);
+                    if (tc::elect_one_sync()) {
                         // T_j = A_ij [v_j | pos_j]  (fresh accumulator every block)
 #pragma unroll
                         for (int pass = (P == 2 ? 0 : 1); pass < 2; ++pass) {
 #pragma unroll
                             for (int kk = 0; kk < BKV / 16; ++kk) {
-                                const uint32_t a_off = (kk >> 2) * P_SUB + (kk & 3) * 32;     // K-major: 16 keys = 32 B
-                                const uint32_t v_off = kk * 16 * 128;                         // MN-major: 16 keys = 16 rows
-                                const uint32_t p_off = (kk >> 2) * POS_SUB + (kk & 3) * 32;
+                                const uint32_t a_off = ((kk >> 2) * P_SUB + (kk & 3) * 32) >> 4;     // K-major: 16 keys = 32 B
+                                const uint32_t v_off = (kk * 16 * 128) >> 4;                         // MN-major: 16 keys = 16 rows
+                                const uint32_t p_off = ((kk >> 2) * POS_SUB + (kk & 3) * 32) >> 4;
                                 const uint32_t first = (pass == (P == 2 ? 0 : 1) && kk == 0) ? 0u : 1u;
                                 if (pass == 0) {
-                                    tc::umma_bf16(tmem_base + T_TV, kdesc(a_tile(P - 1), a_off), mdesc(ring_tile(rs, 0), v_off, 0), idesc_tv, first);
-                                    tc::umma_bf16(tmem_base + T_TV, kdesc(a_tile(0), a_off), mdesc(ring_tile(rs, P - 1), v_off, 0), idesc_tv, 1u);
+                                    tc::umma_bf16(tmem_base + T_TV, da1 + a_off, dv0 + v_off, idesc_tv, first);
+                                    tc::umma_bf16(tmem_base + T_TV, da0 + a_off, dv1 + v_off, idesc_tv, 1u);
                                     if (has_pos) {
-                                        tc::umma_bf16(tmem_base + T_TP, kdesc(a_tile(P - 1), a_off), kdesc(posj_tile(rs, 0), p_off), idesc_tp, first);
-                                        tc::umma_bf16(tmem_base + T_TP, kdesc(a_tile(0), a_off), kdesc(posj_tile(rs, P - 1), p_off), idesc_tp, 1u);
+                                        tc::umma_bf16(tmem_base + T_TP, da1 + a_off, dpj0 + p_off, idesc_tp, first);
+                                        tc::umma_bf16(tmem_base + T_TP, da0 + a_off, dpj1 + p_off, idesc_tp, 1u);
                                     }
                                 } else {
-                                    tc::umma_bf16(tmem_base + T_TV, kdesc(a_tile(0), a_off), mdesc(ring_tile(rs, 0), v_off, 0), idesc_tv, first);
-                                    if (has_pos)
-                                        tc::umma_bf16(tmem_base + T_TP, kdesc(a_tile(0), a_off), kdesc(posj_tile(rs, 0), p_off), idesc_tp, first);
+                                    tc::umma_bf16(tmem_base + T_TV, da0 + a_off, dv0 + v_off, idesc_tv, first);
+                                    if (has_pos) tc::umma_bf16(tmem_base + T_TP, da0 + a_off, dpj0 + p_off, idesc_tp, first);
                                 }
                             }
                         }
                         tc::umma_commit(&ring_free[rs]);
                         tc::umma_commit(pv_done);
-                        if (++rs == RING) { rs = 0; rph ^= 1; }
                     }
-                    // F_t = v_i^T [T_v | T_pos]  and  G_t = [T_v | T_pos]^T pos_i   (K = the 128 rows of the tile)
-                    tc::mbar_wait(t_ready, tt & 1);
-                    tc::mbar_wait(vi_full, tt & 1);
-                    tc::tcgen05_fence_after();
+                    __syncwarp();
+                    if (++rs == RING) { rs = 0; rph ^= 1; }
+                }
+                // F_t = v_i^T [T_v | T_pos]  and  G_t = [T_v | T_pos]^T pos_i   (K = the 128 rows of the tile)
+                tc::mbar_wait(t_ready, tt & 1);
+                tc::mbar_wait(vi_full, tt & 1);
+                tc::tcgen05_fence_after();
+                if (tc::elect_one_sync()) {
 #pragma unroll
                     for (int pass = (P == 2 ? 0 : 1); pass < 2; ++pass) {
 #pragma unroll
                         for (int kk = 0; kk < BM / 16; ++kk) {
-                            const uint32_t mn_off = kk * 16 * 128;                            // 16 rows of an MN-major tile
-                            const uint32_t k_off = (kk >> 2) * POS_SUB + (kk & 3) * 32;       // 16 K elements of a K-major tile
+                            const uint32_t mn_off = (kk * 16 * 128) >> 4;                            // 16 rows of an MN-major tile
+                            const uint32_t k_off = ((kk >> 2) * POS_SUB + (kk & 3) * 32) >> 4;       // 16 K elements, K-major
                             const uint32_t first = (pass == (P == 2 ? 0 : 1) && kk == 0) ? 0u : 1u;
-                            // (A plane, B plane) pairs of this pass
                             const int na = pass == 0 ? 2 : 1;
 #pragma unroll
                             for (int t = 0; t < na; ++t) {
-                                const int pa = pass == 0 ? (t == 0 ? P - 1 : 0) : 0;
-                                const int pb = pass == 0 ? (t == 0 ? 0 : P - 1) : 0;
+                                // pass 0: (a1, b0) then (a0, b1); pass 1: (a0, b0)
+                                const bool a_hi = pass == 0 && t == 0, b_hi = pass == 0 && t == 1;
                                 const uint32_t acc = (t == 0) ? first : 1u;
-                                tc::umma_bf16(tmem_base + T_F1, mdesc(vi_tile(pa), mn_off, 0), mdesc(a_tile(pb), mn_off, 0), idesc_fvv, acc);
+                                tc::umma_bf16(tmem_base + T_F1, (a_hi ? dvi1 : dvi0) + mn_off, (b_hi ? dt1 : dt0) + mn_off, idesc_fvv, acc);
                                 if (has_pos) {
-                                    tc::umma_bf16(tmem_base + T_F1 + 64, mdesc(vi_tile(pa), mn_off, 0), mdesc(a_tile(pb) + P_SUB, mn_off, 0),
+                                    tc::umma_bf16(tmem_base + T_F1 + 64, (a_hi ? dvi1 : dvi0) + mn_off, (b_hi ? dtp1 : dtp0) + mn_off,
                                                   idesc_fvp, acc);
-                                    tc::umma_bf16(tmem_base + T_G, mdesc(a_tile(pa), mn_off, P_SUB), kdesc(posi_tile(pb), k_off), idesc_g, acc);
+                                    tc::umma_bf16(tmem_base + T_G, (a_hi ? dta1 : dta0) + mn_off, (b_hi ? dpi1 : dpi0) + k_off, idesc_g, acc);
                                 }
                             }
                         }
@@ -458,6 +492,7 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     tc::umma_commit(vi_free);
                     tc::umma_commit(f_done);
                 }
+                __syncwarp();
             }
         }
     } else {

@@ -134,15 +134,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto b_tile = [&](int stage, int p) { return smem + stage * C::STAGE_BYTES + P * A_TILE + p * C::B_TILE; };
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
-                const int img = CONV ? tm / g.tiles_per_img : 0;
-                const int oy0 = CONV ? (tm % g.tiles_per_img) * g.R : 0;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    tc::mbar_wait(&empty[stage], phase ^ 1);
+        // ------------------------------------------------------------------ TMA producer (convergent warp)
+        int stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+            const int img = CONV ? tm / g.tiles_per_img : 0;
+            const int oy0 = CONV ? (tm % g.tiles_per_img) * g.R : 0;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                tc::mbar_wait(&empty[stage], phase ^ 1);
+                if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(&full[stage], stage_tx);
                     if (CONV) {
                         const int tap = ks / g.cblocks, cb = ks - tap * g.cblocks;
@@ -160,49 +160,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tc::tma_load_3d(b_tile(stage, p), &tmB, &full[stage], ks * BK, n0, p);
                         }
                     }
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
-            int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        // ------------------------------------------------------------------ MMA issuer (convergent warp)
+        constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+        int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc::tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                tc::mbar_wait(&full[stage], phase);
                 tc::tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    tc::mbar_wait(&full[stage], phase);
-                    tc::tcgen05_fence_after();
-                    uint32_t a_addr[P], b_addr[P];
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        a_addr[p] = tc::smem_u32(a_tile(stage, p));
-                        b_addr[p] = tc::smem_u32(b_tile(stage, p));
-                    }
+                // descriptors of the stage's tiles; a K step of 16 bf16 = 32 B inside the 128-byte swizzle row = +2
+                const uint64_t a0 = tc::make_kmajor_sw128_desc(tc::smem_u32(a_tile(stage, 0)));
+                const uint64_t b0 = tc::make_kmajor_sw128_desc(tc::smem_u32(b_tile(stage, 0)));
+                const uint64_t a1 = tc::make_kmajor_sw128_desc(tc::smem_u32(a_tile(stage, P - 1)));
+                const uint64_t b1 = tc::make_kmajor_sw128_desc(tc::smem_u32(b_tile(stage, P - 1)));
+                if (tc::elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint32_t koff = k * 32;   // 16 bf16 = 32 bytes inside the 128-byte swizzle row
                         uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
                         // smallest terms first; all land in the same fp32 accumulator
                         if (P == 2) {
-                            tc::umma_bf16(d_tmem, tc::make_kmajor_sw128_desc(a_addr[P - 1] + koff),
-                                          tc::make_kmajor_sw128_desc(b_addr[0] + koff), idesc, accum);
-                            tc::umma_bf16(d_tmem, tc::make_kmajor_sw128_desc(a_addr[0] + koff),
-                                          tc::make_kmajor_sw128_desc(b_addr[P - 1] + koff), idesc, 1u);
+                            tc::umma_bf16(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, accum);
+                            tc::umma_bf16(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
                             accum = 1u;
                         }
-                        tc::umma_bf16(d_tmem, tc::make_kmajor_sw128_desc(a_addr[0] + koff),
-                                      tc::make_kmajor_sw128_desc(b_addr[0] + koff), idesc, accum);
+                        tc::umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, accum);
                     }
                     tc::umma_commit(&empty[stage]);           // frees the smem slot when these MMAs retire
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (ks + 1 == ksteps) tc::umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
                 }
-                tc::umma_commit(&tfull[acc]);                 // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..17)

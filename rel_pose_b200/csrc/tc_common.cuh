@@ -13,6 +13,21 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGENT warp.  The producer / issuer warps keep all 32 lanes in the control flow and guard
+// only the TMA / tcgen05 instructions with this predicate: inside a divergent `if (lane == 0)` the compiler
+// cannot prove the operands warp-uniform and wraps every UTCHMMA / UTMALDG in an ELECT + R2UR loop
+// (measured: ~13 dependent instructions, ~100 cycles per MMA -- slower than the tensor core executes it).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %1;\n\t"
+        "@%%px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
