@@ -301,8 +301,16 @@ def main():
         dom = max(stages, key=lambda k: stages[k]["ms"])
         d = stages[dom]
         tfl = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+        traffic = None
+        try:          # per-launch DRAM bytes of the same kernel from the committed ncu capture (same batch / precision only)
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("batch") == B and tj.get("precision") == a.precision:
+                traffic = tj["traffic_bytes"].get(dom)
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": "tensor", "achieved": tfl, "peak": pk["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": tfl / pk["bf16_tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": tfl / pk["bf16_tflops_sustained"], "traffic": traffic,
                     "peak_source": pk["source"] + " (sustained bf16 dense; kernel timed inside a long step)",
                     "avg_launch_ms": d["ms"] / d["calls"], "share_of_step": d["ms"] / tot_ms,
                     "note": ("algorithmic FLOPs (2MNK, one product per MAC) over the CUDA-event duration of the kernel with the "
