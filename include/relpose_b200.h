@@ -202,6 +202,44 @@ int rp_se3_log_bwd_f32(const float* da, const float* X, float* dX, int64_t n, in
 int rp_se3_exp_fwd_f32(const float* a, float* X, int64_t n, int device, void* stream);
 int rp_se3_exp_bwd_f32(const float* dX, const float* a, float* da, int64_t n, int device, void* stream);
 
+/* ---- training path (A11 / config 5): building blocks of the backward pass and of the train-mode forward ----------
+ * fp32, deterministic (two-stage fixed-order reductions, no atomics).  Row-major everywhere.
+ * rp_gemm_f32: strided-batched C = alpha op(A) op(B) + beta C with a two-level batch index
+ *   (b = bo * batch_inner + bi; X_b = X + bo * sXo + bi * sXi): dX = dY W, dW = dY^T X, and the attention / Essential
+ *   Matrix Module products on materialised 576x576 matrices (autograd of vision_transformer.py:198-223,325-329).
+ * rp_im2col / rp_col2im: NHWC convolution gradients as GEMMs (column = (ky*KW+kx)*C + c).
+ * rp_bn_*: nn.BatchNorm2d in training mode on [M][C] (batch statistics, biased variance, running-stat update with
+ *   the unbiased variance; torchvision resnet18 / extractor.py:24-28).   rp_layernorm_*: eps inside the sqrt.
+ * rp_softmax_{rows,cols}: softmax(scale * S) over dim -1 / dim -2 of [mats][n][n]; *_bwd adds into ds if accumulate.
+ * rp_maxpool3x3s2_bwd: gradient to the FIRST maximum of each window (PyTorch's tie-break). */
+int rp_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,              int ldb, float beta, float* C, int ldc, int batch_outer, int batch_inner, int64_t sAo, int64_t sAi,              int64_t sBo, int64_t sBi, int64_t sCo, int64_t sCi, int device, void* stream);
+int rp_gelu_fwd_f32(const float* z, float* y, int64_t n, int device, void* stream);
+int rp_gelu_bwd_f32(const float* dy, const float* z, float* dz, int64_t n, int device, void* stream);
+int rp_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, int device, void* stream);
+int rp_mul_f32(const float* a, const float* b, float* c, int64_t n, int device, void* stream);
+int rp_axpby_f32(float alpha, const float* x, float beta, const float* y, float* out, int64_t n, int device, void* stream);
+int rp_add_bcast_rows_f32(const float* a, const float* b, float* out, int64_t rows, int cols, int period, int device,                   void* stream);
+int rp_sum_over_period_f32(const float* a, float* out, int reps, int period, int cols, int device, void* stream);
+size_t rp_colsum_workspace_bytes(int64_t rows, int cols);
+int rp_colsum_f32(const float* A, const float* B, float* out, int64_t rows, int cols, void* workspace,               size_t workspace_bytes, int device, void* stream);
+int rp_layernorm_train_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,                      int rows, int cols, float eps, int device, void* stream);
+size_t rp_layernorm_bwd_workspace_bytes(int rows, int cols);
+int rp_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,                   float* dx, float* dgamma, float* dbeta, int rows, int cols, void* workspace,                   size_t workspace_bytes, int device, void* stream);
+int rp_softmax_rows_fwd_f32(const float* s, float* p, int64_t rows, int n, float scale, int device, void* stream);
+int rp_softmax_rows_bwd_f32(const float* dp, const float* p, float* ds, int64_t rows, int n, float scale, int accumulate,                    int device, void* stream);
+int rp_softmax_cols_fwd_f32(const float* s, float* p, int mats, int n, float scale, int device, void* stream);
+int rp_softmax_cols_bwd_f32(const float* dp, const float* p, float* ds, int mats, int n, float scale, int accumulate,                    int device, void* stream);
+size_t rp_bn_workspace_bytes(int64_t M, int C);
+int rp_bn_train_stats_f32(const float* x, float* mean, float* var, float* running_mean, float* running_var,                   float momentum, int64_t M, int C, void* workspace, size_t workspace_bytes, int device,                   void* stream);
+int rp_bn_apply_f32(const float* x, const float* mean, const float* var, const float* gamma, const float* beta,                const float* residual, float* y, int64_t M, int C, float eps, int relu, int device, void* stream);
+int rp_bn_bwd_f32(const float* dy, const float* x, const float* mean, const float* var, const float* gamma, float eps,               float* dx, float* dgamma, float* dbeta, int64_t M, int C, void* workspace, size_t workspace_bytes,               int device, void* stream);
+int rp_im2col_nhwc_f32(const float* x, float* cols, int n, int H, int W, int C, int KH, int KW, int stride, int pad,                  int device, void* stream);
+int rp_col2im_nhwc_f32(const float* dcols, float* dx, int n, int H, int W, int C, int KH, int KW, int stride, int pad,                  int device, void* stream);
+int rp_maxpool3x3s2_bwd_f32(const float* dy, const float* x, float* dx, int n, int H, int W, int C, int device, void* stream);
+int rp_normalize_pose_bwd_f32(const float* dout, const float* raw, float* draw, int B, int device, void* stream);
+int rp_concat_vpos_f32(const float* qkv, const float* pos, float* vp, int n_img, int device, void* stream);
+int rp_scatter_dv_f32(const float* dvp, float* dqkv, int n_img, int device, void* stream);
+
 /* ---- BASELINE.json config 3 (no reference counterpart; oracle = LAPACK, parity unpinned) -----
  * E [n,3,3] -> U [n,3,3], S [n,3] (descending, >= 0), V [n,3,3] with E = U diag(S) V^T. */
 int rp_svd3_f32(const float* E, float* U, float* S, float* V, int64_t n, int device, void* stream);

@@ -17,9 +17,12 @@ import torch
 import torch.nn.functional as F
 
 
+TRAIN_BN = False     # set by forward(train=True): nn.BatchNorm2d.train() semantics (batch statistics, running-stat update)
+
+
 def _bn(x, p, pre):
     return F.batch_norm(x, p[pre + ".running_mean"], p[pre + ".running_var"], p[pre + ".weight"], p[pre + ".bias"],
-                        training=False, eps=1e-5)
+                        training=TRAIN_BN, momentum=0.1, eps=1e-5)
 
 
 def _basic(x, p, pre, stride):
@@ -59,9 +62,12 @@ def _posenc(B, intr):
     return torch.stack([p3 * p3, p4 * p4, p3 * p4, p3, p4, torch.ones_like(p3)], -1)
 
 
-def forward(images, Gs, intrinsics, p, depth=6):
+def forward(images, Gs, intrinsics, p, depth=6, train=False):
     """images [B,2,3,H,W] float32 BGR, Gs [B,2,7], intrinsics [B,2,4] or None (NOT mutated),
-    p: dict of float32 CPU tensors.  Returns [B,2,7]."""
+    p: dict of float32 CPU tensors.  Returns [B,2,7].  train=True: BatchNorm in training mode (train.py:140-155;
+    the running statistics in `p` are updated in place like the reference's buffers), differentiable by autograd."""
+    global TRAIN_BN
+    TRAIN_BN = bool(train)
     B, _, _, H, W = images.shape
     x = images[:, :, [2, 1, 0]] / 255.0
     x = (x - torch.tensor([0.485, 0.456, 0.406])[:, None, None]) / torch.tensor([0.229, 0.224, 0.225])[:, None, None]

@@ -61,6 +61,33 @@ _SIGNATURES = {
     "rp_se3_log_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
     "rp_se3_exp_fwd_f32": (_c_int, [_ptr, _ptr, _c_i64, _c_int, _ptr]),
     "rp_se3_exp_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_gemm_f32": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_f32, _ptr, _c_int, _ptr, _c_int, _c_f32, _ptr, _c_int, _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _ptr]),
+    "rp_gelu_fwd_f32": (_c_int, [_ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_gelu_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_relu_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_mul_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_axpby_f32": (_c_int, [_c_f32, _ptr, _c_f32, _ptr, _ptr, _c_i64, _c_int, _ptr]),
+    "rp_add_bcast_rows_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int, _ptr]),
+    "rp_sum_over_period_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_colsum_workspace_bytes": (_c_size, [_c_i64, _c_int]),
+    "rp_colsum_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr, _c_size, _c_int, _ptr]),
+    "rp_layernorm_train_fwd_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_f32, _c_int, _ptr]),
+    "rp_layernorm_bwd_workspace_bytes": (_c_size, [_c_int, _c_int]),
+    "rp_layernorm_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _c_size, _c_int, _ptr]),
+    "rp_softmax_rows_fwd_f32": (_c_int, [_ptr, _ptr, _c_i64, _c_int, _c_f32, _c_int, _ptr]),
+    "rp_softmax_rows_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _c_f32, _c_int, _c_int, _ptr]),
+    "rp_softmax_cols_fwd_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_f32, _c_int, _ptr]),
+    "rp_softmax_cols_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_f32, _c_int, _c_int, _ptr]),
+    "rp_bn_workspace_bytes": (_c_size, [_c_i64, _c_int]),
+    "rp_bn_train_stats_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _c_i64, _c_int, _ptr, _c_size, _c_int, _ptr]),
+    "rp_bn_apply_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_f32, _c_int, _c_int, _ptr]),
+    "rp_bn_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr, _c_size, _c_int, _ptr]),
+    "rp_im2col_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_col2im_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_maxpool3x3s2_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_normalize_pose_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_concat_vpos_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_scatter_dv_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_svd3_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
     "rp_essential_to_rt_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
 }

@@ -312,12 +312,13 @@ class ViTEss(nn.Module):
         """Estimates SE3 between a pair of frames (model.py:161-191)."""
         if not isinstance(Gs, SE3):
             Gs = SE3(torch.from_numpy(np.asarray(Gs)).unsqueeze(0).cuda().float())
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError(
-                "training-mode forward (autograd through the CUDA kernels) is not wired yet; "
-                "call under torch.no_grad() / model.eval()")
         if not images.is_cuda:
             raise ops._lib.RelposeLibraryError("ViTEss.forward: images must live on a CUDA device (no CPU fallback)")
+        if self.training and torch.is_grad_enabled():
+            # train.py:155 -- batch-statistics BatchNorm, autograd through the CUDA kernels (train_path.py)
+            from . import train_path
+            out = SE3(train_path.forward_train(self, images, Gs, intrinsics))
+            return out.data[0].detach().cpu().numpy() if inference else [out]
         stages = {} if self.capture_stages else None
         B = images.shape[0]
         with torch.no_grad():
