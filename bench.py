@@ -172,6 +172,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step (configs[1]: 64)")
     ap.add_argument("--size", type=int, default=384)
+    ap.add_argument("--micro-batch", type=int, default=0,
+                    help="process the per-GPU batch in chunks of this many pairs (config 4: --batch 4096/G --micro-batch 256)")
+    ap.add_argument("--u8", action="store_true", help="device-resident images as uint8 (config 4 at 4096 pairs: 3.6 GB instead of 14.5 GB)")
     ap.add_argument("--ref-batch", type=int, default=8, help="pairs per step of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -205,12 +208,21 @@ def main():
     model.precision = a.precision
     B, size = a.batch, a.size
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    images = (torch.rand(B, 2, 3, size, size, generator=g, device=dev) * 255).floor()     # 226 MB at B=64
+    MB = a.micro_batch if 0 < a.micro_batch < B else B
+    if a.u8:
+        images = torch.empty((B, 2, 3, size, size), dtype=torch.uint8, device=dev)
+        for lo in range(0, B, MB):                              # generated on the device, chunk by chunk
+            images[lo:lo + MB] = (torch.rand(min(MB, B - lo), 2, 3, size, size, generator=g, device=dev) * 255).to(torch.uint8)
+    else:
+        images = (torch.rand(B, 2, 3, size, size, generator=g, device=dev) * 255).floor()     # 226 MB at B=64
     intr0 = torch.from_numpy(S.make_intrinsics_numpy(B)).to(dev)
     Gs = SE3.Identity(B, 2, device=dev)
 
     def step():
-        return model(images, Gs, intrinsics=intr0.clone())      # fresh clone: forward rescales in place
+        if MB == B:
+            return model(images, Gs, intrinsics=intr0.clone())      # fresh clone: forward rescales in place
+        outs = [model(images[lo:lo + MB], Gs[lo:lo + MB], intrinsics=intr0[lo:lo + MB].clone())[0].data for lo in range(0, B, MB)]
+        return [SE3(torch.cat(outs, 0))]
 
     def barrier():
         if world > 1:
@@ -326,7 +338,7 @@ def main():
                 "dtype": {"fp32": "f32", "bf16x3": "bf16x3+f32", "bf16": "bf16+f32"}[a.precision], "data": "synthetic",
                 "config": {"workload": f"batch={B} synthetic {size}x{size} pair inference per GPU, full CNN+ViT+EM "
                                        "module, fp32 (BASELINE.json configs[1]); random-init weights",
-                           "pairs_per_gpu_per_step": B, "precision": {"fp32": "fp32 operands, fp32 accumulate (SIMT)",
+                           "pairs_per_gpu_per_step": B, "micro_batch": MB, "device_image_dtype": "u8" if a.u8 else "f32", "precision": {"fp32": "fp32 operands, fp32 accumulate (SIMT)",
                                          "bf16x3": "transformer GEMMs on tcgen05 with split-bf16 operands (a0b0+a0b1+a1b0), fp32 accumulate; rest fp32",
                                          "bf16": "transformer GEMMs on tcgen05 in bf16, fp32 accumulate; rest fp32"}[a.precision],
                            "l2_policy": f"inputs larger than L2 ({images.numel() * 4 / 1e6:.0f} MB of images per step vs 126 MB L2)",

@@ -374,18 +374,25 @@ struct Svd3 {
     V3 v[3];   // columns
 };
 
-__device__ __forceinline__ void jacobi_pair(V3& ap, V3& aq, V3& vp, V3& vq) {
-    float alpha = dot(ap, ap), beta = dot(aq, aq), gamma = dot(ap, aq);
-    float lim = 1e-9f * sqrtf(alpha * beta);
-    if (fabsf(gamma) > lim && alpha * beta > 0.f) {
-        float zeta = (beta - alpha) / (2.0f * gamma);
-        float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
-        float c = rsqrtf(1.0f + t * t), s = c * t;
-        V3 np_ = c * ap - s * aq, nq = s * ap + c * aq;
-        ap = np_; aq = nq;
-        V3 wp = c * vp - s * vq, wq = s * vp + c * vq;
-        vp = wp; vq = wq;
-    }
+// One Jacobi rotation of columns p, q.  MUFU-only arithmetic (rcp / rsqrt approximations): a slightly inexact
+// angle costs nothing -- the next rotation removes what is left -- while c, s are normalised consistently so the
+// accumulated V stays orthonormal to ~1e-7.  Returns true if another sweep is needed because of this pair.
+__device__ __forceinline__ bool jacobi_pair(V3& ap, V3& aq, V3& vp, V3& vq) {
+    const float alpha = dot(ap, ap), beta = dot(aq, aq), gamma = dot(ap, aq);
+    // already orthogonal to fp32 precision: gamma^2 <= (1e-7)^2 alpha beta  (no sqrt)
+    if (gamma * gamma <= 1e-14f * alpha * beta) return false;
+    // Jacobi converges quadratically: a pair whose cosine is below 3e-4 BEFORE its rotation is orthogonal to ~1e-7
+    // after it, so such a rotation does not ask for another sweep
+    const bool big = gamma * gamma > 1e-7f * alpha * beta;
+    const float zeta = __fdividef(beta - alpha, 2.0f * gamma);
+    const float r = 1.0f + zeta * zeta;
+    const float t = __fdividef(copysignf(1.0f, zeta), fabsf(zeta) + r * rsqrtf(r));
+    const float c = rsqrtf(1.0f + t * t), sn = c * t;
+    const V3 np_ = c * ap - sn * aq, nq = sn * ap + c * aq;
+    ap = np_; aq = nq;
+    const V3 wp = c * vp - sn * vq, wq = sn * vp + c * vq;
+    vp = wp; vq = wq;
+    return big;
 }
 __device__ __forceinline__ void swap_cols(V3& a, V3& b, V3& va, V3& vb, float& na, float& nb) {
     V3 t = a; a = b; b = t;
@@ -396,24 +403,29 @@ __device__ __forceinline__ void swap_cols(V3& a, V3& b, V3& va, V3& vb, float& n
 __device__ Svd3 svd3(const float* e /* row-major 3x3 */) {
     V3 a0 = v3(e[0], e[3], e[6]), a1 = v3(e[1], e[4], e[7]), a2 = v3(e[2], e[5], e[8]);   // columns
     V3 v0 = v3(1, 0, 0), v1 = v3(0, 1, 0), v2 = v3(0, 0, 1);
+    // Cyclic one-sided Jacobi converges quadratically: 3-4 sweeps reach fp32 precision for almost every matrix.
+    // The loop ends as soon as no lane of the warp saw a large rotation during a sweep (warp-uniform exit, no
+    // divergence); 8 is a safety bound.
 #pragma unroll 1
-    for (int sweep = 0; sweep < 6; ++sweep) {
-        jacobi_pair(a0, a1, v0, v1);
-        jacobi_pair(a0, a2, v0, v2);
-        jacobi_pair(a1, a2, v1, v2);
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        bool rot = jacobi_pair(a0, a1, v0, v1);
+        rot |= jacobi_pair(a0, a2, v0, v2);
+        rot |= jacobi_pair(a1, a2, v1, v2);
+        if (!__any_sync(0xffffffffu, rot)) break;
     }
     float n0 = dot(a0, a0), n1 = dot(a1, a1), n2 = dot(a2, a2);
     if (n0 < n1) swap_cols(a0, a1, v0, v1, n0, n1);
     if (n0 < n2) swap_cols(a0, a2, v0, v2, n0, n2);
     if (n1 < n2) swap_cols(a1, a2, v1, v2, n1, n2);
     Svd3 r;
-    r.s[0] = sqrtf(n0); r.s[1] = sqrtf(n1); r.s[2] = sqrtf(n2);
+    const float i0 = n0 > 0.f ? rsqrtf(n0) : 0.f, i1 = n1 > 0.f ? rsqrtf(n1) : 0.f;
+    r.s[0] = n0 * i0; r.s[1] = n1 * i1; r.s[2] = 0.f;    // |a| = n / sqrt(n); s[2] is set from the completed basis below
     r.v[0] = v0; r.v[1] = v1; r.v[2] = v2;
     // U: normalise the two dominant columns, complete by a cross product (rank-deficient safe)
-    V3 u0 = r.s[0] > 0.f ? (1.0f / r.s[0]) * a0 : v3(1, 0, 0);
+    V3 u0 = r.s[0] > 0.f ? i0 * a0 : v3(1, 0, 0);
     V3 u1;
     if (r.s[1] > 1e-12f * r.s[0] && r.s[1] > 0.f) {
-        u1 = (1.0f / r.s[1]) * a1;
+        u1 = i1 * a1;
         u1 = u1 - dot(u1, u0) * u0;                      // one Gram-Schmidt polish
         u1 = rsqrtf(dot(u1, u1)) * u1;
     } else {                                             // rank <= 1: any unit vector orthogonal to u0

@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""BASELINE.json config 3: batched 3x3 SVD / essential->(R,t) / SE3 log-exp-mul-inv microbench on N = 2^20 elements.
+HBM roofline: achieved = N * algorithmic bytes per element / CUDA-event time, peak = MEASURED_PEAKS.json hbm_gbs.
+Prints one JSON line; numbers are recorded in profiles/ and DESIGN.md (parity of these kernels: tests/test_gpu_ops.py)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rel_pose_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=100, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    N = 1 << 20
+    dev = "cuda:0"
+    peak = 6650.0
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    g = torch.Generator(device=dev).manual_seed(0)
+    E = torch.randn(N, 3, 3, generator=g, device=dev)
+    xi = torch.randn(N, 6, generator=g, device=dev) * torch.tensor([1, 1, 1, .5, .5, .5], device=dev)
+    X = ops.se3_exp_fwd(xi)
+    Y = ops.se3_exp_fwd(xi.flip(0).contiguous())
+    # L2 is 126 MB: rotate over 8 input copies (8 x 36 MB for E) so that every launch streams from HBM
+    Es = [E.clone() for _ in range(8)]; Xs = [X.clone() for _ in range(8)]; xis = [xi.clone() for _ in range(8)]
+    cnt = [0]
+
+    def rot(lst):
+        cnt[0] += 1
+        return lst[cnt[0] % 8]
+    rows = {}
+    for name, fn, nbytes in [
+        ("svd3", lambda: ops.svd3(rot(Es)), 36 + 84),
+        ("essential_to_rt", lambda: ops.essential_to_rt(rot(Es)), 36 + 84),
+        ("se3_log", lambda: ops.se3_log_fwd(rot(Xs)), 28 + 24),
+        ("se3_exp", lambda: ops.se3_exp_fwd(rot(xis)), 24 + 28),
+        ("se3_mul", lambda: ops.se3_mul_fwd(rot(Xs), Y), 56 + 28),
+        ("se3_inv", lambda: ops.se3_inv_fwd(rot(Xs)), 28 + 28)]:
+        t = timeit(fn)
+        gbs = N * nbytes / t / 1e9
+        rows[name] = {"us": round(t * 1e6, 2), "GB/s": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peak, 3),
+                      "bytes_per_element": nbytes, "elements_per_s": round(N / t / 1e9, 3)}
+    print(json.dumps({"workload": "config 3: N = 2^20 elements, fp32, inputs rotated over 8 copies (larger than L2)",
+                      "hbm_peak_gbs": peak, "kernels": rows}))
+
+
+if __name__ == "__main__":
+    main()
