@@ -71,7 +71,7 @@ struct EpiParams {
 // re-split to 16 mantissa bits right away, so libdevice's 1-ulp erff (about 3x the instructions) buys nothing.
 __device__ __forceinline__ float fast_erf(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));     // MUFU.RCP, 1 ulp
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
@@ -369,46 +369,51 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     }
 }
 
-// LayerNorm (eps 1e-6, vision_transformer.py:396) writing bf16 planes directly (A operand of the next GEMM)
+// LayerNorm (eps 1e-6, vision_transformer.py:396) writing bf16 planes directly (A operand of the next GEMM).
+// One warp per row; cols % 8 == 0 and cols <= 256: lane l owns columns [8l, 8l+8) -- two 16-byte loads and one
+// 16-byte store per plane (the first version stored 2 bytes per lane: 3.4 TB/s; HBM-bound work wants full sectors).
 __global__ void __launch_bounds__(256) layernorm_planes_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                                const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
                                                                int rows, int cols, float eps, int P) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    const float* xr = x + (size_t)warp * cols;
-    constexpr int PER = 8;
-    float v[PER];
+    const int c0 = lane * 8;
+    const bool act = c0 < cols;
+    float v[8];
     float s = 0.f;
+    if (act) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + (size_t)warp * cols + c0));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + (size_t)warp * cols + c0 + 4));
+        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int c = lane + 32 * i;
-        v[i] = c < cols ? xr[c] : 0.f;
-        s += v[i];
-    }
-    float mean = rp::warp_sum(s) / (float)cols, q = 0.f;
+        for (int i = 0; i < 8; ++i) s += v[i];
+    } else {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int c = lane + 32 * i;
-        float d = c < cols ? v[i] - mean : 0.f;
-        q += d * d;
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
     }
-    float rstd = 1.0f / sqrtf(rp::warp_sum(q) / (float)cols + eps);
+    const float mean = rp::warp_sum(s) / (float)cols;
+    float q = 0.f;
+    if (act) {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int c = lane + 32 * i;
-        if (c < cols) v[i] = (v[i] - mean) * rstd * g[c] + b[c];
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q += d * d; }
     }
+    const float rstd = 1.0f / sqrtf(rp::warp_sum(q) / (float)cols + eps);
+    if (!act) return;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(g + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(b + c0 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
     for (int p = 0; p < P; ++p) {
-        __nv_bfloat16* dst = out + ((size_t)p * rows + warp) * cols;
+        uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            int c = lane + 32 * i;
-            if (c < cols) {
-                __nv_bfloat16 h = __float2bfloat16_rn(v[i]);
-                dst[c] = h;
-                v[i] -= __bfloat162float(h);
-            }
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+            v[2 * i] -= __uint_as_float(w[i] << 16);
+            v[2 * i + 1] -= __uint_as_float(w[i] & 0xffff0000u);
         }
+        *reinterpret_cast<uint4*>(out + ((size_t)p * rows + warp) * cols + c0) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -487,8 +492,10 @@ extern "C" int rp_split_planes_bf16(const float* x, void* planes, int64_t n, int
 
 extern "C" int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* beta, void* planes, int rows,
                                         int cols, float eps, int P, int device, void* stream) {
-    RP_REQUIRE(x && gamma && beta && planes && rows > 0 && cols > 0 && cols <= 256 && (P == 1 || P == 2), RP_EINVAL,
-               "rp_layernorm_planes: bad argument (cols <= 256)");
+    RP_REQUIRE(x && gamma && beta && planes && rows > 0 && cols > 0 && cols <= 256 && (cols % 8) == 0 && (P == 1 || P == 2), RP_EINVAL,
+               "rp_layernorm_planes: bad argument (cols <= 256, cols %% 8 == 0)");
+    RP_REQUIRE(rp::aligned16(x) && rp::aligned16(gamma) && rp::aligned16(beta) && rp::aligned16(planes), RP_EALIGN,
+               "rp_layernorm_planes: 16-byte alignment");
     RP_GUARD(device);
     layernorm_planes_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
         x, gamma, beta, static_cast<__nv_bfloat16*>(planes), rows, cols, eps, P);
