@@ -119,6 +119,16 @@ int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* be
 int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
                  float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
                  void* stream);
+/* Fused MLP half-block  out = x + fc2(GELU(fc1(LayerNorm(x))))  in one launch: Block.forward's
+ * `x = x + self.mlp(self.norm2(x))` (vision_transformer.py:352-353; mlp.py:20-26) and CrossBlock.forward's
+ * `out = f + mlp(norm2(f))` (vision_transformer.py:295-296).  x, out float32 [M,dim]; W1_planes bf16
+ * [P][hidden][dim], W2_planes bf16 [P][dim][hidden] (as written by rp_split_planes_bf16 from the nn.Linear
+ * weights); LayerNorm eps as in vision_transformer.py:396.  The [M,hidden] activation never reaches HBM.
+ * Built for dim = 192, hidden = 768 (the only widths the reference instantiates).  out may alias x. */
+int rp_mlp_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W1_planes,
+              const float* b1, const void* W2_planes, const float* b2, float* out, int M, int dim, int hidden,
+              int P, int device, void* stream);
+
 /* Tensor-core convolution (A2/A3), same epilogue contract as rp_conv2d_nhwc_f32.  x_planes is the NHWC
  * activation as bf16 planes [P][n_img][H][W][C] (C % 64 == 0), w_planes [P][O][KH*KW*C] is the split of
  * the [O][KH][KW][C] weight, O in {64,128,192}, stride 1 or 2.  Every (tap, 64-channel block) K step is

@@ -66,21 +66,7 @@ struct EpiParams {
     int act;
 };
 
-// erf(x) to ~3e-7 absolute (Abramowitz & Stegun 7.1.26: 1 - (a1 t + .. + a5 t^5) exp(-x^2), t = 1/(1 + p|x|)):
-// two MUFU ops and seven FMAs, branch free.  The GELU epilogue is instruction bound, and its output is
-// re-split to 16 mantissa bits right away, so libdevice's 1-ulp erff (about 3x the instructions) buys nothing.
-__device__ __forceinline__ float fast_erf(float x) {
-    const float ax = fabsf(x);
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));     // MUFU.RCP, 1 ulp
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float e = tc::fast_exp2(-1.4426950408889634f * ax * ax);
-    return copysignf(fmaf(-p, e, 1.0f), x);
-}
-__device__ __forceinline__ float gelu_fast(float v) { return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752440f)); }
+using tc::gelu_fast;
 
 __device__ __forceinline__ float act_fn(float v, int act) {
     if (act == RP_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));

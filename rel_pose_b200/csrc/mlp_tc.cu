@@ -1,0 +1,438 @@
+// Fused transformer MLP half-block on sm_100a tensor cores:
+//     out = x + fc2( GELU( fc1( LayerNorm(x) ) ) )          x, out float32 [M,192]; hidden width 768
+// i.e. `x = x + self.mlp(self.norm2(x))` of Block.forward (vision_transformer.py:352-353, mlp.py:20-26) and
+// `out = f + mlp(norm2(f))` of CrossBlock.forward (vision_transformer.py:295-296) in ONE launch.  The unfused
+// sequence (layernorm_planes -> linear_tc+GELU -> linear_tc+residual) wrote the [M,768] hidden activation to HBM
+// as bf16 planes and read it back (2 x 226 MB per layer at 64 pairs) plus a LayerNorm round trip; here the hidden
+// activation never leaves the SM: fc1 accumulates a 64-column chunk in tensor memory, the epilogue warps apply
+// bias + exact-erf GELU and write the chunk back to shared memory as the K-major A operand of fc2, which
+// accumulates the [128,192] output tile in tensor memory over the twelve chunks.
+//
+// Operands are split-bf16 planes as in gemm_tc.cu (P = 1 bf16, P = 2 "bf16x3" = fp32-class products).
+//
+// One persistent CTA per SM, 576 threads, one 128-row tile at a time:
+//   warp 0      TMA producer: weight "units" ([P][64 rows][64 K] bf16, 128-byte swizzle) into a ring.  A unit is
+//               either one K block of the fc1 chunk (rows = hidden columns) or one 64-row third of the fc2
+//               chunk (rows = output columns, K = the chunk's hidden columns): both are 12 MMAs M128 x N64 x K16.
+//   warp 1      MMA issuer.  Issue order fc1_0, fc1_1, fc2_0, fc1_2, fc2_1, ... so the tensor pipe runs fc1 of
+//               chunk j+1 while the epilogue warps compute GELU of chunk j (acc1 is double buffered in TMEM).
+//   warps 2-17  LayerNorm of the tile's rows straight into the swizzled A-operand planes (no HBM round trip),
+//               per-chunk GELU (TMEM -> registers -> bf16 planes in shared memory), final epilogue
+//               (acc2 + bias + residual, transposed through shared memory for coalesced float4 stores).
+// Tensor memory: acc1[2] = columns 0..127, acc2 = columns 128..319.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int D = 192, HID = 768, CH = 64, NCH = HID / CH;   // embed width, hidden width, hidden chunk
+constexpr int BM = 128;
+constexpr int KB = D / 64;                                   // K blocks of fc1 (3)
+constexpr int NT = D / 64;                                   // 64-column thirds of the fc2 output (3)
+constexpr int EPI_WARPS = 16;
+constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
+constexpr int TILE16K = BM * 64 * 2;                         // one [128 x 64] bf16 operand tile
+constexpr int UNIT1 = 64 * 64 * 2;                           // one plane of a weight unit (8 KiB)
+constexpr int ACC1_COL = 0, ACC2_COL = 128, TMEM_COLS = 512;
+constexpr int STG_LD = 16;
+
+template <int P>
+struct MCfg {
+    static constexpr int NH = (P == 1) ? 2 : 1;              // hidden-chunk buffers (A operand of fc2)
+    static constexpr int NU = (P == 1) ? 12 : 6;             // weight ring depth in units
+    static constexpr int UNIT = P * UNIT1;
+    static constexpr int OFF_XN = 0;                         // [P][KB] tiles of 16 KiB
+    static constexpr int OFF_H = OFF_XN + P * KB * TILE16K;  // [NH][P] tiles of 16 KiB (also final-epilogue staging)
+    static constexpr int OFF_W = OFF_H + NH * P * TILE16K;
+    static constexpr int OFF_BAR = OFF_W + NU * UNIT;
+    static constexpr int SMEM = OFF_BAR + 512 + 1024 /*align slack*/;
+    static_assert(NH * P * TILE16K >= EPI_WARPS * 32 * STG_LD * 4, "H buffer doubles as the epilogue staging area");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct MlpParams {
+    const float* x;        // [M,192] input = residual
+    const float* gamma;    // LayerNorm weight / bias [192]
+    const float* beta;
+    const float* b1;       // [768]
+    const float* b2;       // [192]
+    float* out;            // [M,192]
+    int M;
+    float eps;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int P>
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, MlpParams prm) {
+    using C = MCfg<P>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* wfull = bars;                      // [NU]
+    uint64_t* wempty = bars + C::NU;             // [NU]
+    uint64_t* xn_full = bars + 2 * C::NU;
+    uint64_t* xn_empty = xn_full + 1;
+    uint64_t* acc1_full = xn_full + 2;           // [2]
+    uint64_t* acc1_empty = xn_full + 4;          // [2]
+    uint64_t* h_full = xn_full + 6;              // [2]
+    uint64_t* h_empty = xn_full + 8;             // [2]
+    uint64_t* acc2_full = xn_full + 10;
+    uint64_t* acc2_empty = xn_full + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xn_full + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int M = prm.M;
+    const int ntiles = (M + BM - 1) / BM;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmW1);
+        tc::prefetch_tmap(&tmW2);
+        for (int i = 0; i < C::NU; ++i) {
+            tc::mbar_init(&wfull[i], 1);
+            tc::mbar_init(&wempty[i], 1);
+        }
+        tc::mbar_init(xn_full, EPI_WARPS * 32);
+        tc::mbar_init(xn_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&acc1_full[i], 1);
+            tc::mbar_init(&acc1_empty[i], EPI_WARPS * 32);
+            tc::mbar_init(&h_full[i], EPI_WARPS * 32);
+            tc::mbar_init(&h_empty[i], 1);
+        }
+        tc::mbar_init(acc2_full, 1);
+        tc::mbar_init(acc2_empty, EPI_WARPS * 32);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto xn_tile = [&](int p, int kb) { return smem + C::OFF_XN + (p * KB + kb) * TILE16K; };
+    auto h_tile = [&](int hb, int p) { return smem + C::OFF_H + (hb * P + p) * TILE16K; };
+    auto w_unit = [&](int u, int p) { return smem + C::OFF_W + u * C::UNIT + p * UNIT1; };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (convergent warp)
+        int u = 0, uph = 0;
+        auto load_unit = [&](const CUtensorMap* tm, int c0, int c1) {
+            tc::mbar_wait(&wempty[u], uph ^ 1);
+            if (tc::elect_one_sync()) {
+                tc::mbar_expect_tx(&wfull[u], (uint32_t)C::UNIT);
+#pragma unroll
+                for (int p = 0; p < P; ++p) tc::tma_load_3d(w_unit(u, p), tm, &wfull[u], c0, c1, p);
+            }
+            __syncwarp();
+            if (++u == C::NU) { u = 0; uph ^= 1; }
+        };
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int s = 0; s <= NCH; ++s) {
+                if (s < NCH)
+                    for (int kb = 0; kb < KB; ++kb) load_unit(&tmW1, kb * 64, s * CH);        // W1[s*64.., kb*64..]
+                if (s >= 1)
+                    for (int n = 0; n < NT; ++n) load_unit(&tmW2, (s - 1) * CH, n * 64);      // W2[n*64.., (s-1)*64..]
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (convergent warp)
+        constexpr uint32_t idesc = tc::make_idesc_bf16(BM, 64);
+        int u = 0, uph = 0;
+        uint32_t c1 = 0, c2 = 0, it = 0;        // fc1 chunks / fc2 chunks / tiles issued so far by this CTA
+        uint64_t dxn0[KB], dxn1[KB];
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+            dxn0[kb] = tc::make_kmajor_sw128_desc(tc::smem_u32(xn_tile(0, kb)));
+            dxn1[kb] = tc::make_kmajor_sw128_desc(tc::smem_u32(xn_tile(P - 1, kb)));
+        }
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            tc::mbar_wait(xn_full, it & 1);
+            tc::tcgen05_fence_after();
+            for (int s = 0; s <= NCH; ++s) {
+                if (s < NCH) {
+                    // ---- fc1 of chunk s: acc1[b] = LN(x) . W1[s*64 .. s*64+64, :]^T
+                    const uint32_t b = c1 & 1;
+                    tc::mbar_wait(&acc1_empty[b], ((c1 >> 1) & 1) ^ 1);
+                    tc::tcgen05_fence_after();
+                    const uint32_t d = tmem_base + ACC1_COL + b * CH;
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) {
+                        tc::mbar_wait(&wfull[u], uph);
+                        tc::tcgen05_fence_after();
+                        const uint64_t w0 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, 0)));
+                        const uint64_t w1 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, P - 1)));
+                        if (tc::elect_one_sync()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                                if (P == 2) {            // smallest terms first (truncating fp32 accumulation)
+                                    tc::umma_bf16(d, dxn1[kb] + 2 * k, w0 + 2 * k, idesc, accum);
+                                    tc::umma_bf16(d, dxn0[kb] + 2 * k, w1 + 2 * k, idesc, 1u);
+                                    accum = 1u;
+                                }
+                                tc::umma_bf16(d, dxn0[kb] + 2 * k, w0 + 2 * k, idesc, accum);
+                            }
+                            tc::umma_commit(&wempty[u]);
+                            if (kb == KB - 1) {
+                                tc::umma_commit(&acc1_full[b]);
+                                if (s == NCH - 1) tc::umma_commit(xn_empty);     // LN planes of this tile are dead
+                            }
+                        }
+                        __syncwarp();
+                        if (++u == C::NU) { u = 0; uph ^= 1; }
+                    }
+                    ++c1;
+                }
+                if (s >= 1) {
+                    // ---- fc2 of chunk s-1: acc2 += GELU chunk . W2[:, (s-1)*64 ..]^T
+                    const uint32_t hb = c2 % C::NH;
+                    tc::mbar_wait(&h_full[hb], (c2 / C::NH) & 1);
+                    if (s == 1) tc::mbar_wait(acc2_empty, (it & 1) ^ 1);
+                    tc::tcgen05_fence_after();
+                    const uint64_t dh0 = tc::make_kmajor_sw128_desc(tc::smem_u32(h_tile(hb, 0)));
+                    const uint64_t dh1 = tc::make_kmajor_sw128_desc(tc::smem_u32(h_tile(hb, P - 1)));
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        tc::mbar_wait(&wfull[u], uph);
+                        tc::tcgen05_fence_after();
+                        const uint32_t d = tmem_base + ACC2_COL + n * 64;
+                        const uint64_t w0 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, 0)));
+                        const uint64_t w1 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, P - 1)));
+                        if (tc::elect_one_sync()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                uint32_t accum = (s > 1 || k > 0) ? 1u : 0u;
+                                if (P == 2) {
+                                    tc::umma_bf16(d, dh1 + 2 * k, w0 + 2 * k, idesc, accum);
+                                    tc::umma_bf16(d, dh0 + 2 * k, w1 + 2 * k, idesc, 1u);
+                                    accum = 1u;
+                                }
+                                tc::umma_bf16(d, dh0 + 2 * k, w0 + 2 * k, idesc, accum);
+                            }
+                            tc::umma_commit(&wempty[u]);
+                            if (n == NT - 1) {
+                                tc::umma_commit(&h_empty[hb]);
+                                if (s == NCH) tc::umma_commit(acc2_full);
+                            }
+                        }
+                        __syncwarp();
+                        if (++u == C::NU) { u = 0; uph ^= 1; }
+                    }
+                    ++c2;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ LayerNorm / GELU / output warps
+        const int ew = warp - 2;
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int part = ew >> 2;                        // which 16 of a chunk's 64 hidden columns / 48 of the 192 outputs
+        const int r = q * 32 + lane;                     // the thread's row in TMEM-side work
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
+        const uint32_t sw = (uint32_t)(r & 7);
+        float* stg = reinterpret_cast<float*>(smem + C::OFF_H) + ew * 32 * STG_LD;
+        const int rr = lane >> 2, cq = lane & 3;         // coalesced side of the final epilogue
+        uint32_t c1 = 0, c2 = 0, it = 0;
+
+        // LayerNorm (eps 1e-6, vision_transformer.py:396) of the 8 rows this warp owns, written as the bf16 planes
+        // of the fc1 A operand: three K-major SWIZZLE_128B tiles [128 rows x 64 columns] per plane.
+        auto layer_norm_tile = [&](int tile) {
+            float g[6], bt[6];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float2 gg = __ldg(reinterpret_cast<const float2*>(prm.gamma + 64 * i + 2 * lane));
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(prm.beta + 64 * i + 2 * lane));
+                g[2 * i] = gg.x; g[2 * i + 1] = gg.y; bt[2 * i] = bb.x; bt[2 * i + 1] = bb.y;
+            }
+            float v[8][6];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int grow = tile * BM + ew * 8 + j;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    float2 a = make_float2(0.f, 0.f);
+                    if (grow < M) a = __ldg(reinterpret_cast<const float2*>(prm.x + (size_t)grow * D + 64 * i + 2 * lane));
+                    v[j][2 * i] = a.x; v[j][2 * i + 1] = a.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int rl = ew * 8 + j;
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) s += v[j][i];
+                const float mean = rp::warp_sum(s) * (1.0f / D);
+                float qv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { const float dlt = v[j][i] - mean; qv += dlt * dlt; }
+                const float rstd = 1.0f / sqrtf(rp::warp_sum(qv) * (1.0f / D) + prm.eps);
+                const uint32_t off = (uint32_t)(rl >> 3) * 1024 + (uint32_t)(rl & 7) * 128 +
+                                     ((((uint32_t)lane >> 2) ^ (uint32_t)(rl & 7)) << 4) + (uint32_t)(lane & 3) * 4;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    float y0 = (v[j][2 * i] - mean) * rstd * g[2 * i] + bt[2 * i];
+                    float y1 = (v[j][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bt[2 * i + 1];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const uint32_t w = pack_bf16x2(y0, y1);
+                        *reinterpret_cast<uint32_t*>(xn_tile(p, i) + off) = w;
+                        y0 -= __uint_as_float(w << 16);
+                        y1 -= __uint_as_float(w & 0xffff0000u);
+                    }
+                }
+            }
+            tc::fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core (async proxy)
+            tc::mbar_arrive(xn_full);
+        };
+
+        if ((int)blockIdx.x < ntiles) layer_norm_tile(blockIdx.x);
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            // ---- twelve hidden chunks: acc1 -> + b1 -> GELU -> bf16 planes (A operand of fc2)
+#pragma unroll 1
+            for (int j = 0; j < NCH; ++j, ++c1, ++c2) {
+                const uint32_t b = c1 & 1;
+                float bias[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(prm.b1 + j * CH + part * 16 + 4 * i));
+                    bias[4 * i] = t.x; bias[4 * i + 1] = t.y; bias[4 * i + 2] = t.z; bias[4 * i + 3] = t.w;
+                }
+                tc::mbar_wait(&acc1_full[b], (c1 >> 1) & 1);
+                tc::tcgen05_fence_after();
+                uint32_t a[16];
+                tc::tmem_ld_32x32b_x16(t_lane + ACC1_COL + b * CH + part * 16, a);
+                tc::tmem_ld_wait();
+                tc::tcgen05_fence_before();
+                tc::mbar_arrive(&acc1_empty[b]);                 // fc1 of chunk j+2 may overwrite acc1[b]
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = tc::gelu_fast(__uint_as_float(a[i]) + bias[i]);
+                const uint32_t hb = c2 % C::NH;
+                tc::mbar_wait(&h_empty[hb], ((c2 / C::NH) & 1) ^ 1);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+#pragma unroll
+                    for (int hc = 0; hc < 2; ++hc) {
+                        uint4 w;
+                        w.x = pack_bf16x2(v[8 * hc + 0], v[8 * hc + 1]);
+                        w.y = pack_bf16x2(v[8 * hc + 2], v[8 * hc + 3]);
+                        w.z = pack_bf16x2(v[8 * hc + 4], v[8 * hc + 5]);
+                        w.w = pack_bf16x2(v[8 * hc + 6], v[8 * hc + 7]);
+                        const uint32_t c = (uint32_t)(part * 2 + hc);
+                        *reinterpret_cast<uint4*>(h_tile(hb, p) + row_off + ((c ^ sw) << 4)) = w;
+                        if (p + 1 < P) {
+                            v[8 * hc + 0] -= __uint_as_float(w.x << 16); v[8 * hc + 1] -= __uint_as_float(w.x & 0xffff0000u);
+                            v[8 * hc + 2] -= __uint_as_float(w.y << 16); v[8 * hc + 3] -= __uint_as_float(w.y & 0xffff0000u);
+                            v[8 * hc + 4] -= __uint_as_float(w.z << 16); v[8 * hc + 5] -= __uint_as_float(w.z & 0xffff0000u);
+                            v[8 * hc + 6] -= __uint_as_float(w.w << 16); v[8 * hc + 7] -= __uint_as_float(w.w & 0xffff0000u);
+                        }
+                    }
+                }
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&h_full[hb]);
+            }
+            // ---- LayerNorm of the NEXT tile first (its fc1 then overlaps this tile's output epilogue)
+            const int next = tile + gridDim.x;
+            if (next < ntiles) {
+                tc::mbar_wait(xn_empty, it & 1);
+                layer_norm_tile(next);
+            }
+            // ---- output: acc2 + b2 + x, transposed through the (now idle) H buffer for coalesced float4 stores
+            tc::mbar_wait(acc2_full, it & 1);
+            tc::tcgen05_fence_after();
+            const int valid_rows = min(BM, M - tile * BM);
+#pragma unroll 1
+            for (int gi = 0; gi < 3; ++gi) {
+                const int c0 = part * 48 + gi * 16;
+                const int col = c0 + cq * 4;
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(prm.b2 + col));
+                float4 res[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int rt = q * 32 + t * 8 + rr;
+                    res[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rt < valid_rows)
+                        res[t] = __ldg(reinterpret_cast<const float4*>(prm.x + (size_t)(tile * BM + rt) * D + col));
+                }
+                uint32_t a[16];
+                tc::tmem_ld_32x32b_x16(t_lane + ACC2_COL + c0, a);
+                tc::tmem_ld_wait();
+                __syncwarp();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    *reinterpret_cast<uint4*>(stg + lane * STG_LD + ((jj ^ ((lane >> 1) & 3)) << 2)) =
+                        make_uint4(a[4 * jj], a[4 * jj + 1], a[4 * jj + 2], a[4 * jj + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int rl = t * 8 + rr;
+                    const int rt = q * 32 + rl;
+                    if (rt >= valid_rows) continue;
+                    const float4 acc = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2));
+                    float4 o;
+                    o.x = acc.x + sh.x + res[t].x; o.y = acc.y + sh.y + res[t].y;
+                    o.z = acc.z + sh.z + res[t].z; o.w = acc.w + sh.w + res[t].w;
+                    *reinterpret_cast<float4*>(prm.out + (size_t)(tile * BM + rt) * D + col) = o;
+                }
+            }
+            tc::tcgen05_fence_before();
+            tc::mbar_arrive(acc2_empty);
+            // the staging patches live in the H buffer: nobody may start the next tile's GELU writes before all
+            // epilogue warps are done with them (named barrier over the 16 epilogue warps only)
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        }
+    }
+
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int P>
+int launch_mlp(const CUtensorMap& tmW1, const CUtensorMap& tmW2, const MlpParams& prm, int device, cudaStream_t st) {
+    using C = MCfg<P>;
+    static bool attr_set[64] = {false};
+    if (device >= 0 && device < 64 && !attr_set[device]) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) {
+            rp::set_error("rp_mlp_tc: cudaFuncSetAttribute(%d): %s", C::SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_set[device] = true;
+    }
+    const int ntiles = (prm.M + BM - 1) / BM;
+    const int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
+    mlp_fused_tc_kernel<P><<<grid, NTHREADS, C::SMEM, st>>>(tmW1, tmW2, prm);
+    return rp::finish_launch("rp_mlp_tc");
+}
+
+}  // namespace
+
+extern "C" int rp_mlp_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W1_planes,
+                         const float* b1, const void* W2_planes, const float* b2, float* out, int M, int dim, int hidden,
+                         int P, int device, void* stream) {
+    RP_REQUIRE(x && ln_gamma && ln_beta && W1_planes && b1 && W2_planes && b2 && out && M > 0, RP_EINVAL,
+               "rp_mlp_tc: null pointer or M <= 0");
+    RP_REQUIRE(dim == D && hidden == HID, RP_EINVAL, "rp_mlp_tc: built for dim=192, hidden=768 (got %d, %d)", dim, hidden);
+    RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_mlp_tc: P must be 1 (bf16) or 2 (bf16x3)");
+    RP_REQUIRE(rp::aligned16(x) && rp::aligned16(out) && rp::aligned16(W1_planes) && rp::aligned16(W2_planes) &&
+                   rp::aligned16(b1) && rp::aligned16(b2) && rp::aligned16(ln_gamma) && rp::aligned16(ln_beta),
+               RP_EALIGN, "rp_mlp_tc: 16-byte alignment");
+    RP_GUARD(device);
+    CUtensorMap tmW1, tmW2;
+    int rc = tc::make_planes_tmap(&tmW1, W1_planes, P, HID, D, 64);      // [P][768][192], box 64 rows x 64 K
+    if (rc) return rc;
+    rc = tc::make_planes_tmap(&tmW2, W2_planes, P, D, HID, 64);          // [P][192][768]
+    if (rc) return rc;
+    MlpParams prm{x, ln_gamma, ln_beta, b1, b2, out, M, eps};
+    if (P == 1) return launch_mlp<1>(tmW1, tmW2, prm, device, (cudaStream_t)stream);
+    return launch_mlp<2>(tmW1, tmW2, prm, device, (cudaStream_t)stream);
+}

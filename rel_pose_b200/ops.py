@@ -345,6 +345,23 @@ def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f
     return out, outp
 
 
+def mlp_tc(x, gamma, beta, eps, w1_planes, b1, w2_planes, b2):
+    """Fused `x + fc2(gelu(fc1(layernorm(x))))` on tcgen05 (csrc/mlp_tc.cu): x float32 [...,192],
+    w1_planes bf16 [P,768,192], w2_planes bf16 [P,192,768] -> float32 [...,192]."""
+    _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta"); _req(b1, "b1"); _req(b2, "b2")
+    _req(w1_planes, "w1_planes", torch.bfloat16); _req(w2_planes, "w2_planes", torch.bfloat16)
+    P, hidden, dim = w1_planes.shape
+    assert tuple(w2_planes.shape) == (P, dim, hidden) and x.shape[-1] == dim
+    M = x.numel() // dim
+    out = torch.empty_like(x)
+    dev, st = _ctx(x)
+    _tbegin(f"mlp_fused_tc{'x3' if P == 2 else ''}", 4.0 * M * dim * hidden, 8.0 * M * dim + 4.0 * P * dim * hidden)
+    _lib.check(_lib.lib().rp_mlp_tc(_p(x), _p(gamma), _p(beta), float(eps), _p(w1_planes), _p(b1), _p(w2_planes), _p(b2),
+                                    _p(out), M, dim, hidden, P, dev, st), "rp_mlp_tc")
+    _count()
+    return out
+
+
 def conv2d_tc(x_planes, w_planes, KH, KW, scale=None, shift=None, stride=1, pad=0, act=ACT_NONE, res_pre=None,
               res_post=None, res_post_rows=0, want_f32=True, planes_out=0):
     """Tensor-core conv: x_planes [P,n,H,W,C] bf16, w_planes [P,O,KH*KW*C] bf16 -> (f32 [n,Ho,Wo,O] | None, planes | None)."""

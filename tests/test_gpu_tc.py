@@ -96,6 +96,41 @@ def test_linear_tc_only_planes_output():
     assert np.abs(planes_to_f64(outp) - y).max() < 5e-5 * np.abs(y).max()
 
 
+@pytest.mark.parametrize("P", [1, 2])
+@pytest.mark.parametrize("M", [128, 140, 1152, 8960, 148 * 128 * 2 + 77])
+def test_mlp_fused_tc(P, M):
+    """rp_mlp_tc = x + fc2(gelu(fc1(layernorm(x)))) in one launch, against float64 and against the three-kernel path."""
+    x = rnd(20, M, 192, scale=1.5) + 0.2
+    g = 1 + 0.1 * rnd(21, 192); be = 0.1 * rnd(22, 192)
+    w1 = rnd(23, 768, 192, scale=0.07); b1 = rnd(24, 768, scale=0.1)
+    w2 = rnd(25, 192, 768, scale=0.04); b2 = rnd(26, 192, scale=0.1)
+    w1p = ops.split_planes(cu(w1), P); w2p = ops.split_planes(cu(w2), P)
+    xg = cu(x)
+    got = ops.mlp_tc(xg, cu(g), cu(be), 1e-6, w1p, cu(b1), w2p, cu(b2))
+    torch.cuda.synchronize()
+    f64 = np.float64
+    h = O.layernorm(x.astype(f64), g.astype(f64), be.astype(f64))
+    h = O.gelu(h @ w1.astype(f64).T + b1)
+    ref = x + h @ w2.astype(f64).T + b2
+    gotn = got.cpu().numpy().astype(f64)
+    d = gotn - x                      # the MLP branch alone (the residual is added exactly)
+    dref = ref - x
+    tol = (4e-5 if P == 2 else 2e-2) * np.abs(dref).max()
+    err = np.abs(d - dref).max()
+    print(f"[parity] mlp_fused_tc P={P} M={M}: max_abs_err={err:.3e} max_ref={np.abs(dref).max():.3e} ratio={err / tol:.3f}")
+    if not err <= tol:
+        _diagnose(f"mlp P={P} M={M}", d, dref)
+    assert np.isfinite(gotn).all() and err <= tol
+    # the unfused sequence computes the same thing
+    hp = ops.layernorm_planes(xg, cu(g), cu(be), 1e-6, P)
+    _, hp = ops.linear_tc(hp, w1p, cu(b1), act=ops.ACT_GELU, want_f32=False, planes_out=P)
+    un, _ = ops.linear_tc(hp, w2p, cu(b2), residual=xg)
+    assert np.abs(un.cpu().numpy() - gotn).max() <= 2 * tol
+    # bit-reproducible from run to run
+    again = ops.mlp_tc(xg, cu(g), cu(be), 1e-6, w1p, cu(b1), w2p, cu(b2))
+    assert torch.equal(got, again)
+
+
 # ------------------------------------------------------------------------------------------ conv on tcgen05
 class _BN:
     def __init__(self, seed, C):
