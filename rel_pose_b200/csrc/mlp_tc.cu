@@ -10,16 +10,18 @@
 //
 // Operands are split-bf16 planes as in gemm_tc.cu (P = 1 bf16, P = 2 "bf16x3" = fp32-class products).
 //
-// One persistent CTA per SM, 576 threads, one 128-row tile at a time:
+// One persistent CTA per SM, 640 threads, one 128-row tile at a time:
 //   warp 0      TMA producer: weight "units" ([P][64 rows][64 K] bf16, 128-byte swizzle) into a ring.  A unit is
 //               either one K block of the fc1 chunk (rows = hidden columns) or one 64-row third of the fc2
-//               chunk (rows = output columns, K = the chunk's hidden columns): both are 12 MMAs M128 x N64 x K16.
-//   warp 1      MMA issuer.  Issue order fc1_0, fc1_1, fc2_0, fc1_2, fc2_1, ... so the tensor pipe runs fc1 of
-//               chunk j+1 while the epilogue warps compute GELU of chunk j (acc1 is double buffered in TMEM).
-//   warps 2-17  LayerNorm of the tile's rows straight into the swizzled A-operand planes (no HBM round trip),
+//               chunk (rows = output columns, K = the chunk's hidden columns).  Ring order fc1_0, fc1_1, fc1_2,
+//               fc2_0, fc1_3, fc2_1, ...: fc1 runs two chunks ahead of fc2 (three fc1 accumulators in TMEM).
+//   warps 1, 2  fc1 issuers (even / odd chunks): 36 tcgen05.mma M128 x N64 x K16 per chunk (bf16x3).
+//   warp 3      fc2 issuer: 12 tcgen05.mma M128 x N192 x K16 per chunk into the tile's output accumulator.
+//               Three issuer warps on three schedulers because a single issuer was the bottleneck (see below).
+//   warps 4-19  LayerNorm of the tile's rows straight into the swizzled A-operand planes (no HBM round trip),
 //               per-chunk GELU (TMEM -> registers -> bf16 planes in shared memory), final epilogue
 //               (acc2 + bias + residual, transposed through shared memory for coalesced float4 stores).
-// Tensor memory: acc1[2] = columns 0..127, acc2 = columns 128..319.
+// Tensor memory: acc1[3] = columns 0..191, acc2 = columns 192..383.
 #include "tc_common.cuh"
 
 namespace {
@@ -29,16 +31,20 @@ constexpr int BM = 128;
 constexpr int KB = D / 64;                                   // K blocks of fc1 (3)
 constexpr int NT = D / 64;                                   // 64-column thirds of the fc2 output (3)
 constexpr int EPI_WARPS = 16;
-constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
+constexpr int CTRL_WARPS = 4;                                 // TMA producer, two fc1 issuers, fc2 issuer
+constexpr int NTHREADS = 32 * (CTRL_WARPS + EPI_WARPS);
 constexpr int TILE16K = BM * 64 * 2;                         // one [128 x 64] bf16 operand tile
 constexpr int UNIT1 = 64 * 64 * 2;                           // one plane of a weight unit (8 KiB)
-constexpr int ACC1_COL = 0, ACC2_COL = 128, TMEM_COLS = 512;
+constexpr int NA1 = 3, LEAD = 2;                              // fc1 accumulators in TMEM; fc1 runs LEAD chunks ahead of fc2
+constexpr int ACC1_COL = 0, ACC2_COL = NA1 * CH, TMEM_COLS = 512;
 constexpr int STG_LD = 16;
 
 template <int P>
 struct MCfg {
     static constexpr int NH = (P == 1) ? 2 : 1;              // hidden-chunk buffers (A operand of fc2)
-    static constexpr int NU = (P == 1) ? 12 : 6;             // weight ring depth in units
+    static constexpr int G1 = (P == 1) ? 2 : 1;              // fc1 weight ring: groups of three units (one chunk each)
+    static constexpr int G2 = (P == 1) ? 2 : 1;              // fc2 weight ring: groups of three units (one chunk each)
+    static constexpr int NU = 3 * (G1 + G2);                 // units in shared memory: fc1 ring first, then fc2 ring
     static constexpr int UNIT = P * UNIT1;
     static constexpr int OFF_XN = 0;                         // [P][KB] tiles of 16 KiB
     static constexpr int OFF_H = OFF_XN + P * KB * TILE16K;  // [NH][P] tiles of 16 KiB (also final-epilogue staging)
@@ -75,14 +81,14 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     uint64_t* wfull = bars;                      // [NU]
     uint64_t* wempty = bars + C::NU;             // [NU]
     uint64_t* xn_full = bars + 2 * C::NU;
-    uint64_t* xn_empty = xn_full + 1;
-    uint64_t* acc1_full = xn_full + 2;           // [2]
-    uint64_t* acc1_empty = xn_full + 4;          // [2]
-    uint64_t* h_full = xn_full + 6;              // [2]
-    uint64_t* h_empty = xn_full + 8;             // [2]
-    uint64_t* acc2_full = xn_full + 10;
-    uint64_t* acc2_empty = xn_full + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xn_full + 12);
+    uint64_t* acc1_full = xn_full + 2;           // [NA1]
+    uint64_t* acc1_empty = xn_full + 5;          // [NA1]
+    uint64_t* h_full = xn_full + 8;              // [2]
+    uint64_t* h_empty = xn_full + 10;            // [2]
+    uint64_t* acc2_full = xn_full + 12;
+    uint64_t* acc2_empty = xn_full + 13;
+    uint64_t* turn = xn_full + 14;               // [2] hand-off between the two fc1 issuers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xn_full + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = prm.M;
@@ -95,16 +101,20 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
             tc::mbar_init(&wfull[i], 1);
             tc::mbar_init(&wempty[i], 1);
         }
-        tc::mbar_init(xn_full, EPI_WARPS * 32);
-        tc::mbar_init(xn_empty, 1);
-        for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(xn_full, EPI_WARPS);          // one elected arrive per epilogue warp (512 arrives on one
+                                                    // mbarrier serialise in the shared-memory atomic unit)
+        for (int i = 0; i < NA1; ++i) {
             tc::mbar_init(&acc1_full[i], 1);
-            tc::mbar_init(&acc1_empty[i], EPI_WARPS * 32);
-            tc::mbar_init(&h_full[i], EPI_WARPS * 32);
+            tc::mbar_init(&acc1_empty[i], EPI_WARPS);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&h_full[i], EPI_WARPS);
             tc::mbar_init(&h_empty[i], 1);
         }
         tc::mbar_init(acc2_full, 1);
-        tc::mbar_init(acc2_empty, EPI_WARPS * 32);
+        tc::mbar_init(acc2_empty, EPI_WARPS);
+        tc::mbar_init(&turn[0], 1);
+        tc::mbar_init(&turn[1], 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -115,34 +125,49 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 
     auto xn_tile = [&](int p, int kb) { return smem + C::OFF_XN + (p * KB + kb) * TILE16K; };
     auto h_tile = [&](int hb, int p) { return smem + C::OFF_H + (hb * P + p) * TILE16K; };
-    auto w_unit = [&](int u, int p) { return smem + C::OFF_W + u * C::UNIT + p * UNIT1; };
+    // ring units are grouped in threes, planes outermost inside a group: the three units of an fc2 chunk
+    // (output rows 0..63, 64..127, 128..191) then form one contiguous [192 x 64] B tile per plane
+    auto w_unit = [&](int u, int p) { return smem + C::OFF_W + (u / 3) * (3 * C::UNIT) + p * (3 * UNIT1) + (u % 3) * UNIT1; };
 
+    // Every mbarrier of the weight rings has exactly ONE consumer: a parity wait is only unambiguous for a waiter
+    // that observes every phase in order.  The fc1 ring (units 0 .. 3 G1-1) is consumed by the two fc1 issuers,
+    // the fc2 ring (the rest) by the fc2 issuer.  Where both fc1 issuers alternate on the same units (G1 odd),
+    // the `turn` hand-off below makes the later one wait until the earlier one has observed ITS fill.
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (convergent warp)
-        int u = 0, uph = 0;
-        auto load_unit = [&](const CUtensorMap* tm, int c0, int c1) {
-            tc::mbar_wait(&wempty[u], uph ^ 1);
+        uint32_t g1 = 0, g2 = 0;                 // fc1 / fc2 chunks loaded so far by this CTA
+        auto load_unit = [&](int u, uint32_t fill, const CUtensorMap* tm, int c0, int c1) {
+            tc::mbar_wait(&wempty[u], (fill & 1) ^ 1);
             if (tc::elect_one_sync()) {
                 tc::mbar_expect_tx(&wfull[u], (uint32_t)C::UNIT);
 #pragma unroll
                 for (int p = 0; p < P; ++p) tc::tma_load_3d(w_unit(u, p), tm, &wfull[u], c0, c1, p);
             }
             __syncwarp();
-            if (++u == C::NU) { u = 0; uph ^= 1; }
         };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            for (int s = 0; s <= NCH; ++s) {
-                if (s < NCH)
-                    for (int kb = 0; kb < KB; ++kb) load_unit(&tmW1, kb * 64, s * CH);        // W1[s*64.., kb*64..]
-                if (s >= 1)
-                    for (int n = 0; n < NT; ++n) load_unit(&tmW2, (s - 1) * CH, n * 64);      // W2[n*64.., (s-1)*64..]
+            for (int s = 0; s < NCH + LEAD; ++s) {
+                if (s < NCH) {                                                           // W1[s*64.., kb*64..]
+                    const int u0 = 3 * (int)(g1 % C::G1);
+                    for (int kb = 0; kb < KB; ++kb) load_unit(u0 + kb, g1 / C::G1, &tmW1, kb * 64, s * CH);
+                    ++g1;
+                }
+                if (s >= LEAD) {                                                         // W2[n*64.., (s-2)*64..]
+                    const int u0 = 3 * C::G1 + 3 * (int)(g2 % C::G2);
+                    for (int n = 0; n < NT; ++n) load_unit(u0 + n, g2 / C::G2, &tmW2, (s - LEAD) * CH, n * 64);
+                    ++g2;
+                }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (convergent warp)
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------------------------ fc1 issuers (convergent warps)
+        // Two warps share the fc1 chunks (even / odd): ncu showed ONE issuer warp spending 80 % of its time just
+        // executing its own instruction stream (barrier polls, descriptor set-up, R2UR moves: ~90 instructions per
+        // 12-MMA unit at ~11 cycles each next to four busy GELU warps) with the tensor pipe 65 % idle.  The three
+        // issuers sit on different schedulers; MMAs of different issuers touch different accumulators.
         constexpr uint32_t idesc = tc::make_idesc_bf16(BM, 64);
-        int u = 0, uph = 0;
-        uint32_t c1 = 0, c2 = 0, it = 0;        // fc1 chunks / fc2 chunks / tiles issued so far by this CTA
+        const uint32_t sel = (uint32_t)(warp - 1);
+        uint32_t it = 0, n = 0;                 // tiles seen / chunks issued by this warp
         uint64_t dxn0[KB], dxn1[KB];
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
@@ -152,83 +177,89 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             tc::mbar_wait(xn_full, it & 1);
             tc::tcgen05_fence_after();
-            for (int s = 0; s <= NCH; ++s) {
-                if (s < NCH) {
-                    // ---- fc1 of chunk s: acc1[b] = LN(x) . W1[s*64 .. s*64+64, :]^T
-                    const uint32_t b = c1 & 1;
-                    tc::mbar_wait(&acc1_empty[b], ((c1 >> 1) & 1) ^ 1);
+            for (int s = (int)sel; s < NCH; s += 2, ++n) {
+                // ---- fc1 of chunk s: acc1[b] = LN(x) . W1[s*64 .. s*64+64, :]^T       (NCH is even: g = 2n + sel)
+                const uint32_t g = it * NCH + (uint32_t)s;
+                const uint32_t b = g % NA1;
+                const int u0 = 3 * (int)(g % C::G1);
+                const uint32_t fpar = (g / C::G1) & 1;
+                // the other issuer has observed the previous chunk's fill (see the ring comment above)
+                if (sel == 0) { if (n > 0) tc::mbar_wait(&turn[0], (n - 1) & 1); }
+                else tc::mbar_wait(&turn[1], n & 1);
+                tc::mbar_wait(&acc1_empty[b], ((g / NA1) & 1) ^ 1);
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + ACC1_COL + b * CH;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int u = u0 + kb;
+                    tc::mbar_wait(&wfull[u], fpar);
                     tc::tcgen05_fence_after();
-                    const uint32_t d = tmem_base + ACC1_COL + b * CH;
+                    const uint64_t w0 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, 0)));
+                    const uint64_t w1 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, P - 1)));
+                    if (tc::elect_one_sync()) {
 #pragma unroll
-                    for (int kb = 0; kb < KB; ++kb) {
-                        tc::mbar_wait(&wfull[u], uph);
-                        tc::tcgen05_fence_after();
-                        const uint64_t w0 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, 0)));
-                        const uint64_t w1 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, P - 1)));
-                        if (tc::elect_one_sync()) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-                                if (P == 2) {            // smallest terms first (truncating fp32 accumulation)
-                                    tc::umma_bf16(d, dxn1[kb] + 2 * k, w0 + 2 * k, idesc, accum);
-                                    tc::umma_bf16(d, dxn0[kb] + 2 * k, w1 + 2 * k, idesc, 1u);
-                                    accum = 1u;
-                                }
-                                tc::umma_bf16(d, dxn0[kb] + 2 * k, w0 + 2 * k, idesc, accum);
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                            if (P == 2) {            // smallest terms first (truncating fp32 accumulation)
+                                tc::umma_bf16(d, dxn1[kb] + 2 * k, w0 + 2 * k, idesc, accum);
+                                tc::umma_bf16(d, dxn0[kb] + 2 * k, w1 + 2 * k, idesc, 1u);
+                                accum = 1u;
                             }
-                            tc::umma_commit(&wempty[u]);
-                            if (kb == KB - 1) {
-                                tc::umma_commit(&acc1_full[b]);
-                                if (s == NCH - 1) tc::umma_commit(xn_empty);     // LN planes of this tile are dead
-                            }
+                            tc::umma_bf16(d, dxn0[kb] + 2 * k, w0 + 2 * k, idesc, accum);
                         }
-                        __syncwarp();
-                        if (++u == C::NU) { u = 0; uph ^= 1; }
-                    }
-                    ++c1;
-                }
-                if (s >= 1) {
-                    // ---- fc2 of chunk s-1: acc2 += GELU chunk . W2[:, (s-1)*64 ..]^T
-                    const uint32_t hb = c2 % C::NH;
-                    tc::mbar_wait(&h_full[hb], (c2 / C::NH) & 1);
-                    if (s == 1) tc::mbar_wait(acc2_empty, (it & 1) ^ 1);
-                    tc::tcgen05_fence_after();
-                    const uint64_t dh0 = tc::make_kmajor_sw128_desc(tc::smem_u32(h_tile(hb, 0)));
-                    const uint64_t dh1 = tc::make_kmajor_sw128_desc(tc::smem_u32(h_tile(hb, P - 1)));
-#pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        tc::mbar_wait(&wfull[u], uph);
-                        tc::tcgen05_fence_after();
-                        const uint32_t d = tmem_base + ACC2_COL + n * 64;
-                        const uint64_t w0 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, 0)));
-                        const uint64_t w1 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, P - 1)));
-                        if (tc::elect_one_sync()) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                uint32_t accum = (s > 1 || k > 0) ? 1u : 0u;
-                                if (P == 2) {
-                                    tc::umma_bf16(d, dh1 + 2 * k, w0 + 2 * k, idesc, accum);
-                                    tc::umma_bf16(d, dh0 + 2 * k, w1 + 2 * k, idesc, 1u);
-                                    accum = 1u;
-                                }
-                                tc::umma_bf16(d, dh0 + 2 * k, w0 + 2 * k, idesc, accum);
-                            }
-                            tc::umma_commit(&wempty[u]);
-                            if (n == NT - 1) {
-                                tc::umma_commit(&h_empty[hb]);
-                                if (s == NCH) tc::umma_commit(acc2_full);
-                            }
+                        tc::umma_commit(&wempty[u]);
+                        if (kb == KB - 1) {
+                            tc::umma_commit(&acc1_full[b]);
+                            tc::mbar_arrive(&turn[sel ^ 1]);
                         }
-                        __syncwarp();
-                        if (++u == C::NU) { u = 0; uph ^= 1; }
                     }
-                    ++c2;
+                    __syncwarp();
                 }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ fc2 issuer (convergent warp)
+        // acc2[128 x 192] += GELU chunk [128 x 64] . W2[:, chunk]^T : the chunk's three ring units are one
+        // contiguous [192 rows x 64 K] tile per plane, so every K step is ONE N = 192 instruction.
+        constexpr uint32_t idesc = tc::make_idesc_bf16(BM, D);
+        uint32_t c2 = 0, it = 0;                // fc2 chunks / tiles issued so far by this CTA
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            for (int j = 0; j < NCH; ++j, ++c2) {
+                const uint32_t hb = c2 % C::NH;
+                const int u = 3 * C::G1 + 3 * (int)(c2 % C::G2);
+                const uint32_t fpar = (c2 / C::G2) & 1;
+                tc::mbar_wait(&h_full[hb], (c2 / C::NH) & 1);
+                if (j == 0) tc::mbar_wait(acc2_empty, (it & 1) ^ 1);
+#pragma unroll
+                for (int nn = 0; nn < NT; ++nn) tc::mbar_wait(&wfull[u + nn], fpar);
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + ACC2_COL;
+                const uint64_t dh0 = tc::make_kmajor_sw128_desc(tc::smem_u32(h_tile(hb, 0)));
+                const uint64_t dh1 = tc::make_kmajor_sw128_desc(tc::smem_u32(h_tile(hb, P - 1)));
+                const uint64_t w0 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, 0)));
+                const uint64_t w1 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, P - 1)));
+                if (tc::elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t accum = (j > 0 || k > 0) ? 1u : 0u;
+                        if (P == 2) {
+                            tc::umma_bf16(d, dh1 + 2 * k, w0 + 2 * k, idesc, accum);
+                            tc::umma_bf16(d, dh0 + 2 * k, w1 + 2 * k, idesc, 1u);
+                            accum = 1u;
+                        }
+                        tc::umma_bf16(d, dh0 + 2 * k, w0 + 2 * k, idesc, accum);
+                    }
+#pragma unroll
+                    for (int nn = 0; nn < NT; ++nn) tc::umma_commit(&wempty[u + nn]);
+                    tc::umma_commit(&h_empty[hb]);
+                    if (j == NCH - 1) tc::umma_commit(acc2_full);
+                }
+                __syncwarp();
             }
         }
     } else {
         // ------------------------------------------------------------------ LayerNorm / GELU / output warps
-        const int ew = warp - 2;
+        const int ew = warp - CTRL_WARPS;
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int part = ew >> 2;                        // which 16 of a chunk's 64 hidden columns / 48 of the 192 outputs
         const int r = q * 32 + lane;                     // the thread's row in TMEM-side work
@@ -237,7 +268,7 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         const uint32_t sw = (uint32_t)(r & 7);
         float* stg = reinterpret_cast<float*>(smem + C::OFF_H) + ew * 32 * STG_LD;
         const int rr = lane >> 2, cq = lane & 3;         // coalesced side of the final epilogue
-        uint32_t c1 = 0, c2 = 0, it = 0;
+        uint32_t b1 = 0, ph1 = 0, c2 = 0, it = 0;
 
         // LayerNorm (eps 1e-6, vision_transformer.py:396) of the 8 rows this warp owns, written as the bf16 planes
         // of the fc1 A operand: three K-major SWIZZLE_128B tiles [128 rows x 64 columns] per plane.
@@ -287,28 +318,39 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 }
             }
             tc::fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core (async proxy)
-            tc::mbar_arrive(xn_full);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(xn_full);
         };
 
         if ((int)blockIdx.x < ntiles) layer_norm_tile(blockIdx.x);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             // ---- twelve hidden chunks: acc1 -> + b1 -> GELU -> bf16 planes (A operand of fc2)
 #pragma unroll 1
-            for (int j = 0; j < NCH; ++j, ++c1, ++c2) {
-                const uint32_t b = c1 & 1;
+            for (int j = 0; j < NCH; ++j, ++c2) {
+                const uint32_t b = b1;
+                if (j == 2) {
+                    // pull the next tile's rows towards L2 now; its LayerNorm runs right after this tile's last chunk
+                    const int nrow = (tile + (int)gridDim.x) * BM + ew * 8 + (lane >> 2);
+                    if (nrow < M && (lane & 3) < 3)      // 8 rows x 768 B = 48 lines of 128 B: 24 lanes x 2
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.x + (size_t)nrow * D + (lane & 3) * 64));
+                    if (nrow < M && (lane & 3) < 3)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.x + (size_t)nrow * D + (lane & 3) * 64 + 32));
+                }
                 float bias[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 t = __ldg(reinterpret_cast<const float4*>(prm.b1 + j * CH + part * 16 + 4 * i));
                     bias[4 * i] = t.x; bias[4 * i + 1] = t.y; bias[4 * i + 2] = t.z; bias[4 * i + 3] = t.w;
                 }
-                tc::mbar_wait(&acc1_full[b], (c1 >> 1) & 1);
+                tc::mbar_wait(&acc1_full[b], ph1);
+                if (++b1 == NA1) { b1 = 0; ph1 ^= 1; }
                 tc::tcgen05_fence_after();
                 uint32_t a[16];
                 tc::tmem_ld_32x32b_x16(t_lane + ACC1_COL + b * CH + part * 16, a);
                 tc::tmem_ld_wait();
                 tc::tcgen05_fence_before();
-                tc::mbar_arrive(&acc1_empty[b]);                 // fc1 of chunk j+2 may overwrite acc1[b]
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&acc1_empty[b]);  // fc1 of chunk j+2 may overwrite acc1[b]
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = tc::gelu_fast(__uint_as_float(a[i]) + bias[i]);
@@ -334,31 +376,35 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     }
                 }
                 tc::fence_proxy_async_smem();
-                tc::mbar_arrive(&h_full[hb]);
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&h_full[hb]);
             }
             // ---- LayerNorm of the NEXT tile first (its fc1 then overlaps this tile's output epilogue)
             const int next = tile + gridDim.x;
-            if (next < ntiles) {
-                tc::mbar_wait(xn_empty, it & 1);
-                layer_norm_tile(next);
+            if (next < ntiles) layer_norm_tile(next);   // every fc1 of this tile has completed (acc1_full was observed
+                                                         // for all twelve chunks): its LayerNorm planes are dead
+            // ---- output: acc2 + b2 + x, transposed through the (now idle) H buffer for coalesced float4 stores.
+            // The residual rows (L2 hits: this CTA read them for the LayerNorm) are requested before the wait.
+            const int valid_rows = min(BM, M - tile * BM);
+            float4 res[3][4];
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) {
+                const int col = part * 48 + gi * 16 + cq * 4;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int rt = q * 32 + t * 8 + rr;
+                    res[gi][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rt < valid_rows)
+                        res[gi][t] = __ldg(reinterpret_cast<const float4*>(prm.x + (size_t)(tile * BM + rt) * D + col));
+                }
             }
-            // ---- output: acc2 + b2 + x, transposed through the (now idle) H buffer for coalesced float4 stores
             tc::mbar_wait(acc2_full, it & 1);
             tc::tcgen05_fence_after();
-            const int valid_rows = min(BM, M - tile * BM);
-#pragma unroll 1
+#pragma unroll
             for (int gi = 0; gi < 3; ++gi) {
                 const int c0 = part * 48 + gi * 16;
                 const int col = c0 + cq * 4;
                 const float4 sh = __ldg(reinterpret_cast<const float4*>(prm.b2 + col));
-                float4 res[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int rt = q * 32 + t * 8 + rr;
-                    res[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rt < valid_rows)
-                        res[t] = __ldg(reinterpret_cast<const float4*>(prm.x + (size_t)(tile * BM + rt) * D + col));
-                }
                 uint32_t a[16];
                 tc::tmem_ld_32x32b_x16(t_lane + ACC2_COL + c0, a);
                 tc::tmem_ld_wait();
@@ -375,13 +421,14 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     if (rt >= valid_rows) continue;
                     const float4 acc = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2));
                     float4 o;
-                    o.x = acc.x + sh.x + res[t].x; o.y = acc.y + sh.y + res[t].y;
-                    o.z = acc.z + sh.z + res[t].z; o.w = acc.w + sh.w + res[t].w;
+                    o.x = acc.x + sh.x + res[gi][t].x; o.y = acc.y + sh.y + res[gi][t].y;
+                    o.z = acc.z + sh.z + res[gi][t].z; o.w = acc.w + sh.w + res[gi][t].w;
                     *reinterpret_cast<float4*>(prm.out + (size_t)(tile * BM + rt) * D + col) = o;
                 }
             }
             tc::tcgen05_fence_before();
-            tc::mbar_arrive(acc2_empty);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc2_empty);
             // the staging patches live in the H buffer: nobody may start the next tile's GELU writes before all
             // epilogue warps are done with them (named barrier over the 16 epilogue warps only)
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");

@@ -144,21 +144,29 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-// erf(x) to ~3e-7 absolute (Abramowitz & Stegun 7.1.26: 1 - (a1 t + .. + a5 t^5) exp(-x^2), t = 1/(1 + p|x|)):
-// two MUFU ops and seven FMAs, branch free.  The GELU epilogue is instruction bound, and its output is
-// re-split to 16 mantissa bits right away, so libdevice's 1-ulp erff (about 3x the instructions) buys nothing.
-__device__ __forceinline__ float fast_erf(float x) {
-    const float ax = fabsf(x);
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));     // MUFU.RCP, 1 ulp
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float e = fast_exp2(-1.4426950408889634f * ax * ax);
-    return copysignf(fmaf(-p, e, 1.0f), x);
+// 1/x for x >= 1 (MUFU.RCP, 1 ulp).  __fdividef(1, x) wraps the MUFU in a denormal range check (FSETP, two
+// predicated FMULs, FSEL): four extra issue slots per GELU for a case that cannot occur here.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ float gelu_fast(float v) { return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752440f)); }
+// Exact-erf GELU (nn.GELU(), mlp.py:12) to ~2e-7 absolute:  gelu(v) = v Phi(v) = relu(v) - |v| q(|v|),
+// q(a) = 1/2 erfc(a / sqrt 2) = 1/2 (a1 t + .. + a5 t^5) exp(-a^2 / 2),  t = 1 / (1 + p a / sqrt 2)
+// (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 on erf).  Branch free: 2 MUFU + 12 FMA-pipe instructions.
+// The GELU epilogues are instruction bound and their output is re-split to 16 mantissa bits right away, so
+// libdevice's 1-ulp erff (about 3x the instructions) buys nothing.
+__device__ __forceinline__ float gelu_fast(float v) {
+    const float a = fabsf(v);
+    const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752440f, a, 1.0f));
+    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    p *= t;
+    const float e = fast_exp2((-0.5f * 1.4426950408889634f * a) * a);
+    return fmaf(-(p * e), a, fmaxf(v, 0.0f));
+}
 
 // ------------------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 bytes (64 bf16) with the

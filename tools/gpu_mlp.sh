@@ -6,8 +6,8 @@ timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -q -rA -p no:cacheprovi
 grep -E "parity\] mlp|tc-diag|FAILED|passed|failed|Error|error" $OUT/pytest_mlp.log | head -40
 timeout 900 python -m pytest tests/test_gpu_forward.py -m gpu -q -rA -p no:cacheprovider > $OUT/pytest_fwd.log 2>&1; echo "fwd rc=$?"
 grep -E "parity\].*(precision|rot_err)|FAILED|passed|failed|Error" $OUT/pytest_fwd.log | head -30
-for cfg in "bf16x3 1" "bf16x3 0" "bf16 1"; do
-  set -- $cfg
+for cfg in ${BENCH_CFGS:-bf16x3:1 bf16:1}; do
+  set -- ${cfg%%:*} ${cfg##*:}
   RELPOSE_FUSED_MLP=$2 timeout 600 python bench.py --steps 10 --warmup 3 --precision $1 --no-cpu-baseline > $OUT/bench_$1_f$2.json 2> $OUT/bench_$1_f$2.err; echo "bench $1 fused=$2 rc=$?"; tail -3 $OUT/bench_$1_f$2.err
   python - <<PY
 import json
