@@ -36,22 +36,23 @@ constexpr int NTHREADS = 32 * (CTRL_WARPS + EPI_WARPS);
 constexpr int TILE16K = BM * 64 * 2;                         // one [128 x 64] bf16 operand tile
 constexpr int UNIT1 = 64 * 64 * 2;                           // one plane of a weight unit (8 KiB)
 constexpr int NA1 = 3, LEAD = 2;                              // fc1 accumulators in TMEM; fc1 runs LEAD chunks ahead of fc2
-constexpr int ACC1_COL = 0, ACC2_COL = NA1 * CH, TMEM_COLS = 512;
+constexpr int ACC1_COL = 0, ACC2_COL = NA1 * CH, H_COL = ACC2_COL + D, TMEM_COLS = 512;   // 192 + 192 + 128
 constexpr int STG_LD = 16;
 
 template <int P>
 struct MCfg {
-    static constexpr int NH = (P == 1) ? 2 : 1;              // hidden-chunk buffers (A operand of fc2)
+    static constexpr int NH = 2;                             // hidden-chunk buffers (A operand of fc2) in TENSOR memory
+    static constexpr int H_STRIDE = P * (CH / 2);            // columns per buffer: 32 per plane (two bf16 per column)
     static constexpr int G1 = (P == 1) ? 2 : 1;              // fc1 weight ring: groups of three units (one chunk each)
     static constexpr int G2 = (P == 1) ? 2 : 1;              // fc2 weight ring: groups of three units (one chunk each)
     static constexpr int NU = 3 * (G1 + G2);                 // units in shared memory: fc1 ring first, then fc2 ring
     static constexpr int UNIT = P * UNIT1;
     static constexpr int OFF_XN = 0;                         // [P][KB] tiles of 16 KiB
-    static constexpr int OFF_H = OFF_XN + P * KB * TILE16K;  // [NH][P] tiles of 16 KiB (also final-epilogue staging)
-    static constexpr int OFF_W = OFF_H + NH * P * TILE16K;
+    static constexpr int OFF_H = OFF_XN + P * KB * TILE16K;  // staging patches of the output epilogue (32 KiB)
+    static constexpr int OFF_W = OFF_H + EPI_WARPS * 32 * STG_LD * 4;
     static constexpr int OFF_BAR = OFF_W + NU * UNIT;
     static constexpr int SMEM = OFF_BAR + 512 + 1024 /*align slack*/;
-    static_assert(NH * P * TILE16K >= EPI_WARPS * 32 * STG_LD * 4, "H buffer doubles as the epilogue staging area");
+    static_assert(H_COL + NH * H_STRIDE <= TMEM_COLS, "tensor memory budget");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -124,7 +125,6 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     auto xn_tile = [&](int p, int kb) { return smem + C::OFF_XN + (p * KB + kb) * TILE16K; };
-    auto h_tile = [&](int hb, int p) { return smem + C::OFF_H + (hb * P + p) * TILE16K; };
     // ring units are grouped in threes, planes outermost inside a group: the three units of an fc2 chunk
     // (output rows 0..63, 64..127, 128..191) then form one contiguous [192 x 64] B tile per plane
     auto w_unit = [&](int u, int p) { return smem + C::OFF_W + (u / 3) * (3 * C::UNIT) + p * (3 * UNIT1) + (u % 3) * UNIT1; };
@@ -234,8 +234,8 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 for (int nn = 0; nn < NT; ++nn) tc::mbar_wait(&wfull[u + nn], fpar);
                 tc::tcgen05_fence_after();
                 const uint32_t d = tmem_base + ACC2_COL;
-                const uint64_t dh0 = tc::make_kmajor_sw128_desc(tc::smem_u32(h_tile(hb, 0)));
-                const uint64_t dh1 = tc::make_kmajor_sw128_desc(tc::smem_u32(h_tile(hb, P - 1)));
+                const uint32_t ah0 = tmem_base + H_COL + hb * C::H_STRIDE;              // GELU chunk, plane 0 / plane 1
+                const uint32_t ah1 = ah0 + (P - 1) * (CH / 2);
                 const uint64_t w0 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, 0)));
                 const uint64_t w1 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(u, P - 1)));
                 if (tc::elect_one_sync()) {
@@ -243,11 +243,11 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     for (int k = 0; k < 4; ++k) {
                         uint32_t accum = (j > 0 || k > 0) ? 1u : 0u;
                         if (P == 2) {
-                            tc::umma_bf16(d, dh1 + 2 * k, w0 + 2 * k, idesc, accum);
-                            tc::umma_bf16(d, dh0 + 2 * k, w1 + 2 * k, idesc, 1u);
+                            tc::umma_bf16_ts(d, ah1 + 8 * k, w0 + 2 * k, idesc, accum);
+                            tc::umma_bf16_ts(d, ah0 + 8 * k, w1 + 2 * k, idesc, 1u);
                             accum = 1u;
                         }
-                        tc::umma_bf16(d, dh0 + 2 * k, w0 + 2 * k, idesc, accum);
+                        tc::umma_bf16_ts(d, ah0 + 8 * k, w0 + 2 * k, idesc, accum);
                     }
 #pragma unroll
                     for (int nn = 0; nn < NT; ++nn) tc::umma_commit(&wempty[u + nn]);
@@ -264,8 +264,6 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         const int part = ew >> 2;                        // which 16 of a chunk's 64 hidden columns / 48 of the 192 outputs
         const int r = q * 32 + lane;                     // the thread's row in TMEM-side work
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t row_off = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
-        const uint32_t sw = (uint32_t)(r & 7);
         float* stg = reinterpret_cast<float*>(smem + C::OFF_H) + ew * 32 * STG_LD;
         const int rr = lane >> 2, cq = lane & 3;         // coalesced side of the final epilogue
         uint32_t b1 = 0, ph1 = 0, c2 = 0, it = 0;
@@ -356,26 +354,24 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 for (int i = 0; i < 16; ++i) v[i] = tc::gelu_fast(__uint_as_float(a[i]) + bias[i]);
                 const uint32_t hb = c2 % C::NH;
                 tc::mbar_wait(&h_empty[hb], ((c2 / C::NH) & 1) ^ 1);
+                tc::tcgen05_fence_after();
+                // the chunk goes back to TENSOR memory as the K-major A operand of fc2 (two bf16 per column): no
+                // shared-memory traffic, no generic->async proxy fence, and room for two buffers
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
+                    uint32_t w[8];
 #pragma unroll
-                    for (int hc = 0; hc < 2; ++hc) {
-                        uint4 w;
-                        w.x = pack_bf16x2(v[8 * hc + 0], v[8 * hc + 1]);
-                        w.y = pack_bf16x2(v[8 * hc + 2], v[8 * hc + 3]);
-                        w.z = pack_bf16x2(v[8 * hc + 4], v[8 * hc + 5]);
-                        w.w = pack_bf16x2(v[8 * hc + 6], v[8 * hc + 7]);
-                        const uint32_t c = (uint32_t)(part * 2 + hc);
-                        *reinterpret_cast<uint4*>(h_tile(hb, p) + row_off + ((c ^ sw) << 4)) = w;
+                    for (int i = 0; i < 8; ++i) {
+                        w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
                         if (p + 1 < P) {
-                            v[8 * hc + 0] -= __uint_as_float(w.x << 16); v[8 * hc + 1] -= __uint_as_float(w.x & 0xffff0000u);
-                            v[8 * hc + 2] -= __uint_as_float(w.y << 16); v[8 * hc + 3] -= __uint_as_float(w.y & 0xffff0000u);
-                            v[8 * hc + 4] -= __uint_as_float(w.z << 16); v[8 * hc + 5] -= __uint_as_float(w.z & 0xffff0000u);
-                            v[8 * hc + 6] -= __uint_as_float(w.w << 16); v[8 * hc + 7] -= __uint_as_float(w.w & 0xffff0000u);
+                            v[2 * i] -= __uint_as_float(w[i] << 16);
+                            v[2 * i + 1] -= __uint_as_float(w[i] & 0xffff0000u);
                         }
                     }
+                    tc::tmem_st_32x32b_x8(t_lane + H_COL + hb * C::H_STRIDE + p * (CH / 2) + part * 8, w);
                 }
-                tc::fence_proxy_async_smem();
+                tc::tmem_st_wait();
+                tc::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&h_full[hb]);
             }
