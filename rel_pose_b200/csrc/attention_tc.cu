@@ -28,17 +28,18 @@ constexpr int Q_TILE = BM * 128;          // bytes of one [128 x 64] bf16 tile
 constexpr int KV_TILE = BKV * 128;        // bytes of one [96 x 64] bf16 tile
 constexpr int P_SUB = BM * 128;           // P_j is [128 x 96] = one full and one half-used 64-wide K-major sub-tile
 constexpr int KV_STAGES = 2;
-constexpr int ATT_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quarter)
+constexpr int ATT_CTRL = 3;              // warp 0 TMA, warp 1 S = QK^T issuer, warp 2 O = PV issuer
+constexpr int ATT_THREADS = 32 * (ATT_CTRL + 8);   // + warps 3..10 softmax (two per TMEM lane quarter)
 constexpr int HB = BKV / 2, HO = HD / 2;  // key columns / output columns per softmax thread
-constexpr int TMEM_COLS_ATT = 256;        // S[0] 0..95, S[1] 96..191, O 192..255
-constexpr int S_COL = 0, O_COL = 2 * BKV;
+constexpr int TMEM_COLS_ATT = 512;        // S[0] 0..95, S[1] 96..191, O 192..255, P planes 256..351 (two bf16 per column)
+constexpr int S_COL = 0, O_COL = 2 * BKV, P_COL = O_COL + HD, P_PLANE = BKV / 2;
 static_assert(NTOK % BKV == 0 && BKV % 16 == 0 && (NBLK % 2) == 0, "key blocking");
 
 template <int P>
 struct ACfg {
     static constexpr int Q_BYTES = P * Q_TILE;
     static constexpr int KV_BYTES = P * KV_TILE;
-    static constexpr int P_BYTES = P * 2 * P_SUB;
+    static constexpr int P_BYTES = 0;                         // P_j lives in tensor memory
     static constexpr int OFF_K = Q_BYTES;
     static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
     static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;
@@ -70,7 +71,8 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     uint64_t* s_full = bars + 10;    // [2]
     uint64_t* p_ready = bars + 12;
     uint64_t* pv_done = bars + 13;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* s_free = bars + 14;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = n_img * HEADS * QTILES;
@@ -86,8 +88,9 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc::mbar_init(&v_full[i], 1);
             tc::mbar_init(&v_free[i], 1);
             tc::mbar_init(&s_full[i], 1);
+            tc::mbar_init(&s_free[i], 8);       // one elected arrive per softmax warp
         }
-        tc::mbar_init(p_ready, 256);
+        tc::mbar_init(p_ready, 8);
         tc::mbar_init(pv_done, 1);
         tc::fence_barrier_init();
     }
@@ -100,7 +103,6 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     auto q_tile = [&](int p) { return smem + p * Q_TILE; };
     auto k_tile = [&](int st, int p) { return smem + C::OFF_K + st * C::KV_BYTES + p * KV_TILE; };
     auto v_tile = [&](int st, int p) { return smem + C::OFF_V + st * C::KV_BYTES + p * KV_TILE; };
-    auto p_tile = [&](int p) { return smem + C::OFF_P + p * 2 * P_SUB; };
 
     if (warp == 0) {
         // ---------------------------------------------------------------------------- TMA producer (convergent warp)
@@ -136,62 +138,63 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------------------- MMA issuer (convergent warp)
-        // All 32 lanes run the control flow and the barrier waits; one elected lane issues.  Descriptors are
-        // built once per tile and advanced by adding to their address field (16-byte units).
+        // ---------------------------------------------------------------------------- S = Q K^T issuer (convergent warp)
+        // Two issuer warps on two schedulers: a single issuer spent most of its time executing its own instruction
+        // stream (barrier polls, descriptor set-up, ~250 instructions per key block) while the tensor pipe idled.
+        // This one runs up to two key blocks ahead of the softmax (S is double buffered in tensor memory).
         constexpr uint32_t idesc_s = tc::make_idesc_bf16(BM, BKV);
-        constexpr uint32_t idesc_o = tc::make_idesc_bf16(BM, HD) | tc::IDESC_B_MN;
-        int ks = 0, kph = 0, vs = 0, vph = 0, it = 0;
+        int ks = 0, kph = 0, it = 0;
         uint32_t g = 0;     // global key-block counter of this CTA
         const uint64_t dq0 = tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(0)));
         const uint64_t dq1 = tc::make_kmajor_sw128_desc(tc::smem_u32(q_tile(P - 1)));
-        const uint64_t dp0 = tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(0)));
-        const uint64_t dp1 = tc::make_kmajor_sw128_desc(tc::smem_u32(p_tile(P - 1)));
-        auto issue_s = [&](uint32_t gb) {
-            tc::mbar_wait(&k_full[ks], kph);
-            tc::tcgen05_fence_after();
-            const uint32_t d = tmem_base + S_COL + (gb & 1) * BKV;
-            const uint64_t dk0 = tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)));
-            const uint64_t dk1 = tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, P - 1)));
-            if (tc::elect_one_sync()) {
-                // tcgen05 accumulates with truncation (bias ~ chain length x 2^-25): the small correction terms of
-                // ALL K steps go first, the main terms last, so the full-magnitude chain is K/16 long, not 3K/16
-                uint32_t accum = 0u;
-                if (P == 2) {
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {          // 16 bf16 = 32 B inside the swizzle row = +2
-                        tc::umma_bf16(d, dq1 + 2 * k, dk0 + 2 * k, idesc_s, accum);
-                        tc::umma_bf16(d, dq0 + 2 * k, dk1 + 2 * k, idesc_s, 1u);
-                        accum = 1u;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    tc::umma_bf16(d, dq0 + 2 * k, dk0 + 2 * k, idesc_s, accum);
-                    accum = 1u;
-                }
-                tc::umma_commit(&k_free[ks]);
-                tc::umma_commit(&s_full[gb & 1]);
-            }
-            __syncwarp();
-            if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
-        };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             tc::mbar_wait(q_full, it & 1);
-            tc::tcgen05_fence_after();
-            issue_s(g);
             for (int j = 0; j < NBLK; ++j, ++g) {
-                if (j + 1 < NBLK) {
-                    issue_s(g + 1);
-                    if (j + 2 == NBLK) {
-                        if (tc::elect_one_sync()) tc::umma_commit(q_free);    // last S of this item is in flight
-                        __syncwarp();
+                tc::mbar_wait(&s_free[g & 1], ((g >> 1) & 1) ^ 1);      // softmax has read S_{g-2} out of this buffer
+                tc::mbar_wait(&k_full[ks], kph);
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + S_COL + (g & 1) * BKV;
+                const uint64_t dk0 = tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, 0)));
+                const uint64_t dk1 = tc::make_kmajor_sw128_desc(tc::smem_u32(k_tile(ks, P - 1)));
+                if (tc::elect_one_sync()) {
+                    // tcgen05 accumulates with truncation (bias ~ chain length x 2^-25): the small correction terms of
+                    // ALL K steps go first, the main terms last, so the full-magnitude chain is K/16 long, not 3K/16
+                    uint32_t accum = 0u;
+                    if (P == 2) {
+#pragma unroll
+                        for (int k = 0; k < HD / 16; ++k) {          // 16 bf16 = 32 B inside the swizzle row = +2
+                            tc::umma_bf16(d, dq1 + 2 * k, dk0 + 2 * k, idesc_s, accum);
+                            tc::umma_bf16(d, dq0 + 2 * k, dk1 + 2 * k, idesc_s, 1u);
+                            accum = 1u;
+                        }
                     }
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k) {
+                        tc::umma_bf16(d, dq0 + 2 * k, dk0 + 2 * k, idesc_s, accum);
+                        accum = 1u;
+                    }
+                    tc::umma_commit(&k_free[ks]);
+                    tc::umma_commit(&s_full[g & 1]);
+                    if (j + 1 == NBLK) tc::umma_commit(q_free);       // last S of this item is in flight
                 }
+                __syncwarp();
+                if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ---------------------------------------------------------------------------- O = P V issuer (convergent warp)
+        // A = P_j read from TENSOR memory (K-major, two bf16 per column, written by the softmax threads with
+        // tcgen05.st), B = V_j as loaded by TMA ([key][d] rows = MN-major SWIZZLE_128B).
+        constexpr uint32_t idesc_o = tc::make_idesc_bf16(BM, HD) | tc::IDESC_B_MN;
+        int vs = 0, vph = 0;
+        uint32_t g = 0;
+        const uint32_t d = tmem_base + O_COL;
+        const uint32_t ap0 = tmem_base + P_COL, ap1 = tmem_base + P_COL + (P - 1) * P_PLANE;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int j = 0; j < NBLK; ++j, ++g) {
                 tc::mbar_wait(p_ready, g & 1);
                 tc::mbar_wait(&v_full[vs], vph);
                 tc::tcgen05_fence_after();
-                const uint32_t d = tmem_base + O_COL;
                 const uint64_t dv0 = tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)), 0);
                 const uint64_t dv1 = tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, P - 1)), 0);
                 if (tc::elect_one_sync()) {
@@ -199,18 +202,16 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     if (P == 2) {
 #pragma unroll
                         for (int kk = 0; kk < BKV / 16; ++kk) {
-                            const uint32_t a_off = ((kk >> 2) * P_SUB + (kk & 3) * 32) >> 4;   // K-major: 16 keys = 32 B in the row
                             const uint32_t b_off = (kk * 16 * 128) >> 4;                       // MN-major: 16 keys = 16 rows
-                            tc::umma_bf16(d, dp1 + a_off, dv0 + b_off, idesc_o, accum);
-                            tc::umma_bf16(d, dp0 + a_off, dv1 + b_off, idesc_o, 1u);
+                            tc::umma_bf16_ts(d, ap1 + 8 * kk, dv0 + b_off, idesc_o, accum);    // 16 keys = 8 columns
+                            tc::umma_bf16_ts(d, ap0 + 8 * kk, dv1 + b_off, idesc_o, 1u);
                             accum = 1u;
                         }
                     }
 #pragma unroll
                     for (int kk = 0; kk < BKV / 16; ++kk) {
-                        const uint32_t a_off = ((kk >> 2) * P_SUB + (kk & 3) * 32) >> 4;
                         const uint32_t b_off = (kk * 16 * 128) >> 4;
-                        tc::umma_bf16(d, dp0 + a_off, dv0 + b_off, idesc_o, accum);
+                        tc::umma_bf16_ts(d, ap0 + 8 * kk, dv0 + b_off, idesc_o, accum);
                         accum = 1u;
                     }
                     tc::umma_commit(&v_free[vs]);
@@ -228,12 +229,9 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         // block; the partial sums are only combined at the end.  (ncu on the one-thread-per-row version: one
         // softmax warp per scheduler at 0.22 IPC, MUFU / F2FP bound with nothing to overlap.)
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
-        const int hsel = (warp - 2) >> 2;                  // which half of the columns
+        const int hsel = (warp - ATT_CTRL) >> 2;           // which half of the columns
         const int r = quarter * 32 + lane;                 // query row inside the tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        // byte offset of 16-byte chunk c (8 keys) of row r inside a K-major SWIZZLE_128B tile
-        const uint32_t row_off = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
-        const uint32_t sw = (uint32_t)(r & 7);
         float* xch = reinterpret_cast<float*>(smem + C::OFF_XCH);
         const int bar_id = 1 + quarter;
         uint32_t g = 0;
@@ -262,6 +260,9 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     tc::tmem_ld_32x32b_x16(t_s + 32, s1);
                     tc::tmem_ld_wait();
                 }
+                tc::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s_free[g & 1]);     // S_{g+2} may overwrite this buffer
                 float bmax = __uint_as_float(s[0]);
 #pragma unroll
                 for (int i = 1; i < HB; ++i) bmax = fmaxf(bmax, __uint_as_float(s[i]));
@@ -289,33 +290,28 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     fold_o();
                 }
                 alpha_prev = alpha;
-                // P_j -> bf16 planes in shared memory (A operand of the PV product)
+                // P_j -> bf16 planes in TENSOR memory (K-major A operand of the PV product: key 2c, 2c+1 in column c)
 #pragma unroll
-                for (int ci = 0; ci < HB / 8; ++ci) {
-                    const int c = hsel * (HB / 8) + ci;
-                    float v[8];
+                for (int p = 0; p < P; ++p) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(s[ci * 8 + i]);
-                    const uint32_t off = (uint32_t)(c >> 3) * P_SUB + row_off + ((((uint32_t)c & 7) ^ sw) << 4);
+                    for (int ci = 0; ci < HB / 16; ++ci) {
+                        uint32_t w[8];
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        uint4 w;
-                        w.x = pack_bf16x2(v[0], v[1]);
-                        w.y = pack_bf16x2(v[2], v[3]);
-                        w.z = pack_bf16x2(v[4], v[5]);
-                        w.w = pack_bf16x2(v[6], v[7]);
-                        *reinterpret_cast<uint4*>(p_tile(p) + off) = w;
-                        if (p + 1 < P) {
-                            v[0] -= __uint_as_float(w.x << 16); v[1] -= __uint_as_float(w.x & 0xffff0000u);
-                            v[2] -= __uint_as_float(w.y << 16); v[3] -= __uint_as_float(w.y & 0xffff0000u);
-                            v[4] -= __uint_as_float(w.z << 16); v[5] -= __uint_as_float(w.z & 0xffff0000u);
-                            v[6] -= __uint_as_float(w.w << 16); v[7] -= __uint_as_float(w.w & 0xffff0000u);
+                        for (int i = 0; i < 8; ++i) {
+                            const float v0 = __uint_as_float(s[ci * 16 + 2 * i]), v1 = __uint_as_float(s[ci * 16 + 2 * i + 1]);
+                            w[i] = pack_bf16x2(v0, v1);
+                            if (p + 1 < P) {
+                                s[ci * 16 + 2 * i] = __float_as_uint(v0 - __uint_as_float(w[i] << 16));
+                                s[ci * 16 + 2 * i + 1] = __float_as_uint(v1 - __uint_as_float(w[i] & 0xffff0000u));
+                            }
                         }
+                        tc::tmem_st_32x32b_x8(t_lane + P_COL + p * P_PLANE + hsel * (HB / 2) + ci * 8, w);
                     }
                 }
-                tc::fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+                tc::tmem_st_wait();
                 tc::tcgen05_fence_before();
-                tc::mbar_arrive(p_ready);
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(p_ready);
             }
             // last product of the item
             tc::mbar_wait(pv_done, (g - 1) & 1);

@@ -135,7 +135,9 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     // the `turn` hand-off below makes the later one wait until the earlier one has observed ITS fill.
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (convergent warp)
-        uint32_t g1 = 0, g2 = 0;                 // fc1 / fc2 chunks loaded so far by this CTA
+        // fc1 weights only: the fc2 issuer feeds its own ring, so a full fc2 ring (waiting for a GELU chunk) never
+        // holds back the fc1 weights of the next chunks / the next tile behind it in a common load order
+        uint32_t g1 = 0;                         // fc1 chunks loaded so far by this CTA
         auto load_unit = [&](int u, uint32_t fill, const CUtensorMap* tm, int c0, int c1) {
             tc::mbar_wait(&wempty[u], (fill & 1) ^ 1);
             if (tc::elect_one_sync()) {
@@ -146,17 +148,9 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
             __syncwarp();
         };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            for (int s = 0; s < NCH + LEAD; ++s) {
-                if (s < NCH) {                                                           // W1[s*64.., kb*64..]
-                    const int u0 = 3 * (int)(g1 % C::G1);
-                    for (int kb = 0; kb < KB; ++kb) load_unit(u0 + kb, g1 / C::G1, &tmW1, kb * 64, s * CH);
-                    ++g1;
-                }
-                if (s >= LEAD) {                                                         // W2[n*64.., (s-2)*64..]
-                    const int u0 = 3 * C::G1 + 3 * (int)(g2 % C::G2);
-                    for (int n = 0; n < NT; ++n) load_unit(u0 + n, g2 / C::G2, &tmW2, (s - LEAD) * CH, n * 64);
-                    ++g2;
-                }
+            for (int s = 0; s < NCH; ++s, ++g1) {                                        // W1[s*64.., kb*64..]
+                const int u0 = 3 * (int)(g1 % C::G1);
+                for (int kb = 0; kb < KB; ++kb) load_unit(u0 + kb, g1 / C::G1, &tmW1, kb * 64, s * CH);
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -221,8 +215,25 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         // ------------------------------------------------------------------ fc2 issuer (convergent warp)
         // acc2[128 x 192] += GELU chunk [128 x 64] . W2[:, chunk]^T : the chunk's three ring units are one
         // contiguous [192 rows x 64 K] tile per plane, so every K step is ONE N = 192 instruction.
+        // The warp also loads its own weights: a ring slot can only be refilled once the MMAs reading it have
+        // retired, which this warp is the first to know.
         constexpr uint32_t idesc = tc::make_idesc_bf16(BM, D);
         uint32_t c2 = 0, it = 0;                // fc2 chunks / tiles issued so far by this CTA
+        const uint32_t total = (uint32_t)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * NCH;
+        auto load_chunk = [&](uint32_t c) {     // W2[:, (c % 12)*64 ..] -> ring group c % G2 (three 64-row units)
+            const int u0 = 3 * C::G1 + 3 * (int)(c % C::G2);
+            if (tc::elect_one_sync()) {
+#pragma unroll
+                for (int nn = 0; nn < NT; ++nn) {
+                    tc::mbar_expect_tx(&wfull[u0 + nn], (uint32_t)C::UNIT);
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        tc::tma_load_3d(w_unit(u0 + nn, p), &tmW2, &wfull[u0 + nn], (int)(c % NCH) * CH, nn * 64, p);
+                }
+            }
+            __syncwarp();
+        };
+        for (uint32_t c = 0; c < (uint32_t)C::G2 && c < total; ++c) load_chunk(c);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             for (int j = 0; j < NCH; ++j, ++c2) {
                 const uint32_t hb = c2 % C::NH;
@@ -255,6 +266,11 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     if (j == NCH - 1) tc::umma_commit(acc2_full);
                 }
                 __syncwarp();
+                if (c2 + C::G2 < total) {       // refill this slot with the chunk G2 ahead as soon as it is free
+#pragma unroll
+                    for (int nn = 0; nn < NT; ++nn) tc::mbar_wait(&wempty[u + nn], fpar);
+                    load_chunk(c2 + C::G2);
+                }
             }
         }
     } else {
@@ -327,12 +343,21 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
             for (int j = 0; j < NCH; ++j, ++c2) {
                 const uint32_t b = b1;
                 if (j == 2) {
-                    // pull the next tile's rows towards L2 now; its LayerNorm runs right after this tile's last chunk
+                    // pull the next tile's rows towards L2 now; its LayerNorm runs before this tile's last two chunks
                     const int nrow = (tile + (int)gridDim.x) * BM + ew * 8 + (lane >> 2);
                     if (nrow < M && (lane & 3) < 3)      // 8 rows x 768 B = 48 lines of 128 B: 24 lanes x 2
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.x + (size_t)nrow * D + (lane & 3) * 64));
                     if (nrow < M && (lane & 3) < 3)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.x + (size_t)nrow * D + (lane & 3) * 64 + 32));
+                }
+                if (j == NCH - 2 && tile + (int)gridDim.x < ntiles) {
+                    // LayerNorm of the NEXT tile, two chunks before this tile ends: once the last two fc1 products
+                    // have completed (all earlier ones were observed chunk by chunk) this tile's LayerNorm planes
+                    // are dead, and the next tile's fc1 / this tile's last fc2 and output epilogue overlap.
+                    const uint32_t bn = (b1 + 1 == NA1) ? 0u : b1 + 1;
+                    tc::mbar_wait(&acc1_full[b1], ph1);
+                    tc::mbar_wait(&acc1_full[bn], bn == 0 ? ph1 ^ 1 : ph1);
+                    layer_norm_tile(tile + (int)gridDim.x);
                 }
                 float bias[16];
 #pragma unroll
@@ -375,10 +400,6 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&h_full[hb]);
             }
-            // ---- LayerNorm of the NEXT tile first (its fc1 then overlaps this tile's output epilogue)
-            const int next = tile + gridDim.x;
-            if (next < ntiles) layer_norm_tile(next);   // every fc1 of this tile has completed (acc1_full was observed
-                                                         // for all twelve chunks): its LayerNorm planes are dead
             // ---- output: acc2 + b2 + x, transposed through the (now idle) H buffer for coalesced float4 stores.
             // The residual rows (L2 hits: this CTA read them for the LayerNorm) are requested before the wait.
             const int valid_rows = min(BM, M - tile * BM);
