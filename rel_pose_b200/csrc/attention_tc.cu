@@ -5,19 +5,21 @@
 // (x = x0 + x1; every product is evaluated as a0 b0 + a0 b1 + a1 b0 into one fp32 TMEM accumulator, fp32 class).
 //
 // Work item = (image, head, 128-query tile); 576 = 4.5 tiles, the 5th tile is half empty (TMA zero fill, rows
-// never stored).  Keys/values stream in 6 blocks of 96.  Persistent CTAs (one per SM), 192 threads:
+// never stored).  Keys/values stream in 6 blocks of 96.  Persistent CTAs (one per SM), 352 threads:
 //   warp 0      TMA producer: Q tile (once per item), K and V blocks through two independent 2-stage rings
-//   warp 1      MMA issuer (one lane) + TMEM owner:
-//                 S_j  = Q K_j^T      M=128 N=96 K=64   A,B K-major SWIZZLE_128B            -> TMEM S[j&1]
-//                 O_j  = P_j V_j      M=128 N=64 K=96   A = P_j (smem, K-major), B = V_j as loaded by TMA
-//                                                       ([key][d] rows = MN-major SWIZZLE_128B) -> TMEM O
-//   warps 2-5   softmax: thread = query row (TMEM lane).  tcgen05.ld S_j, online max / sum, p = 2^((s-m) c),
-//               P_j re-split into bf16 planes and written to shared memory in the UMMA K-major swizzle,
-//               fence.proxy.async, mbarrier arrive.  The un-normalised output is carried in registers:
+//   warp 1      S issuer + TMEM owner:  S_j = Q K_j^T   M=128 N=96 K=64, A,B K-major SWIZZLE_128B -> TMEM S[j&1];
+//               runs up to two key blocks ahead of the softmax (s_free mbarriers)
+//   warp 2      O issuer:  O_j = P_j V_j   M=128 N=64 K=96, A = P_j read from TENSOR memory (K-major, two bf16 per
+//               column), B = V_j as loaded by TMA ([key][d] rows = MN-major SWIZZLE_128B) -> TMEM O
+//   warps 3-10  softmax: NSPLIT = 2 threads per query row (TMEM lane).  tcgen05.ld S_j, online max / sum,
+//               p = 2^((s-m) c), P_j re-split into bf16 planes and written back to tensor memory (tcgen05.st),
+//               mbarrier arrive.  The un-normalised output is carried in registers:
 //               o = o * alpha + O_j (tcgen05.ld of the per-block product), so TMEM is never rescaled.
-// S is double buffered in TMEM (S_{j+1} is issued before P_j is consumed), O and P are single buffers:
-// P_j may only be overwritten / O_j only be replaced after the softmax threads have seen pv_done(j-1),
-// and the issuer starts PV_j only after p_ready(j), which each softmax thread signals after reading O_{j-1}.
+// S is double buffered in TMEM, O and P are single buffers: P_j may only be overwritten / O_j only be replaced
+// after the softmax threads have seen pv_done(j-1), and the O issuer starts PV_j only after p_ready(j), which
+// each softmax warp signals after reading O_{j-1}.
+// Measured at 64 pairs, bf16x3: 140 us (one issuer warp, P through shared memory) -> 127 us; four threads per
+// row (NSPLIT = 4, 93 registers) measured 132 us, i.e. the softmax chain is not short of warps.
 #include "tc_common.cuh"
 
 namespace {
@@ -29,8 +31,10 @@ constexpr int KV_TILE = BKV * 128;        // bytes of one [96 x 64] bf16 tile
 constexpr int P_SUB = BM * 128;           // P_j is [128 x 96] = one full and one half-used 64-wide K-major sub-tile
 constexpr int KV_STAGES = 2;
 constexpr int ATT_CTRL = 3;              // warp 0 TMA, warp 1 S = QK^T issuer, warp 2 O = PV issuer
-constexpr int ATT_THREADS = 32 * (ATT_CTRL + 8);   // + warps 3..10 softmax (two per TMEM lane quarter)
-constexpr int HB = BKV / 2, HO = HD / 2;  // key columns / output columns per softmax thread
+constexpr int NSPLIT = 2;                // softmax threads per query row (4 NSPLIT warps: NSPLIT per TMEM lane quarter)
+constexpr int ATT_THREADS = 32 * (ATT_CTRL + 4 * NSPLIT);
+constexpr int HB = BKV / NSPLIT, HO = HD / NSPLIT;  // key columns / output columns per softmax thread
+static_assert((NSPLIT == 2 || NSPLIT == 4) && HB % 8 == 0 && HO % 16 == 0, "softmax split");
 constexpr int TMEM_COLS_ATT = 512;        // S[0] 0..95, S[1] 96..191, O 192..255, P planes 256..351 (two bf16 per column)
 constexpr int S_COL = 0, O_COL = 2 * BKV, P_COL = O_COL + HD, P_PLANE = BKV / 2;
 static_assert(NTOK % BKV == 0 && BKV % 16 == 0 && (NBLK % 2) == 0, "key blocking");
@@ -43,8 +47,8 @@ struct ACfg {
     static constexpr int OFF_K = Q_BYTES;
     static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
     static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;
-    static constexpr int OFF_XCH = OFF_P + P_BYTES;          // float [2 parity][2 halves][128 rows]: row-max exchange
-    static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * BM * 4;
+    static constexpr int OFF_XCH = OFF_P + P_BYTES;          // float [2 parity][NSPLIT][128 rows]: row-max exchange
+    static constexpr int OFF_BAR = OFF_XCH + 2 * NSPLIT * BM * 4;
     static constexpr int SMEM = OFF_BAR + 256 + 1024 /*align slack*/;
 };
 
@@ -88,9 +92,9 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc::mbar_init(&v_full[i], 1);
             tc::mbar_init(&v_free[i], 1);
             tc::mbar_init(&s_full[i], 1);
-            tc::mbar_init(&s_free[i], 8);       // one elected arrive per softmax warp
+            tc::mbar_init(&s_free[i], 4 * NSPLIT);     // one elected arrive per softmax warp
         }
-        tc::mbar_init(p_ready, 8);
+        tc::mbar_init(p_ready, 4 * NSPLIT);
         tc::mbar_init(pv_done, 1);
         tc::fence_barrier_init();
     }
@@ -223,13 +227,14 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
     } else {
         // ---------------------------------------------------------------------------- softmax warps
-        // Two threads per query row: warps w and w+4 share a TMEM lane quarter, thread `hsel` owns key columns
-        // [48 hsel, 48 hsel + 48) of every block and output columns [32 hsel, 32 hsel + 32).  The pair agrees on
-        // the running maximum through a double-buffered shared-memory slot and a 64-thread named barrier per
-        // block; the partial sums are only combined at the end.  (ncu on the one-thread-per-row version: one
-        // softmax warp per scheduler at 0.22 IPC, MUFU / F2FP bound with nothing to overlap.)
+        // NSPLIT threads per query row: warps w, w+4, .. share a TMEM lane quarter, thread `hsel` owns key columns
+        // [HB hsel, HB hsel + HB) of every block and output columns [HO hsel, HO hsel + HO).  They agree on the
+        // running maximum through a double-buffered shared-memory slot and a named barrier per block; the
+        // partial sums are only combined at the end.  ncu history: one thread per row = one softmax warp per
+        // scheduler at 0.22 IPC; two per row (143 registers) still left the schedulers two warps each to hide
+        // the MUFU / TMEM latencies of a serial chain; four per row halves the registers and doubles the warps.
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
-        const int hsel = (warp - ATT_CTRL) >> 2;           // which half of the columns
+        const int hsel = (warp - ATT_CTRL) >> 2;           // which slice of the columns
         const int r = quarter * 32 + lane;                 // query row inside the tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float* xch = reinterpret_cast<float*>(smem + C::OFF_XCH);
@@ -242,8 +247,12 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
             for (int i = 0; i < HO; ++i) o[i] = 0.f;
             auto fold_o = [&]() {                           // o = o * alpha_prev + O_j (this thread's 32 columns)
-                uint32_t t[32];
-                tc::tmem_ld_32x32b_x32(t_lane + O_COL + hsel * HO, t);
+                uint32_t t[HO];
+                if constexpr (HO == 32) {
+                    tc::tmem_ld_32x32b_x32(t_lane + O_COL + hsel * HO, *reinterpret_cast<uint32_t(*)[32]>(&t[0]));
+                } else {
+                    tc::tmem_ld_32x32b_x16(t_lane + O_COL + hsel * HO, *reinterpret_cast<uint32_t(*)[16]>(&t[0]));
+                }
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < HO; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(t[i]));
@@ -253,11 +262,14 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 tc::tcgen05_fence_after();
                 uint32_t s[HB];
                 {
-                    uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-                    uint32_t(&s1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&s[32]);
                     const uint32_t t_s = t_lane + S_COL + (g & 1) * BKV + hsel * HB;
-                    tc::tmem_ld_32x32b_x32(t_s, s0);
-                    tc::tmem_ld_32x32b_x16(t_s + 32, s1);
+                    if constexpr (HB == 48) {
+                        tc::tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                        tc::tmem_ld_32x32b_x16(t_s + 32, *reinterpret_cast<uint32_t(*)[16]>(&s[32]));
+                    } else {
+                        tc::tmem_ld_32x32b_x16(t_s, *reinterpret_cast<uint32_t(*)[16]>(&s[0]));
+                        tc::tmem_ld_32x32b_x8(t_s + 16, *reinterpret_cast<uint32_t(*)[8]>(&s[16]));
+                    }
                     tc::tmem_ld_wait();
                 }
                 tc::tcgen05_fence_before();
@@ -266,10 +278,11 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 float bmax = __uint_as_float(s[0]);
 #pragma unroll
                 for (int i = 1; i < HB; ++i) bmax = fmaxf(bmax, __uint_as_float(s[i]));
-                float* slot = xch + (g & 1) * 2 * BM;
+                float* slot = xch + (g & 1) * NSPLIT * BM;
                 slot[hsel * BM + r] = bmax;
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                bmax = fmaxf(bmax, slot[(hsel ^ 1) * BM + r]);
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSPLIT) : "memory");
+#pragma unroll
+                for (int o2 = 1; o2 < NSPLIT; ++o2) bmax = fmaxf(bmax, slot[((hsel + o2) % NSPLIT) * BM + r]);
                 const float m_new = fmaxf(m, bmax);
                 const float alpha = tc::fast_exp2((m - m_new) * scale_log2);      // 0 on the first block
                 const float ms = m_new * scale_log2;
@@ -294,19 +307,22 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
 #pragma unroll
-                    for (int ci = 0; ci < HB / 16; ++ci) {
-                        uint32_t w[8];
+                    uint32_t w[HB / 2];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float v0 = __uint_as_float(s[ci * 16 + 2 * i]), v1 = __uint_as_float(s[ci * 16 + 2 * i + 1]);
-                            w[i] = pack_bf16x2(v0, v1);
-                            if (p + 1 < P) {
-                                s[ci * 16 + 2 * i] = __float_as_uint(v0 - __uint_as_float(w[i] << 16));
-                                s[ci * 16 + 2 * i + 1] = __float_as_uint(v1 - __uint_as_float(w[i] & 0xffff0000u));
-                            }
+                    for (int i = 0; i < HB / 2; ++i) {
+                        const float v0 = __uint_as_float(s[2 * i]), v1 = __uint_as_float(s[2 * i + 1]);
+                        w[i] = pack_bf16x2(v0, v1);
+                        if (p + 1 < P) {
+                            s[2 * i] = __float_as_uint(v0 - __uint_as_float(w[i] << 16));
+                            s[2 * i + 1] = __float_as_uint(v1 - __uint_as_float(w[i] & 0xffff0000u));
                         }
-                        tc::tmem_st_32x32b_x8(t_lane + P_COL + p * P_PLANE + hsel * (HB / 2) + ci * 8, w);
                     }
+                    const uint32_t t_p = t_lane + P_COL + p * P_PLANE + hsel * (HB / 2);
+#pragma unroll
+                    for (int ci = 0; ci < HB / 16; ++ci)
+                        tc::tmem_st_32x32b_x8(t_p + ci * 8, *reinterpret_cast<uint32_t(*)[8]>(&w[ci * 8]));
+                    if constexpr ((HB / 2) % 8 == 4)
+                        tc::tmem_st_32x32b_x4(t_p + (HB / 16) * 8, *reinterpret_cast<uint32_t(*)[4]>(&w[(HB / 16) * 8]));
                 }
                 tc::tmem_st_wait();
                 tc::tcgen05_fence_before();
@@ -318,11 +334,14 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc::tcgen05_fence_after();
             fold_o();
             // combine the two partial sums of the row (same slot discipline as the maxima: one more barrier)
-            float* slot = xch + (g & 1) * 2 * BM;
+            float* slot = xch + (g & 1) * NSPLIT * BM;
             slot[hsel * BM + r] = l;
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-            const float inv = 1.0f / (l + slot[(hsel ^ 1) * BM + r]);
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // slot parity g&1 is reused by the next tile's block 0
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSPLIT) : "memory");
+            float lsum = 0.f;                                   // same order in every thread of the row
+#pragma unroll
+            for (int o2 = 0; o2 < NSPLIT; ++o2) lsum += slot[o2 * BM + r];
+            const float inv = 1.0f / lsum;
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSPLIT) : "memory");      // slot parity g&1 is reused by the next tile's block 0
             const int row = qt * BM + r;
             if (row < NTOK) {
                 // out[n, row, h*64 + d]  ((attn @ v).transpose(1,2).reshape(B,N,C), vision_transformer.py:329)

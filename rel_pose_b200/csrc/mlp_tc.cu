@@ -5,23 +5,30 @@
 // sequence (layernorm_planes -> linear_tc+GELU -> linear_tc+residual) wrote the [M,768] hidden activation to HBM
 // as bf16 planes and read it back (2 x 226 MB per layer at 64 pairs) plus a LayerNorm round trip; here the hidden
 // activation never leaves the SM: fc1 accumulates a 64-column chunk in tensor memory, the epilogue warps apply
-// bias + exact-erf GELU and write the chunk back to shared memory as the K-major A operand of fc2, which
-// accumulates the [128,192] output tile in tensor memory over the twelve chunks.
+// bias + exact-erf GELU and hand the chunk back THROUGH TENSOR MEMORY (tcgen05.st, two bf16 per column) as the
+// K-major A operand of fc2 (tcgen05.mma with A in TMEM), which accumulates the [128,192] output tile in tensor
+// memory over the twelve chunks.
 //
 // Operands are split-bf16 planes as in gemm_tc.cu (P = 1 bf16, P = 2 "bf16x3" = fp32-class products).
 //
 // One persistent CTA per SM, 640 threads, one 128-row tile at a time:
-//   warp 0      TMA producer: weight "units" ([P][64 rows][64 K] bf16, 128-byte swizzle) into a ring.  A unit is
-//               either one K block of the fc1 chunk (rows = hidden columns) or one 64-row third of the fc2
-//               chunk (rows = output columns, K = the chunk's hidden columns).  Ring order fc1_0, fc1_1, fc1_2,
-//               fc2_0, fc1_3, fc2_1, ...: fc1 runs two chunks ahead of fc2 (three fc1 accumulators in TMEM).
-//   warps 1, 2  fc1 issuers (even / odd chunks): 36 tcgen05.mma M128 x N64 x K16 per chunk (bf16x3).
-//   warp 3      fc2 issuer: 12 tcgen05.mma M128 x N192 x K16 per chunk into the tile's output accumulator.
-//               Three issuer warps on three schedulers because a single issuer was the bottleneck (see below).
-//   warps 4-19  LayerNorm of the tile's rows straight into the swizzled A-operand planes (no HBM round trip),
-//               per-chunk GELU (TMEM -> registers -> bf16 planes in shared memory), final epilogue
-//               (acc2 + bias + residual, transposed through shared memory for coalesced float4 stores).
-// Tensor memory: acc1[3] = columns 0..191, acc2 = columns 192..383.
+//   warp 0      TMA producer of the fc1 weights: "units" [P][64 hidden rows][64 K] bf16 (128-byte swizzle), three
+//               per chunk, into the fc1 ring.
+//   warps 1, 2  fc1 issuers (even / odd chunks): 36 tcgen05.mma M128 x N64 x K16 per chunk (bf16x3), up to three
+//               chunks ahead of the GELU (three fc1 accumulators in TMEM).
+//   warp 3      fc2 issuer: 12 tcgen05.mma M128 x N192 x K16 per chunk, A = GELU chunk in TMEM, B = the chunk's
+//               [192 x 64] slice of W2, which this warp also loads (its ring slot is free exactly when its own
+//               MMAs retire).  Three issuer warps on three schedulers because a single issuer was the bottleneck.
+//   warps 4-19  LayerNorm of the tile's rows straight into the swizzled A-operand planes (no HBM round trip; the
+//               next tile's LayerNorm runs two chunks before the current tile ends), per-chunk GELU
+//               (TMEM -> registers -> TMEM), output epilogue (acc2 + bias + residual, transposed through shared
+//               memory for coalesced float4 stores).
+// Tensor memory (512 columns): acc1[3] = 0..191, acc2 = 192..383, GELU chunk buffers [2][P][32] = 384..511.
+//
+// Measured history at 64 pairs, bf16x3 (profiles/r01_mlp_fused_history.md): unfused 214 (+27 LayerNorm) us ->
+// 161 (first fused version, one issuer, fc1 one chunk ahead) -> 150 (fc1 two ahead) -> 131 (three issuers,
+// N = 192 fc2) -> 116 (GELU chunk through TMEM, double buffered) -> 114 us.  Remaining bound: the N = 64 fc1
+// MMAs read 6 KB of shared memory per 32-cycle instruction (128 B/clk limit -> 48 cycles), tile-boundary drain.
 #include "tc_common.cuh"
 
 namespace {
