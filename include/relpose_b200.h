@@ -256,6 +256,21 @@ int rp_svd3_f32(const float* E, float* U, float* S, float* V, int64_t n, int dev
 /* E [n,3,3] -> R1 = U W V^T, R2 = U W^T V^T (det +1), t = U[:,2]   ([n,3,3],[n,3,3],[n,3]) */
 int rp_essential_to_rt_f32(const float* E, float* R1, float* R2, float* t, int64_t n, int device, void* stream);
 
+/* ---- training step after the path: clip_grad_norm_ + Adam + this step's learning rate ----
+ * train.py:161-165 (torch.nn.utils.clip_grad_norm_(params, 2.5); optimizer.step(); scheduler.step()) with
+ * torch.optim.Adam(lr, weight_decay) of train.py:69, as two multi-tensor launches and no host synchronisation.
+ * descs: device array of {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64 numel}
+ * (40 bytes each); blk_tensor / blk_off: for every thread block the tensor it works on and its first element
+ * (chunks of `chunk` elements, chunk % 4 == 0).  rp_grad_norm_multi writes the global L2 norm of all gradients to
+ * norm_out[0] (partial: nblk floats of scratch; fixed summation order).  rp_adam_clip_step_multi applies
+ * clip_coef = min(1, max_norm / (norm + 1e-6)) (max_norm <= 0: no clipping), L2 weight decay, and the Adam update
+ * of torch/optim/adam.py::_single_tensor_adam for step number `step` (>= 1) with learning rate lr. */
+int rp_grad_norm_multi(const void* descs, const int* blk_tensor, const int64_t* blk_off, int nblk, int chunk,
+                       float* partial, float* norm_out, int device, void* stream);
+int rp_adam_clip_step_multi(const void* descs, const int* blk_tensor, const int64_t* blk_off, int nblk, int chunk,
+                            const float* total_norm, double max_norm, double lr, double beta1, double beta2, double eps,
+                            double weight_decay, int step, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

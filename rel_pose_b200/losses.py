@@ -2,9 +2,11 @@
 import torch
 
 
-def geodesic_loss(Ps, Gs, train_val="train"):
+def geodesic_loss(Ps, Gs, train_val="train", sync_metrics=True):
     """Ps: ground-truth SE3 [B,2]; Gs: list holding the predicted SE3 [B,2] (model output).
-    d = log((G_j G_i^-1) (P_j P_i^-1)^-1) for (i,j) in ((0,1),(1,0)); mean |tau|, mean |phi|."""
+    d = log((G_j G_i^-1) (P_j P_i^-1)^-1) for (i,j) in ((0,1),(1,0)); mean |tau|, mean |phi|.
+    The reference turns both losses into Python floats (`.item()`, losses.py:17-18): a device->host sync per step.
+    sync_metrics=False keeps them as 0-d device tensors for callers that log asynchronously."""
     ii = torch.tensor([0, 1], device=Ps.data.device)
     jj = torch.tensor([1, 0], device=Ps.data.device)
     dP = Ps[:, jj] * Ps[:, ii].inv()
@@ -13,8 +15,11 @@ def geodesic_loss(Ps, Gs, train_val="train"):
     tau, phi = d.split([3, 3], dim=-1)
     loss_tr = tau.norm(dim=-1).mean()
     loss_rot = phi.norm(dim=-1).mean()
-    metrics = {
-        train_val + "_geo_loss_tr": loss_tr.detach().item(),
-        train_val + "_geo_loss_rot": loss_rot.detach().item(),
-    }
+    if sync_metrics:
+        metrics = {
+            train_val + "_geo_loss_tr": loss_tr.detach().item(),
+            train_val + "_geo_loss_rot": loss_rot.detach().item(),
+        }
+    else:
+        metrics = {train_val + "_geo_loss_tr": loss_tr.detach(), train_val + "_geo_loss_rot": loss_rot.detach()}
     return loss_tr, loss_rot, metrics

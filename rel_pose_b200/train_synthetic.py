@@ -50,6 +50,10 @@ def main():
     ap.add_argument("--w_rot", type=float, default=10.0)
     ap.add_argument("--total_steps", type=int, default=120000)
     ap.add_argument("--warmup", type=int, default=10000)
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: rel_pose_b200.optim.FusedAdamOneCycle (clip + Adam + OneCycle in 3 launches, no host sync); "
+                         "torch: the reference's own calls (clip_grad_norm_, Adam.step, OneCycleLR.step)")
+    ap.add_argument("--pool", type=int, default=8, help="synthetic batches generated up front on the device and cycled")
     a = ap.parse_args()
     from . import ViTEss
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -68,31 +72,50 @@ def main():
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
-    opt = torch.optim.Adam(net.parameters(), lr=a.lr, weight_decay=a.weight_decay)
-    sched = torch.optim.lr_scheduler.OneCycleLR(opt, a.lr, a.total_steps, pct_start=a.warmup / a.total_steps, div_factor=25,
-                                                cycle_momentum=False)
+    if a.optimizer == "fused":
+        from .optim import FusedAdamOneCycle
+        opt = FusedAdamOneCycle(list(net.parameters()), a.lr, a.total_steps, a.warmup / a.total_steps, div_factor=25,
+                                weight_decay=a.weight_decay, clip=a.clip)
+        sched = None
+    else:
+        opt = torch.optim.Adam(net.parameters(), lr=a.lr, weight_decay=a.weight_decay)
+        sched = torch.optim.lr_scheduler.OneCycleLR(opt, a.lr, a.total_steps, pct_start=a.warmup / a.total_steps, div_factor=25,
+                                                    cycle_momentum=False)
     H, W = a.size
-    losses = []
+    # the data loader is outside the path: batches are synthesised up front on the device and cycled
+    pool = [make_batch(i, rank, a.batch, H, W, dev) for i in range(max(1, a.pool))]
+    nsteps = a.warmup_steps + a.steps
+    loss_log = torch.zeros(nsteps, 2, device=dev)            # read back once at the end: no per-step host sync
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nsteps)]
     t0 = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for step in range(a.warmup_steps + a.steps):
+    for step in range(nsteps):
         if step == a.warmup_steps:
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             e0.record(); t0 = time.perf_counter()
-        images, poses, intr = make_batch(step, rank, a.batch, H, W, dev)
+        images, poses, intr = pool[step % len(pool)]
+        intr = intr.clone()                                   # forward rescales the intrinsics in place
         opt.zero_grad()
+        ev[step][0].record()
         Ps = SE3(poses)
         Gs = SE3.IdentityLike(Ps)
         poses_est = net(images, Gs, intrinsics=intr)
-        ltr, lrot, metrics = geodesic_loss(SE3(Ps.data.clone()), poses_est)
+        ltr, lrot, metrics = geodesic_loss(SE3(Ps.data.clone()), poses_est, sync_metrics=False) if a.optimizer == "fused" \
+            else geodesic_loss(SE3(Ps.data.clone()), poses_est)
         loss = a.w_tr * ltr + a.w_rot * lrot
+        ev[step][1].record()
         loss.backward()
-        gn = torch.nn.utils.clip_grad_norm_(net.parameters(), a.clip)
-        opt.step()
-        sched.step()
-        losses.append((float(loss.detach()), float(gn)))
+        ev[step][2].record()
+        if a.optimizer == "fused":
+            gn = opt.step()
+        else:
+            gn = torch.nn.utils.clip_grad_norm_(net.parameters(), a.clip)
+            opt.step()
+            sched.step()
+        ev[step][3].record()
+        loss_log[step, 0] = loss.detach(); loss_log[step, 1] = gn.reshape(())
     e1.record()
     if world > 1:
         dist.barrier()
@@ -102,6 +125,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    losses = [(float(x), float(y)) for x, y in loss_log.cpu().tolist()]
+    timed = range(a.warmup_steps, nsteps)
+    phase = [sum(ev[i][k].elapsed_time(ev[i][k + 1]) for i in timed) / len(timed) for k in range(3)]
     if rank == 0:
         ls = [l for l, _ in losses]
         print(json.dumps({"metric": "training steps/sec (config 5, synthetic pairs, fp32 SIMT backward)", "n_gpus": world,
@@ -109,7 +135,9 @@ def main():
                           "steps_per_s": a.steps / (ms * 1e-3), "pairs_per_s": world * a.batch * a.steps / (ms * 1e-3),
                           "loss_first5": [round(x, 4) for x in ls[:5]], "loss_last5": [round(x, 4) for x in ls[-5:]],
                           "grad_norm_first": round(losses[0][1], 3), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 2),
-                          "ddp": world > 1, "allreduce": "NCCL via DistributedDataParallel (77 MB fp32 gradients per step)"}), flush=True)
+                          "ddp": world > 1, "optimizer": a.optimizer,
+                          "phase_ms": {"forward+loss": round(phase[0], 3), "backward(+allreduce)": round(phase[1], 3),
+                                       "clip+adam+lr": round(phase[2], 3)}, "allreduce": "NCCL via DistributedDataParallel (77 MB fp32 gradients per step)"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

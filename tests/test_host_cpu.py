@@ -104,3 +104,24 @@ def test_synthetic_generators_are_stable():
     a = S.make_images_numpy(3, 1, 8, 8)
     assert a.shape == (1, 2, 3, 8, 8) and a.dtype == np.float32 and a.max() <= 255 and np.all(a == np.floor(a))
     assert float(a.sum()) == float(S.make_images_numpy(3, 1, 8, 8).sum())
+
+
+def test_one_cycle_lr_closed_form_matches_torch():
+    """rel_pose_b200.optim.one_cycle_lr == torch OneCycleLR as train.py:71-73 configures it (div_factor 25, cos)."""
+    import torch
+    from rel_pose_b200.optim import one_cycle_lr
+    w = torch.nn.Parameter(torch.zeros(1))
+    for total, warm, lr in [(120000, 10000, 5e-4), (60, 7, 1e-3), (1000, 300, 2e-4)]:
+        opt = torch.optim.Adam([w], lr=lr)
+        sch = torch.optim.lr_scheduler.OneCycleLR(opt, lr, total, pct_start=warm / total, div_factor=25, cycle_momentum=False)
+        for k in range(min(total, 1500)):
+            assert abs(opt.param_groups[0]["lr"] - one_cycle_lr(k, lr, total, warm / total)) <= 1e-12 * lr
+            opt.step(); sch.step()
+
+
+def test_fused_optimizer_refuses_cpu_parameters():
+    import torch
+    from rel_pose_b200 import _lib
+    from rel_pose_b200.optim import FusedAdamOneCycle
+    with pytest.raises(_lib.RelposeLibraryError):
+        FusedAdamOneCycle([torch.nn.Parameter(torch.zeros(4))], 1e-3, 10, 0.3)
