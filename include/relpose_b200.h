@@ -53,6 +53,14 @@ int rp_version(void);
 /* Compute capability major*10+minor of `device` (100 on B200), or a negative code. */
 int rp_device_arch(int device);
 
+/* ---- input pipeline step before the path -----------------------------------
+ * Copies from PINNED host memory only the rows that A1's nearest resize (src row = floor(d*H/out_rows),
+ * model.py:125) reads: src [planes][H][row_bytes] -> dst (device) [planes][out_rows][row_bytes], as
+ * out_rows/gcd strided 2-D DMAs on `stream`.  The compact tensor is a valid input of the rp_preprocess_*
+ * kernels (rows already selected, columns untouched): same pixels, 224/H of the PCIe traffic. */
+int rp_copy_rows_h2d(void* dst, const void* src_pinned, int64_t planes, int H, int64_t row_bytes, int out_rows,
+                     int device, void* stream);
+
 /* ---- A1  src/model.py:114-125 -------------------------------------------------------------
  * images [n_img,3,H,W] BGR 0..255  ->  out [n_img,3,224,224] RGB, (x/255-mean)/std, legacy
  * nearest resize (src = floor(dst*in/out)).  Bit-exact w.r.t. the reference's float32 ops. */

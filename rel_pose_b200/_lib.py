@@ -22,6 +22,7 @@ _SIGNATURES = {
     "rp_last_error": (ctypes.c_char_p, []),
     "rp_version": (_c_int, []),
     "rp_device_arch": (_c_int, [_c_int]),
+    "rp_copy_rows_h2d": (_c_int, [_ptr, _ptr, _c_i64, _c_int, _c_i64, _c_int, _c_int, _ptr]),
     "rp_preprocess_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_preprocess_u8": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_conv2d_workspace_bytes": (_c_size, [_c_int] * 9),

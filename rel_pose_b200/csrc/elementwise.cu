@@ -28,6 +28,64 @@ extern "C" int rp_device_arch(int device) {
     return major * 10 + minor;
 }
 
+// ------------------------------------------------------------------------------------------ input pipeline (8 f-2)
+// Host -> device copy of only the image ROWS the nearest resize of A1 (model.py:125) will read: legacy `nearest`
+// picks source row floor(d * H / out_rows) for output row d, i.e. b = out_rows / g rows out of every a = H / g
+// (g = gcd), the same pattern in every period and every plane.  One pitched 3-D DMA per residue j < b moves
+// row (k a + floor(j a / b)) of the host tensor to row (k b + j) of a compact [planes][out_rows][W] device tensor:
+// 224 of 384 rows = 58 % of the PCIe bytes, nothing touched by the CPU.  The compact tensor is then an ordinary
+// input of the preprocessing kernels (its row map is the identity, its column map unchanged) -> identical pixels.
+extern "C" int rp_copy_rows_h2d(void* dst, const void* src_pinned, int64_t planes, int H, int64_t row_bytes,
+                                int out_rows, int device, void* stream) {
+    RP_REQUIRE(dst && src_pinned && planes > 0 && H > 0 && row_bytes > 0 && out_rows > 0 && out_rows <= H, RP_EINVAL,
+               "rp_copy_rows_h2d: bad argument (out_rows must not exceed H)");
+    int g = H, t = out_rows;
+    while (t) { const int r = g % t; g = t; t = r; }
+    const int a = H / g, b = out_rows / g;
+    RP_REQUIRE(b <= 64, RP_EINVAL, "rp_copy_rows_h2d: %d -> %d rows needs %d strided copies (limit 64); copy the whole tensor",
+               H, out_rows, b);
+    // The row map is evaluated exactly as the preprocessing kernels (and ATen's legacy nearest) do, in float32:
+    // floorf(d * (float)H / out_rows).  Rounding of the scale can move a row down by one from some period on
+    // (480 -> 224: output row 119 reads source row 254, not 255), so every residue j is copied in runs of periods
+    // with a constant offset -- one pitched 3-D DMA (row, period, plane) per run.
+    const float scale = (float)H / (float)out_rows;
+    auto src_row = [&](int d) {
+        int sr = (int)floorf((float)d * scale);
+        return sr > H - 1 ? H - 1 : sr;
+    };
+    RP_GUARD(device);
+    int ncopies = 0;
+    for (int j = 0; j < b; ++j) {
+        int k = 0;
+        while (k < g) {
+            const int off = src_row(k * b + j) - k * a;
+            // off = -1 happens when float rounding pushes a row into the previous period: (period k, offset -1) is
+            // (period k - 1, offset a - 1)
+            RP_REQUIRE(off >= -a && off < a && (off >= 0 || k > 0), RP_EINVAL, "rp_copy_rows_h2d: unexpected row map (%d -> %d rows)",
+                       H, out_rows);
+            const int ky = off < 0 ? k - 1 : k, ox = off < 0 ? off + a : off;
+            int k1 = k + 1;
+            while (k1 < g && src_row(k1 * b + j) - k1 * a == off) ++k1;
+            cudaMemcpy3DParms p;
+            memset(&p, 0, sizeof(p));
+            p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src_pinned), (size_t)a * row_bytes, (size_t)a * row_bytes, (size_t)g);
+            p.srcPos = make_cudaPos((size_t)ox * row_bytes, (size_t)ky, 0);
+            p.dstPtr = make_cudaPitchedPtr(dst, (size_t)b * row_bytes, (size_t)b * row_bytes, (size_t)g);
+            p.dstPos = make_cudaPos((size_t)j * row_bytes, (size_t)k, 0);
+            p.extent = make_cudaExtent((size_t)row_bytes, (size_t)(k1 - k), (size_t)planes);
+            p.kind = cudaMemcpyHostToDevice;
+            cudaError_t e = cudaMemcpy3DAsync(&p, (cudaStream_t)stream);
+            if (e != cudaSuccess) {
+                rp::set_error("rp_copy_rows_h2d: cudaMemcpy3DAsync: %s", cudaGetErrorString(e));
+                return (int)e;
+            }
+            RP_REQUIRE(++ncopies <= 256, RP_EINVAL, "rp_copy_rows_h2d: row map needs too many copies; copy the whole tensor");
+            k = k1;
+        }
+    }
+    return RP_OK;
+}
+
 // ------------------------------------------------------------------------------------------ A1
 // One thread per output pixel (all three channels): out[n,c,oy,ox] = ((img[n,2-c,iy,ix]/255)-mean[c])/std[c].
 // Writes are fully coalesced; reads are a strided gather inside one input row (L1/L2 absorb it).

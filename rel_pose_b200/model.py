@@ -314,8 +314,10 @@ class ViTEss(nn.Module):
             return out.data[0].cpu().numpy()
         return [out]
 
-    def forward(self, images, Gs, intrinsics=None, inference=False):
-        """Estimates SE3 between a pair of frames (model.py:161-191)."""
+    def forward(self, images, Gs, intrinsics=None, inference=False, *, _orig_hw=None):
+        """Estimates SE3 between a pair of frames (model.py:161-191).
+        `_orig_hw` (private, used by parallel.StreamedInference): `images` is a row-compacted copy holding only the
+        224 rows the nearest resize reads; the intrinsics are rescaled with the ORIGINAL image size."""
         if not isinstance(Gs, SE3):
             Gs = SE3(torch.from_numpy(np.asarray(Gs)).unsqueeze(0).cuda().float())
         if not images.is_cuda:
@@ -339,7 +341,7 @@ class ViTEss(nn.Module):
                 x = ops.preprocess_stem_windows(images, self._tc_planes())    # A1 in the stem's window layout
             kxy = flags = None
             if intrinsics is not None:
-                intrinsics, kxy, flags = self.update_intrinsics(images.shape, intrinsics)
+                intrinsics, kxy, flags = self.update_intrinsics(_orig_hw if _orig_hw is not None else images.shape, intrinsics)
                 flags_host = self.__dict__.get("_flags_host")
                 if flags_host is None:
                     flags_host = self.__dict__["_flags_host"] = torch.empty((1,), dtype=torch.int32, pin_memory=True)

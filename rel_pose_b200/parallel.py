@@ -66,16 +66,40 @@ class StreamedInference:
             raise RuntimeError("StreamedInference needs the model on a CUDA device (no CPU path)")
         self.copy_stream = torch.cuda.Stream(self.device)
         self._bufs = [None, None]
+        self.row_selective = True            # copy only the rows the nearest resize reads
+        self.last_image_h2d_bytes = 0
+
+    def _copy_images(self, images):
+        """H2D of the image batch on the copy stream.  Pinned float32 / uint8 images taller than 224 rows are
+        copied row-selectively (rp_copy_rows_h2d): only the rows the nearest resize reads cross PCIe."""
+        H, W = int(images.shape[-2]), int(images.shape[-1])
+        if (self.row_selective and images.is_pinned() and images.is_contiguous() and H > 224 and images.dim() == 5
+                and images.dtype in (torch.float32, torch.uint8)):
+            import ctypes
+            from math import gcd
+            from . import _lib
+            if 224 // gcd(H, 224) <= 64:
+                d = torch.empty(tuple(images.shape[:-2]) + (224, W), dtype=images.dtype, device=self.device)
+                planes = images.numel() // (H * W)
+                dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+                rc = _lib.lib().rp_copy_rows_h2d(ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(images.data_ptr()), planes, H,
+                                                 W * images.element_size(), 224, dev,
+                                                 ctypes.c_void_p(self.copy_stream.cuda_stream))
+                if rc == 0:
+                    return d, (H, W), d.numel() * d.element_size()
+                # RP_EINVAL: the float32 row map of this height is not periodic -> plain copy of the whole tensor
+        return images.to(self.device, non_blocking=True), None, images.numel() * images.element_size()
 
     def _stage(self, slot, batch):
         images, gs, intr = batch
         with torch.cuda.stream(self.copy_stream):
-            d_img = images.to(self.device, non_blocking=True)
+            d_img, orig_hw, nbytes = self._copy_images(images)
+            self.last_image_h2d_bytes = nbytes
             d_gs = gs.to(self.device, non_blocking=True)
             d_k = intr.to(self.device, non_blocking=True) if intr is not None else None
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        self._bufs[slot] = (d_img, d_gs, d_k, ev)
+        self._bufs[slot] = (d_img, d_gs, d_k, ev, orig_hw)
 
     def run(self, batches):
         from .lietorch import SE3
@@ -89,7 +113,7 @@ class StreamedInference:
         pending = None                       # (host result, event) of the previous batch
         compute = torch.cuda.current_stream(self.device)
         while True:
-            d_img, d_gs, d_k, ev = self._bufs[slot]
+            d_img, d_gs, d_k, ev, orig_hw = self._bufs[slot]
             try:
                 nxt = next(it)
             except StopIteration:
@@ -98,7 +122,7 @@ class StreamedInference:
                 self._stage(slot ^ 1, nxt)   # overlaps with the kernels launched below
             compute.wait_event(ev)
             with torch.no_grad():
-                out = self.model(d_img, SE3(d_gs), intrinsics=d_k)[0].data
+                out = self.model(d_img, SE3(d_gs), intrinsics=d_k, _orig_hw=orig_hw)[0].data
             for t in (d_img, d_gs, d_k):     # the copy stream allocated them, the compute stream used them
                 if t is not None:
                     t.record_stream(compute)

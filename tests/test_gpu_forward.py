@@ -188,6 +188,32 @@ def test_streamed_inference_matches_direct_calls():
         m.precision = "fp32"
 
 
+@pytest.mark.parametrize("H,W,dtype,selective", [(384, 384, "f32", True), (480, 640, "u8", True), (256, 320, "f32", True),
+                                                 (225, 240, "f32", False), (96, 128, "u8", False)])
+def test_streamed_inference_row_selective_copy_is_bit_identical(H, W, dtype, selective):
+    """StreamedInference copies only the 224 rows the nearest resize reads (rp_copy_rows_h2d, strided
+    2-D DMAs) -- the poses must be bit-identical to the full copy, the intrinsics rescaled with the original size."""
+    from rel_pose_b200.parallel import StreamedInference
+    m = _model(0, "stress")
+    m.precision = "bf16x3"
+    try:
+        b = 2
+        img = torch.from_numpy(S.make_images_numpy(31, b, H, W, True))
+        img = (img.to(torch.uint8) if dtype == "u8" else img).pin_memory()
+        k = torch.from_numpy(S.make_intrinsics_numpy(b)).pin_memory()
+        gs = SE3.Identity(b, 2).data.pin_memory()
+        full = StreamedInference(m); full.row_selective = False
+        sel = StreamedInference(m)
+        a = list(full.run([(img, gs, k.clone().pin_memory())]))[0]
+        c = list(sel.run([(img, gs, k.clone().pin_memory())]))[0]
+        assert torch.equal(a, c)
+        nbytes = img.numel() * img.element_size()
+        assert full.last_image_h2d_bytes == nbytes
+        assert sel.last_image_h2d_bytes == (nbytes * 224 // H if selective else nbytes)
+    finally:
+        m.precision = "fp32"
+
+
 def test_dropin_runs_a_reference_style_script_unchanged(tmp_path):
     """A caller written against `src.model.ViTEss` / `lietorch.SE3` only (tests/scripts/demo_like.py, the call
     sequence of the reference's demo.py) runs through `python -m rel_pose_b200.run` and reproduces the oracle."""
