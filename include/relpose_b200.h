@@ -127,6 +127,14 @@ int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* be
 int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
                  float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
                  void* stream);
+/* LayerNorm fused into a projection  out = LayerNorm(x) W^T + bias  in one launch: `self.qkv(self.norm1(x))` of
+ * Block / Attention.forward (vision_transformer.py:350,323) and of CrossBlock / CrossAttention.forward
+ * (vision_transformer.py:288-289,191-194).  x float32 [M,K]; W_planes bf16 [P][N][K]; outputs as in rp_linear_tc
+ * (float32 [M,N] and/or P_out bf16 planes [P_out][M][N]).  Built for K = 192; N % 4 == 0 for the vector path. */
+int rp_ln_linear_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W_planes,
+                    const float* bias, float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out,
+                    int device, void* stream);
+
 /* Fused MLP half-block  out = x + fc2(GELU(fc1(LayerNorm(x))))  in one launch: Block.forward's
  * `x = x + self.mlp(self.norm2(x))` (vision_transformer.py:352-353; mlp.py:20-26) and CrossBlock.forward's
  * `out = f + mlp(norm2(f))` (vision_transformer.py:295-296).  x, out float32 [M,dim]; W1_planes bf16

@@ -1,0 +1,342 @@
+// LayerNorm fused into the QKV projection on sm_100a tensor cores:
+//     out = LayerNorm(x) W^T + b            x float32 [M,192], W [N,192] (N = 576 for qkv), out as bf16 planes
+// i.e. `self.qkv(self.norm1(x))` of Block.forward / Attention.forward (vision_transformer.py:350,323) and of
+// CrossBlock.forward / CrossAttention.forward (vision_transformer.py:288-289,191-194) in ONE launch.  The unfused
+// pair (layernorm_planes -> linear_tc) wrote the normalised activations to HBM as bf16 planes and read them back
+// (2 x 57 MB per layer at 64 pairs, one extra launch); here the LayerNorm output goes straight into the swizzled
+// shared-memory A operand and stays there for all N / 192 column tiles of the row tile.
+//
+// Operands are split-bf16 planes as in gemm_tc.cu (P = 1 bf16, P = 2 "bf16x3").  One persistent CTA per SM,
+// 576 threads, one 128-row tile at a time:
+//   warp 0      TMA producer: weight units [P][192 rows][64 K] (128-byte swizzle) into a ring
+//   warp 1      MMA issuer: per column tile 3 K blocks x 4 K steps x (3 | 1) tcgen05.mma M128 x N192 x K16 into one of
+//               two TMEM accumulators (the epilogue of column tile i overlaps the MMAs of tile i+1)
+//   warps 2-17  LayerNorm of the tile's rows into the A-operand planes; epilogue (tcgen05.ld -> transpose through a
+//               warp-private shared-memory patch -> + bias -> float32 and/or re-split bf16 planes, coalesced).
+//               The next row tile's LayerNorm runs as soon as the last column tile's MMAs have retired, before that
+//               tile's epilogue, so the tensor pipe does not drain at row-tile boundaries.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int D = 192, BM = 128, BN = 192, KB = D / 64;
+constexpr int EPI_WARPS = 16;
+constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
+constexpr int TILE16K = BM * 64 * 2;                  // one [128 x 64] bf16 A tile
+constexpr int BTILE = BN * 64 * 2;                    // one plane of a weight unit: [192 x 64] bf16 = 24 KiB
+constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;
+constexpr int STG_LD = 16;
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+
+template <int P>
+struct LCfg {
+    static constexpr int NS = (P == 1) ? 4 : 2;       // weight ring depth
+    static constexpr int UNIT = P * BTILE;
+    static constexpr int OFF_XN = 0;                  // [P][KB] tiles of 16 KiB
+    static constexpr int OFF_STG = OFF_XN + P * KB * TILE16K;
+    static constexpr int OFF_W = OFF_STG + STG_BYTES;
+    static constexpr int OFF_BAR = OFF_W + NS * UNIT;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024 /*align slack*/;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct LnLinParams {
+    const float* x;        // [M,192]
+    const float* gamma;
+    const float* beta;
+    const float* bias;     // [N] or null
+    float* out_f32;        // [M,N] or null
+    __nv_bfloat16* out_planes;   // [P_out][M][N] or null
+    int p_out;
+    int M, N;
+    float eps;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int P>
+__global__ void __launch_bounds__(NTHREADS, 1)
+ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, LnLinParams prm) {
+    using C = LCfg<P>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* wfull = bars;                      // [NS]
+    uint64_t* wempty = bars + C::NS;             // [NS]
+    uint64_t* xn_full = bars + 2 * C::NS;
+    uint64_t* tfull = xn_full + 1;               // [2]
+    uint64_t* tempty = xn_full + 3;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xn_full + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int M = prm.M, N = prm.N;
+    const int ntiles = (M + BM - 1) / BM;
+    const int NT = (N + BN - 1) / BN;            // column tiles per row tile
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmW);
+        for (int i = 0; i < C::NS; ++i) {
+            tc::mbar_init(&wfull[i], 1);
+            tc::mbar_init(&wempty[i], 1);
+        }
+        tc::mbar_init(xn_full, EPI_WARPS);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&tfull[i], 1);
+            tc::mbar_init(&tempty[i], EPI_WARPS);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto xn_tile = [&](int p, int kb) { return smem + C::OFF_XN + (p * KB + kb) * TILE16K; };
+    auto w_unit = [&](int s, int p) { return smem + C::OFF_W + s * C::UNIT + p * BTILE; };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (convergent warp)
+        int s = 0, ph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int nt = 0; nt < NT; ++nt) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    tc::mbar_wait(&wempty[s], ph ^ 1);
+                    if (tc::elect_one_sync()) {
+                        tc::mbar_expect_tx(&wfull[s], (uint32_t)C::UNIT);
+#pragma unroll
+                        for (int p = 0; p < P; ++p) tc::tma_load_3d(w_unit(s, p), &tmW, &wfull[s], kb * 64, nt * BN, p);
+                    }
+                    __syncwarp();
+                    if (++s == C::NS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (convergent warp)
+        constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
+        int s = 0, ph = 0;
+        uint32_t c = 0, it = 0;                 // column tiles / row tiles issued so far by this CTA
+        uint64_t dxn0[KB], dxn1[KB];
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+            dxn0[kb] = tc::make_kmajor_sw128_desc(tc::smem_u32(xn_tile(0, kb)));
+            dxn1[kb] = tc::make_kmajor_sw128_desc(tc::smem_u32(xn_tile(P - 1, kb)));
+        }
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            tc::mbar_wait(xn_full, it & 1);
+            tc::tcgen05_fence_after();
+            for (int nt = 0; nt < NT; ++nt, ++c) {
+                const uint32_t acc = c & 1;
+                tc::mbar_wait(&tempty[acc], ((c >> 1) & 1) ^ 1);
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + acc * ACC_STRIDE;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    tc::mbar_wait(&wfull[s], ph);
+                    tc::tcgen05_fence_after();
+                    const uint64_t w0 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(s, 0)));
+                    const uint64_t w1 = tc::make_kmajor_sw128_desc(tc::smem_u32(w_unit(s, P - 1)));
+                    if (tc::elect_one_sync()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+                            if (P == 2) {            // smallest terms first (truncating fp32 accumulation)
+                                tc::umma_bf16(d, dxn1[kb] + 2 * k, w0 + 2 * k, idesc, accum);
+                                tc::umma_bf16(d, dxn0[kb] + 2 * k, w1 + 2 * k, idesc, 1u);
+                                accum = 1u;
+                            }
+                            tc::umma_bf16(d, dxn0[kb] + 2 * k, w0 + 2 * k, idesc, accum);
+                        }
+                        tc::umma_commit(&wempty[s]);
+                        if (kb == KB - 1) tc::umma_commit(&tfull[acc]);
+                    }
+                    __syncwarp();
+                    if (++s == C::NS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ LayerNorm / epilogue warps
+        const int ew = warp - 2;
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int part = ew >> 2;                        // 48-column slab of the 192-column tile
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* stg = reinterpret_cast<float*>(smem + C::OFF_STG) + ew * 32 * STG_LD;
+        const int rr = lane >> 2, cq = lane & 3;
+        const bool vec4 = (N % 4) == 0;
+        uint32_t c = 0;
+
+        auto layer_norm_tile = [&](int tile) {           // same arithmetic as mlp_tc.cu / layernorm_planes_kernel
+            float g[6], bt[6];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float2 gg = __ldg(reinterpret_cast<const float2*>(prm.gamma + 64 * i + 2 * lane));
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(prm.beta + 64 * i + 2 * lane));
+                g[2 * i] = gg.x; g[2 * i + 1] = gg.y; bt[2 * i] = bb.x; bt[2 * i + 1] = bb.y;
+            }
+            float v[8][6];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int grow = tile * BM + ew * 8 + j;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    float2 a = make_float2(0.f, 0.f);
+                    if (grow < M) a = __ldg(reinterpret_cast<const float2*>(prm.x + (size_t)grow * D + 64 * i + 2 * lane));
+                    v[j][2 * i] = a.x; v[j][2 * i + 1] = a.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int rl = ew * 8 + j;
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) s += v[j][i];
+                const float mean = rp::warp_sum(s) * (1.0f / D);
+                float qv = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { const float dlt = v[j][i] - mean; qv += dlt * dlt; }
+                const float rstd = 1.0f / sqrtf(rp::warp_sum(qv) * (1.0f / D) + prm.eps);
+                const uint32_t off = (uint32_t)(rl >> 3) * 1024 + (uint32_t)(rl & 7) * 128 +
+                                     ((((uint32_t)lane >> 2) ^ (uint32_t)(rl & 7)) << 4) + (uint32_t)(lane & 3) * 4;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    float y0 = (v[j][2 * i] - mean) * rstd * g[2 * i] + bt[2 * i];
+                    float y1 = (v[j][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bt[2 * i + 1];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const uint32_t w = pack_bf16x2(y0, y1);
+                        *reinterpret_cast<uint32_t*>(xn_tile(p, i) + off) = w;
+                        y0 -= __uint_as_float(w << 16);
+                        y1 -= __uint_as_float(w & 0xffff0000u);
+                    }
+                }
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(xn_full);
+        };
+
+        if ((int)blockIdx.x < ntiles) layer_norm_tile(blockIdx.x);
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int row_base = tile * BM;
+            const int valid_rows = min(BM, M - row_base);
+            for (int nt = 0; nt < NT; ++nt, ++c) {
+                const uint32_t acc = c & 1;
+                const int n0 = nt * BN;
+                tc::mbar_wait(&tfull[acc], (c >> 1) & 1);
+                tc::tcgen05_fence_after();
+                // every MMA of this row tile has retired once its last column tile is complete: the LayerNorm planes
+                // are dead, write the next row tile's before draining this accumulator
+                if (nt == NT - 1 && tile + (int)gridDim.x < ntiles) layer_norm_tile(tile + (int)gridDim.x);
+                const uint32_t t_row = t_lane + acc * ACC_STRIDE;
+#pragma unroll 1
+                for (int ci = 0; ci < 3; ++ci) {
+                    const int c0 = part * 48 + ci * 16;
+                    if (n0 + c0 >= N) break;                 // warp-uniform
+                    const int col = n0 + c0 + cq * 4;
+                    const bool colv = vec4 && col < N;
+                    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (colv && prm.bias) sh = __ldg(reinterpret_cast<const float4*>(prm.bias + col));
+                    uint32_t r[16];
+                    tc::tmem_ld_32x32b_x16(t_row + c0, r);
+                    tc::tmem_ld_wait();
+                    __syncwarp();                            // the previous chunk's readers are done with the patch
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(stg + lane * STG_LD + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                            make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int rl = t * 8 + rr;
+                        const int rt = q * 32 + rl;
+                        if (rt >= valid_rows) continue;
+                        const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2));
+                        float vv[4] = {a.x + sh.x, a.y + sh.y, a.z + sh.z, a.w + sh.w};
+                        const size_t o = (size_t)(row_base + rt) * N + col;
+                        if (colv) {
+                            if (prm.out_f32) *reinterpret_cast<float4*>(prm.out_f32 + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                            if (prm.out_planes) {
+                                for (int p = 0; p < prm.p_out; ++p) {
+                                    uint2 w;
+                                    w.x = pack_bf16x2(vv[0], vv[1]);
+                                    w.y = pack_bf16x2(vv[2], vv[3]);
+                                    *reinterpret_cast<uint2*>(prm.out_planes + (size_t)p * M * N + o) = w;
+                                    vv[0] -= __uint_as_float(w.x << 16); vv[1] -= __uint_as_float(w.x & 0xffff0000u);
+                                    vv[2] -= __uint_as_float(w.y << 16); vv[3] -= __uint_as_float(w.y & 0xffff0000u);
+                                }
+                            }
+                        } else {
+                            const int colx = n0 + c0 + cq * 4;
+                            for (int j = 0; j < 4 && colx + j < N; ++j) {
+                                float xj = (&a.x)[j] + (prm.bias ? prm.bias[colx + j] : 0.f);
+                                const size_t oj = (size_t)(row_base + rt) * N + colx + j;
+                                if (prm.out_f32) prm.out_f32[oj] = xj;
+                                if (prm.out_planes)
+                                    for (int p = 0; p < prm.p_out; ++p) {
+                                        const __nv_bfloat16 h = __float2bfloat16_rn(xj);
+                                        prm.out_planes[(size_t)p * M * N + oj] = h;
+                                        xj -= __bfloat162float(h);
+                                    }
+                            }
+                        }
+                    }
+                }
+                tc::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            }
+        }
+    }
+
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int P>
+int launch_ln_linear(const CUtensorMap& tmW, const LnLinParams& prm, int device, cudaStream_t st) {
+    using C = LCfg<P>;
+    static bool attr_set[64] = {false};
+    if (device >= 0 && device < 64 && !attr_set[device]) {
+        cudaError_t e = cudaFuncSetAttribute(ln_linear_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) {
+            rp::set_error("rp_ln_linear_tc: cudaFuncSetAttribute(%d): %s", C::SMEM, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_set[device] = true;
+    }
+    const int ntiles = (prm.M + BM - 1) / BM;
+    const int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
+    ln_linear_tc_kernel<P><<<grid, NTHREADS, C::SMEM, st>>>(tmW, prm);
+    return rp::finish_launch("rp_ln_linear_tc");
+}
+
+}  // namespace
+
+extern "C" int rp_ln_linear_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W_planes,
+                               const float* bias, float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out,
+                               int device, void* stream) {
+    RP_REQUIRE(x && ln_gamma && ln_beta && W_planes && (out_f32 || out_planes) && M > 0 && N > 0, RP_EINVAL,
+               "rp_ln_linear_tc: null pointer or empty shape");
+    RP_REQUIRE(K == D, RP_EINVAL, "rp_ln_linear_tc: built for K = 192 (got %d)", K);
+    RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_ln_linear_tc: P must be 1 (bf16) or 2 (bf16x3)");
+    RP_REQUIRE(!out_planes || (P_out >= 1 && P_out <= 2), RP_EINVAL, "rp_ln_linear_tc: bad P_out");
+    RP_REQUIRE(rp::aligned16(x) && rp::aligned16(W_planes) && rp::aligned16(ln_gamma) && rp::aligned16(ln_beta) &&
+                   rp::aligned16(bias) && rp::aligned16(out_f32) && rp::aligned16(out_planes),
+               RP_EALIGN, "rp_ln_linear_tc: 16-byte alignment");
+    RP_GUARD(device);
+    CUtensorMap tmW;
+    int rc = tc::make_planes_tmap(&tmW, W_planes, P, N, D, BN);           // [P][N][192], box 192 rows x 64 K
+    if (rc) return rc;
+    LnLinParams prm{x, ln_gamma, ln_beta, bias, out_f32, static_cast<__nv_bfloat16*>(out_planes), P_out, M, N, eps};
+    if (P == 1) return launch_ln_linear<1>(tmW, prm, device, (cudaStream_t)stream);
+    return launch_ln_linear<2>(tmW, prm, device, (cudaStream_t)stream);
+}

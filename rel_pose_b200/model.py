@@ -138,6 +138,7 @@ class ViTEss(nn.Module):
         # one-launch LayerNorm+fc1+GELU+fc2+residual (csrc/mlp_tc.cu); RELPOSE_FUSED_MLP=0 keeps the three-kernel
         # sequence for A/B measurements
         self.fused_mlp = os.environ.get("RELPOSE_FUSED_MLP", "1") != "0"
+        self.fused_ln_qkv = os.environ.get("RELPOSE_FUSED_LNQKV", "1") != "0"     # csrc/ln_linear_tc.cu
         self.check_intrinsics = True      # reproduce the reference's assert on per-view intrinsics
         self.last_stages = None           # filled when `capture_stages` is set (parity tests)
         self.capture_stages = False
@@ -269,11 +270,17 @@ class ViTEss(nn.Module):
             h = ops.linear(h, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
             return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=x)
         # tensor-core engine: LayerNorm and the GEMM epilogues emit the bf16 planes the next GEMM reads
-        h = ops.layernorm_planes(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, P)
-        _, qkv = ops.linear_tc(h, self._planes(blk.attn.qkv.weight, P), blk.attn.qkv.bias, want_f32=False, planes_out=P)
+        qkv = self._ln_qkv_tc(x, blk.norm1, blk.attn.qkv, P)
         _, a = ops.self_attention_tc(qkv, planes_out=P)
         x, _ = ops.linear_tc(a, self._planes(blk.attn.proj.weight, P), blk.attn.proj.bias, residual=x)
         return self._mlp_tc(blk, x, P)
+
+    def _ln_qkv_tc(self, x, norm, qkv, P):
+        """qkv(norm1(x)) as bf16 planes: one fused launch (LayerNorm -> shared-memory A operand -> GEMM)."""
+        if self.fused_ln_qkv:
+            return ops.ln_linear_tc(x, norm.weight, norm.bias, norm.eps, self._planes(qkv.weight, P), qkv.bias, planes_out=P)[1]
+        h = ops.layernorm_planes(x, norm.weight, norm.bias, norm.eps, P)
+        return ops.linear_tc(h, self._planes(qkv.weight, P), qkv.bias, want_f32=False, planes_out=P)[1]
 
     def _mlp_tc(self, blk, x, P):
         """x + mlp(norm2(x)): one fused launch (LayerNorm -> fc1 -> GELU -> fc2 -> +x), hidden activation on chip."""
@@ -295,8 +302,7 @@ class ViTEss(nn.Module):
             h = ops.layernorm(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)     # norm1 on both views
             qkv = ops.linear(h, ca.qkv.weight, ca.qkv.bias)
         else:
-            h = ops.layernorm_planes(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, P)
-            _, qkv = ops.linear_tc(h, self._planes(ca.qkv.weight, P), ca.qkv.bias, want_f32=False, planes_out=P)
+            qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
         pos = ops.posenc(B, kxy, x.device)
         bil = ops.essential(qkv, pos) if P == 0 else ops.essential_tc(qkv, pos)
         if stages is not None:

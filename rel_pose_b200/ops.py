@@ -345,6 +345,28 @@ def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f
     return out, outp
 
 
+def ln_linear_tc(x, gamma, beta, eps, w_planes, bias=None, want_f32=False, planes_out=0):
+    """Fused `linear(layernorm(x))` on tcgen05 (csrc/ln_linear_tc.cu): x float32 [...,192], w_planes bf16 [P,N,192]
+    -> (float32 [...,N] | None, bf16 planes [planes_out,...,N] | None)."""
+    _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta")
+    _req(w_planes, "w_planes", torch.bfloat16)
+    P, N, K = w_planes.shape
+    assert x.shape[-1] == K and (want_f32 or planes_out)
+    if bias is not None:
+        _req(bias, "bias")
+    lead = tuple(x.shape[:-1])
+    M = x.numel() // K
+    out = torch.empty(lead + (N,), dtype=torch.float32, device=x.device) if want_f32 else None
+    outp = torch.empty((planes_out,) + lead + (N,), dtype=torch.bfloat16, device=x.device) if planes_out else None
+    dev, st = _ctx(x)
+    _tbegin(f"ln_linear_tc{'x3' if P == 2 else ''}[{N}x{K}]", 2.0 * M * N * K,
+            4.0 * M * K + 2.0 * P * N * K + (4.0 * M * N if want_f32 else 0.0) + 2.0 * planes_out * M * N)
+    _lib.check(_lib.lib().rp_ln_linear_tc(_p(x), _p(gamma), _p(beta), float(eps), _p(w_planes), _p(bias), _p(out), _p(outp),
+                                          M, N, K, P, int(planes_out), dev, st), "rp_ln_linear_tc")
+    _count()
+    return out, outp
+
+
 def mlp_tc(x, gamma, beta, eps, w1_planes, b1, w2_planes, b2):
     """Fused `x + fc2(gelu(fc1(layernorm(x))))` on tcgen05 (csrc/mlp_tc.cu): x float32 [...,192],
     w1_planes bf16 [P,768,192], w2_planes bf16 [P,192,768] -> float32 [...,192]."""

@@ -97,6 +97,35 @@ def test_linear_tc_only_planes_output():
 
 
 @pytest.mark.parametrize("P", [1, 2])
+@pytest.mark.parametrize("M,N,f32", [(128, 576, True), (140, 576, False), (1152, 192, True), (8960, 576, False),
+                                     (148 * 128 * 2 + 77, 576, False), (300, 200, True), (64, 70, True)])
+def test_ln_linear_tc(P, M, N, f32):
+    """rp_ln_linear_tc = linear(layernorm(x)) in one launch, against float64 and against the two-kernel path."""
+    x = rnd(30, M, 192, scale=1.5) + 0.2
+    g = 1 + 0.1 * rnd(31, 192); be = 0.1 * rnd(32, 192)
+    w = rnd(33, N, 192, scale=0.07); b = rnd(34, N, scale=0.1)
+    wp = ops.split_planes(cu(w), P)
+    out, outp = ops.ln_linear_tc(cu(x), cu(g), cu(be), 1e-6, wp, cu(b), want_f32=f32, planes_out=P)
+    torch.cuda.synchronize()
+    f64 = np.float64
+    ref = O.layernorm(x.astype(f64), g.astype(f64), be.astype(f64)) @ w.astype(f64).T + b
+    got = planes_to_f64(outp)
+    tol = (3e-5 if P == 2 else 2e-2) * np.abs(ref).max()
+    err = np.abs(got - ref).max()
+    print(f"[parity] ln_linear_tc P={P} {M}x{N}: max_abs_err={err:.3e} max_ref={np.abs(ref).max():.3e} ratio={err / tol:.3f}")
+    if not err <= tol:
+        _diagnose(f"ln_linear P={P} {M}x{N}", got, ref)
+    assert np.isfinite(got).all() and err <= tol
+    if f32:
+        assert np.abs(out.cpu().numpy().astype(f64) - ref).max() <= tol
+    hp = ops.layernorm_planes(cu(x), cu(g), cu(be), 1e-6, P)
+    _, un = ops.linear_tc(hp, wp, cu(b), want_f32=False, planes_out=P)
+    assert np.abs(planes_to_f64(un) - got).max() <= 2 * tol
+    again = ops.ln_linear_tc(cu(x), cu(g), cu(be), 1e-6, wp, cu(b), want_f32=False, planes_out=P)[1]
+    assert torch.equal(outp, again)
+
+
+@pytest.mark.parametrize("P", [1, 2])
 @pytest.mark.parametrize("M", [128, 140, 1152, 8960, 148 * 128 * 2 + 77])
 def test_mlp_fused_tc(P, M):
     """rp_mlp_tc = x + fc2(gelu(fc1(layernorm(x)))) in one launch, against float64 and against the three-kernel path."""
