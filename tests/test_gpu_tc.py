@@ -98,7 +98,7 @@ def test_linear_tc_only_planes_output():
 
 @pytest.mark.parametrize("P", [1, 2])
 @pytest.mark.parametrize("M,N,f32", [(128, 576, True), (140, 576, False), (1152, 192, True), (8960, 576, False),
-                                     (148 * 128 * 2 + 77, 576, False), (300, 200, True), (64, 70, True)])
+                                     (148 * 128 * 2 + 77, 576, False), (300, 200, True), (300, 200, False), (64, 70, True)])
 def test_ln_linear_tc(P, M, N, f32):
     """rp_ln_linear_tc = linear(layernorm(x)) in one launch, against float64 and against the two-kernel path."""
     x = rnd(30, M, 192, scale=1.5) + 0.2
