@@ -185,6 +185,8 @@ int rp_self_attention_tc(const void* qkv_planes, float* out_f32, void* out_plane
  * lin24: host pointer to the 24 floats of torch.linspace(-1,1,24); kxy [B,2] from
  * rp_intrinsics_prepare_f32 or NULL (intrinsics=None: kx = ky = 1 without multiplication). */
 int rp_posenc_f32(const float* kxy, const float* host_lin24, float* pos, int B, int device, void* stream);
+/* l1 != 0: --l1_pos_encoding, get_l1_positional_encodings (vision_transformer.py:36-87): channels [1,1,1,p3,p4,1] */
+int rp_posenc_ex_f32(const float* kxy, const float* host_lin24, float* pos, int B, int l1, int device, void* stream);
 
 /* ---- A7 Essential Matrix Module core  vision_transformer.py:198-223 -------------------------
  * qkv [2B,576,576] with the two views of pair b at rows 2b, 2b+1; pos [B,576,6] or NULL
@@ -195,6 +197,13 @@ int rp_posenc_f32(const float* kxy, const float* host_lin24, float* pos, int B, 
 size_t rp_essential_workspace_bytes(int B);
 int rp_essential_f32(const float* qkv, const float* pos, float* bil, int B, void* workspace,
                      size_t workspace_bytes, int device, void* stream);
+/* Ablation branches of the same module, fp32 SIMT kernels: flags = RP_EM_SINGLE_SOFTMAX
+ * (--use_single_softmax, vision_transformer.py:201-203: A = softmax(S,-1) only) | RP_EM_CROSS_FEATURES
+ * (--cross_features, :219-220: F1 = V2^T A1 V1, F2 = V1^T A2 V2). */
+#define RP_EM_SINGLE_SOFTMAX 1
+#define RP_EM_CROSS_FEATURES 2
+int rp_essential_ex_f32(const float* qkv, const float* pos, float* bil, int B, int flags, void* workspace,
+                        size_t workspace_bytes, int device, void* stream);
 /* Same contract on tcgen05 tensor cores.  qkv_planes = bf16 planes [P][2B][576][576] of the cross block's QKV GEMM
  * (P = 1 bf16, P = 2 split bf16 = fp32 class).  Two kernels: row/column log-sum-exp of S, then the fused
  * dual-softmax -> A [v|pos] -> [v|pos]^T T accumulation with F resident in tensor memory (no partials, no

@@ -29,6 +29,14 @@ CASES = [
     ("init_b1_384x512_demo_shape", 4, "init", 1, 384, 512, "matterport", True),
 ]
 
+# ablation branches of the Essential Matrix Module: same generator, reference built with the flag(s)
+ABLATION_CASES = [
+    ("ablate_single_softmax_b2_64x80", 11, "stress", 2, 64, 80, "matterport", True, ("use_single_softmax",)),
+    ("ablate_cross_features_b2_64x80", 12, "stress", 2, 64, 80, "varied", True, ("cross_features",)),
+    ("ablate_l1_pos_b2_64x80", 13, "stress", 2, 64, 80, "matterport", True, ("l1_pos_encoding",)),
+    ("ablate_all_three_b1_96x128", 14, "stress", 1, 96, 128, "matterport", True, ("use_single_softmax", "cross_features", "l1_pos_encoding")),
+]
+
 TOK_SAMPLE = (slice(None), slice(None, None, 9), slice(None, None, 4))
 
 
@@ -43,8 +51,8 @@ def sample(name, t):
     return a
 
 
-def run_case(name, seed, profile, B, H, W, ikind, integer):
-    model, SE3 = ref_loader.load_reference_model()
+def run_case(name, seed, profile, B, H, W, ikind, integer, flags=()):
+    model, SE3 = ref_loader.load_reference_model(**{f: True for f in flags})
     model.load_state_dict(S.make_state_dict(seed, profile))
     model.eval()
     images = torch.from_numpy(S.make_images_numpy(seed, B, H, W, integer))
@@ -96,6 +104,7 @@ def run_case(name, seed, profile, B, H, W, ikind, integer):
     rec["meta"] = np.array([seed, B, H, W, int(integer)], np.int64)
     rec["profile"] = np.array(profile)
     rec["intrinsics_kind"] = np.array("none" if ikind is None else ikind)
+    rec["flags"] = np.array(",".join(flags))
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **rec)
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB", "pose1[0] =", rec["poses"][0, 1])
@@ -121,6 +130,10 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    posenc_golden()
-    for c in CASES:
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only != "ablations":
+        posenc_golden()
+        for c in CASES:
+            run_case(*c)
+    for c in ABLATION_CASES:
         run_case(*c)

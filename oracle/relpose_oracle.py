@@ -217,7 +217,7 @@ def linspace_pm1(steps=GRID):
     return out
 
 
-def positional_encodings(B, intrinsics=None):
+def positional_encodings(B, intrinsics=None, l1=False):
     """get_positional_encodings, vision_transformer.py:90-158, N=576, float32 like the reference
     (it builds the table on the CPU in float32 irrespective of the model dtype).
 
@@ -243,16 +243,17 @@ def positional_encodings(B, intrinsics=None):
         p3 = (ky[:, None] * ys[i % GRID][None]).astype(np.float32)
         p4 = (kx[:, None] * xs[i // GRID][None]).astype(np.float32)
     pos = np.ones((B, NTOK, NPOS), np.float32)
-    pos[:, :, 0] = p3 * p3
-    pos[:, :, 1] = p4 * p4
-    pos[:, :, 2] = p3 * p4
+    if not l1:          # get_l1_positional_encodings (vision_transformer.py:36-87) leaves the quadratic channels at 1
+        pos[:, :, 0] = p3 * p3
+        pos[:, :, 1] = p4 * p4
+        pos[:, :, 2] = p3 * p4
     pos[:, :, 3] = p3
     pos[:, :, 4] = p4
     return pos
 
 
 # ------------------------------------------------------------------ A7: Essential Matrix Module
-def essential_matrix_module(x1, x2, p, prefix, intrinsics=None, return_bilinear=False):
+def essential_matrix_module(x1, x2, p, prefix, intrinsics=None, return_bilinear=False, flags=()):
     """CrossAttention.forward, non-noess branch, vision_transformer.py:188-238.
     x1,x2 [B,576,192] (already norm1'ed).  Returns (Y2, Y1) -- note the flip at :238."""
     dt = x1.dtype.type
@@ -262,14 +263,21 @@ def essential_matrix_module(x1, x2, p, prefix, intrinsics=None, return_bilinear=
     scale = dt(HDIM ** -0.5)
     s1 = (q2 @ k1.transpose(0, 1, 3, 2)) * scale      # :198
     s2 = (q1 @ k2.transpose(0, 1, 3, 2)) * scale      # :199
-    a1 = softmax(s1, -1) * softmax(s1, -2)            # :205
-    a2 = softmax(s2, -1) * softmax(s2, -2)            # :206
-    pos = positional_encodings(B, intrinsics).astype(dt)                     # :211
+    if "use_single_softmax" in flags:                 # :201-203
+        a1, a2 = softmax(s1, -1), softmax(s2, -1)
+    else:
+        a1 = softmax(s1, -1) * softmax(s1, -2)        # :205
+        a2 = softmax(s2, -1) * softmax(s2, -2)        # :206
+    pos = positional_encodings(B, intrinsics, "l1_pos_encoding" in flags).astype(dt)      # :208-211
     posh = np.broadcast_to(pos[:, None], (B, HEADS, NTOK, NPOS))
     V1 = np.concatenate([v1, posh], 3)                # :215
     V2 = np.concatenate([v2, posh], 3)                # :216
-    f1 = (V1.transpose(0, 1, 3, 2) @ a1) @ V1         # :222  [B,3,70,70]
-    f2 = (V2.transpose(0, 1, 3, 2) @ a2) @ V2         # :223
+    if "cross_features" in flags:                     # :219-220
+        f1 = (V2.transpose(0, 1, 3, 2) @ a1) @ V1
+        f2 = (V1.transpose(0, 1, 3, 2) @ a2) @ V2
+    else:
+        f1 = (V1.transpose(0, 1, 3, 2) @ a1) @ V1     # :222  [B,3,70,70]
+        f2 = (V2.transpose(0, 1, 3, 2) @ a2) @ V2     # :223
     z1 = f1.reshape(B, HEADS * EMW, EMW).transpose(0, 2, 1)   # :229  Z[b,c,h*70+a] = F[b,h,a,c]
     z2 = f2.reshape(B, HEADS * EMW, EMW).transpose(0, 2, 1)   # :230
     y2 = linear(z2, p[prefix + ".proj_fundamental.weight"], p[prefix + ".proj_fundamental.bias"])
@@ -279,13 +287,13 @@ def essential_matrix_module(x1, x2, p, prefix, intrinsics=None, return_bilinear=
     return y2, y1
 
 
-def cross_block(x, p, prefix, intrinsics=None, return_bilinear=False):
+def cross_block(x, p, prefix, intrinsics=None, return_bilinear=False, flags=()):
     """CrossBlock.forward, vision_transformer.py:285-296.  x [2B,576,192] -> [2B,70,192]."""
     n2, N, C = x.shape
     xp = x.reshape(n2 // 2, 2, N, C)
     g, b = p[prefix + ".norm1.weight"], p[prefix + ".norm1.bias"]
     res = essential_matrix_module(layernorm(xp[:, 0], g, b), layernorm(xp[:, 1], g, b), p,
-                                  prefix + ".cross_attn", intrinsics, return_bilinear)
+                                  prefix + ".cross_attn", intrinsics, return_bilinear, flags)
     (fa, fb), bil = (res if return_bilinear else (res, None))
     f = np.stack([fa, fb], 1).reshape(n2, EMW, C)
     out = f + mlp(layernorm(f, p[prefix + ".norm2.weight"], p[prefix + ".norm2.bias"]), p, prefix + ".mlp")
@@ -310,7 +318,7 @@ def normalize_preds(Gs, pose_preds):
 
 
 # ------------------------------------------------------------------ the whole path
-def vitess_forward(images, Gs, intrinsics, p, dtype=np.float32, depth=6, stages=None):
+def vitess_forward(images, Gs, intrinsics, p, dtype=np.float32, depth=6, stages=None, flags=()):
     """ViTEss.forward (src/model.py:161-191), default flags.  `p` maps state-dict keys to
     numpy arrays.  If `stages` is a dict it is filled with named intermediate activations.
     Returns ([B,2,7] poses, rescaled intrinsics)."""
@@ -329,7 +337,7 @@ def vitess_forward(images, Gs, intrinsics, p, dtype=np.float32, depth=6, stages=
         x = block(x, p, f"fusion_transformer.blocks.{i}")
         if stages is not None:
             stages[f"block{i}"] = x
-    x, bil = cross_block(x, p, f"fusion_transformer.blocks.{depth - 1}", intr, return_bilinear=True)
+    x, bil = cross_block(x, p, f"fusion_transformer.blocks.{depth - 1}", intr, return_bilinear=True, flags=flags)
     if stages is not None:
         stages["bilinear1"], stages["bilinear2"] = bil
         stages["cross"] = x

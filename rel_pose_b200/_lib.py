@@ -51,6 +51,8 @@ _SIGNATURES = {
     "rp_self_attention_tc": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_posenc_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_essential_workspace_bytes": (_c_size, [_c_int]),
+    "rp_posenc_ex_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr]),
+    "rp_essential_ex_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_essential_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_essential_tc_workspace_bytes": (_c_size, [_c_int, _c_int]),
     "rp_essential_tc": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _c_size, _c_int, _ptr]),

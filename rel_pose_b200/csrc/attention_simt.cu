@@ -249,7 +249,7 @@ constexpr int AC_SMEM = (TILE * LQ * 2 + TILE * LP * 3 + TILE + NTOK) * (int)siz
 
 __global__ void __launch_bounds__(THREADS, 2)
 em_accum_kernel(const float* __restrict__ qkv, const float* __restrict__ pos, const float* __restrict__ lse,
-                float* __restrict__ part, int width) {
+                float* __restrict__ part, int width, int flags) {
     extern __shared__ __align__(16) float sm[];
     float* Qs = sm;                    // [64][LQ]   q rows of this row tile
     float* Ks = Qs + TILE * LQ;        // [64][LQ]
@@ -265,12 +265,16 @@ em_accum_kernel(const float* __restrict__ qkv, const float* __restrict__ pos, co
     const float* qsrc = qkv + (size_t)q_img * NTOK * LDQKV + h * HD;
     const float* ksrc = qkv + (size_t)kv_img * NTOK * LDQKV + RP_EMBED + h * HD;
     const float* vsrc = qkv + (size_t)kv_img * NTOK * LDQKV + 2 * RP_EMBED + h * HD;
+    // left factor of V^T A V: the key/value image's own [v|pos] (vision_transformer.py:222-223) or, with
+    // --cross_features, the query image's (:219-220)
+    const float* vleft = (flags & RP_EM_CROSS_FEATURES) ? qkv + (size_t)q_img * NTOK * LDQKV + 2 * RP_EMBED + h * HD : vsrc;
+    const bool single = (flags & RP_EM_SINGLE_SOFTMAX) != 0;       // --use_single_softmax (:201-203)
     const float* posb = pos ? pos + (size_t)b * NTOK * RP_NPOS : nullptr;
     const float* lse_r = lse + ((((size_t)b * 2 + dir) * 2 + 0) * RP_HEADS + h) * NTOK;
     const float* lse_c = lse + ((((size_t)b * 2 + dir) * 2 + 1) * RP_HEADS + h) * NTOK;
 
     load_tile64<LQ>(Qs, qsrc + (size_t)(it * TILE) * LDQKV, tid);
-    load_vpos_tile(Vi, vsrc, posb, it * TILE, tid);
+    load_vpos_tile(Vi, vleft, posb, it * TILE, tid);
     rp::cp_async_commit();
     for (int c = tid; c < TILE; c += THREADS) lr[c] = lse_r[it * TILE + c];
     for (int c = tid; c < NTOK; c += THREADS) lc[c] = lse_c[c];
@@ -298,7 +302,8 @@ em_accum_kernel(const float* __restrict__ qkv, const float* __restrict__ pos, co
             for (int jj = 0; jj < 8; ++jj) {
                 float sv = s[ii][jj] * 0.125f;
                 // softmax(S,-1)*softmax(S,-2) = exp(S-lse_r) * exp(S-lse_c)      (:205-206)
-                Ps[(ty + 16 * ii) * LP + tx + 8 * jj] = expf((sv - r) + (sv - lc[jt * TILE + tx + 8 * jj]));
+                Ps[(ty + 16 * ii) * LP + tx + 8 * jj] =
+                    single ? expf(sv - r) : expf((sv - r) + (sv - lc[jt * TILE + tx + 8 * jj]));
             }
         }
         __syncwarp();
@@ -459,7 +464,13 @@ extern "C" size_t rp_essential_workspace_bytes(int B) {
 
 extern "C" int rp_essential_f32(const float* qkv, const float* pos, float* bil, int B, void* workspace,
                                 size_t workspace_bytes, int device, void* stream) {
-    RP_REQUIRE(qkv && bil && B > 0, RP_EINVAL, "rp_essential: bad argument");
+    return rp_essential_ex_f32(qkv, pos, bil, B, 0, workspace, workspace_bytes, device, stream);
+}
+
+extern "C" int rp_essential_ex_f32(const float* qkv, const float* pos, float* bil, int B, int flags, void* workspace,
+                                   size_t workspace_bytes, int device, void* stream) {
+    RP_REQUIRE(qkv && bil && B > 0 && (flags & ~(RP_EM_SINGLE_SOFTMAX | RP_EM_CROSS_FEATURES)) == 0, RP_EINVAL,
+               "rp_essential: bad argument");
     RP_REQUIRE(rp::aligned16(qkv), RP_EALIGN, "rp_essential: qkv must be 16-byte aligned");
     RP_REQUIRE(workspace && workspace_bytes >= rp_essential_workspace_bytes(B), RP_EWORKSPACE,
                "rp_essential: workspace %zu < %zu bytes", workspace_bytes, rp_essential_workspace_bytes(B));
@@ -476,7 +487,7 @@ extern "C" int rp_essential_f32(const float* qkv, const float* pos, float* bil, 
     em_stats_kernel<<<dim3(NTILES, RP_HEADS, B * 4), THREADS, ST_SMEM, st>>>(qkv, lse);
     rc = rp::finish_launch("rp_essential(stats)");
     if (rc) return rc;
-    em_accum_kernel<<<dim3(NTILES, RP_HEADS, B * 2), THREADS, AC_SMEM, st>>>(qkv, pos, lse, part, width);
+    em_accum_kernel<<<dim3(NTILES, RP_HEADS, B * 2), THREADS, AC_SMEM, st>>>(qkv, pos, lse, part, width, flags);
     rc = rp::finish_launch("rp_essential(accum)");
     if (rc) return rc;
     size_t n_mats = (size_t)B * 2 * RP_HEADS;

@@ -256,7 +256,7 @@ struct Lin24 {
     float v[RP_GRID];
 };
 
-__global__ void posenc_kernel(const float* __restrict__ kxy, Lin24 lin, float* __restrict__ pos, int B) {
+__global__ void posenc_kernel(const float* __restrict__ kxy, Lin24 lin, float* __restrict__ pos, int B, int l1) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * RP_NTOK) return;
     int b = idx / RP_NTOK, i = idx % RP_NTOK;
@@ -267,21 +267,27 @@ __global__ void posenc_kernel(const float* __restrict__ kxy, Lin24 lin, float* _
         p3 = __fmul_rn(kxy[b * 2 + 1], p3);
     }
     float* o = pos + (long long)idx * RP_NPOS;
-    o[0] = __fmul_rn(p3, p3);
-    o[1] = __fmul_rn(p4, p4);
-    o[2] = __fmul_rn(p3, p4);
+    // --l1_pos_encoding (get_l1_positional_encodings, vision_transformer.py:36-87): the quadratic channels stay 1
+    o[0] = l1 ? 1.0f : __fmul_rn(p3, p3);
+    o[1] = l1 ? 1.0f : __fmul_rn(p4, p4);
+    o[2] = l1 ? 1.0f : __fmul_rn(p3, p4);
     o[3] = p3;
     o[4] = p4;
     o[5] = 1.0f;
 }
 
 extern "C" int rp_posenc_f32(const float* kxy, const float* host_lin24, float* pos, int B, int device, void* stream) {
+    return rp_posenc_ex_f32(kxy, host_lin24, pos, B, 0, device, stream);
+}
+
+extern "C" int rp_posenc_ex_f32(const float* kxy, const float* host_lin24, float* pos, int B, int l1, int device,
+                                void* stream) {
     RP_REQUIRE(host_lin24 && pos && B > 0, RP_EINVAL, "rp_posenc: bad argument");
     RP_GUARD(device);
     Lin24 lin;
     memcpy(lin.v, host_lin24, sizeof(lin.v));
     int total = B * RP_NTOK;
-    posenc_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kxy, lin, pos, B);
+    posenc_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kxy, lin, pos, B, l1);
     return rp::finish_launch("rp_posenc");
 }
 

@@ -100,12 +100,19 @@ def _flag(args, name, default=False):
 class ViTEss(nn.Module):
     def __init__(self, args):
         super().__init__()
-        # Only the configuration every reference script runs is built natively:
-        # --fusion_transformer, dual softmax, quadratic positional encoding.
-        for name in ("noess", "cross_features", "use_single_softmax", "no_pos_encoding", "l1_pos_encoding"):
+        # The configuration every reference script runs (--fusion_transformer, dual softmax, quadratic positional
+        # encoding) is the hot path.  Of the ablation branches the three that only vary the
+        # Essential Matrix Module are supported -- --use_single_softmax / --cross_features on the fp32 SIMT module
+        # kernels (rp_essential_ex_f32), --l1_pos_encoding in every precision -- inference only.
+        for name in ("noess", "no_pos_encoding"):
             if _flag(args, name):
                 raise NotImplementedError(
-                    f"--{name} is an ablation branch outside the B200 hot path (SURVEY.md 8(f) rank 4)")
+                    f"--{name} is an ablation branch outside the B200 hot path (SURVEY.md 8(f) rank 4)"
+                    + ("; the reference itself cannot run it: proj_fundamental stays 210 wide (vision_transformer.py:179,226)"
+                       if name == "no_pos_encoding" else ""))
+        self.em_flags = (ops.EM_SINGLE_SOFTMAX if _flag(args, "use_single_softmax") else 0) | \
+                        (ops.EM_CROSS_FEATURES if _flag(args, "cross_features") else 0)
+        self.l1_pos_encoding = bool(_flag(args, "l1_pos_encoding"))
         if not _flag(args, "fusion_transformer", False):
             raise NotImplementedError("the CNN-only path (no --fusion_transformer) is outside the B200 hot path")
         self.noess = None
@@ -302,9 +309,14 @@ class ViTEss(nn.Module):
             h = ops.layernorm(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)     # norm1 on both views
             qkv = ops.linear(h, ca.qkv.weight, ca.qkv.bias)
         else:
-            qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
-        pos = ops.posenc(B, kxy, x.device)
-        bil = ops.essential(qkv, pos) if P == 0 else ops.essential_tc(qkv, pos)
+            if self.em_flags:
+                # ablation variants of the module run on the fp32 SIMT kernels: ask the projection for float32 qkv
+                qkv = ops.ln_linear_tc(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, self._planes(ca.qkv.weight, P),
+                                       ca.qkv.bias, want_f32=True)[0]
+            else:
+                qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
+        pos = ops.posenc(B, kxy, x.device, self.l1_pos_encoding)
+        bil = ops.essential(qkv, pos, self.em_flags) if (P == 0 or self.em_flags) else ops.essential_tc(qkv, pos)
         if stages is not None:
             stages["bilinear1"], stages["bilinear2"] = bil[:, 0], bil[:, 1]
         f = ops.em_project(bil, ca.proj_fundamental.weight, ca.proj_fundamental.bias)
@@ -329,6 +341,8 @@ class ViTEss(nn.Module):
         if not images.is_cuda:
             raise ops._lib.RelposeLibraryError("ViTEss.forward: images must live on a CUDA device (no CPU fallback)")
         if self.training and torch.is_grad_enabled():
+            if self.em_flags or self.l1_pos_encoding:
+                raise NotImplementedError("the ablation branches are built for inference only")
             # train.py:155 -- batch-statistics BatchNorm, autograd through the CUDA kernels (train_path.py)
             from . import train_path
             out = SE3(train_path.forward_train(self, images, Gs, intrinsics))

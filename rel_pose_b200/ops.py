@@ -465,20 +465,23 @@ def lin24():
     return _LIN24
 
 
-def posenc(B, kxy, device):
-    """[B,576,6] positional monomials; kxy [B,2] or None (intrinsics=None)."""
+EM_SINGLE_SOFTMAX, EM_CROSS_FEATURES = 1, 2      # RP_EM_* flags of rp_essential_ex_f32
+
+
+def posenc(B, kxy, device, l1=False):
+    """[B,576,6] positional monomials; kxy [B,2] or None (intrinsics=None).  l1: --l1_pos_encoding ([1,1,1,p3,p4,1])."""
     pos = torch.empty((B, NTOK, NPOS), dtype=torch.float32, device=device)
     if kxy is not None:
         _req(kxy, "kxy")
     t = lin24()
     dev, st = _ctx(pos)
-    _lib.check(_lib.lib().rp_posenc_f32(_p(kxy), ctypes.c_void_p(t.data_ptr()), _p(pos), B, dev, st), "rp_posenc")
+    _lib.check(_lib.lib().rp_posenc_ex_f32(_p(kxy), ctypes.c_void_p(t.data_ptr()), _p(pos), B, int(bool(l1)), dev, st), "rp_posenc")
     _count()
     return pos
 
 
-def essential(qkv, pos):
-    """qkv [2B,576,576], pos [B,576,6] or None -> bilinear forms [B,2,3,W,W]."""
+def essential(qkv, pos, flags=0):
+    """qkv [2B,576,576], pos [B,576,6] or None -> bilinear forms [B,2,3,W,W].  flags: EM_SINGLE_SOFTMAX | EM_CROSS_FEATURES."""
     _req(qkv, "qkv")
     B = qkv.shape[0] // 2
     assert qkv.shape[0] == 2 * B and tuple(qkv.shape[1:]) == (NTOK, 3 * EMBED)
@@ -494,7 +497,7 @@ def essential(qkv, pos):
     # per (pair, head, direction): scores 2*N*N*64 (x3: two stat passes + recompute), A*V 2*N*N*W, V^T*T 2*N*W*W
     _tbegin("essential", B * 2.0 * HEADS * (2.0 * NTOK * NTOK * HDIM + 2.0 * NTOK * NTOK * width + 2.0 * NTOK * width * width),
             4.0 * (2 * B * NTOK * 3 * EMBED + B * 2 * HEADS * width * width))
-    _lib.check(L.rp_essential_f32(_p(qkv), _p(pos), _p(bil), B, _p(ws), ws_bytes, dev, st), "rp_essential")
+    _lib.check(L.rp_essential_ex_f32(_p(qkv), _p(pos), _p(bil), B, int(flags), _p(ws), ws_bytes, dev, st), "rp_essential")
     _count(3)
     return bil
 

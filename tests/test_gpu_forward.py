@@ -20,21 +20,28 @@ CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, 
 TOK = (slice(None), slice(None, None, 9), slice(None, None, 4))
 
 
-def _args():
-    return argparse.Namespace(noess=False, pool_size=60, fc_hidden_size=512, fusion_transformer=True,
-                              transformer_depth=6, cross_features=False, use_single_softmax=False,
-                              no_pos_encoding=False, l1_pos_encoding=False)
+def _args(flags=()):
+    a = argparse.Namespace(noess=False, pool_size=60, fc_hidden_size=512, fusion_transformer=True,
+                           transformer_depth=6, cross_features=False, use_single_softmax=False,
+                           no_pos_encoding=False, l1_pos_encoding=False)
+    for f in flags:                      # ablation branches of the Essential Matrix Module
+        setattr(a, f, True)
+    return a
+
+
+def _flags(g):
+    return tuple(f for f in (str(g["flags"]).split(",") if "flags" in g.files else []) if f)
 
 
 _models = {}
 
 
-def _model(seed, profile):
+def _model(seed, profile, flags=()):
     from rel_pose_b200 import ViTEss
-    key = (seed, profile)
+    key = (seed, profile, flags)
     if key not in _models:
         _models.clear()
-        m = ViTEss(_args())
+        m = ViTEss(_args(flags))
         m.load_state_dict(S.make_state_dict(seed, profile))
         m.precision = "fp32"          # these tests pin the fp32 engine unless they select a tensor-core mode
         _models[key] = m.to(DEV).eval()
@@ -54,7 +61,7 @@ def test_forward_matches_reference_golden(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     seed, B, H, W, integer = (int(v) for v in g["meta"])
     profile, ikind = str(g["profile"]), str(g["intrinsics_kind"])
-    m = _model(seed, profile)
+    m = _model(seed, profile, _flags(g))
     m.capture_stages = True
     images = torch.from_numpy(S.make_images_numpy(seed, B, H, W, bool(integer))).to(DEV)
     intr = None if ikind == "none" else torch.from_numpy(S.make_intrinsics_numpy(B, ikind, seed)).to(DEV)
@@ -72,8 +79,8 @@ def test_forward_matches_reference_golden(name):
     _err("tokens", st["tokens"][TOK], g["stage_tokens"], 2e-4, 2e-4)
     for i in range(5):
         _err(f"block{i}", st[f"block{i}"][TOK], g[f"stage_block{i}"], 5e-4, 5e-4)
-    _err("bilinear1", st["bilinear1"], g["stage_bilinear1"], 2e-5, 1e-3)
-    _err("bilinear2", st["bilinear2"], g["stage_bilinear2"], 2e-5, 1e-3)
+    for kk in ("bilinear1", "bilinear2"):     # absolute floor relative to the magnitude (single softmax: ~576x larger forms)
+        _err(kk, st[kk], g["stage_" + kk], 2e-5 + 2e-7 * float(np.abs(g["stage_" + kk]).max()), 1e-3)
     _err("features", st["features"][:, ::3], g["stage_features"], 1e-3, 1e-3)
     rot = O.rotation_error_rad(poses[:, 1, 3:], g["poses"][:, 1, 3:])
     tr = O.translation_rel_error(poses[:, 1, :3], g["poses"][:, 1, :3])
@@ -92,7 +99,7 @@ def test_forward_tensor_core_precisions(name, precision):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     seed, B, H, W, integer = (int(v) for v in g["meta"])
     profile, ikind = str(g["profile"]), str(g["intrinsics_kind"])
-    m = _model(seed, profile)
+    m = _model(seed, profile, _flags(g))
     images = torch.from_numpy(S.make_images_numpy(seed, B, H, W, bool(integer))).to(DEV)
     intr = None if ikind == "none" else torch.from_numpy(S.make_intrinsics_numpy(B, ikind, seed)).to(DEV)
     Gs = SE3.Identity(B, 2, device=DEV)

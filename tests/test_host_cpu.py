@@ -57,11 +57,17 @@ def test_state_dict_layout_matches_reference_spec():
     assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 19258510
 
 
-def test_ablation_flags_are_rejected_loudly():
-    from rel_pose_b200 import ViTEss
-    for flag in ("noess", "cross_features", "use_single_softmax", "no_pos_encoding", "l1_pos_encoding"):
+def test_ablation_flags():
+    """--noess / --no_pos_encoding / CNN-only are rejected loudly; the Essential-Matrix-Module variants are accepted."""
+    from rel_pose_b200 import ViTEss, ops
+    for flag in ("noess", "no_pos_encoding"):
         with pytest.raises(NotImplementedError):
             ViTEss(_args(**{flag: True}))
+    with pytest.raises(NotImplementedError):
+        ViTEss(_args(fusion_transformer=False))
+    m = ViTEss(_args(cross_features=True, use_single_softmax=True, l1_pos_encoding=True))
+    assert m.em_flags == (ops.EM_SINGLE_SOFTMAX | ops.EM_CROSS_FEATURES) and m.l1_pos_encoding
+    assert ViTEss(_args()).em_flags == 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-CUDA behaviour")

@@ -19,7 +19,8 @@ def _load(name):
     seed, B, H, W, integer = (int(v) for v in g["meta"])
     profile = str(g["profile"])
     ikind = str(g["intrinsics_kind"])
-    return g, seed, B, H, W, bool(integer), profile, (None if ikind == "none" else ikind)
+    flags = tuple(f for f in (str(g["flags"]).split(",") if "flags" in g.files else []) if f)   # ablation branches (8 f-4)
+    return g, seed, B, H, W, bool(integer), profile, (None if ikind == "none" else ikind), flags
 
 
 def test_have_cases():
@@ -51,14 +52,14 @@ def test_posenc_golden_bit_exact():
 
 @pytest.mark.parametrize("name", CASES)
 def test_forward_matches_reference(name):
-    g, seed, B, H, W, integer, profile, ikind = _load(name)
+    g, seed, B, H, W, integer, profile, ikind, flags = _load(name)
     p = S.make_state_dict_numpy(seed, profile)
     images = S.make_images_numpy(seed, B, H, W, integer)
     intr = None if ikind is None else S.make_intrinsics_numpy(B, ikind, seed)
     Gs = np.zeros((B, 2, 7), np.float32)
     Gs[..., 6] = 1
     st = {}
-    poses, intr_after = O.vitess_forward(images, Gs, intr, p, np.float32, stages=st)
+    poses, intr_after = O.vitess_forward(images, Gs, intr, p, np.float32, stages=st, flags=flags)
     # bit-exact index work
     assert np.array_equal(st["preprocessed"][:, :, ::7, ::5], g["stage_preprocessed"])
     if intr is not None:
@@ -67,8 +68,9 @@ def test_forward_matches_reference(name):
     np.testing.assert_allclose(st["tokens"][TOK], g["stage_tokens"], **tol)
     for i in range(5):
         np.testing.assert_allclose(st[f"block{i}"][TOK], g[f"stage_block{i}"], rtol=5e-4, atol=5e-4)
-    np.testing.assert_allclose(st["bilinear1"], g["stage_bilinear1"], rtol=1e-3, atol=2e-5)
-    np.testing.assert_allclose(st["bilinear2"], g["stage_bilinear2"], rtol=1e-3, atol=2e-5)
+    # absolute floor relative to the magnitude of the forms: with --use_single_softmax they are ~576x larger
+    for kk in ("bilinear1", "bilinear2"):
+        np.testing.assert_allclose(st[kk], g["stage_" + kk], rtol=1e-3, atol=2e-5 + 2e-7 * np.abs(g["stage_" + kk]).max())
     np.testing.assert_allclose(st["features"][:, ::3], g["stage_features"], rtol=1e-3, atol=1e-3)
     rot = O.rotation_error_rad(poses[:, 1, 3:], g["poses"][:, 1, 3:])
     tr = O.translation_rel_error(poses[:, 1, :3], g["poses"][:, 1, :3])
@@ -81,7 +83,9 @@ def test_forward_matches_reference(name):
 def test_torch_port_matches_reference(name):
     """The CPU-baseline port (oracle/torch_port.py) is pinned to the same golden vectors."""
     import torch_port
-    g, seed, B, H, W, integer, profile, ikind = _load(name)
+    g, seed, B, H, W, integer, profile, ikind, flags = _load(name)
+    if flags:
+        pytest.skip("the CPU-baseline port covers the default configuration only")
     p = S.make_state_dict_numpy(seed, profile)
     images = S.make_images_numpy(seed, B, H, W, integer)
     intr = None if ikind is None else S.make_intrinsics_numpy(B, ikind, seed)
