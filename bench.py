@@ -136,6 +136,29 @@ def time_cpu(run, batch, min_seconds, max_iters):
     return batch * n / dt, n, dt
 
 
+_JSON_FD = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." to stdout
+    when NCCL_DEBUG=VERSION is set in the environment): everything written to fd 1 during the run goes to stderr, the
+    JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -159,7 +182,7 @@ def run_reference_arm(a):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -182,6 +205,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="arithmetic of the transformer GEMMs (fp32 SIMT | tcgen05 split-bf16 | tcgen05 bf16)")
     a = ap.parse_args()
+    guard_stdout()
     if a.impl == "reference":
         return run_reference_arm(a)
 
@@ -366,7 +390,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{n} forwards x {a.ref_batch} pairs of {size}x{size} in {dt:.1f} s on "
                                               f"{cores} host threads; {desc}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
