@@ -127,6 +127,15 @@ int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* be
 int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
                  float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
                  void* stream);
+/* 3x3 / stride 1 / pad 1 convolution with 64 input channels (ResNet layer1, src/model.py:127-131), "halo" variant of
+ * rp_conv2d_tc: one TMA box per tile brings the activation halo, the nine filter taps read it through shifted
+ * shared-memory descriptors (2x less L2 -> SM traffic on layers that are bound by it).  Same operands and epilogue
+ * as rp_conv2d_tc (no res_post).  rp_conv3x3_halo_supported tells whether a shape qualifies. */
+int rp_conv3x3_halo_supported(int H, int W, int C, int O, int KH, int KW, int stride, int pad);
+int rp_conv3x3_halo_tc(const void* x_planes, const void* w_planes, const float* scale, const float* shift,
+                       const float* res_pre, float* out_f32, void* out_planes, int n_img, int H, int W, int C, int O,
+                       int P, int P_out, int act, int device, void* stream);
+
 /* LayerNorm fused into a projection  out = LayerNorm(x) W^T + bias  in one launch: `self.qkv(self.norm1(x))` of
  * Block / Attention.forward (vision_transformer.py:350,323) and of CrossBlock / CrossAttention.forward
  * (vision_transformer.py:288-289,191-194).  x float32 [M,K]; W_planes bf16 [P][N][K]; outputs as in rp_linear_tc

@@ -3,12 +3,14 @@ streams; every computation below is a call into librelpose_b200.so.  Inputs must
 there is no CPU or eager-PyTorch fallback.
 """
 import ctypes
+import os
 
 import torch
 
 from . import _lib
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+CONV_HALO = os.environ.get("RELPOSE_CONV_HALO", "1") != "0"      # halo variant of the 3x3 / 64-channel convolutions
 NTOK, EMBED, HEADS, HDIM, NPOS, EMW = 576, 192, 3, 64, 6, 70
 
 _launch_count = 0     # number of kernels launched through the library (bench.py reports it)
@@ -400,6 +402,16 @@ def conv2d_tc(x_planes, w_planes, KH, KW, scale=None, shift=None, stride=1, pad=
     outp = torch.empty((planes_out, n, Ho, Wo, O), dtype=torch.bfloat16, device=x_planes.device) if planes_out else None
     dev, st = _ctx(x_planes)
     M, K = n * Ho * Wo, KH * KW * C
+    L = _lib.lib()
+    if (CONV_HALO and res_post is None and act in (ACT_NONE, ACT_RELU)
+            and L.rp_conv3x3_halo_supported(H, W, C, O, KH, KW, stride, pad)):
+        # layers bound by L2 -> SM traffic: one halo box per tile, taps as shifted descriptors (csrc/conv_halo_tc.cu)
+        _tbegin(f"conv_halo_tc{'x3' if P == 2 else ''}[{O}x{KH}x{KW}x{C}/s{stride}]", 2.0 * M * O * K,
+                2.0 * P * (x_planes[0].numel() + O * K) + (4.0 * M * O if want_f32 else 0.0) + 2.0 * planes_out * M * O)
+        _lib.check(L.rp_conv3x3_halo_tc(_p(x_planes), _p(w_planes), _p(scale), _p(shift), _p(res_pre), _p(out), _p(outp),
+                                        n, H, W, C, O, P, int(planes_out), int(act), dev, st), "rp_conv3x3_halo_tc")
+        _count()
+        return out, outp
     _tbegin(f"conv_tc{'x3' if P == 2 else ''}[{O}x{KH}x{KW}x{C}/s{stride}]", 2.0 * M * O * K,
             2.0 * P * (x_planes[0].numel() + O * K) + (4.0 * M * O if want_f32 else 0.0) + 2.0 * planes_out * M * O)
     _lib.check(_lib.lib().rp_conv2d_tc(_p(x_planes), _p(w_planes), _p(scale), _p(shift), _p(res_pre), _p(res_post),

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import relpose_oracle as O
-from rel_pose_b200 import ops, synthetic as S
+from rel_pose_b200 import _lib, ops, synthetic as S
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -177,7 +177,8 @@ class _BN:
     (2, 20, 20, 64, 64, 3, 1, 1, False, 2, "pre"), (3, 56, 56, 64, 64, 3, 1, 1, False, 2, "none"),
     (2, 21, 19, 64, 128, 3, 2, 1, False, 2, "none"), (2, 56, 56, 64, 128, 1, 2, 0, False, 0, "none"),
     (2, 28, 28, 128, 128, 3, 1, 1, False, 2, "pre"), (2, 28, 28, 128, 192, 5, 1, 0, True, 2, "pre+post"),
-    (1, 28, 28, 192, 192, 5, 1, 0, True, 2, "none"), (5, 9, 130, 64, 64, 3, 1, 1, True, 0, "none")])
+    (1, 28, 28, 192, 192, 5, 1, 0, True, 2, "none"), (5, 9, 130, 64, 64, 3, 1, 1, True, 0, "none"),
+    (2, 13, 37, 64, 64, 3, 1, 1, True, 2, "pre"), (1, 7, 126, 64, 64, 3, 1, 1, False, 0, "none"), (2, 5, 8, 64, 128, 3, 1, 1, True, 2, "none")])
 def test_conv2d_tc(P, n, H, W, C, Oc, k, stride, pad, bias, act, res):
     if W > 128 and stride == 1 and (W + 2 * pad - k) // stride + 1 > 128:
         pytest.skip("output rows wider than 128 pixels are outside the tile scheme (not used by the model)")
@@ -219,6 +220,17 @@ def test_conv2d_tc(P, n, H, W, C, Oc, k, stride, pad, bias, act, res):
     assert np.isfinite(got).all() and err <= tol
     gp = planes_to_f64(outp).transpose(0, 3, 1, 2)
     assert np.abs(gp - got).max() <= (2.0 ** -15 if P == 2 else 2.0 ** -7) * np.abs(got).max()
+    if ops.CONV_HALO and rq is None and _lib.lib().rp_conv3x3_halo_supported(H, W, C, Oc, k, k, stride, pad):
+        # this shape ran on the halo kernel (conv_halo_tc.cu): same products in the same order as the per-tap kernel
+        ops.CONV_HALO = False
+        try:
+            out2, outp2 = ops.conv2d_tc(xp, wp, k, k, scale, shift, stride, pad, act,
+                                        cu(rp.transpose(0, 2, 3, 1)) if rp is not None else None, None, 0,
+                                        want_f32=True, planes_out=P)
+        finally:
+            ops.CONV_HALO = True
+        assert torch.equal(out, out2) and torch.equal(outp, outp2)
+        print(f"[parity] conv_halo_tc P={P} {C}->{Oc} {H}x{W}: bit-identical to the per-tap kernel")
 
 
 def test_maxpool_planes():
