@@ -113,13 +113,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Every shared-memory descriptor built in this library (K-major or MN-major, SWIZZLE_128B, SBO = 1024 B, sm_100
+// version bit) has the same upper word; only the lower word (start address, LBO) varies.  The MMA wrappers take the
+// 64-bit descriptor but hand the instruction {lower word, constant}: the issuing warp then moves ONE register per
+// descriptor into the uniform register file instead of two (R2UR is a large part of an issuer's instruction stream,
+// and the issuer's instruction stream is what bounds the small-N kernels).
+constexpr uint32_t DESC_HI = 0x40004040u;       // bits 32..63 of make_*_sw128_desc(): SBO >> 4 = 64, version 1, layout 2
+
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 operands, fp32 accumulate), issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"((uint32_t)adesc), "r"((uint32_t)bdesc), "r"(idesc), "r"(accumulate), "n"(DESC_HI)
         : "memory");
 }
 // Same with the A operand read from TENSOR MEMORY (K-major only): lane = row, 16-bit elements packed two per
@@ -128,10 +137,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 // elements is 8 columns.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"((uint32_t)bdesc), "r"(idesc), "r"(accumulate), "n"(DESC_HI)
         : "memory");
 }
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
@@ -226,7 +236,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= 1ull << 46;
     d |= 2ull << 61;
-    return d;
+    return d;                                  // upper word == DESC_HI
 }
 // Shared-memory matrix descriptor, MN-major operand (the MN index is the contiguous one): a tile stored as
 // K rows of 128 bytes (64 bf16 along MN) with the 128-byte swizzle -- exactly what a TMA box {64, K} produces.
