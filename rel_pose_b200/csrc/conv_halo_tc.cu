@@ -51,7 +51,10 @@ template <int P, int BN>
 struct HCfg {
     static constexpr int B_TILE = BN * 64 * 2;            // one filter tap, one plane
     static constexpr int STAGE_BYTES = P * B_TILE;
-    static constexpr int NSTAGE = 3;
+    // filter-tap ring depth.  A tap (16 KiB in bf16x3) is consumed in ~580 cycles of tensor work but takes ~2900 cycles
+    // to arrive (148 SMs fetch the same L2 lines): with 3 stages in flight the kernel ran at one tap per ~980 cycles
+    // whatever the issuer or the activation traffic did.  4 stages is what fits next to two halo buffers (bf16x3).
+    static constexpr int NSTAGE = (P == 1) ? 8 : 4;
 };
 
 template <int P, int BN>
@@ -129,20 +132,12 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (convergent warp)
-        // The issuer's own instruction stream is what bounds these layers (ncu + A/B: ~90 instructions = ~1000 cycles
-        // per 12-MMA tap next to 16 epilogue warps, against 576 cycles of tensor work; halving the L2 traffic alone
-        // changed nothing).  The tap loop is therefore fully unrolled: 9 taps = 3 turns of the 3-stage ring, so the
-        // stage of every tap, its filter descriptors and its halo shift are compile-time / kernel-lifetime constants.
+        // tap loop unrolled: halo shifts are constants, the filter descriptors are base + stage * stride
         constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
-        static_assert(TAPS % C::NSTAGE == 0, "the ring position must be the same at every tile start");
-        uint32_t phase = 0;                     // parity of ring turn 0 of the current tile
-        uint32_t it = 0;
-        uint64_t bd0[C::NSTAGE], bd1[C::NSTAGE];
-#pragma unroll
-        for (int s = 0; s < C::NSTAGE; ++s) {
-            bd0[s] = tc::make_kmajor_sw128_desc(tc::smem_u32(b_tile(s, 0)));
-            bd1[s] = tc::make_kmajor_sw128_desc(tc::smem_u32(b_tile(s, P - 1)));
-        }
+        int stage = 0;
+        uint32_t phase = 0, it = 0;
+        const uint64_t bd_base0 = tc::make_kmajor_sw128_desc(tc::smem_u32(b_tile(0, 0)));
+        const uint64_t bd_base1 = tc::make_kmajor_sw128_desc(tc::smem_u32(b_tile(0, P - 1)));
         const uint32_t row_shift = (uint32_t)(g.pitch * 128) >> 4;     // one halo row, in descriptor units
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const uint32_t hb = it & 1, acc = it & 1;
@@ -154,14 +149,13 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint64_t h1 = tc::make_kmajor_sw128_desc(tc::smem_u32(halo(hb, P - 1)));
 #pragma unroll
             for (int tap = 0; tap < TAPS; ++tap) {
-                constexpr int NS = C::NSTAGE;
-                const int stage = tap % NS;
-                tc::mbar_wait(&full[stage], phase ^ ((tap / NS) & 1));
+                tc::mbar_wait(&full[stage], phase);
                 tc::tcgen05_fence_after();
                 const int ky = tap / 3, kx = tap - 3 * ky;
                 const uint32_t shift = ky * row_shift + (uint32_t)(kx * 128 >> 4);      // whole 128-byte rows
                 const uint64_t a0 = h0 + shift, a1 = h1 + shift;
-                const uint64_t b0 = bd0[stage], b1 = bd1[stage];
+                const uint32_t soff = (uint32_t)stage * (uint32_t)(C::STAGE_BYTES >> 4);
+                const uint64_t b0 = bd_base0 + soff, b1 = bd_base1 + soff;
                 if (tc::elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -180,8 +174,8 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     }
                 }
                 __syncwarp();
+                if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
             }
-            phase ^= (TAPS / C::NSTAGE) & 1;    // three ring turns per tile: the parity flips from tile to tile
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..17), as in gemm_tc.cu
@@ -300,7 +294,7 @@ extern "C" int rp_conv3x3_halo_supported(int H, int W, int C, int O, int KH, int
     if (R > H) R = H;
     // two double-plane halo buffers + filter ring + staging must fit the 227 KiB of shared memory
     const int halo_bytes = (((R + 2) * (W + 2) * 128) + 1023) & ~1023;
-    return 4 * halo_bytes + 3 * 2 * O * 128 + STG_BYTES + 2048 <= 227 * 1024;
+    return 4 * halo_bytes + 4 * 2 * O * 128 + STG_BYTES + 2048 <= 227 * 1024;
 }
 
 extern "C" int rp_conv3x3_halo_tc(const void* x_planes, const void* w_planes, const float* scale, const float* shift,
