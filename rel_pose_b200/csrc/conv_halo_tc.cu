@@ -201,13 +201,14 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 gok[t] = r < rows_valid && x < g.W;
                 grow[t] = row_base + (long long)r * g.W + x;
             }
-            tc::mbar_wait(&tfull[acc], (it >> 1) & 1);
-            tc::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+            bool waited = false;
 #pragma unroll 1
             for (int ci = 0; ci < CH_PER_PART; ++ci) {
                 const int c0 = (part * CH_PER_PART + ci) * 16;
                 const int col = c0 + cq * 4;
+                // per-channel constants and the residual rows are requested BEFORE waiting for the accumulator: the
+                // HBM round trip of the residual (~2 us) then hides behind this tile's MMAs
                 float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ep.scale) sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col));
                 if (ep.shift) sh = __ldg(reinterpret_cast<const float4*>(ep.shift + col));
@@ -216,6 +217,11 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 for (int t = 0; t < 4; ++t) {
                     rpre[t] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (gok[t] && ep.res_pre) rpre[t] = __ldg(reinterpret_cast<const float4*>(ep.res_pre + grow[t] * N + col));
+                }
+                if (!waited) {
+                    tc::mbar_wait(&tfull[acc], (it >> 1) & 1);
+                    tc::tcgen05_fence_after();
+                    waited = true;
                 }
                 uint32_t r[16];
                 tc::tmem_ld_32x32b_x16(t_row + c0, r);
