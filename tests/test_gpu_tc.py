@@ -178,7 +178,8 @@ class _BN:
     (2, 21, 19, 64, 128, 3, 2, 1, False, 2, "none"), (2, 56, 56, 64, 128, 1, 2, 0, False, 0, "none"),
     (2, 28, 28, 128, 128, 3, 1, 1, False, 2, "pre"), (2, 28, 28, 128, 192, 5, 1, 0, True, 2, "pre+post"),
     (1, 28, 28, 192, 192, 5, 1, 0, True, 2, "none"), (5, 9, 130, 64, 64, 3, 1, 1, True, 0, "none"),
-    (2, 13, 37, 64, 64, 3, 1, 1, True, 2, "pre"), (1, 7, 126, 64, 64, 3, 1, 1, False, 0, "none"), (2, 5, 8, 64, 128, 3, 1, 1, True, 2, "none")])
+    (2, 13, 37, 64, 64, 3, 1, 1, True, 2, "pre"), (1, 7, 126, 64, 64, 3, 1, 1, False, 0, "none"), (2, 5, 8, 64, 128, 3, 1, 1, True, 2, "none"),
+    (1, 13, 37, 64, 64, 3, 1, 1, False, 2, "none"), (3, 9, 56, 64, 64, 3, 1, 1, False, 2, "pre")])
 def test_conv2d_tc(P, n, H, W, C, Oc, k, stride, pad, bias, act, res):
     if W > 128 and stride == 1 and (W + 2 * pad - k) // stride + 1 > 128:
         pytest.skip("output rows wider than 128 pixels are outside the tile scheme (not used by the model)")

@@ -14,10 +14,10 @@ timeout 300 python tools/bench_geom.py > $OUT/geom.json 2> $OUT/geom.err; echo "
 timeout 600 python -m rel_pose_b200.train_synthetic --steps 20 --warmup_steps 5 --batch 6 > $OUT/train_fused.json 2> $OUT/train_fused.err; echo "train rc=$?"
 BENCH="python bench.py --steps 1 --warmup 1 --batch 64 --precision bf16x3 --no-cpu-baseline --no-e2e"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_bf16x3.csv $BENCH > $OUT/ncu_list.log 2>&1; echo "list rc=$?"
-for K in mlp_fused_tc_kernel self_attention_tc_kernel ln_linear_tc_kernel em_accum_tc_kernel; do
+for K in mlp_fused_tc_kernel self_attention_tc_kernel ln_linear_tc_kernel em_accum_tc_kernel conv3x3_halo_tc_kernel; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -f -o $OUT/final_$K $BENCH > $OUT/ncu_$K.log 2>&1; echo "$K rc=$?"
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 30 -c 14 -f -o $OUT/final_gemm_tc $BENCH > $OUT/ncu_gemm.log 2>&1; echo "gemm rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 26 -c 10 -f -o $OUT/final_gemm_tc $BENCH > $OUT/ncu_gemm.log 2>&1; echo "gemm rc=$?"
 python - <<PY
 import json
 for n in ("bench_default","bench_bf16"):
