@@ -127,6 +127,13 @@ int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* be
 int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
                  float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
                  void* stream);
+/* Split-K variant of rp_linear_tc for skinny, weight-bandwidth-bound layers (pose_regressor.0: K = 26 880,
+ * src/model.py:91-98,189): out_f32 = act(A W^T + bias), float32 partials of K / ksplit blocks in `workspace`
+ * (rp_linear_tc_splitk_workspace_bytes; ksplit_out may be NULL), added in a fixed order.  N % 4 == 0, K % 8 == 0. */
+size_t rp_linear_tc_splitk_workspace_bytes(int M, int N, int K, int* ksplit_out);
+int rp_linear_tc_splitk(const void* A_planes, const void* W_planes, const float* bias, float* out_f32, int M, int N, int K,
+                        int P, int act, void* workspace, size_t workspace_bytes, int device, void* stream);
+
 /* 3x3 / stride 1 / pad 1 convolution with 64 input channels (ResNet layer1, src/model.py:127-131), "halo" variant of
  * rp_conv2d_tc: one TMA box per tile brings the activation halo, the nine filter taps read it through shifted
  * shared-memory descriptors (2x less L2 -> SM traffic on layers that are bound by it).  Same operands and epilogue

@@ -50,6 +50,7 @@ struct Cfg {
 
 struct Geom {
     int M, N, K;          // GEMM view: output rows (pixels), output columns, reduction length
+    int ksplit, kb_per_split;   // nn.Linear only: split the reduction over `ksplit` tiles writing float32 partials (0: off)
     // convolution only
     int Ho, Wo, R, tiles_per_img, C, KW, stride, pad, cblocks, taps;
 };
@@ -92,8 +93,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int M = g.M, N = g.N;
     const int tiles_n = CONV ? 1 : (N + BN - 1) / BN;
     const int tiles_m = CONV ? (g.M / (g.Ho * g.Wo)) * g.tiles_per_img : (M + BM - 1) / BM;
-    const int ntiles = tiles_m * tiles_n;
-    const int ksteps = CONV ? g.taps * g.cblocks : (g.K + BK - 1) / BK;
+    const int nsplit = (!CONV && g.ksplit > 1) ? g.ksplit : 1;
+    const int ntiles = tiles_m * tiles_n * nsplit;
+    const int ksteps_all = CONV ? g.taps * g.cblocks : (g.K + BK - 1) / BK;
+    // split-K (weight-bandwidth-bound skinny GEMMs: the 26880 -> 512 regressor layer): tile = (split, m, n), every
+    // split reduces kb_per_split K blocks into its own float32 partial [split][M][N]; short accumulation chains
+    auto k_range = [&](int tile, int& ks0, int& ks1) {
+        const int split = tile / (tiles_m * tiles_n);
+        ks0 = nsplit > 1 ? split * g.kb_per_split : 0;
+        ks1 = nsplit > 1 ? min(ksteps_all, ks0 + g.kb_per_split) : ksteps_all;
+    };
     // bytes one stage receives from TMA: full boxes, zero-filled where out of bounds
     const uint32_t stage_tx = CONV ? (uint32_t)(P * (g.R * g.Wo * 128 + C::B_TILE)) : (uint32_t)C::STAGE_BYTES;
 
@@ -123,10 +132,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ TMA producer (convergent warp)
         int stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+            const int tmn = tile % (tiles_m * tiles_n);
+            const int tm = tmn / tiles_n, n0 = (tmn % tiles_n) * BN;
             const int img = CONV ? tm / g.tiles_per_img : 0;
             const int oy0 = CONV ? (tm % g.tiles_per_img) * g.R : 0;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            int ks0, ks1;
+            k_range(tile, ks0, ks1);
+            for (int ks = ks0; ks < ks1; ++ks) {
                 tc::mbar_wait(&empty[stage], phase ^ 1);
                 if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(&full[stage], stage_tx);
@@ -159,7 +171,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc::tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            int ks0, ks1;
+            k_range(tile, ks0, ks1);
+            for (int ks = ks0; ks < ks1; ++ks) {
                 tc::mbar_wait(&full[stage], phase);
                 tc::tcgen05_fence_after();
                 // descriptors of the stage's tiles; a K step of 16 bf16 = 32 B inside the 128-byte swizzle row = +2
@@ -170,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (tc::elect_one_sync()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
+                        uint32_t accum = (ks > ks0 || k > 0) ? 1u : 0u;
                         // smallest terms first; all land in the same fp32 accumulator
                         if (P == 2) {
                             tc::umma_bf16(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, accum);
@@ -180,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tc::umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, accum);
                     }
                     tc::umma_commit(&empty[stage]);           // frees the smem slot when these MMAs retire
-                    if (ks + 1 == ksteps) tc::umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+                    if (ks + 1 == ks1) tc::umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -205,7 +219,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int NCHUNK = BN / 16;                  // 16-column chunks per tile (4, 8 or 12)
         constexpr int CH_PER_PART = NCHUNK / 4;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int tm = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+            const int tmn = tile % (tiles_m * tiles_n);
+            const int tm = tmn / tiles_n, n0 = (tmn % tiles_n) * BN;
+            float* const out_f32 = ep.out_f32 ? ep.out_f32 + (size_t)(tile / (tiles_m * tiles_n)) * M * N : nullptr;   // split-K partial
             int row_base, valid_rows;                    // global row of tile row 0; rows of the tile that exist
             if (CONV) {
                 const int img = tm / g.tiles_per_img, oy0 = (tm % g.tiles_per_img) * g.R;
@@ -268,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
                         }
                         v0 += rpost[it].x; v1 += rpost[it].y; v2 += rpost[it].z; v3 += rpost[it].w;
-                        if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + o) = make_float4(v0, v1, v2, v3);
+                        if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v0, v1, v2, v3);
                         if (ep.out_planes) {
                             for (int p = 0; p < ep.p_out; ++p) {
                                 __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
@@ -301,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int rq = ep.res_post_rows > 0 ? row % ep.res_post_rows : row;
                                 x += ep.res_post[(size_t)rq * N + colx + j];
                             }
-                            if (ep.out_f32) ep.out_f32[o + j] = x;
+                            if (out_f32) out_f32[o + j] = x;
                             if (ep.out_planes)
                                 for (int p = 0; p < ep.p_out; ++p) {
                                     __nv_bfloat16 h = __float2bfloat16_rn(x);
@@ -502,6 +518,76 @@ extern "C" int rp_maxpool3x3s2_planes(const float* x, float* y_f32, void* y_plan
         reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y_f32), static_cast<__nv_bfloat16*>(y_planes), P,
         n_img, H, W, C / 4, Ho, Wo);
     return rp::finish_launch("rp_maxpool3x3s2_planes");
+}
+
+// out[m][n] = act(bias[n] + sum over splits of part[s][m][n]), fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias,
+                                                            float* __restrict__ out, long long mn, int N, int nsplit, int act) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= mn) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s2 = 0; s2 < nsplit; ++s2) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)s2 * mn + i));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + (i % N)));
+        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    }
+    acc.x = act_fn(acc.x, act); acc.y = act_fn(acc.y, act); acc.z = act_fn(acc.z, act); acc.w = act_fn(acc.w, act);
+    *reinterpret_cast<float4*>(out + i) = acc;
+}
+
+extern "C" size_t rp_linear_tc_splitk_workspace_bytes(int M, int N, int K, int* ksplit_out) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const int kblocks = (K + BK - 1) / BK;
+    const int tiles_mn = ((M + BM - 1) / BM) * ((N + 191) / 192);
+    int want = (148 + tiles_mn - 1) / tiles_mn;            // about one tile per SM
+    if (want > kblocks) want = kblocks;
+    if (want < 1) want = 1;
+    const int kbps = (kblocks + want - 1) / want;
+    const int ksplit = (kblocks + kbps - 1) / kbps;
+    if (ksplit_out) *ksplit_out = ksplit;
+    return (size_t)ksplit * M * N * sizeof(float);
+}
+
+// Split-K nn.Linear for skinny problems whose time is the weight stream (pose_regressor.0: [B,26880] x [512,26880]^T,
+// src/model.py:91-98,189): every tile reduces a slice of K into a float32 partial, a second kernel adds the partials
+// in a fixed order and applies bias + activation.  Accumulation chains stay short (K / ksplit), which also keeps the
+// truncation bias of the tensor-memory accumulator away from a 26 880-long reduction.
+extern "C" int rp_linear_tc_splitk(const void* A_planes, const void* W_planes, const float* bias, float* out_f32, int M, int N,
+                                   int K, int P, int act, void* workspace, size_t workspace_bytes, int device, void* stream) {
+    RP_REQUIRE(A_planes && W_planes && out_f32 && workspace, RP_EINVAL, "rp_linear_tc_splitk: null pointer");
+    RP_REQUIRE(M > 0 && N > 0 && (N % 4) == 0 && K > 0 && (K % 8) == 0, RP_EINVAL, "rp_linear_tc_splitk: bad shape M=%d N=%d K=%d", M, N, K);
+    RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_linear_tc_splitk: P must be 1 or 2");
+    RP_REQUIRE(act >= RP_ACT_NONE && act <= RP_ACT_RELU, RP_EINVAL, "rp_linear_tc_splitk: bad act %d", act);
+    int ksplit = 1;
+    const size_t need = rp_linear_tc_splitk_workspace_bytes(M, N, K, &ksplit);
+    RP_REQUIRE(workspace_bytes >= need, RP_EWORKSPACE, "rp_linear_tc_splitk: workspace %zu < %zu bytes", workspace_bytes, need);
+    RP_REQUIRE(rp::aligned16(A_planes) && rp::aligned16(W_planes) && rp::aligned16(workspace) && rp::aligned16(out_f32) &&
+                   rp::aligned16(bias), RP_EALIGN, "rp_linear_tc_splitk: 16-byte alignment");
+    RP_GUARD(device);
+    constexpr int BN = 192;
+    CUtensorMap tmA, tmB;
+    int rc = tc::make_planes_tmap(&tmA, A_planes, P, M, K, BM);
+    if (rc) return rc;
+    rc = tc::make_planes_tmap(&tmB, W_planes, P, N, K, BN);
+    if (rc) return rc;
+    EpiParams ep{nullptr, nullptr, nullptr, nullptr, 0, static_cast<float*>(workspace), nullptr, 0, RP_ACT_NONE};
+    Geom g{};
+    g.M = M; g.N = N; g.K = K;
+    const int kblocks = (K + BK - 1) / BK;
+    g.ksplit = ksplit;
+    g.kb_per_split = (kblocks + ksplit - 1) / ksplit;
+    const int ntiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * ksplit;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = (P == 1) ? launch_gemm_tc<1, BN, false>(tmA, tmB, ep, g, ntiles, device, st, "rp_linear_tc_splitk")
+                  : launch_gemm_tc<2, BN, false>(tmA, tmB, ep, g, ntiles, device, st, "rp_linear_tc_splitk");
+    if (rc) return rc;
+    const long long mn = (long long)M * N;
+    splitk_reduce_kernel<<<(unsigned)((mn / 4 + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), bias, out_f32, mn, N,
+                                                                        ksplit, act);
+    return rp::finish_launch("rp_linear_tc_splitk(reduce)");
 }
 
 extern "C" int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,

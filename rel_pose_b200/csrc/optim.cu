@@ -72,7 +72,6 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
 struct AdamArgs {
     float max_norm;        // <= 0: no clipping
     float lr_over_bc1;     // lr / (1 - beta1^t)
-    float inv_bc2_sqrt;    // unused directly; kept for clarity
     float bc2_sqrt;        // sqrt(1 - beta2^t)
     float beta1, beta2, eps, weight_decay;
     float omb1, omb2;      // 1 - beta1, 1 - beta2 evaluated in double like torch's Python scalars
@@ -149,7 +148,6 @@ extern "C" int rp_adam_clip_step_multi(const void* descs, const int* blk_tensor,
     const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
     a.lr_over_bc1 = (float)(lr / bc1);
     a.bc2_sqrt = (float)sqrt(bc2);
-    a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
     a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.weight_decay = (float)weight_decay;
     a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
     adam_clip_multi_kernel<<<nblk, OPT_TPB, 0, (cudaStream_t)stream>>>(static_cast<const TensorDesc*>(descs), blk_tensor,

@@ -146,6 +146,7 @@ class ViTEss(nn.Module):
         # sequence for A/B measurements
         self.fused_mlp = os.environ.get("RELPOSE_FUSED_MLP", "1") != "0"
         self.fused_ln_qkv = os.environ.get("RELPOSE_FUSED_LNQKV", "1") != "0"     # csrc/ln_linear_tc.cu
+        self.tc_regressor = os.environ.get("RELPOSE_TC_REGRESSOR", "1") != "0"    # split-K tcgen05 GEMM for pose_regressor.0
         self.check_intrinsics = True      # reproduce the reference's assert on per-view intrinsics
         self.last_stages = None           # filled when `capture_stages` is set (parity tests)
         self.capture_stages = False
@@ -382,7 +383,12 @@ class ViTEss(nn.Module):
             x = ops.layernorm(x, vt.norm.weight, vt.norm.bias, vt.norm.eps)   # A9
             feat = x.reshape(B, -1)
             reg = self.pose_regressor
-            h = ops.linear(feat, reg[0].weight, reg[0].bias, act=ops.ACT_RELU)
+            if self._tc_planes() == 2 and self.tc_regressor:
+                # 26880 -> 512: 55 MB of weights for 64 rows; split-K on the tensor cores (bf16x3, short accumulation chains)
+                h = ops.linear_tc_splitk(ops.split_planes(feat.contiguous(), 2), self._planes(reg[0].weight, 2), reg[0].bias,
+                                         act=ops.ACT_RELU)
+            else:
+                h = ops.linear(feat, reg[0].weight, reg[0].bias, act=ops.ACT_RELU)
             h = ops.linear(h, reg[2].weight, reg[2].bias, act=ops.ACT_RELU)
             raw = ops.linear(h, reg[4].weight, reg[4].bias).reshape(B, 2, 7)
             if stages is not None:

@@ -347,6 +347,26 @@ def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f
     return out, outp
 
 
+def linear_tc_splitk(a_planes, w_planes, bias=None, act=ACT_NONE):
+    """Split-K tcgen05 GEMM for skinny weight-bandwidth-bound layers: a_planes [P,M,K] bf16, w_planes [P,N,K] -> float32 [M,N]."""
+    _req(a_planes, "a_planes", torch.bfloat16); _req(w_planes, "w_planes", torch.bfloat16)
+    P, M, K = a_planes.shape
+    N = w_planes.shape[1]
+    assert w_planes.shape[0] == P and w_planes.shape[2] == K
+    if bias is not None:
+        _req(bias, "bias")
+    L = _lib.lib()
+    ws_bytes = L.rp_linear_tc_splitk_workspace_bytes(M, N, K, None)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=a_planes.device)
+    out = torch.empty((M, N), dtype=torch.float32, device=a_planes.device)
+    dev, st = _ctx(a_planes)
+    _tbegin(f"linear_tc_splitk{'x3' if P == 2 else ''}[{N}x{K}]", 2.0 * M * N * K, 2.0 * P * (M * K + N * K) + 4.0 * M * N)
+    _lib.check(L.rp_linear_tc_splitk(_p(a_planes), _p(w_planes), _p(bias), _p(out), M, N, K, P, int(act), _p(ws), ws_bytes, dev, st),
+               "rp_linear_tc_splitk")
+    _count(2)
+    return out
+
+
 def ln_linear_tc(x, gamma, beta, eps, w_planes, bias=None, want_f32=False, planes_out=0):
     """Fused `linear(layernorm(x))` on tcgen05 (csrc/ln_linear_tc.cu): x float32 [...,192], w_planes bf16 [P,N,192]
     -> (float32 [...,N] | None, bf16 planes [planes_out,...,N] | None)."""

@@ -88,6 +88,24 @@ def test_linear_tc(P, M, N, K, act, res, pout):
         assert np.abs(gp - got).max() <= lim
 
 
+@pytest.mark.parametrize("M,N,K,act", [(64, 512, 26880, 2), (2, 512, 26880, 2), (130, 200, 1000, 0), (1, 512, 192, 0)])
+def test_linear_tc_splitk(M, N, K, act):
+    """rp_linear_tc_splitk (pose_regressor.0: short accumulation chains + fixed-order float32 reduction) against float64."""
+    a = rnd(11, M, K); w = rnd(12, N, K, scale=1.0 / np.sqrt(K)); b = rnd(13, N, scale=0.1)
+    out = ops.linear_tc_splitk(ops.split_planes(cu(a), 2), ops.split_planes(cu(w), 2), cu(b), act=act)
+    torch.cuda.synchronize()
+    y = a.astype(np.float64) @ w.astype(np.float64).T + b
+    if act == 2:
+        y = np.maximum(y, 0)
+    got = out.cpu().numpy().astype(np.float64)
+    err = np.abs(got - y).max()
+    tol = 4e-5 * np.abs(y).max()
+    print(f"[parity] linear_tc_splitk {M}x{N}x{K} act={act}: max_abs_err={err:.3e} max_ref={np.abs(y).max():.3e} ratio={err / tol:.3f}")
+    assert np.isfinite(got).all() and err <= tol
+    again = ops.linear_tc_splitk(ops.split_planes(cu(a), 2), ops.split_planes(cu(w), 2), cu(b), act=act)
+    assert torch.equal(out, again)
+
+
 def test_linear_tc_only_planes_output():
     a = rnd(9, 256, 192); w = rnd(10, 768, 192, scale=0.07)
     out, outp = ops.linear_tc(ops.split_planes(cu(a), 2), ops.split_planes(cu(w), 2), None, act=1, want_f32=False, planes_out=2)
