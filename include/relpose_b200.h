@@ -127,6 +127,12 @@ int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* be
 int rp_linear_tc(const void* A_planes, const void* W_planes, const float* bias, const float* residual,
                  float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out, int act, int device,
                  void* stream);
+/* pose_regressor[2:5] (src/model.py:93-97) in one launch: out [B,14] = W2 relu(W1 h + b1) + b2 for h [B,512]
+ * (the ReLU'ed output of layer 0).  W1T is pose_regressor.2.weight TRANSPOSED ([in][out], contiguous); W2 is
+ * pose_regressor.4.weight as stored ([14][512]). */
+int rp_regressor_tail_f32(const float* h, const float* W1T, const float* b1, const float* W2, const float* b2, float* out,
+                          int B, int hidden, int n_out, int device, void* stream);
+
 /* Split-K variant of rp_linear_tc for skinny, weight-bandwidth-bound layers (pose_regressor.0: K = 26 880,
  * src/model.py:91-98,189): out_f32 = act(A W^T + bias), float32 partials of K / ksplit blocks in `workspace`
  * (rp_linear_tc_splitk_workspace_bytes; ksplit_out may be NULL), added in a fixed order.  N % 4 == 0, K % 8 == 0. */

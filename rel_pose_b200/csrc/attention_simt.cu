@@ -395,12 +395,15 @@ __global__ void __launch_bounds__(256) em_reduce_kernel(const float* __restrict_
 
 // ============================================================================ proj_fundamental (A7 tail)
 // out[2b + (1-dir)][c][o] = bias[o] + sum_{h,a} bil[b,dir,h,a,c] * W[o][h*70+a]
-constexpr int PJ_CC = 10, PJ_KC = 30, PJ_K = RP_HEADS * EMW;   // 210
+// 35 of the 70 columns c per CTA (the first version took 10: 896 CTAs each re-staging the whole 161 KB weight through
+// shared memory = 144 MB of L2 traffic for a 0.36 GFLOP product, 72 us); K chunks of 14 keep the padded weight rows at
+// an odd stride (15 floats, conflict free).  Same fmaf order per output as before: bit-identical results.
+constexpr int PJ_CC = 35, PJ_KC = 14, PJ_K = RP_HEADS * EMW;   // 210
 
 __global__ void __launch_bounds__(RP_EMBED)
 em_project_kernel(const float* __restrict__ bil, const float* __restrict__ W, const float* __restrict__ bias,
                   float* __restrict__ out) {
-    __shared__ float Zs[PJ_CC][PJ_K];          // Z[c][h*70+a]
+    __shared__ __align__(16) float Zs[PJ_CC][PJ_K + 2];   // Z[c][h*70+a]; row pitch 212 floats keeps float2 reads aligned
     __shared__ float Ws[RP_EMBED][PJ_KC + 1];
     const int o = threadIdx.x;
     const int c0 = blockIdx.x * PJ_CC;
@@ -420,11 +423,17 @@ em_project_kernel(const float* __restrict__ bil, const float* __restrict__ W, co
             Ws[r][kk] = W[(size_t)r * PJ_K + k0 + kk];
         }
         __syncthreads();
-#pragma unroll 6
-        for (int kk = 0; kk < PJ_KC; ++kk) {
-            float w = Ws[o][kk];
+        // the loop is bound by shared-memory instructions (one broadcast read per FMA): read Z two k at a time
+        static_assert(PJ_KC % 2 == 0, "float2 reads of Z");
 #pragma unroll
-            for (int cc = 0; cc < PJ_CC; ++cc) acc[cc] = fmaf(Zs[cc][k0 + kk], w, acc[cc]);
+        for (int kk = 0; kk < PJ_KC; kk += 2) {
+            const float w0 = Ws[o][kk], w1 = Ws[o][kk + 1];
+#pragma unroll
+            for (int cc = 0; cc < PJ_CC; ++cc) {
+                const float2 z = *reinterpret_cast<const float2*>(&Zs[cc][k0 + kk]);
+                acc[cc] = fmaf(z.x, w0, acc[cc]);       // same order over k as before: bit-identical
+                acc[cc] = fmaf(z.y, w1, acc[cc]);
+            }
         }
     }
     float bo = bias[o];

@@ -291,6 +291,65 @@ extern "C" int rp_posenc_ex_f32(const float* kxy, const float* host_lin24, float
     return rp::finish_launch("rp_posenc");
 }
 
+// ----------------------------------------------------------------------------------------- A9 tail
+// pose_regressor[2:5] (src/model.py:93-97): out = W2 relu(W1 h + b1) + b2 for h [B,512] -> [B,14], one launch.
+// Two 64-row GEMMs of 17 MFLOP took 27 us each on the tiled SIMT engine (a 128 x 96 tile per 64 x 14 output, plus
+// its split-K reduction launch); here a CTA takes RT_ROWS rows, thread j owns hidden unit j and walks the TRANSPOSED
+// layer-1 weight (coalesced across the CTA), the 14 outputs are warp reductions.
+constexpr int RT_ROWS = 1, RT_H = 512, RT_OUT = 14;     // one row per CTA: 64 CTAs at 64 pairs; the weight (1 MB) stays in L2
+
+__global__ void __launch_bounds__(RT_H) regressor_tail_kernel(const float* __restrict__ h, const float* __restrict__ W1T,
+                                                              const float* __restrict__ b1, const float* __restrict__ W2,
+                                                              const float* __restrict__ b2, float* __restrict__ out, int B) {
+    __shared__ __align__(16) float hs[RT_ROWS][RT_H];
+    __shared__ __align__(16) float h2[RT_ROWS][RT_H];
+    const int j = threadIdx.x, row0 = blockIdx.x * RT_ROWS;
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; ++r) hs[r][j] = row0 + r < B ? h[(size_t)(row0 + r) * RT_H + j] : 0.f;
+    __syncthreads();
+    float acc[RT_ROWS];
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; ++r) acc[r] = 0.f;
+    // 32 independent weight loads in flight per thread: the loop is a chain of L2 round trips otherwise
+#pragma unroll 1
+    for (int k = 0; k < RT_H; k += 32) {
+        float w[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) w[u] = __ldg(W1T + (size_t)(k + u) * RT_H + j);
+#pragma unroll
+        for (int r = 0; r < RT_ROWS; ++r) {
+#pragma unroll
+            for (int u = 0; u < 32; u += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(&hs[r][k + u]);
+                acc[r] = fmaf(x.x, w[u], acc[r]); acc[r] = fmaf(x.y, w[u + 1], acc[r]);
+                acc[r] = fmaf(x.z, w[u + 2], acc[r]); acc[r] = fmaf(x.w, w[u + 3], acc[r]);
+            }
+        }
+    }
+    const float bj = b1[j];
+#pragma unroll
+    for (int r = 0; r < RT_ROWS; ++r) h2[r][j] = fmaxf(acc[r] + bj, 0.f);
+    __syncthreads();
+    const int warp = j >> 5, lane = j & 31;
+    for (int item = warp; item < RT_ROWS * RT_OUT; item += RT_H / 32) {
+        const int r = item / RT_OUT, n = item - r * RT_OUT;
+        float s = 0.f;
+        for (int k = lane; k < RT_H; k += 32) s = fmaf(h2[r][k], __ldg(W2 + (size_t)n * RT_H + k), s);
+        s = rp::warp_sum(s);
+        if (lane == 0 && row0 + r < B) out[(size_t)(row0 + r) * RT_OUT + n] = s + b2[n];
+    }
+}
+
+extern "C" int rp_regressor_tail_f32(const float* h, const float* W1T, const float* b1, const float* W2, const float* b2,
+                                     float* out, int B, int hidden, int n_out, int device, void* stream) {
+    RP_REQUIRE(h && W1T && b1 && W2 && b2 && out && B > 0, RP_EINVAL, "rp_regressor_tail: bad argument");
+    RP_REQUIRE(hidden == RT_H && n_out == RT_OUT, RP_EINVAL, "rp_regressor_tail: built for 512 hidden units and 14 outputs (got %d, %d)",
+               hidden, n_out);
+    RP_GUARD(device);
+    regressor_tail_kernel<<<(B + RT_ROWS - 1) / RT_ROWS, RT_H, 0, (cudaStream_t)stream>>>(h, W1T, b1, W2, b2, out, B);
+    return rp::finish_launch("rp_regressor_tail");
+}
+
 // ----------------------------------------------------------------------------------------- A10
 __global__ void normalize_pose_kernel(const float* __restrict__ raw, const float* __restrict__ Gs,
                                       float* __restrict__ out, int B) {

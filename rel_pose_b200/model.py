@@ -262,6 +262,16 @@ class ViTEss(nn.Module):
             cache[key] = hit
         return hit[1]
 
+    def _transposed(self, weight):
+        """Contiguous transpose of a weight matrix, rebuilt once per parameter version (parameter preparation)."""
+        cache = self.__dict__.setdefault("_transpose_cache", {})
+        tag = (weight.data_ptr(), weight._version)
+        hit = cache.get(id(weight))
+        if hit is None or hit[0] != tag:
+            hit = (tag, weight.detach().t().contiguous())
+            cache[id(weight)] = hit
+        return hit[1]
+
     def _tc_planes(self):
         """0 -> fp32 SIMT engine; 1 -> bf16 tensor cores; 2 -> bf16x3 tensor cores (fp32-class)."""
         return {"fp32": 0, "bf16": 1, "bf16x3": 2}[self.precision]
@@ -389,8 +399,12 @@ class ViTEss(nn.Module):
                                          act=ops.ACT_RELU)
             else:
                 h = ops.linear(feat, reg[0].weight, reg[0].bias, act=ops.ACT_RELU)
-            h = ops.linear(h, reg[2].weight, reg[2].bias, act=ops.ACT_RELU)
-            raw = ops.linear(h, reg[4].weight, reg[4].bias).reshape(B, 2, 7)
+            if self.H2 == 512:
+                raw = ops.regressor_tail(h, self._transposed(reg[2].weight), reg[2].bias, reg[4].weight.detach().contiguous(),
+                                         reg[4].bias).reshape(B, 2, 7)
+            else:
+                h = ops.linear(h, reg[2].weight, reg[2].bias, act=ops.ACT_RELU)
+                raw = ops.linear(h, reg[4].weight, reg[4].bias).reshape(B, 2, 7)
             if stages is not None:
                 stages["features"], stages["raw_pose"] = feat, raw
                 self.last_stages = stages

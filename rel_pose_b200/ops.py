@@ -347,6 +347,22 @@ def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f
     return out, outp
 
 
+def regressor_tail(h, w1t, b1, w2, b2):
+    """pose_regressor[2:5]: h [B,512] (post-ReLU layer 0) -> [B,14]; w1t = layer-1 weight transposed [in,out]."""
+    for t, nm in ((h, "h"), (w1t, "w1t"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
+        _req(t, nm)
+    B, hidden = h.shape
+    n_out = w2.shape[0]
+    assert tuple(w1t.shape) == (hidden, hidden) and w2.shape[1] == hidden
+    out = torch.empty((B, n_out), dtype=torch.float32, device=h.device)
+    dev, st = _ctx(h)
+    _tbegin("regressor_tail", 2.0 * B * hidden * (hidden + n_out), 4.0 * (hidden * hidden + n_out * hidden + B * hidden))
+    _lib.check(_lib.lib().rp_regressor_tail_f32(_p(h), _p(w1t), _p(b1), _p(w2), _p(b2), _p(out), B, hidden, n_out, dev, st),
+               "rp_regressor_tail")
+    _count()
+    return out
+
+
 def linear_tc_splitk(a_planes, w_planes, bias=None, act=ACT_NONE):
     """Split-K tcgen05 GEMM for skinny weight-bandwidth-bound layers: a_planes [P,M,K] bf16, w_planes [P,N,K] -> float32 [M,N]."""
     _req(a_planes, "a_planes", torch.bfloat16); _req(w_planes, "w_planes", torch.bfloat16)

@@ -118,6 +118,17 @@ def test_linear(M, N, K, act, res):
     report(f"linear-nobias {M}x{N}x{K}", got2, a.astype(np.float64) @ w.astype(np.float64).T, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("B", [1, 3, 64, 130])
+def test_regressor_tail(B):
+    """rp_regressor_tail_f32 = pose_regressor[2:5] (src/model.py:93-97) in one launch, against float64."""
+    h = np.maximum(rnd(40, B, 512), 0); w1 = rnd(41, 512, 512, scale=1.0 / np.sqrt(512)); b1 = rnd(42, 512, scale=0.1)
+    w2 = rnd(43, 14, 512, scale=1.0 / np.sqrt(512)); b2 = rnd(44, 14, scale=0.1)
+    got = ops.regressor_tail(cu(h), cu(np.ascontiguousarray(w1.T)), cu(b1), cu(w2), cu(b2)).cpu().numpy()
+    h2 = np.maximum(h.astype(np.float64) @ w1.astype(np.float64).T + b1, 0)
+    ref = h2 @ w2.astype(np.float64).T + b2
+    report(f"regressor_tail B={B}", got, ref, atol=1e-5, rtol=1e-5)
+
+
 def test_linear_residual_may_alias_output():
     a = rnd(1, 300, 192); w = rnd(2, 192, 192, scale=0.07); b = rnd(3, 192, scale=0.1); r = rnd(4, 300, 192)
     x = cu(r)
