@@ -11,8 +11,11 @@
 //   warp 0      TMA producer: weight units [P][192 rows][64 K] (128-byte swizzle) into a ring
 //   warp 1      MMA issuer: per column tile 3 K blocks x 4 K steps x (3 | 1) tcgen05.mma M128 x N192 x K16 into one of
 //               two TMEM accumulators (the epilogue of column tile i overlaps the MMAs of tile i+1)
-//   warps 2-17  LayerNorm of the tile's rows into the A-operand planes; epilogue (tcgen05.ld -> transpose through a
-//               warp-private shared-memory patch -> + bias -> float32 and/or re-split bf16 planes, coalesced).
+//   warps 2-17  LayerNorm of the tile's rows into the A-operand planes; epilogue.  Planes-only outputs (the QKV case)
+//               take the TMA-store epilogue: a thread keeps its TMEM row, adds the bias, splits the planes and writes
+//               them into the swizzled box layout of a [128 x 64] tile, one thread issues a bulk tensor store per
+//               64-column round (85 us instead of 105 us with the generic epilogue: tcgen05.ld -> transpose through
+//               a warp-private shared-memory patch -> float32 and/or planes with per-lane stores).
 //               The next row tile's LayerNorm runs as soon as the last column tile's MMAs have retired, before that
 //               tile's epilogue, so the tensor pipe does not drain at row-tile boundaries.
 #include "tc_common.cuh"
