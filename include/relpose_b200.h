@@ -201,6 +201,13 @@ int rp_self_attention_f32(const float* qkv, float* out, int n_img, int device, v
  * (out_f32, may be NULL) and/or P_out bf16 planes [P_out][n_img][576][192] (A operand of attn.proj). */
 int rp_self_attention_tc(const void* qkv_planes, float* out_f32, void* out_planes, int n_img, int P, int P_out,
                          int device, void* stream);
+/* --noess ablation, CrossAttention.forward vision_transformer.py:239-253: plain cross attention
+ * between the two views of a pair.  Same layouts as above; image n's queries attend to the keys / values of image
+ * n^1 (n_img must be even): out[2b] = softmax(q1 k2^T * 0.125) v2, out[2b+1] = softmax(q2 k1^T * 0.125) v1, i.e.
+ * already in the flipped order the reference returns (:262). */
+int rp_cross_attention_f32(const float* qkv, float* out, int n_img, int device, void* stream);
+int rp_cross_attention_tc(const void* qkv_planes, float* out_f32, void* out_planes, int n_img, int P, int P_out,
+                          int device, void* stream);
 
 /* ---- A6  vision_transformer.py:90-158 ------------------------------------------------------
  * pos [B,576,6] = [p3^2,p4^2,p3*p4,p3,p4,1], p3 = ys[i%24]*ky, p4 = xs[i/24]*kx (transposed grid).

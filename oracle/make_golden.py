@@ -35,6 +35,9 @@ ABLATION_CASES = [
     ("ablate_cross_features_b2_64x80", 12, "stress", 2, 64, 80, "varied", True, ("cross_features",)),
     ("ablate_l1_pos_b2_64x80", 13, "stress", 2, 64, 80, "matterport", True, ("l1_pos_encoding",)),
     ("ablate_all_three_b1_96x128", 14, "stress", 1, 96, 128, "matterport", True, ("use_single_softmax", "cross_features", "l1_pos_encoding")),
+    # --noess: plain cross attention + pool_attn head instead of the module (model.py:71-88,183-187)
+    ("ablate_noess_b2_64x80", 15, "stress", 2, 64, 80, "matterport", True, ("noess",)),
+    ("ablate_noess_b3_96x128_init", 16, "init", 3, 96, 128, None, False, ("noess",)),
 ]
 
 TOK_SAMPLE = (slice(None), slice(None, None, 9), slice(None, None, 4))
@@ -42,7 +45,7 @@ TOK_SAMPLE = (slice(None), slice(None, None, 9), slice(None, None, 4))
 
 def sample(name, t):
     a = t.detach().cpu().numpy()
-    if name in ("tokens",) or name.startswith("block"):
+    if name in ("tokens",) or name.startswith("block") or (name == "cross" and a.shape[1] == 576):
         return np.ascontiguousarray(a[TOK_SAMPLE])
     if name == "preprocessed":
         return np.ascontiguousarray(a[:, :, ::7, ::5])
@@ -53,7 +56,8 @@ def sample(name, t):
 
 def run_case(name, seed, profile, B, H, W, ikind, integer, flags=()):
     model, SE3 = ref_loader.load_reference_model(**{f: True for f in flags})
-    model.load_state_dict(S.make_state_dict(seed, profile))
+    noess = "noess" in flags
+    model.load_state_dict(S.make_state_dict(seed, profile, noess=noess))
     model.eval()
     images = torch.from_numpy(S.make_images_numpy(seed, B, H, W, integer))
     intr = None if ikind is None else torch.from_numpy(S.make_intrinsics_numpy(B, ikind, seed))
@@ -79,7 +83,8 @@ def run_case(name, seed, profile, B, H, W, ikind, integer, flags=()):
     def _z_hook(m, i):
         zs.append(i[0])
 
-    hooks.append(vt.blocks[5].cross_attn.proj_fundamental.register_forward_pre_hook(_z_hook))
+    if not noess:
+        hooks.append(vt.blocks[5].cross_attn.proj_fundamental.register_forward_pre_hook(_z_hook))
 
     def _reg_hook(m, i, o):
         stages["features"] = i[0]
@@ -92,10 +97,11 @@ def run_case(name, seed, profile, B, H, W, ikind, integer, flags=()):
         h.remove()
     # proj_fundamental is applied to z2 first, then z1 (vision_transformer.py:233-234);
     # z[b,c,h*70+a] = F[b,h,a,c]  ->  recover F[b,h,a,c]
-    z2, z1 = zs
-    unz = lambda z: z.reshape(B, 70, 3, 70).permute(0, 2, 3, 1)
-    stages["bilinear1"] = unz(z1)
-    stages["bilinear2"] = unz(z2)
+    if not noess:
+        z2, z1 = zs
+        unz = lambda z: z.reshape(B, 70, 3, 70).permute(0, 2, 3, 1)
+        stages["bilinear1"] = unz(z1)
+        stages["bilinear2"] = unz(z2)
     rec = {"poses": out[0].data.numpy()}
     if intr is not None:
         rec["intrinsics_after"] = intr.numpy()          # mutated in place by the reference
@@ -131,9 +137,10 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else ""
-    if only != "ablations":
+    if only not in ("ablations", "noess"):
         posenc_golden()
         for c in CASES:
             run_case(*c)
     for c in ABLATION_CASES:
-        run_case(*c)
+        if only != "noess" or "noess" in c[-1]:
+            run_case(*c)

@@ -287,6 +287,43 @@ def essential_matrix_module(x1, x2, p, prefix, intrinsics=None, return_bilinear=
     return y2, y1
 
 
+def cross_attention_noess(x1, x2, p, prefix):
+    """CrossAttention.forward, --noess branch, vision_transformer.py:239-262: plain cross attention
+    (queries of one view, keys/values of the other), shared output projection.  Returns (X2, X1) -- the flip at :262."""
+    dt = x1.dtype.type
+    B, N, C = x1.shape
+    q1, k1, v1 = split_qkv(linear(x1, p[prefix + ".qkv.weight"], p[prefix + ".qkv.bias"]))
+    q2, k2, v2 = split_qkv(linear(x2, p[prefix + ".qkv.weight"], p[prefix + ".qkv.bias"]))
+    scale = dt(HDIM ** -0.5)
+    a1 = softmax((q2 @ k1.transpose(0, 1, 3, 2)) * scale, -1)         # :241-242
+    o1 = (a1 @ v1).transpose(0, 2, 1, 3).reshape(B, N, C)             # :245
+    a2 = softmax((q1 @ k2.transpose(0, 1, 3, 2)) * scale, -1)         # :248-249
+    o2 = (a2 @ v2).transpose(0, 2, 1, 3).reshape(B, N, C)             # :252
+    o1 = linear(o1, p[prefix + ".proj.weight"], p[prefix + ".proj.bias"])
+    o2 = linear(o2, p[prefix + ".proj.weight"], p[prefix + ".proj.bias"])
+    return o2, o1
+
+
+def cross_block_noess(x, p, prefix):
+    """CrossBlock.forward, --noess branch, vision_transformer.py:297-303.  x [2B,576,192] -> [2B,576,192]."""
+    n2, N, C = x.shape
+    xp = x.reshape(n2 // 2, 2, N, C)
+    g, b = p[prefix + ".norm1.weight"], p[prefix + ".norm1.bias"]
+    ya, yb = cross_attention_noess(layernorm(xp[:, 0], g, b), layernorm(xp[:, 1], g, b), p, prefix + ".cross_attn")
+    x = x + np.stack([ya, yb], 1).reshape(n2, N, C)
+    return x + mlp(layernorm(x, p[prefix + ".norm2.weight"], p[prefix + ".norm2.bias"]), p, prefix + ".mlp")
+
+
+def pool_attn_noess(x, p, B):
+    """src/model.py:183-187 with the pool_attn head of :71-80.  x [2B,576,192] is re-read as [B,24,24,384]
+    (the reference's reshape: "pixel" j of a pair holds tokens 2j and 2j+1 of the pair's flat token list),
+    1x1 conv 384->96 + BN + ReLU + 1x1 conv 96->43 + BN, flattened channel-major to [B, 43*576]."""
+    f = x.reshape(B, GRID, GRID, -1).transpose(0, 3, 1, 2)
+    h = relu(batchnorm_eval(conv2d(f, p["pool_attn.0.weight"], p["pool_attn.0.bias"]), p, "pool_attn.1"))
+    h = batchnorm_eval(conv2d(h, p["pool_attn.3.weight"], p["pool_attn.3.bias"]), p, "pool_attn.4")
+    return h.reshape(B, -1)
+
+
 def cross_block(x, p, prefix, intrinsics=None, return_bilinear=False, flags=()):
     """CrossBlock.forward, vision_transformer.py:285-296.  x [2B,576,192] -> [2B,70,192]."""
     n2, N, C = x.shape
@@ -337,12 +374,16 @@ def vitess_forward(images, Gs, intrinsics, p, dtype=np.float32, depth=6, stages=
         x = block(x, p, f"fusion_transformer.blocks.{i}")
         if stages is not None:
             stages[f"block{i}"] = x
-    x, bil = cross_block(x, p, f"fusion_transformer.blocks.{depth - 1}", intr, return_bilinear=True, flags=flags)
+    if "noess" in flags:
+        x = cross_block_noess(x, p, f"fusion_transformer.blocks.{depth - 1}")
+    else:
+        x, bil = cross_block(x, p, f"fusion_transformer.blocks.{depth - 1}", intr, return_bilinear=True, flags=flags)
+        if stages is not None:
+            stages["bilinear1"], stages["bilinear2"] = bil
     if stages is not None:
-        stages["bilinear1"], stages["bilinear2"] = bil
         stages["cross"] = x
     x = layernorm(x, p["fusion_transformer.norm.weight"], p["fusion_transformer.norm.bias"])
-    feat = x.reshape(B, -1)
+    feat = pool_attn_noess(x, p, B) if "noess" in flags else x.reshape(B, -1)
     if stages is not None:
         stages["features"] = feat
     raw = pose_regressor(feat, p)

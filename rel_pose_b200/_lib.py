@@ -54,6 +54,8 @@ _SIGNATURES = {
     "rp_maxpool3x3s2_planes": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_self_attention_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_self_attention_tc": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_cross_attention_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_cross_attention_tc": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_posenc_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_essential_workspace_bytes": (_c_size, [_c_int]),
     "rp_posenc_ex_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr]),

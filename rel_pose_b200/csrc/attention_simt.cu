@@ -79,7 +79,7 @@ __device__ __forceinline__ float row_sum8(float v) {
 constexpr int SA_SMEM = (TILE * LQ * 2 + TILE * HD + TILE * LP) * (int)sizeof(float);
 
 __global__ void __launch_bounds__(THREADS, 3)
-self_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
+self_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int kv_xor) {
     extern __shared__ __align__(16) float sm[];
     float* Qs = sm;
     float* Ks = Qs + TILE * LQ;
@@ -87,9 +87,10 @@ self_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
     float* Ps = Vs + TILE * HD;      // [64][LP]
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
     const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-    const float* base = qkv + (size_t)n * NTOK * LDQKV;
+    // kv_xor = 1: keys/values of the OTHER view of the pair (plain cross attention of the --noess ablation)
+    const float* base = qkv + (size_t)(n ^ kv_xor) * NTOK * LDQKV;
 
-    load_tile64<LQ>(Qs, base + (size_t)(qt * TILE) * LDQKV + h * HD, tid);
+    load_tile64<LQ>(Qs, qkv + ((size_t)n * NTOK + qt * TILE) * LDQKV + h * HD, tid);
     rp::cp_async_commit();
 
     float m[4], l[4], o[4][8];
@@ -460,8 +461,19 @@ extern "C" int rp_self_attention_f32(const float* qkv, float* out, int n_img, in
     int rc = set_smem((const void*)self_attention_kernel, SA_SMEM, "rp_self_attention");
     if (rc) return rc;
     dim3 grid(NTILES, RP_HEADS, n_img);
-    self_attention_kernel<<<grid, THREADS, SA_SMEM, (cudaStream_t)stream>>>(qkv, out);
+    self_attention_kernel<<<grid, THREADS, SA_SMEM, (cudaStream_t)stream>>>(qkv, out, 0);
     return rp::finish_launch("rp_self_attention");
+}
+
+extern "C" int rp_cross_attention_f32(const float* qkv, float* out, int n_img, int device, void* stream) {
+    RP_REQUIRE(qkv && out && n_img > 0 && n_img % 2 == 0, RP_EINVAL, "rp_cross_attention: n_img must be a positive even number");
+    RP_REQUIRE(rp::aligned16(qkv) && rp::aligned16(out), RP_EALIGN, "rp_cross_attention: 16-byte alignment");
+    RP_GUARD(device);
+    int rc = set_smem((const void*)self_attention_kernel, SA_SMEM, "rp_cross_attention");
+    if (rc) return rc;
+    dim3 grid(NTILES, RP_HEADS, n_img);
+    self_attention_kernel<<<grid, THREADS, SA_SMEM, (cudaStream_t)stream>>>(qkv, out, 1);
+    return rp::finish_launch("rp_cross_attention");
 }
 
 extern "C" size_t rp_essential_workspace_bytes(int B) {

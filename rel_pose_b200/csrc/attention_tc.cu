@@ -61,7 +61,7 @@ template <int P>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_planes, int p_out, int n_img,
-                         float scale_log2) {
+                         float scale_log2, int kv_xor) {
     using C = ACfg<P>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,7 +126,7 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     tc::mbar_expect_tx(&k_full[ks], C::KV_BYTES);
 #pragma unroll
                     for (int p = 0; p < P; ++p)
-                        tc::tma_load_4d(k_tile(ks, p), &tmKV, &k_full[ks], EMB + h * HD, j * BKV, img, p);
+                        tc::tma_load_4d(k_tile(ks, p), &tmKV, &k_full[ks], EMB + h * HD, j * BKV, img ^ kv_xor, p);
                 }
                 __syncwarp();
                 if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
@@ -135,7 +135,7 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     tc::mbar_expect_tx(&v_full[vs], C::KV_BYTES);
 #pragma unroll
                     for (int p = 0; p < P; ++p)
-                        tc::tma_load_4d(v_tile(vs, p), &tmKV, &v_full[vs], 2 * EMB + h * HD, j * BKV, img, p);
+                        tc::tma_load_4d(v_tile(vs, p), &tmKV, &v_full[vs], 2 * EMB + h * HD, j * BKV, img ^ kv_xor, p);
                 }
                 __syncwarp();
                 if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
@@ -407,7 +407,7 @@ int make_qkv_tmap(CUtensorMap* out, const void* base, int P, int n_img, int box_
 
 template <int P>
 int launch_attention(const void* qkv_planes, float* out_f32, void* out_planes, int p_out, int n_img, int device,
-                     cudaStream_t st) {
+                     cudaStream_t st, int kv_xor = 0) {
     using C = ACfg<P>;
     CUtensorMap tmQ, tmKV;
     int rc = make_qkv_tmap(&tmQ, qkv_planes, P, n_img, BM);
@@ -427,7 +427,7 @@ int launch_attention(const void* qkv_planes, float* out_f32, void* out_planes, i
     const int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
     const float scale_log2 = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
     self_attention_tc_kernel<P><<<grid, ATT_THREADS, C::SMEM, st>>>(tmQ, tmKV, out_f32, static_cast<__nv_bfloat16*>(out_planes),
-                                                                  p_out, n_img, scale_log2);
+                                                                  p_out, n_img, scale_log2, kv_xor);
     return rp::finish_launch("rp_self_attention_tc");
 }
 
@@ -443,4 +443,19 @@ extern "C" int rp_self_attention_tc(const void* qkv_planes, float* out_f32, void
     RP_GUARD(device);
     if (P == 1) return launch_attention<1>(qkv_planes, out_f32, out_planes, P_out, n_img, device, (cudaStream_t)stream);
     return launch_attention<2>(qkv_planes, out_f32, out_planes, P_out, n_img, device, (cudaStream_t)stream);
+}
+
+// Plain cross attention between the two views of each pair (--noess ablation, vision_transformer.py:239-253):
+// image n's queries attend to the keys/values of image n^1.  Same kernel; only the TMA coordinates of K and V change.
+extern "C" int rp_cross_attention_tc(const void* qkv_planes, float* out_f32, void* out_planes, int n_img, int P, int P_out,
+                                     int device, void* stream) {
+    RP_REQUIRE(qkv_planes && (out_f32 || out_planes) && n_img > 0 && n_img % 2 == 0, RP_EINVAL,
+               "rp_cross_attention_tc: n_img must be a positive even number");
+    RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_cross_attention_tc: P must be 1 (bf16) or 2 (bf16x3)");
+    RP_REQUIRE(!out_planes || (P_out >= 1 && P_out <= 2), RP_EINVAL, "rp_cross_attention_tc: bad P_out");
+    RP_REQUIRE(rp::aligned16(qkv_planes) && rp::aligned16(out_f32) && rp::aligned16(out_planes), RP_EALIGN,
+               "rp_cross_attention_tc: 16-byte alignment");
+    RP_GUARD(device);
+    if (P == 1) return launch_attention<1>(qkv_planes, out_f32, out_planes, P_out, n_img, device, (cudaStream_t)stream, 1);
+    return launch_attention<2>(qkv_planes, out_f32, out_planes, P_out, n_img, device, (cudaStream_t)stream, 1);
 }

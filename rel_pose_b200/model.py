@@ -12,6 +12,8 @@ Parameter containers mirror the reference's module tree only so that `state_dict
   extractor_final_conv.*      ResidualBlock(128,192,'batch',5)   (src/modules/extractor.py:5-49)
   fusion_transformer.*        pos_embed, blocks.0-4 (Block), blocks.5 (CrossBlock), norm
   pose_regressor.{0,2,4}.*    26880->512->512->14
+With `args.noess` (ablation, model.py:71-88): blocks.5.cross_attn.proj replaces proj_fundamental, pool_attn.{0,1,3,4}.* is
+added and pose_regressor.0 is 24768 wide.
 """
 import math
 import os
@@ -40,10 +42,13 @@ class _Attention(nn.Module):
 
 
 class _CrossAttention(nn.Module):
-    def __init__(self, dim, heads):
+    def __init__(self, dim, heads, noess=False):
         super().__init__()
         self.qkv = nn.Linear(dim, dim * 3, bias=True)
-        self.proj_fundamental = nn.Linear(dim + 6 * heads, dim)
+        if noess:
+            self.proj = nn.Linear(dim, dim)                          # vision_transformer.py:176-177
+        else:
+            self.proj_fundamental = nn.Linear(dim + 6 * heads, dim)
 
 
 class _Block(nn.Module):
@@ -56,10 +61,10 @@ class _Block(nn.Module):
 
 
 class _CrossBlock(nn.Module):
-    def __init__(self, dim, heads):
+    def __init__(self, dim, heads, noess=False):
         super().__init__()
         self.norm1 = nn.LayerNorm(dim, eps=1e-6)
-        self.cross_attn = _CrossAttention(dim, heads)
+        self.cross_attn = _CrossAttention(dim, heads, noess)
         self.norm2 = nn.LayerNorm(dim, eps=1e-6)
         self.mlp = _Mlp(dim, dim * 4)
 
@@ -67,10 +72,11 @@ class _CrossBlock(nn.Module):
 class _FusionTransformer(nn.Module):
     """Parameter layout of the reference's VisionTransformer after the surgery in model.py:45-56."""
 
-    def __init__(self, depth, dim=192, heads=3, ntok=576):
+    def __init__(self, depth, dim=192, heads=3, ntok=576, noess=False):
         super().__init__()
         self.pos_embed = nn.Parameter(torch.zeros(1, ntok, dim))
-        self.blocks = nn.Sequential(*[(_CrossBlock if i == depth - 1 else _Block)(dim, heads) for i in range(depth)])
+        self.blocks = nn.Sequential(*[_CrossBlock(dim, heads, noess) if i == depth - 1 else _Block(dim, heads)
+                                      for i in range(depth)])
         self.norm = nn.LayerNorm(dim, eps=1e-6)
         # timm-style init (vision_transformer.py:477-497): trunc_normal(.02) weights, zero biases
         for m in self.modules():
@@ -103,19 +109,18 @@ class ViTEss(nn.Module):
         # The configuration every reference script runs (--fusion_transformer, dual softmax, quadratic positional
         # encoding) is the hot path.  Of the ablation branches the three that only vary the
         # Essential Matrix Module are supported -- --use_single_softmax / --cross_features on the fp32 SIMT module
-        # kernels (rp_essential_ex_f32), --l1_pos_encoding in every precision -- inference only.
-        for name in ("noess", "no_pos_encoding"):
-            if _flag(args, name):
-                raise NotImplementedError(
-                    f"--{name} is an ablation branch outside the B200 hot path (SURVEY.md 8(f) rank 4)"
-                    + ("; the reference itself cannot run it: proj_fundamental stays 210 wide (vision_transformer.py:179,226)"
-                       if name == "no_pos_encoding" else ""))
+        # kernels (rp_essential_ex_f32), --l1_pos_encoding in every precision -- and so is --noess (plain cross
+        # attention + the pool_attn head, every precision).  All inference only.
+        if _flag(args, "no_pos_encoding"):
+            raise NotImplementedError(
+                "--no_pos_encoding is an ablation branch outside the B200 hot path (SURVEY.md 8(f) rank 4); the reference "
+                "itself cannot run it: proj_fundamental stays 210 wide (vision_transformer.py:179,226)")
         self.em_flags = (ops.EM_SINGLE_SOFTMAX if _flag(args, "use_single_softmax") else 0) | \
                         (ops.EM_CROSS_FEATURES if _flag(args, "cross_features") else 0)
         self.l1_pos_encoding = bool(_flag(args, "l1_pos_encoding"))
         if not _flag(args, "fusion_transformer", False):
             raise NotImplementedError("the CNN-only path (no --fusion_transformer) is outside the B200 hot path")
-        self.noess = None
+        self.noess = _flag(args, "noess", None) if _flag(args, "noess", "") != "" else None     # model.py:16-18
         self.total_num_features = 192
         self.feature_resolution = (24, 24)
         self.num_images = 2
@@ -125,6 +130,8 @@ class ViTEss(nn.Module):
         self.transformer_depth = int(args.transformer_depth)
         self.H2 = int(args.fc_hidden_size)
         self.H = self.num_heads * 2 * (64 + 6) * 64           # 26880, model.py:61
+        self.pool_feat1 = min(96, 4 * int(getattr(args, "pool_size", 60)))
+        self.pool_feat2 = int(getattr(args, "pool_size", 60))
 
         import torchvision.models as tvm
         # The reference asks for ImageNet weights (model.py:31) which every caller then overwrites with a
@@ -132,7 +139,15 @@ class ViTEss(nn.Module):
         self.resnet = tvm.resnet18(weights=None)
         self.resnet.fc = nn.Identity()
         self.extractor_final_conv = _ResidualBlock(128, self.total_num_features, 5)
-        self.fusion_transformer = _FusionTransformer(self.transformer_depth)
+        self.fusion_transformer = _FusionTransformer(self.transformer_depth, noess=bool(self.noess))
+        if self.noess:                                        # model.py:71-80
+            self.H = 24 * 24 * 43
+            self.pool_feat2 = 43
+            self.pool_attn = nn.Sequential(
+                nn.Conv2d(2 * self.total_num_features, self.pool_feat1, kernel_size=1, bias=True),
+                nn.BatchNorm2d(self.pool_feat1), nn.ReLU(),
+                nn.Conv2d(self.pool_feat1, self.pool_feat2, kernel_size=1, bias=True),
+                nn.BatchNorm2d(self.pool_feat2))
         self.pose_regressor = nn.Sequential(
             nn.Linear(self.H, self.H2), nn.ReLU(),
             nn.Linear(self.H2, self.H2), nn.ReLU(),
@@ -337,6 +352,61 @@ class ViTEss(nn.Module):
             return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=f)
         return self._mlp_tc(blk, f, P)
 
+    def _cross_block_noess(self, blk, x):
+        """CrossBlock.forward, --noess branch (vision_transformer.py:297-303): x + proj(cross attention), then the MLP.
+        The attention kernels read the other view's keys/values in place (image n -> n^1), which also yields the
+        flipped return order of :262; no copy, no 576x576 tensor in HBM."""
+        P = self._tc_planes()
+        ca = blk.cross_attn
+        if P == 0:
+            h = ops.layernorm(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+            qkv = ops.linear(h, ca.qkv.weight, ca.qkv.bias)
+            a = ops.self_attention(qkv, cross=True)
+            x = ops.linear(a, ca.proj.weight, ca.proj.bias, residual=x)
+            h = ops.layernorm(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+            h = ops.linear(h, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
+            return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=x)
+        qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
+        _, a = ops.self_attention_tc(qkv, planes_out=P, cross=True)
+        x, _ = ops.linear_tc(a, self._planes(ca.proj.weight, P), ca.proj.bias, residual=x)
+        return self._mlp_tc(blk, x, P)
+
+    def _pool_head_params(self):
+        """Parameter preparation for the --noess head (model.py:71-80,183-187), rebuilt once per parameter version:
+        eval-mode BatchNorm folded into the two 1x1 convolutions, and pose_regressor.0's columns permuted from the
+        reference's channel-major flattening (c*576 + pixel) to the pixel-major order the GEMM output already has."""
+        pa, reg0 = self.pool_attn, self.pose_regressor[0]
+        srcs = [pa[0].weight, pa[0].bias, pa[3].weight, pa[3].bias, reg0.weight]
+        for bn in (pa[1], pa[4]):
+            srcs += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        tag = tuple((t.data_ptr(), t._version) for t in srcs)
+        hit = self.__dict__.get("_pool_head_cache")
+        if hit is None or hit[0] != tag:
+            with torch.no_grad():
+                def fold(conv, bn):
+                    s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                    w = (conv.weight.reshape(conv.weight.shape[0], -1) * s[:, None]).contiguous()
+                    return w, ((conv.bias - bn.running_mean) * s + bn.bias).contiguous()
+                w1, b1 = fold(pa[0], pa[1])
+                w2, b2 = fold(pa[3], pa[4])
+                w0 = reg0.weight.reshape(self.H2, self.pool_feat2, 576).permute(0, 2, 1).reshape(self.H2, self.H).contiguous()
+            hit = (tag, (w1, b1, w2, b2, w0))
+            self.__dict__["_pool_head_cache"] = hit
+        return hit[1]
+
+    def _pool_attn_head(self, x, B):
+        """features.reshape([B,24,24,-1]) -> pool_attn (model.py:185-186).  The reference's reshape makes "pixel" j of a pair
+        the concatenation of rows 2j and 2j+1 of the pair's [1152,192] token matrix, so the 1x1 convolutions are two
+        GEMMs over x viewed as [B*576, 384].  Returns ([B, 576*43] pixel-major, permuted pose_regressor.0 weight)."""
+        w1, b1, w2, b2, w0 = self._pool_head_params()
+        P = self._tc_planes()
+        f = x.reshape(B * 576, 2 * self.total_num_features)
+        if P == 0:
+            h = ops.linear(f, w1, b1, act=ops.ACT_RELU)
+        else:
+            h, _ = ops.linear_tc(ops.split_planes(f, P), self._planes(w1, P), b1, act=ops.ACT_RELU)
+        return ops.linear(h, w2, b2).reshape(B, self.H), w0
+
     def normalize_preds(self, Gs, pose_preds, inference):
         out = SE3(ops.normalize_pose(pose_preds.contiguous(), Gs.data.contiguous()))
         if inference:
@@ -352,7 +422,7 @@ class ViTEss(nn.Module):
         if not images.is_cuda:
             raise ops._lib.RelposeLibraryError("ViTEss.forward: images must live on a CUDA device (no CPU fallback)")
         if self.training and torch.is_grad_enabled():
-            if self.em_flags or self.l1_pos_encoding:
+            if self.em_flags or self.l1_pos_encoding or self.noess:
                 raise NotImplementedError("the ablation branches are built for inference only")
             # train.py:155 -- batch-statistics BatchNorm, autograd through the CUDA kernels (train_path.py)
             from . import train_path
@@ -387,18 +457,24 @@ class ViTEss(nn.Module):
                 x = self._block(vt.blocks[i], x)
                 if stages is not None:
                     stages[f"block{i}"] = x
-            x = self._cross_block(vt.blocks[self.transformer_depth - 1], x, kxy, stages)   # A6-A8
+            if self.noess:
+                x = self._cross_block_noess(vt.blocks[self.transformer_depth - 1], x)
+            else:
+                x = self._cross_block(vt.blocks[self.transformer_depth - 1], x, kxy, stages)   # A6-A8
             if stages is not None:
                 stages["cross"] = x
             x = ops.layernorm(x, vt.norm.weight, vt.norm.bias, vt.norm.eps)   # A9
-            feat = x.reshape(B, -1)
             reg = self.pose_regressor
+            if self.noess:
+                feat, w0 = self._pool_attn_head(x, B)
+            else:
+                feat, w0 = x.reshape(B, -1), reg[0].weight
             if self._tc_planes() == 2 and self.tc_regressor:
                 # 26880 -> 512: 55 MB of weights for 64 rows; split-K on the tensor cores (bf16x3, short accumulation chains)
-                h = ops.linear_tc_splitk(ops.split_planes(feat.contiguous(), 2), self._planes(reg[0].weight, 2), reg[0].bias,
+                h = ops.linear_tc_splitk(ops.split_planes(feat.contiguous(), 2), self._planes(w0, 2), reg[0].bias,
                                          act=ops.ACT_RELU)
             else:
-                h = ops.linear(feat, reg[0].weight, reg[0].bias, act=ops.ACT_RELU)
+                h = ops.linear(feat, w0, reg[0].bias, act=ops.ACT_RELU)
             if self.H2 == 512:
                 raw = ops.regressor_tail(h, self._transposed(reg[2].weight), reg[2].bias, reg[4].weight.detach().contiguous(),
                                          reg[4].bias).reshape(B, 2, 7)
@@ -406,10 +482,12 @@ class ViTEss(nn.Module):
                 h = ops.linear(h, reg[2].weight, reg[2].bias, act=ops.ACT_RELU)
                 raw = ops.linear(h, reg[4].weight, reg[4].bias).reshape(B, 2, 7)
             if stages is not None:
+                if self.noess:      # back to the reference's channel-major flattening (model.py:187)
+                    feat = feat.reshape(B, 576, self.pool_feat2).permute(0, 2, 1).reshape(B, -1)
                 stages["features"], stages["raw_pose"] = feat, raw
                 self.last_stages = stages
             out = self.normalize_preds(Gs, raw, inference)                    # A10
-            if flags is not None and self.check_intrinsics:
+            if flags is not None and self.check_intrinsics and not self.noess:   # the checks live in the module's encodings
                 flags_event.synchronize()      # the tiny kernel finished long ago; no pipeline stall
                 f = int(flags_host.item())
                 if f & 1:

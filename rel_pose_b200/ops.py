@@ -471,21 +471,23 @@ def maxpool3x3s2_planes(x, P, want_f32=True):
     return y, yp
 
 
-def self_attention(qkv):
-    """qkv [n,576,576] -> [n,576,192]."""
+def self_attention(qkv, cross=False):
+    """qkv [n,576,576] -> [n,576,192].  cross=True: image i attends to the keys/values of image i^1 (--noess)."""
     _req(qkv, "qkv")
     n = qkv.shape[0]
     assert tuple(qkv.shape[1:]) == (NTOK, 3 * EMBED)
     out = torch.empty((n, NTOK, EMBED), dtype=torch.float32, device=qkv.device)
     dev, st = _ctx(qkv)
     _tbegin("self_attention", 4.0 * n * HEADS * NTOK * NTOK * HDIM, 4.0 * n * NTOK * 4 * EMBED)
-    _lib.check(_lib.lib().rp_self_attention_f32(_p(qkv), _p(out), n, dev, st), "rp_self_attention")
+    fn = _lib.lib().rp_cross_attention_f32 if cross else _lib.lib().rp_self_attention_f32
+    _lib.check(fn(_p(qkv), _p(out), n, dev, st), "rp_cross_attention" if cross else "rp_self_attention")
     _count()
     return out
 
 
-def self_attention_tc(qkv_planes, want_f32=False, planes_out=0):
-    """qkv_planes bf16 [P,n,576,576] -> (float32 [n,576,192] | None, bf16 planes [planes_out,n,576,192] | None)."""
+def self_attention_tc(qkv_planes, want_f32=False, planes_out=0, cross=False):
+    """qkv_planes bf16 [P,n,576,576] -> (float32 [n,576,192] | None, bf16 planes [planes_out,n,576,192] | None).
+    cross=True: image i attends to the keys/values of image i^1 (--noess)."""
     _req(qkv_planes, "qkv_planes", torch.bfloat16)
     P, n = qkv_planes.shape[0], qkv_planes.shape[1]
     assert tuple(qkv_planes.shape[2:]) == (NTOK, 3 * EMBED)
@@ -495,8 +497,9 @@ def self_attention_tc(qkv_planes, want_f32=False, planes_out=0):
     dev, st = _ctx(qkv_planes)
     _tbegin(f"self_attention_tc{'x3' if P == 2 else ''}", 4.0 * n * HEADS * NTOK * NTOK * HDIM,
             2.0 * P * n * NTOK * 3 * EMBED + (4.0 if want_f32 else 0.0) * n * NTOK * EMBED + 2.0 * planes_out * n * NTOK * EMBED)
-    _lib.check(_lib.lib().rp_self_attention_tc(_p(qkv_planes), _p(out), _p(outp), n, P, int(planes_out), dev, st),
-               "rp_self_attention_tc")
+    fn = _lib.lib().rp_cross_attention_tc if cross else _lib.lib().rp_self_attention_tc
+    _lib.check(fn(_p(qkv_planes), _p(out), _p(outp), n, P, int(planes_out), dev, st),
+               "rp_cross_attention_tc" if cross else "rp_self_attention_tc")
     _count()
     return out, outp
 

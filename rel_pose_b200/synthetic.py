@@ -49,8 +49,9 @@ def hash_normal(seed, name, n):
 
 
 # ----------------------------------------------------------------------------------------------
-def state_dict_spec(transformer_depth=6, fc_hidden=512):
-    """[(key, shape, kind)] in the reference's state_dict order.  kind drives the value profile."""
+def state_dict_spec(transformer_depth=6, fc_hidden=512, noess=False):
+    """[(key, shape, kind)] in the reference's state_dict order.  kind drives the value profile.
+    `noess` = the layout of the --noess ablation (model.py:71-88, vision_transformer.py:176-177)."""
     spec = []
 
     def conv(prefix, co, ci, k, bias):
@@ -104,7 +105,10 @@ def state_dict_spec(transformer_depth=6, fc_hidden=512):
         ln(b + ".norm1", 192)
         if i == transformer_depth - 1:
             lin(b + ".cross_attn.qkv", 576, 192, "qkv")
-            lin(b + ".cross_attn.proj_fundamental", 192, 210)
+            if noess:
+                lin(b + ".cross_attn.proj", 192, 192)
+            else:
+                lin(b + ".cross_attn.proj_fundamental", 192, 210)
         else:
             lin(b + ".attn.qkv", 576, 192, "qkv")
             lin(b + ".attn.proj", 192, 192)
@@ -113,6 +117,12 @@ def state_dict_spec(transformer_depth=6, fc_hidden=512):
         lin(b + ".mlp.fc2", 192, 768)
     ln(f + ".norm", 192)
     H = 3 * 2 * (64 + 6) * 64
+    if noess:
+        H = 24 * 24 * 43
+        conv("pool_attn.0", 96, 384, 1, True)
+        bn("pool_attn.1", 96)
+        conv("pool_attn.3", 43, 96, 1, True)
+        bn("pool_attn.4", 43)
     lin("pose_regressor.0", fc_hidden, H)
     lin("pose_regressor.2", fc_hidden, fc_hidden)
     lin("pose_regressor.4", 14, fc_hidden)
@@ -122,7 +132,7 @@ def state_dict_spec(transformer_depth=6, fc_hidden=512):
 ALIASES = {"extractor_final_conv.downsample.1": "extractor_final_conv.norm3"}
 
 
-def make_state_dict_numpy(seed=0, profile="stress", transformer_depth=6, fc_hidden=512):
+def make_state_dict_numpy(seed=0, profile="stress", transformer_depth=6, fc_hidden=512, noess=False):
     """OrderedDict key -> np.ndarray (float32, int64 for num_batches_tracked).
 
     profile "init":   statistics close to the reference's random init (small ViT weights,
@@ -132,7 +142,7 @@ def make_state_dict_numpy(seed=0, profile="stress", transformer_depth=6, fc_hidd
     """
     assert profile in ("init", "stress")
     out = OrderedDict()
-    for key, shape, kind in state_dict_spec(transformer_depth, fc_hidden):
+    for key, shape, kind in state_dict_spec(transformer_depth, fc_hidden, noess):
         gen_key = key
         for a, tgt in ALIASES.items():
             if key.startswith(a + "."):

@@ -42,7 +42,7 @@ def _model(seed, profile, flags=()):
     if key not in _models:
         _models.clear()
         m = ViTEss(_args(flags))
-        m.load_state_dict(S.make_state_dict(seed, profile))
+        m.load_state_dict(S.make_state_dict(seed, profile, noess="noess" in flags))
         m.precision = "fp32"          # these tests pin the fp32 engine unless they select a tensor-core mode
         _models[key] = m.to(DEV).eval()
     return _models[key]
@@ -79,7 +79,9 @@ def test_forward_matches_reference_golden(name):
     _err("tokens", st["tokens"][TOK], g["stage_tokens"], 2e-4, 2e-4)
     for i in range(5):
         _err(f"block{i}", st[f"block{i}"][TOK], g[f"stage_block{i}"], 5e-4, 5e-4)
-    for kk in ("bilinear1", "bilinear2"):     # absolute floor relative to the magnitude (single softmax: ~576x larger forms)
+    if "noess" in _flags(g):                  # plain cross attention: no bilinear forms, 576-token output
+        _err("cross", st["cross"][TOK], g["stage_cross"], 5e-4, 5e-4)
+    for kk in (() if "noess" in _flags(g) else ("bilinear1", "bilinear2")):     # absolute floor relative to the magnitude (single softmax: ~576x larger forms)
         _err(kk, st[kk], g["stage_" + kk], 2e-5 + 2e-7 * float(np.abs(g["stage_" + kk]).max()), 1e-3)
     _err("features", st["features"][:, ::3], g["stage_features"], 1e-3, 1e-3)
     rot = O.rotation_error_rad(poses[:, 1, 3:], g["poses"][:, 1, 3:])

@@ -59,7 +59,8 @@ def _diagnose(name, got, ref):
     (128, 192, 64, 0, False, 0), (128, 192, 192, 0, False, 0), (256, 384, 128, 0, False, 0),
     (1152, 576, 192, 0, False, 0), (1152, 192, 192, 0, True, 0), (1152, 768, 192, 1, False, 2),
     (1152, 192, 768, 0, True, 0), (140, 768, 192, 1, False, 1), (2, 512, 26880, 2, False, 2),
-    (3, 14, 512, 0, False, 0), (300, 200, 72, 2, True, 2), (20000, 576, 192, 0, False, 0)])
+    (3, 14, 512, 0, False, 0), (300, 200, 72, 2, True, 2), (20000, 576, 192, 0, False, 0),
+    (1152, 96, 384, 2, False, 0)])
 def test_linear_tc(P, M, N, K, act, res, pout):
     a = rnd(5, M, K); w = rnd(6, N, K, scale=1.0 / np.sqrt(K)); b = rnd(7, N, scale=0.1)
     r = rnd(8, M, N) if res else None
@@ -88,7 +89,8 @@ def test_linear_tc(P, M, N, K, act, res, pout):
         assert np.abs(gp - got).max() <= lim
 
 
-@pytest.mark.parametrize("M,N,K,act", [(64, 512, 26880, 2), (2, 512, 26880, 2), (130, 200, 1000, 0), (1, 512, 192, 0)])
+@pytest.mark.parametrize("M,N,K,act", [(64, 512, 26880, 2), (2, 512, 26880, 2), (130, 200, 1000, 0), (1, 512, 192, 0),
+                                         (3, 512, 24768, 2)])
 def test_linear_tc_splitk(M, N, K, act):
     """rp_linear_tc_splitk (pose_regressor.0: short accumulation chains + fixed-order float32 reduction) against float64."""
     a = rnd(11, M, K); w = rnd(12, N, K, scale=1.0 / np.sqrt(K)); b = rnd(13, N, scale=0.1)
@@ -299,6 +301,30 @@ def test_self_attention_tc(P, n, scale):
     # agreement with the fp32 SIMT kernel of the same op
     simt = ops.self_attention(cu(qkv)).cpu().numpy().astype(np.float64)
     assert np.abs(simt - ref).max() < 1e-5 * scale_ref
+
+
+@pytest.mark.parametrize("n", [2, 6])
+def test_cross_attention_pairs(n):
+    """--noess ablation (vision_transformer.py:239-253): image i's queries against the keys/values of image i^1.
+    Bit-identical to self attention over a copy whose K/V columns are swapped inside each pair (fp32 and tcgen05)."""
+    qkv = rnd(77 + n, n, 576, 576, scale=1.5)
+    qkv[:, :, 384:] += 0.25
+    swapped = qkv.copy().reshape(n // 2, 2, 576, 576)
+    swapped[:, :, :, 192:] = swapped[:, ::-1, :, 192:].copy()
+    swapped = swapped.reshape(n, 576, 576)
+    ref = _attention_ref(swapped)
+    got = ops.self_attention(cu(qkv), cross=True)
+    assert torch.equal(got, ops.self_attention(cu(swapped)))
+    assert np.abs(got.cpu().numpy() - ref).max() < 1e-5 * np.abs(ref).max()
+    for P in (2, 1):
+        out, outp = ops.self_attention_tc(ops.split_planes(cu(qkv), P), want_f32=True, planes_out=P, cross=True)
+        out2, outp2 = ops.self_attention_tc(ops.split_planes(cu(swapped), P), want_f32=True, planes_out=P)
+        assert torch.equal(out, out2) and torch.equal(outp, outp2)
+        err = np.abs(out.cpu().numpy() - ref).max()
+        print(f"[parity] cross_attention_tc P={P} n={n}: max_abs_err={err:.3e} max_ref={np.abs(ref).max():.3e}")
+        assert err <= (1e-4 if P == 2 else 2e-2) * np.abs(ref).max()
+    with pytest.raises(Exception):
+        ops.self_attention(cu(qkv[:1]), cross=True)          # odd image count: not pairs
 
 
 @pytest.mark.parametrize("P", [2, 1])

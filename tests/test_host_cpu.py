@@ -57,12 +57,28 @@ def test_state_dict_layout_matches_reference_spec():
     assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 19258510
 
 
+def test_noess_state_dict_layout():
+    """--noess (model.py:71-88): proj instead of proj_fundamental, the pool_attn head, a 24768-wide regressor.  The spec
+    is the one oracle/make_golden.py loads strictly into the real reference."""
+    from rel_pose_b200 import ViTEss
+    m = ViTEss(_args(noess=True))
+    sd = m.state_dict()
+    spec = S.state_dict_spec(noess=True)
+    assert sorted(sd.keys()) == sorted(k for k, _, _ in spec)
+    for k, shape, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert "fusion_transformer.blocks.5.cross_attn.proj.weight" in sd and m.H == 24768
+    assert tuple(sd["pool_attn.0.weight"].shape) == (96, 384, 1, 1) and tuple(sd["pool_attn.3.weight"].shape) == (43, 96, 1, 1)
+    res = m.load_state_dict(S.make_state_dict(0, "stress", noess=True), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert ViTEss(_args()).noess is False and not hasattr(ViTEss(_args()), "pool_attn")
+
+
 def test_ablation_flags():
-    """--noess / --no_pos_encoding / CNN-only are rejected loudly; the Essential-Matrix-Module variants are accepted."""
+    """--no_pos_encoding / CNN-only are rejected loudly; --noess and the Essential-Matrix-Module variants are accepted."""
     from rel_pose_b200 import ViTEss, ops
-    for flag in ("noess", "no_pos_encoding"):
-        with pytest.raises(NotImplementedError):
-            ViTEss(_args(**{flag: True}))
+    with pytest.raises(NotImplementedError):
+        ViTEss(_args(no_pos_encoding=True))
     with pytest.raises(NotImplementedError):
         ViTEss(_args(fusion_transformer=False))
     m = ViTEss(_args(cross_features=True, use_single_softmax=True, l1_pos_encoding=True))
