@@ -38,6 +38,8 @@ ABLATION_CASES = [
     # --noess: plain cross attention + pool_attn head instead of the module (model.py:71-88,183-187)
     ("ablate_noess_b2_64x80", 15, "stress", 2, 64, 80, "matterport", True, ("noess",)),
     ("ablate_noess_b3_96x128_init", 16, "init", 3, 96, 128, None, False, ("noess",)),
+    # no --fusion_transformer: CNN front end + pool_transformer_output head only (model.py:62-69,179-181)
+    ("ablate_cnn_only_b3_64x80", 17, "stress", 3, 64, 80, "matterport", True, ("cnn_only",)),
 ]
 
 TOK_SAMPLE = (slice(None), slice(None, None, 9), slice(None, None, 4))
@@ -55,9 +57,10 @@ def sample(name, t):
 
 
 def run_case(name, seed, profile, B, H, W, ikind, integer, flags=()):
-    model, SE3 = ref_loader.load_reference_model(**{f: True for f in flags})
+    cnn_only = "cnn_only" in flags
+    model, SE3 = ref_loader.load_reference_model(**{("fusion_transformer" if f == "cnn_only" else f): f != "cnn_only" for f in flags})
     noess = "noess" in flags
-    model.load_state_dict(S.make_state_dict(seed, profile, noess=noess))
+    model.load_state_dict(S.make_state_dict(seed, profile, noess=noess, cnn_only=cnn_only))
     model.eval()
     images = torch.from_numpy(S.make_images_numpy(seed, B, H, W, integer))
     intr = None if ikind is None else torch.from_numpy(S.make_intrinsics_numpy(B, ikind, seed))
@@ -75,15 +78,16 @@ def run_case(name, seed, profile, B, H, W, ikind, integer, flags=()):
     hooks.append(model.extractor_final_conv.register_forward_hook(
         put("tokens", lambda i, o: o.reshape(o.shape[0], 192, 576).permute(0, 2, 1))))
     hooks.append(model.resnet.conv1.register_forward_hook(put("preprocessed", lambda i, o: i[0])))
-    for li in range(5):
+    for li in range(0 if cnn_only else 5):
         hooks.append(vt.blocks[li].register_forward_hook(put(f"block{li}", lambda i, o: o)))
-    hooks.append(vt.blocks[5].register_forward_hook(put("cross", lambda i, o: o)))
+    if not cnn_only:
+        hooks.append(vt.blocks[5].register_forward_hook(put("cross", lambda i, o: o)))
     zs = []
 
     def _z_hook(m, i):
         zs.append(i[0])
 
-    if not noess:
+    if not noess and not cnn_only:
         hooks.append(vt.blocks[5].cross_attn.proj_fundamental.register_forward_pre_hook(_z_hook))
 
     def _reg_hook(m, i, o):
@@ -97,7 +101,7 @@ def run_case(name, seed, profile, B, H, W, ikind, integer, flags=()):
         h.remove()
     # proj_fundamental is applied to z2 first, then z1 (vision_transformer.py:233-234);
     # z[b,c,h*70+a] = F[b,h,a,c]  ->  recover F[b,h,a,c]
-    if not noess:
+    if not noess and not cnn_only:
         z2, z1 = zs
         unz = lambda z: z.reshape(B, 70, 3, 70).permute(0, 2, 3, 1)
         stages["bilinear1"] = unz(z1)
@@ -137,10 +141,10 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else ""
-    if only not in ("ablations", "noess"):
+    if only not in ("ablations", "noess", "cnn_only"):
         posenc_golden()
         for c in CASES:
             run_case(*c)
     for c in ABLATION_CASES:
-        if only != "noess" or "noess" in c[-1]:
+        if only not in ("noess", "cnn_only") or only in c[-1]:
             run_case(*c)

@@ -324,6 +324,17 @@ def pool_attn_noess(x, p, B):
     return h.reshape(B, -1)
 
 
+def pool_transformer_output_cnn_only(tok, p, B):
+    """The model without --fusion_transformer (src/model.py:62-69,138-139,179-181,189): the first 96 channels of every
+    token, re-read as [B,24,24,192] (two consecutive tokens of the pair's flat list per "pixel"), 1x1 conv 192->96 + BN
+    + ReLU + 1x1 conv 96->pool_size + BN, flattened channel-major."""
+    f = np.ascontiguousarray(tok[:, :, :EMBED // 2]).reshape(B, GRID, GRID, EMBED).transpose(0, 3, 1, 2)
+    pre = "pool_transformer_output"
+    h = relu(batchnorm_eval(conv2d(f, p[pre + ".0.weight"], p[pre + ".0.bias"]), p, pre + ".1"))
+    h = batchnorm_eval(conv2d(h, p[pre + ".3.weight"], p[pre + ".3.bias"]), p, pre + ".4")
+    return h.reshape(B, -1)
+
+
 def cross_block(x, p, prefix, intrinsics=None, return_bilinear=False, flags=()):
     """CrossBlock.forward, vision_transformer.py:285-296.  x [2B,576,192] -> [2B,70,192]."""
     n2, N, C = x.shape
@@ -369,6 +380,12 @@ def vitess_forward(images, Gs, intrinsics, p, dtype=np.float32, depth=6, stages=
     tok = tokens_from_feature_map(fm)
     if stages is not None:
         stages["tokens"] = tok
+    if "cnn_only" in flags:
+        feat = pool_transformer_output_cnn_only(tok, p, B)
+        raw = pose_regressor(feat, p)
+        if stages is not None:
+            stages["features"], stages["raw_pose"] = feat, raw
+        return normalize_preds(Gs, raw), intr
     x = tok + p["fusion_transformer.pos_embed"].astype(dtype)
     for i in range(depth - 1):
         x = block(x, p, f"fusion_transformer.blocks.{i}")

@@ -49,9 +49,10 @@ def hash_normal(seed, name, n):
 
 
 # ----------------------------------------------------------------------------------------------
-def state_dict_spec(transformer_depth=6, fc_hidden=512, noess=False):
+def state_dict_spec(transformer_depth=6, fc_hidden=512, noess=False, cnn_only=False, pool_size=60):
     """[(key, shape, kind)] in the reference's state_dict order.  kind drives the value profile.
-    `noess` = the layout of the --noess ablation (model.py:71-88, vision_transformer.py:176-177)."""
+    `noess` = the layout of the --noess ablation (model.py:71-88, vision_transformer.py:176-177); `cnn_only` = the
+    model built without --fusion_transformer (model.py:62-69): no transformer, a pool_transformer_output head."""
     spec = []
 
     def conv(prefix, co, ci, k, bias):
@@ -98,6 +99,16 @@ def state_dict_spec(transformer_depth=6, fc_hidden=512, noess=False):
     bn(e + ".norm3", 192)
     conv(e + ".downsample.0", 192, 128, 5, True)
     bn(e + ".downsample.1", 192)  # alias of norm3 (same tensors)
+    if cnn_only:
+        pf1 = min(96, 4 * pool_size)
+        conv("pool_transformer_output.0", pf1, 192, 1, True)
+        bn("pool_transformer_output.1", pf1)
+        conv("pool_transformer_output.3", pool_size, pf1, 1, True)
+        bn("pool_transformer_output.4", pool_size)
+        lin("pose_regressor.0", fc_hidden, pool_size * 576)
+        lin("pose_regressor.2", fc_hidden, fc_hidden)
+        lin("pose_regressor.4", 14, fc_hidden)
+        return spec
     f = "fusion_transformer"
     spec.append((f + ".pos_embed", (1, 576, 192), "posemb"))
     for i in range(transformer_depth):
@@ -132,7 +143,7 @@ def state_dict_spec(transformer_depth=6, fc_hidden=512, noess=False):
 ALIASES = {"extractor_final_conv.downsample.1": "extractor_final_conv.norm3"}
 
 
-def make_state_dict_numpy(seed=0, profile="stress", transformer_depth=6, fc_hidden=512, noess=False):
+def make_state_dict_numpy(seed=0, profile="stress", transformer_depth=6, fc_hidden=512, noess=False, cnn_only=False):
     """OrderedDict key -> np.ndarray (float32, int64 for num_batches_tracked).
 
     profile "init":   statistics close to the reference's random init (small ViT weights,
@@ -142,7 +153,7 @@ def make_state_dict_numpy(seed=0, profile="stress", transformer_depth=6, fc_hidd
     """
     assert profile in ("init", "stress")
     out = OrderedDict()
-    for key, shape, kind in state_dict_spec(transformer_depth, fc_hidden, noess):
+    for key, shape, kind in state_dict_spec(transformer_depth, fc_hidden, noess, cnn_only):
         gen_key = key
         for a, tgt in ALIASES.items():
             if key.startswith(a + "."):

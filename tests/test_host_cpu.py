@@ -75,12 +75,18 @@ def test_noess_state_dict_layout():
 
 
 def test_ablation_flags():
-    """--no_pos_encoding / CNN-only are rejected loudly; --noess and the Essential-Matrix-Module variants are accepted."""
+    """--no_pos_encoding (and --noess without a transformer) cannot run in the reference either and are rejected loudly;
+    --noess, the CNN-only model and the Essential-Matrix-Module variants are accepted."""
     from rel_pose_b200 import ViTEss, ops
     with pytest.raises(NotImplementedError):
         ViTEss(_args(no_pos_encoding=True))
     with pytest.raises(NotImplementedError):
-        ViTEss(_args(fusion_transformer=False))
+        ViTEss(_args(fusion_transformer=False, noess=True))
+    m = ViTEss(_args(fusion_transformer=False))
+    spec = S.state_dict_spec(cnn_only=True)
+    assert sorted(m.state_dict().keys()) == sorted(k for k, _, _ in spec) and m.fusion_transformer is None and m.H == 34560
+    res = m.load_state_dict(S.make_state_dict(0, "init", cnn_only=True), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
     m = ViTEss(_args(cross_features=True, use_single_softmax=True, l1_pos_encoding=True))
     assert m.em_flags == (ops.EM_SINGLE_SOFTMAX | ops.EM_CROSS_FEATURES) and m.l1_pos_encoding
     assert ViTEss(_args()).em_flags == 0
