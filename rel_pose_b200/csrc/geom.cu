@@ -7,6 +7,7 @@
 // call sites src/geom/losses.py:8-10.  Backward: gradient w.r.t. a LEFT perturbation exp(d)X, written
 // to the first 6 of 7 slots, slot 7 = 0 (lietorch group_ops convention).  Parity unpinned by the
 // reference (lietorch absent) -- checked against oracle/geom_oracle.py.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -186,8 +187,30 @@ struct SE3e {
 };
 
 // ------------------------------------------------------------------ coalesced AoS <-> registers
-template <int W>
+// VEC: a full block moves its TPB*W contiguous floats as 128-bit words with streaming hints (one address computation
+// per thread, no per-element bounds test: ~6 instead of ~45 instructions for W = 9); the last partial block and
+// unaligned bases take the scalar path.  Measured A/B on one B200 (N = 2^20, profiles/r01_geom_staging_ab.md): the
+// instruction-heavy kernels gain (svd3 39.7 -> 34.5 us, essential_to_rt 43.4 -> 37.8 us), the short bandwidth-bound SE3
+// kernels LOSE (se3_mul 16.6 -> 20.0 us with streaming hints, 17.2 us without; se3_inv 11.6 -> 13.1 us): with only
+// 2-4 wide requests per thread fewer bytes are in flight than with 7-14 scalar ones.  So VEC is per kernel.
+template <int W, bool VEC>
+__device__ __forceinline__ bool stage_fast(const float* g, int64_t base_elem, int64_t n) {
+    return VEC && base_elem + TPB <= n && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+}
+template <int W, bool VEC = false>
 __device__ __forceinline__ void stage_in(const float* __restrict__ g, float* s, int64_t base_elem, int64_t n) {
+    constexpr int NV = TPB * W / 4;
+    static_assert((TPB * W) % 4 == 0, "a block's slab must be a whole number of float4");
+    if (stage_fast<W, VEC>(g, base_elem, n)) {
+        const float4* g4 = reinterpret_cast<const float4*>(g + base_elem * W);
+        float4* s4 = reinterpret_cast<float4*>(s);
+#pragma unroll
+        for (int k = 0; k < (NV + TPB - 1) / TPB; ++k) {
+            const int i = k * TPB + threadIdx.x;
+            if ((k + 1) * TPB <= NV || i < NV) s4[i] = __ldcs(g4 + i);
+        }
+        return;
+    }
     int64_t first = base_elem * W;
     int64_t total = n * W;
 #pragma unroll
@@ -196,8 +219,19 @@ __device__ __forceinline__ void stage_in(const float* __restrict__ g, float* s, 
         s[k * TPB + threadIdx.x] = (i < total) ? g[i] : 0.f;
     }
 }
-template <int W>
+template <int W, bool VEC = false>
 __device__ __forceinline__ void stage_out(float* __restrict__ g, const float* s, int64_t base_elem, int64_t n) {
+    constexpr int NV = TPB * W / 4;
+    if (stage_fast<W, VEC>(g, base_elem, n)) {
+        float4* g4 = reinterpret_cast<float4*>(g + base_elem * W);
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+        for (int k = 0; k < (NV + TPB - 1) / TPB; ++k) {
+            const int i = k * TPB + threadIdx.x;
+            if ((k + 1) * TPB <= NV || i < NV) __stcs(g4 + i, s4[i]);
+        }
+        return;
+    }
     int64_t first = base_elem * W;
     int64_t total = n * W;
 #pragma unroll
@@ -224,7 +258,7 @@ __device__ __forceinline__ void write6(float* s, V3 a, V3 b) {
 
 // ------------------------------------------------------------------ SE3 kernels
 __global__ void __launch_bounds__(TPB) se3_mul_fwd_kernel(const float* X, const float* Y, float* Z, int64_t n) {
-    __shared__ float sx[TPB * 7], sy[TPB * 7];
+    __shared__ __align__(16) float sx[TPB * 7], sy[TPB * 7];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<7>(X, sx, base, n);
     stage_in<7>(Y, sy, base, n);
@@ -240,7 +274,7 @@ __global__ void __launch_bounds__(TPB) se3_mul_fwd_kernel(const float* X, const 
 
 __global__ void __launch_bounds__(TPB)
 se3_mul_bwd_kernel(const float* dZ, const float* X, const float* Y, float* dX, float* dY, int64_t n) {
-    __shared__ float sg[TPB * 7], sx[TPB * 7];
+    __shared__ __align__(16) float sg[TPB * 7], sx[TPB * 7];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<7>(dZ, sg, base, n);
     stage_in<7>(X, sx, base, n);
@@ -261,7 +295,7 @@ se3_mul_bwd_kernel(const float* dZ, const float* X, const float* Y, float* dX, f
 }
 
 __global__ void __launch_bounds__(TPB) se3_inv_fwd_kernel(const float* X, float* Y, int64_t n) {
-    __shared__ float sx[TPB * 7];
+    __shared__ __align__(16) float sx[TPB * 7];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<7>(X, sx, base, n);
     __syncthreads();
@@ -275,7 +309,7 @@ __global__ void __launch_bounds__(TPB) se3_inv_fwd_kernel(const float* X, float*
 }
 
 __global__ void __launch_bounds__(TPB) se3_inv_bwd_kernel(const float* dY, const float* X, float* dX, int64_t n) {
-    __shared__ float sg[TPB * 7], sx[TPB * 7];
+    __shared__ __align__(16) float sg[TPB * 7], sx[TPB * 7];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<7>(dY, sg, base, n);
     stage_in<7>(X, sx, base, n);
@@ -294,7 +328,7 @@ __global__ void __launch_bounds__(TPB) se3_inv_bwd_kernel(const float* dY, const
 }
 
 __global__ void __launch_bounds__(TPB) se3_log_fwd_kernel(const float* X, float* A, int64_t n) {
-    __shared__ float sx[TPB * 7];
+    __shared__ __align__(16) float sx[TPB * 7];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<7>(X, sx, base, n);
     __syncthreads();
@@ -308,7 +342,7 @@ __global__ void __launch_bounds__(TPB) se3_log_fwd_kernel(const float* X, float*
 }
 
 __global__ void __launch_bounds__(TPB) se3_log_bwd_kernel(const float* dA, const float* X, float* dX, int64_t n) {
-    __shared__ float sg[TPB * 7], sx[TPB * 7];
+    __shared__ __align__(16) float sg[TPB * 7], sx[TPB * 7];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<6>(dA, sg, base, n);
     stage_in<7>(X, sx, base, n);
@@ -330,7 +364,7 @@ __global__ void __launch_bounds__(TPB) se3_log_bwd_kernel(const float* dA, const
 }
 
 __global__ void __launch_bounds__(TPB) se3_exp_fwd_kernel(const float* A, float* X, int64_t n) {
-    __shared__ float sx[TPB * 7];
+    __shared__ __align__(16) float sx[TPB * 7];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<6>(A, sx, base, n);
     __syncthreads();
@@ -345,7 +379,7 @@ __global__ void __launch_bounds__(TPB) se3_exp_fwd_kernel(const float* A, float*
 }
 
 __global__ void __launch_bounds__(TPB) se3_exp_bwd_kernel(const float* dX, const float* A, float* dA, int64_t n) {
-    __shared__ float sg[TPB * 7], sa[TPB * 6];
+    __shared__ __align__(16) float sg[TPB * 7], sa[TPB * 6];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<7>(dX, sg, base, n);
     stage_in<6>(A, sa, base, n);
@@ -374,6 +408,20 @@ struct Svd3 {
     V3 v[3];   // columns
 };
 
+// Bare MUFU.RCP / MUFU.RSQ.  `__fdividef` and `rsqrtf` wrap each MUFU in a denormal range check (FSETP + two FMUL:
+// 12 of the 72 instructions of one rotation); the rotation only feeds them r >= 1, 1 + t^2 >= 1 and quantities whose
+// flush-to-zero limit is a harmless identity rotation (2*gamma -> 0 gives t = 0, c = 1, s = 0).
+__device__ __forceinline__ float mufu_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_rsq(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // One Jacobi rotation of columns p, q.  MUFU-only arithmetic (rcp / rsqrt approximations): a slightly inexact
 // angle costs nothing -- the next rotation removes what is left -- while c, s are normalised consistently so the
 // accumulated V stays orthonormal to ~1e-7.  Returns true if another sweep is needed because of this pair.
@@ -384,10 +432,10 @@ __device__ __forceinline__ bool jacobi_pair(V3& ap, V3& aq, V3& vp, V3& vq) {
     // Jacobi converges quadratically: a pair whose cosine is below 3e-4 BEFORE its rotation is orthogonal to ~1e-7
     // after it, so such a rotation does not ask for another sweep
     const bool big = gamma * gamma > 1e-7f * alpha * beta;
-    const float zeta = __fdividef(beta - alpha, 2.0f * gamma);
+    const float zeta = (beta - alpha) * mufu_rcp(2.0f * gamma);
     const float r = 1.0f + zeta * zeta;
-    const float t = __fdividef(copysignf(1.0f, zeta), fabsf(zeta) + r * rsqrtf(r));
-    const float c = rsqrtf(1.0f + t * t), sn = c * t;
+    const float t = copysignf(mufu_rcp(fabsf(zeta) + r * mufu_rsq(r)), zeta);
+    const float c = mufu_rsq(1.0f + t * t), sn = c * t;
     const V3 np_ = c * ap - sn * aq, nq = sn * ap + c * aq;
     ap = np_; aq = nq;
     const V3 wp = c * vp - sn * vq, wq = sn * vp + c * vq;
@@ -442,9 +490,9 @@ __device__ Svd3 svd3(const float* e /* row-major 3x3 */) {
 }
 
 __global__ void __launch_bounds__(TPB) svd3_kernel(const float* E, float* U, float* S, float* V, int64_t n) {
-    __shared__ float se[TPB * 9], sv[TPB * 9], ss[TPB * 3];
+    __shared__ __align__(16) float se[TPB * 9], sv[TPB * 9], ss[TPB * 3];
     int64_t base = (int64_t)blockIdx.x * TPB;
-    stage_in<9>(E, se, base, n);
+    stage_in<9, true>(E, se, base, n);
     __syncthreads();
     Svd3 r = svd3(se + threadIdx.x * 9);
     __syncthreads();
@@ -457,17 +505,17 @@ __global__ void __launch_bounds__(TPB) svd3_kernel(const float* E, float* U, flo
         ss[threadIdx.x * 3 + c] = r.s[c];
     }
     __syncthreads();
-    stage_out<9>(U, se, base, n);
-    stage_out<9>(V, sv, base, n);
-    stage_out<3>(S, ss, base, n);
+    stage_out<9, true>(U, se, base, n);
+    stage_out<9, true>(V, sv, base, n);
+    stage_out<3, true>(S, ss, base, n);
 }
 
 __device__ __forceinline__ float det3(V3 a, V3 b, V3 c) { return dot(a, cross(b, c)); }
 
 __global__ void __launch_bounds__(TPB) essential_to_rt_kernel(const float* E, float* R1, float* R2, float* T, int64_t n) {
-    __shared__ float se[TPB * 9], s2[TPB * 9], st[TPB * 3];
+    __shared__ __align__(16) float se[TPB * 9], s2[TPB * 9], st[TPB * 3];
     int64_t base = (int64_t)blockIdx.x * TPB;
-    stage_in<9>(E, se, base, n);
+    stage_in<9, true>(E, se, base, n);
     __syncthreads();
     Svd3 r = svd3(se + threadIdx.x * 9);
     __syncthreads();
@@ -492,9 +540,9 @@ __global__ void __launch_bounds__(TPB) essential_to_rt_kernel(const float* E, fl
         }
     st[threadIdx.x * 3 + 0] = u2.x; st[threadIdx.x * 3 + 1] = u2.y; st[threadIdx.x * 3 + 2] = u2.z;
     __syncthreads();
-    stage_out<9>(R1, se, base, n);
-    stage_out<9>(R2, s2, base, n);
-    stage_out<3>(T, st, base, n);
+    stage_out<9, true>(R1, se, base, n);
+    stage_out<9, true>(R2, s2, base, n);
+    stage_out<3, true>(T, st, base, n);
 }
 
 inline int nblocks(int64_t n) { return (int)((n + TPB - 1) / TPB); }
