@@ -240,6 +240,11 @@ int rp_essential_ex_f32(const float* qkv, const float* pos, float* bil, int B, i
 size_t rp_essential_tc_workspace_bytes(int B, int P);
 int rp_essential_tc(const void* qkv_planes, const float* pos, float* bil, int B, int P, void* workspace,
                     size_t workspace_bytes, int device, void* stream);
+/* The same two kernels with the ablation flags of rp_essential_ex_f32 (vision_transformer.py:201-203,219-220):
+ * RP_EM_SINGLE_SOFTMAX drops the column term of the exponent, RP_EM_CROSS_FEATURES takes the left factor of F from
+ * the other view.  flags = 0 is rp_essential_tc. */
+int rp_essential_ex_tc(const void* qkv_planes, const float* pos, float* bil, int B, int P, int flags, void* workspace,
+                       size_t workspace_bytes, int device, void* stream);
 
 
 /* ---- A7 tail  vision_transformer.py:229-238 + :292-294 --------------------------------------

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "rp_essential_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_essential_tc_workspace_bytes": (_c_size, [_c_int, _c_int]),
     "rp_essential_tc": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _c_size, _c_int, _ptr]),
+    "rp_essential_ex_tc": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_em_project_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_normalize_pose_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_se3_mul_fwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),

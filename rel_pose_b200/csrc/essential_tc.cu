@@ -240,7 +240,7 @@ template <int P>
 __global__ void __launch_bounds__(EM_THREADS, 1)
 em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmPos, const float* __restrict__ lse2, float* __restrict__ bil,
-                   int B, int width) {
+                   int B, int width, int em_flags) {
     using C = ECfg<P>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -351,7 +351,9 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             tc::mbar_expect_tx(vi_full, P * R_TILE + (has_pos ? P * 2 * POS_SUB : 0));
 #pragma unroll
                             for (int p = 0; p < P; ++p) {
-                                tc::tma_load_4d(vi_tile(p), &tmQ, vi_full, 2 * EMB + h * HD, tile * BM, kv_img, p);
+                                // --cross_features (:219-220): the left factor is the OTHER view's [v | pos]
+                                tc::tma_load_4d(vi_tile(p), &tmQ, vi_full, 2 * EMB + h * HD, tile * BM,
+                                                (em_flags & RP_EM_CROSS_FEATURES) ? q_img : kv_img, p);
                                 if (has_pos) {
                                     tc::tma_load_4d(posi_tile(p), &tmPos, vi_full, tile * BM, 0, b, p);
                                     tc::tma_load_4d(posi_tile(p) + POS_SUB, &tmPos, vi_full, tile * BM + 64, 0, b, p);
@@ -552,7 +554,10 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
             };
             asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone is done with the previous item's cl[]
-            for (int c = st; c < NTOK; c += 128) cl[c] = lse_c[c];
+            // --use_single_softmax (:201-203): A = softmax(S,-1) = 2^(c s - lse2_r): no column term, exponent counted once
+            const bool single = (em_flags & RP_EM_SINGLE_SOFTMAX) != 0;
+            const float emul = single ? SCALE_LOG2 : 2.f * SCALE_LOG2;
+            for (int c = st; c < NTOK; c += 128) cl[c] = single ? 0.f : lse_c[c];
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int tile = 0; tile < RTILES; ++tile, ++tt) {
                 const int row = tile * BM + r;
@@ -596,10 +601,10 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < BKV; i += 4) {
                         const float4 c4 = cl4[i >> 2];
-                        s[i] = __float_as_uint(tc::fast_exp2(fmaf(__uint_as_float(s[i]), 2.f * SCALE_LOG2, -(rl + c4.x))));
-                        s[i + 1] = __float_as_uint(tc::fast_exp2(fmaf(__uint_as_float(s[i + 1]), 2.f * SCALE_LOG2, -(rl + c4.y))));
-                        s[i + 2] = __float_as_uint(tc::fast_exp2(fmaf(__uint_as_float(s[i + 2]), 2.f * SCALE_LOG2, -(rl + c4.z))));
-                        s[i + 3] = __float_as_uint(tc::fast_exp2(fmaf(__uint_as_float(s[i + 3]), 2.f * SCALE_LOG2, -(rl + c4.w))));
+                        s[i] = __float_as_uint(tc::fast_exp2(fmaf(__uint_as_float(s[i]), emul, -(rl + c4.x))));
+                        s[i + 1] = __float_as_uint(tc::fast_exp2(fmaf(__uint_as_float(s[i + 1]), emul, -(rl + c4.y))));
+                        s[i + 2] = __float_as_uint(tc::fast_exp2(fmaf(__uint_as_float(s[i + 2]), emul, -(rl + c4.z))));
+                        s[i + 3] = __float_as_uint(tc::fast_exp2(fmaf(__uint_as_float(s[i + 3]), emul, -(rl + c4.w))));
                     }
                     // The A buffer and the T / F accumulator region are free once the previous product has retired:
                     // inside a tile that is PV_{j-1} (fold its T_j), at a tile start the F update of the previous
@@ -721,8 +726,8 @@ int make_map4(CUtensorMap* out, const void* base, cuuint64_t d0, cuuint64_t d1, 
 }
 
 template <int P>
-int launch_essential(const void* qkv_planes, const float* pos, float* bil, int B, float* lse2, void* pos_planes, int device,
-                     cudaStream_t st) {
+int launch_essential(const void* qkv_planes, const float* pos, float* bil, int B, int flags, float* lse2, void* pos_planes,
+                     int device, cudaStream_t st) {
     const int width = pos ? EMW : HD;
     CUtensorMap tmR, tmC, tmPos;
     int rc = make_map4(&tmR, qkv_planes, 3 * EMB, NTOK, 2 * (cuuint64_t)B, P, 64, BM, "rp_essential_tc(rows)");
@@ -754,7 +759,7 @@ int launch_essential(const void* qkv_planes, const float* pos, float* bil, int B
     em_stats_tc_kernel<P><<<n_stats < sms ? n_stats : sms, EM_THREADS, SCfg<P>::SMEM, st>>>(tmR, tmC, lse2, B);
     rc = rp::finish_launch("rp_essential_tc(stats)");
     if (rc) return rc;
-    em_accum_tc_kernel<P><<<n_acc < sms ? n_acc : sms, EM_THREADS, ECfg<P>::SMEM, st>>>(tmR, tmC, tmPos, lse2, bil, B, width);
+    em_accum_tc_kernel<P><<<n_acc < sms ? n_acc : sms, EM_THREADS, ECfg<P>::SMEM, st>>>(tmR, tmC, tmPos, lse2, bil, B, width, flags);
     return rp::finish_launch("rp_essential_tc(accum)");
 }
 
@@ -767,9 +772,10 @@ extern "C" size_t rp_essential_tc_workspace_bytes(int B, int P) {
     return lse + posp;
 }
 
-extern "C" int rp_essential_tc(const void* qkv_planes, const float* pos, float* bil, int B, int P, void* workspace,
-                               size_t workspace_bytes, int device, void* stream) {
-    RP_REQUIRE(qkv_planes && bil && B > 0, RP_EINVAL, "rp_essential_tc: bad argument");
+extern "C" int rp_essential_ex_tc(const void* qkv_planes, const float* pos, float* bil, int B, int P, int flags, void* workspace,
+                                  size_t workspace_bytes, int device, void* stream) {
+    RP_REQUIRE(qkv_planes && bil && B > 0 && (flags & ~(RP_EM_SINGLE_SOFTMAX | RP_EM_CROSS_FEATURES)) == 0, RP_EINVAL,
+               "rp_essential_tc: bad argument");
     RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_essential_tc: P must be 1 (bf16) or 2 (bf16x3)");
     RP_REQUIRE(rp::aligned16(qkv_planes), RP_EALIGN, "rp_essential_tc: qkv planes must be 16-byte aligned");
     RP_REQUIRE(workspace && workspace_bytes >= rp_essential_tc_workspace_bytes(B, P), RP_EWORKSPACE,
@@ -778,6 +784,11 @@ extern "C" int rp_essential_tc(const void* qkv_planes, const float* pos, float* 
     RP_GUARD(device);
     float* lse2 = static_cast<float*>(workspace);
     void* posp = static_cast<char*>(workspace) + (size_t)B * 2 * 2 * HEADS * NTOK * sizeof(float);
-    if (P == 1) return launch_essential<1>(qkv_planes, pos, bil, B, lse2, posp, device, (cudaStream_t)stream);
-    return launch_essential<2>(qkv_planes, pos, bil, B, lse2, posp, device, (cudaStream_t)stream);
+    if (P == 1) return launch_essential<1>(qkv_planes, pos, bil, B, flags, lse2, posp, device, (cudaStream_t)stream);
+    return launch_essential<2>(qkv_planes, pos, bil, B, flags, lse2, posp, device, (cudaStream_t)stream);
+}
+
+extern "C" int rp_essential_tc(const void* qkv_planes, const float* pos, float* bil, int B, int P, void* workspace,
+                               size_t workspace_bytes, int device, void* stream) {
+    return rp_essential_ex_tc(qkv_planes, pos, bil, B, P, 0, workspace, workspace_bytes, device, stream);
 }

@@ -108,9 +108,9 @@ class ViTEss(nn.Module):
         super().__init__()
         # The configuration every reference script runs (--fusion_transformer, dual softmax, quadratic positional
         # encoding) is the hot path.  Of the ablation branches the three that only vary the
-        # Essential Matrix Module are supported -- --use_single_softmax / --cross_features on the fp32 SIMT module
-        # kernels (rp_essential_ex_f32), --l1_pos_encoding in every precision -- and so is --noess (plain cross
-        # attention + the pool_attn head, every precision).  All inference only.
+        # Essential Matrix Module are supported in every precision -- --use_single_softmax / --cross_features as flags
+        # of the module kernels (rp_essential_ex_f32 / rp_essential_ex_tc), --l1_pos_encoding in the encoding kernel --
+        # and so is --noess (plain cross attention + the pool_attn head).  All inference only.
         if _flag(args, "no_pos_encoding"):
             raise NotImplementedError(
                 "--no_pos_encoding is an ablation branch outside the B200 hot path (SURVEY.md 8(f) rank 4); the reference "
@@ -351,14 +351,9 @@ class ViTEss(nn.Module):
             h = ops.layernorm(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)     # norm1 on both views
             qkv = ops.linear(h, ca.qkv.weight, ca.qkv.bias)
         else:
-            if self.em_flags:
-                # ablation variants of the module run on the fp32 SIMT kernels: ask the projection for float32 qkv
-                qkv = ops.ln_linear_tc(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, self._planes(ca.qkv.weight, P),
-                                       ca.qkv.bias, want_f32=True)[0]
-            else:
-                qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
+            qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
         pos = ops.posenc(B, kxy, x.device, self.l1_pos_encoding)
-        bil = ops.essential(qkv, pos, self.em_flags) if (P == 0 or self.em_flags) else ops.essential_tc(qkv, pos)
+        bil = ops.essential(qkv, pos, self.em_flags) if P == 0 else ops.essential_tc(qkv, pos, self.em_flags)
         if stages is not None:
             stages["bilinear1"], stages["bilinear2"] = bil[:, 0], bil[:, 1]
         f = ops.em_project(bil, ca.proj_fundamental.weight, ca.proj_fundamental.bias)

@@ -553,8 +553,9 @@ def essential(qkv, pos, flags=0):
     return bil
 
 
-def essential_tc(qkv_planes, pos):
-    """qkv_planes bf16 [P,2B,576,576], pos [B,576,6] or None -> bilinear forms [B,2,3,W,W] (tensor cores)."""
+def essential_tc(qkv_planes, pos, flags=0):
+    """qkv_planes bf16 [P,2B,576,576], pos [B,576,6] or None -> bilinear forms [B,2,3,W,W] (tensor cores).
+    flags: EM_SINGLE_SOFTMAX | EM_CROSS_FEATURES (ablation branches)."""
     _req(qkv_planes, "qkv_planes", torch.bfloat16)
     P, n = qkv_planes.shape[0], qkv_planes.shape[1]
     B = n // 2
@@ -571,7 +572,7 @@ def essential_tc(qkv_planes, pos):
     _tbegin(f"essential_tc{'x3' if P == 2 else ''}",
             B * 2.0 * HEADS * (3 * 2.0 * NTOK * NTOK * HDIM + 2.0 * NTOK * NTOK * width + 2.0 * NTOK * width * width),
             2.0 * P * n * NTOK * 3 * EMBED + 4.0 * B * 2 * HEADS * width * width)
-    _lib.check(L.rp_essential_tc(_p(qkv_planes), _p(pos), _p(bil), B, P, _p(ws), ws_bytes, dev, st), "rp_essential_tc")
+    _lib.check(L.rp_essential_ex_tc(_p(qkv_planes), _p(pos), _p(bil), B, P, int(flags), _p(ws), ws_bytes, dev, st), "rp_essential_tc")
     _count(3 if pos is not None else 2)
     return bil
 

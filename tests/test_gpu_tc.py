@@ -363,6 +363,32 @@ def test_stem_windows_conv(P, B, H, W, u8):
 
 
 @pytest.mark.parametrize("P", [2, 1])
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_essential_tc_ablation_flags(P, flags):
+    """--use_single_softmax (1) / --cross_features (2) on the tensor-core module kernels vs the fp32 SIMT kernels of the
+    same variants (which the goldens from the real reference pin, tests/test_gpu_forward.py)."""
+    B = 3
+    x = rnd(52, 2 * B, 576, 192)
+    w = rnd(53, 576, 192, scale=2.0 / np.sqrt(192)); bq = rnd(54, 576, scale=0.1)
+    k = O.update_intrinsics(S.make_intrinsics_numpy(B, "varied", 3), 384, 512)
+    qkv = ops.linear(cu(x), cu(w), cu(bq))
+    kxy = cu(np.stack([1 / (k[:, 0, 0] / k[:, 0, 2]), 1 / (k[:, 0, 1] / k[:, 0, 3])], -1).astype(np.float32))
+    pos = ops.posenc(B, kxy, qkv.device)
+    ref = ops.essential(qkv, pos, flags).cpu().numpy().astype(np.float64)
+    plain = ops.essential(qkv, pos, 0).cpu().numpy().astype(np.float64)
+    assert np.abs(ref - plain).max() > 1e-3 * np.abs(ref).max()          # the flag changes the result
+    qp = ops.split_planes(qkv, P)
+    got = ops.essential_tc(qp, pos, flags)
+    assert torch.equal(got, ops.essential_tc(qp, pos, flags))             # bit-reproducible
+    got = got.cpu().numpy().astype(np.float64)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    print(f"[parity] essential_tc flags={flags} P={P}: max_abs_err/max_ref={err:.3e} max_ref={np.abs(ref).max():.3e}")
+    assert err <= (5e-5 if P == 2 else 3e-2)       # same bars as test_essential_tc
+    # flags = 0 through the extended entry point is the plain kernel
+    assert torch.equal(ops.essential_tc(qp, pos, 0), ops.essential_tc(qp, pos))
+
+
+@pytest.mark.parametrize("P", [2, 1])
 @pytest.mark.parametrize("B,scale,use_pos", [(1, 1.0, True), (2, 3.0, True), (2, 1.0, False), (30, 1.0, True)])
 def test_essential_tc(P, B, scale, use_pos):
     """Essential Matrix Module core on tensor cores vs the float64 oracle (and vs the fp32 SIMT kernels)."""

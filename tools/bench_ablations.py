@@ -66,7 +66,7 @@ def main():
         out["variants"][name] = {"ms_per_step": round(ms, 3), "pairs_per_s": round(B / ms * 1e3, 1),
                                  "launches_per_step": (ops.launches() - l0) // a.steps,
                                  "engine": "fp32 SIMT" if model._tc_planes() == 0 else
-                                           ("bf16x3 tcgen05" + (", module on the fp32 SIMT kernels" if model.em_flags else ""))}
+                                           ("bf16x3 tcgen05" + (" (module flags on rp_essential_ex_tc)" if model.em_flags else ""))}
         del model
         torch.cuda.empty_cache()
     print(json.dumps(out))
