@@ -1,12 +1,6 @@
 #!/bin/bash
-# geometry kernels (config 3): parity tests + CUDA-graph microbench; staging-mode A/B on one box
+# geometry kernels (config 3): parity tests + CUDA-graph microbench
 set -u
 OUT=gpurun_out; mkdir -p $OUT
-for m in 0 1 2 0 1 2; do
-  RELPOSE_GEOM_STAGE=$m timeout 300 python tools/bench_geom.py > $OUT/geom_mode$m.json 2> $OUT/geom.err; echo "mode $m rc=$?"
-  python - <<PY
-import json
-d=json.load(open("$OUT/geom_mode$m.json"))["kernels"]
-print("mode $m", {k: v["us"] for k,v in d.items()})
-PY
-done
+timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -s -p no:cacheprovider -k "se3 or svd3 or essential_to_rt or lietorch or SE3" > $OUT/pytest_geom.log 2>&1; echo "geom tests rc=$?"; tail -3 $OUT/pytest_geom.log; grep "parity\] svd3\|parity\] essential_to_rt" $OUT/pytest_geom.log
+timeout 300 python tools/bench_geom.py > $OUT/geom.json 2> $OUT/geom.err; echo "geom bench rc=$?"; cat $OUT/geom.json
