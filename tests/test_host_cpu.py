@@ -74,6 +74,42 @@ def test_noess_state_dict_layout():
     assert ViTEss(_args()).noess is False and not hasattr(ViTEss(_args()), "pool_attn")
 
 
+@pytest.mark.parametrize("variant", ["noess", "cnn_only"])
+def test_pool_head_parameter_preparation(variant):
+    """Host logic of the two pooling heads (model.py:62-88,179-187): BatchNorm folded into the 1x1 convolutions, the CNN-only
+    head's weight widened over the token matrix, pose_regressor.0's columns permuted to pixel-major order.  Checked against
+    the torch modules of the parameter containers themselves (eval mode), i.e. the reference's formula."""
+    from rel_pose_b200 import ViTEss
+    cnn_only = variant == "cnn_only"
+    m = ViTEss(_args(fusion_transformer=False) if cnn_only else _args(noess=True)).eval()
+    m.load_state_dict(S.make_state_dict(5, "stress", noess=not cnn_only, cnn_only=cnn_only))
+    B = 2
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2 * B, 576, 192, generator=g, dtype=torch.float64)      # tokens (CNN-only) / final-norm output (noess)
+    m = m.double()
+    with torch.no_grad():
+        # the reference: model.py:138-139,179-181 (CNN-only) / :183-187 (noess)
+        if cnn_only:
+            feats = x[:, :, :96].reshape(-1, 24, 24, 192).permute(0, 3, 1, 2)
+            pooled = m.pool_transformer_output(feats)
+        else:
+            feats = x.reshape(B, 24, 24, -1).permute(0, 3, 1, 2)
+            pooled = m.pool_attn(feats)
+        ref = m.pose_regressor[0](pooled.reshape(B, -1))
+        # the product's parameter preparation, evaluated with plain matmuls in the order the kernels run them
+        w1, b1, w2, b2, w0 = m._pool_head_params()
+        f = x.reshape(B * 576, 384)
+        h = torch.relu(f @ w1.T + b1)
+        y = (h @ w2.T + b2).reshape(B, m.H)
+        got = y @ w0.T + m.pose_regressor[0].bias
+    assert tuple(w1.shape) == (96, 384) and tuple(w0.shape) == (512, m.H)
+    assert torch.allclose(got, ref, rtol=1e-10, atol=1e-10), float((got - ref).abs().max())
+    assert m._pool_head_params()[4] is w0                  # cached until a parameter changes
+    with torch.no_grad():
+        m.pose_regressor[0].weight.mul_(2.0)
+    assert m._pool_head_params()[4] is not w0
+
+
 def test_ablation_flags():
     """--no_pos_encoding (and --noess without a transformer) cannot run in the reference either and are rejected loudly;
     --noess, the CNN-only model and the Essential-Matrix-Module variants are accepted."""
