@@ -21,7 +21,21 @@ import argparse
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("RELPOSE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def find_reference_root():
+    """$RELPOSE_REFERENCE_ROOT, else /root/reference (build container), else baseline/_ref (the byte-for-byte copy
+    oracle/install_reference.py makes; it travels to the GPU box).  None when no tree is present."""
+    cands = [os.environ.get("RELPOSE_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "src", "model.py")):
+            return c
+    return None
+
+
+REFERENCE_ROOT = find_reference_root() or "/root/reference"
 
 
 class _StubSE3:
@@ -100,7 +114,8 @@ def default_args(**over):
 
 
 def load_reference_model(**over):
-    """Returns (ViTEss instance on CPU in eval mode, SE3 stub class)."""
+    """Returns (ViTEss instance on CPU in eval mode, SE3 stub class).  The model may be moved to a CUDA device by the
+    caller (bench.py's gpu_eager_baseline leg): the reference then runs exactly as its scripts run it."""
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
         raise FileNotFoundError(f"reference tree not found at {REFERENCE_ROOT}")
     install_shims()

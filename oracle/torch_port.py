@@ -1,4 +1,5 @@
-"""ORACLE -- TEST / BASELINE INFRASTRUCTURE ONLY.  CPU PyTorch port of the reference forward path.
+"""ORACLE -- TEST / BASELINE INFRASTRUCTURE ONLY.  PyTorch port of the reference forward path (CPU; also runs on a CUDA
+device through torch's own eager kernels -- cuBLAS / cuDNN -- for bench.py's `gpu_eager_baseline` leg).
 
 The reference's own CPU implementation of this path *is* PyTorch on CPU (ATen + oneDNN/MKL); the
 reference tree does not exist on the GPU box, so `bench.py --impl reference` and the `cpu_baseline`
@@ -48,9 +49,9 @@ def _qkv(x, p, pre):
     return t[0], t[1], t[2]
 
 
-def _posenc(B, intr):
-    lin = torch.linspace(-1, 1, 24)
-    i = torch.arange(576)
+def _posenc(B, intr, device="cpu"):
+    lin = torch.linspace(-1, 1, 24).to(device)      # evaluated on the host like the reference, then moved
+    i = torch.arange(576, device=device)
     p3 = lin[i % 24].repeat(B, 1)
     p4 = lin[i // 24].repeat(B, 1)
     if intr is not None:
@@ -70,7 +71,8 @@ def forward(images, Gs, intrinsics, p, depth=6, train=False):
     TRAIN_BN = bool(train)
     B, _, _, H, W = images.shape
     x = images[:, :, [2, 1, 0]] / 255.0
-    x = (x - torch.tensor([0.485, 0.456, 0.406])[:, None, None]) / torch.tensor([0.229, 0.224, 0.225])[:, None, None]
+    dev = images.device       # CPU for the oracle / cpu_baseline; a CUDA device for bench.py's gpu_eager_baseline leg
+    x = (x - torch.tensor([0.485, 0.456, 0.406], device=dev)[:, None, None]) / torch.tensor([0.229, 0.224, 0.225], device=dev)[:, None, None]
     intr = None
     if intrinsics is not None:
         intr = intrinsics.clone()
@@ -103,7 +105,7 @@ def forward(images, Gs, intrinsics, p, depth=6, train=False):
     s2 = (q1 @ k2.transpose(-2, -1)) * 0.125
     a1 = s1.softmax(-1) * s1.softmax(-2)
     a2 = s2.softmax(-1) * s2.softmax(-2)
-    pos = _posenc(B, intr)[:, None].expand(B, 3, 576, 6)
+    pos = _posenc(B, intr, dev)[:, None].expand(B, 3, 576, 6)
     V1 = torch.cat([v1, pos], 3)
     V2 = torch.cat([v2, pos], 3)
     f1 = (V1.transpose(-2, -1) @ a1) @ V1

@@ -184,7 +184,7 @@ class ViTEss(nn.Module):
         if intrinsics.is_cuda:
             dev_k = intrinsics if intrinsics.is_contiguous() else intrinsics.contiguous()
         else:
-            dev_k = intrinsics.to(self.fusion_transformer.pos_embed.device).contiguous()
+            dev_k = intrinsics.to(next(self.parameters()).device).contiguous()
         kxy, flags = ops.intrinsics_prepare(dev_k, H, W)
         if dev_k is not intrinsics:
             intrinsics.copy_(dev_k)                   # keep the caller-visible side effect
@@ -208,7 +208,7 @@ class ViTEss(nn.Module):
         parameter preparation, not per-step work."""
         layers = self._cnn_layers()
         P = self._tc_planes()
-        key = [P]
+        key = [P, ops.param_generation()]
         for _, conv, bn in layers:
             for t in (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var):
                 if t is not None:
@@ -281,7 +281,7 @@ class ViTEss(nn.Module):
         """bf16 planes of a weight matrix, split once per parameter version (parameter preparation)."""
         cache = self.__dict__.setdefault("_plane_cache", {})
         key = id(weight)
-        tag = (weight.data_ptr(), weight._version, P)
+        tag = (weight.data_ptr(), weight._version, P, ops.param_generation())
         hit = cache.get(key)
         if hit is None or hit[0] != tag:
             hit = (tag, ops.split_planes(weight.detach().contiguous(), P))
@@ -291,7 +291,7 @@ class ViTEss(nn.Module):
     def _transposed(self, weight):
         """Contiguous transpose of a weight matrix, rebuilt once per parameter version (parameter preparation)."""
         cache = self.__dict__.setdefault("_transpose_cache", {})
-        tag = (weight.data_ptr(), weight._version)
+        tag = (weight.data_ptr(), weight._version, ops.param_generation())
         hit = cache.get(id(weight))
         if hit is None or hit[0] != tag:
             hit = (tag, weight.detach().t().contiguous())
@@ -391,7 +391,7 @@ class ViTEss(nn.Module):
         srcs = [pa[0].weight, pa[0].bias, pa[3].weight, pa[3].bias, reg0.weight]
         for bn in (pa[1], pa[4]):
             srcs += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
-        tag = tuple((t.data_ptr(), t._version) for t in srcs)
+        tag = tuple((t.data_ptr(), t._version) for t in srcs) + (ops.param_generation(),)
         hit = self.__dict__.get("_pool_head_cache")
         if hit is None or hit[0] != tag:
             with torch.no_grad():
@@ -410,9 +410,19 @@ class ViTEss(nn.Module):
                     wide[:, 2 * half:3 * half] = w1[:, half:]
                     w1 = wide
                 w0 = reg0.weight.reshape(self.H2, self.pool_feat2, 576).permute(0, 2, 1).reshape(self.H2, self.H).contiguous()
-            hit = (tag, (w1, b1, w2, b2, w0))
+            hit = (tag, (w1, b1, w2, b2, w0), {})      # third slot: bf16 planes of these derived tensors, same lifetime
             self.__dict__["_pool_head_cache"] = hit
         return hit[1]
+
+    def _pool_head_planes(self, name, P):
+        """bf16 planes of a derived head tensor ("w1" / "w0").  They are stored inside the head cache entry -- not in the
+        id()-keyed weight cache: a rebuilt temporary can reuse a freed tensor's id and address, and a stale entry would
+        then match."""
+        tensors = dict(zip(("w1", "b1", "w2", "b2", "w0"), self._pool_head_params()))
+        planes = self.__dict__["_pool_head_cache"][2]
+        if (name, P) not in planes:
+            planes[(name, P)] = ops.split_planes(tensors[name], P)
+        return planes[(name, P)]
 
     def _pool_attn_head(self, x, B):
         """features.reshape([B,24,24,-1]) -> pool_attn (model.py:185-186).  The reference's reshape makes "pixel" j of a pair
@@ -424,7 +434,7 @@ class ViTEss(nn.Module):
         if P == 0:
             h = ops.linear(f, w1, b1, act=ops.ACT_RELU)
         else:
-            h, _ = ops.linear_tc(ops.split_planes(f, P), self._planes(w1, P), b1, act=ops.ACT_RELU)
+            h, _ = ops.linear_tc(ops.split_planes(f, P), self._pool_head_planes("w1", P), b1, act=ops.ACT_RELU)
         return ops.linear(h, w2, b2).reshape(B, self.H), w0
 
     def normalize_preds(self, Gs, pose_preds, inference):
@@ -441,10 +451,11 @@ class ViTEss(nn.Module):
             Gs = SE3(torch.from_numpy(np.asarray(Gs)).unsqueeze(0).cuda().float())
         if not images.is_cuda:
             raise ops._lib.RelposeLibraryError("ViTEss.forward: images must live on a CUDA device (no CPU fallback)")
-        if self.training and torch.is_grad_enabled():
+        if self.training:
             if self.em_flags or self.l1_pos_encoding or self.noess or self.cnn_only:
                 raise NotImplementedError("the ablation branches are built for inference only")
-            # train.py:155 -- batch-statistics BatchNorm, autograd through the CUDA kernels (train_path.py)
+            # train.py:155 -- batch-statistics BatchNorm (also under torch.no_grad(), like nn.BatchNorm2d.train(): the
+            # running statistics are updated), autograd through the CUDA kernels (train_path.py)
             from . import train_path
             out = SE3(train_path.forward_train(self, images, Gs, intrinsics))
             return out.data[0].detach().cpu().numpy() if inference else [out]
@@ -494,8 +505,8 @@ class ViTEss(nn.Module):
                 feat, w0 = x.reshape(B, -1), reg[0].weight
             if self._tc_planes() == 2 and self.tc_regressor:
                 # 26880 -> 512: 55 MB of weights for 64 rows; split-K on the tensor cores (bf16x3, short accumulation chains)
-                h = ops.linear_tc_splitk(ops.split_planes(feat.contiguous(), 2), self._planes(w0, 2), reg[0].bias,
-                                         act=ops.ACT_RELU)
+                w0p = self._pool_head_planes("w0", 2) if (self.noess or self.cnn_only) else self._planes(w0, 2)
+                h = ops.linear_tc_splitk(ops.split_planes(feat.contiguous(), 2), w0p, reg[0].bias, act=ops.ACT_RELU)
             else:
                 h = ops.linear(feat, w0, reg[0].bias, act=ops.ACT_RELU)
             if self.H2 == 512:

@@ -14,6 +14,21 @@ CONV_HALO = os.environ.get("RELPOSE_CONV_HALO", "1") != "0"      # halo variant 
 NTOK, EMBED, HEADS, HDIM, NPOS, EMW = 576, 192, 3, 64, 6, 70
 
 _launch_count = 0     # number of kernels launched through the library (bench.py reports it)
+_param_generation = 0   # bumped whenever the library writes parameters / buffers through raw pointers (see below)
+
+
+def param_generation():
+    """Torch's `tensor._version` does not see writes made through `data_ptr()`: the fused optimizer (optim.py) and the
+    train-mode BatchNorm kernels (train_path.py) update parameters / running statistics that way.  Every such write
+    bumps this counter, and every cache of derived parameter data (folded BatchNorm, bf16 planes, transposes) carries
+    it in its tag, so an eval forward after a training step never reuses stale weights."""
+    return _param_generation
+
+
+def bump_param_generation():
+    global _param_generation
+    _param_generation += 1
+
 _timer = None         # optional StageTimer: CUDA-event timing of every library call (bench.py)
 
 

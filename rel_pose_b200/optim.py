@@ -15,13 +15,15 @@ import math
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 _DESC = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8")])     # struct TensorDesc, 40 bytes
 
 
 def one_cycle_lr(step_num, max_lr, total_steps, pct_start=0.3, div_factor=25.0, final_div_factor=1e4):
     """Learning rate OneCycleLR has set for optimizer step number `step_num` (0-based) -- torch/optim/lr_scheduler.py."""
+    if step_num > total_steps:          # torch: "Tried to step {step_num} times. The specified number of total steps is ..."
+        raise ValueError(f"Tried to step {step_num} times. The specified number of total steps is {total_steps}")
     initial_lr = max_lr / div_factor
     min_lr = initial_lr / final_div_factor
     phases = [(float(pct_start * total_steps) - 1, initial_lr, max_lr), (total_steps - 1, max_lr, min_lr)]
@@ -70,6 +72,7 @@ class FusedAdamOneCycle:
         self._key = None
         self._tables = None
         self._upload_done = None
+        self._ever_updated = set()
 
     # --------------------------------------------------------------------------------------------
     def lr_at(self, step_num):
@@ -122,6 +125,7 @@ class FusedAdamOneCycle:
         if not active:
             self.step_num += 1
             return self.grad_norm
+        self._ever_updated.update(i for i, _ in active)
         d_desc, d_t, d_o, partial, nblk = self._build_tables(active)
         L = _lib.lib()
         dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -136,18 +140,92 @@ class FusedAdamOneCycle:
                                              self.clip if self.clip is not None else 0.0, lr, self.betas[0], self.betas[1],
                                              self.eps, self.weight_decay, self.step_num + 1, dev, ctypes.c_void_p(st)),
                    "rp_adam_clip_step_multi")
+        ops.bump_param_generation()          # parameters were written through raw pointers: derived-data caches are stale
         self.step_num += 1
         return self.grad_norm
 
-    # ---- checkpoint layout compatible in spirit with {"optimizer", "scheduler"} of train.py:191-194 -------------
+    # ---- checkpoints: the layouts train.py:191-194 stores under "optimizer" and "scheduler" ---------------------
+    def _updated(self):
+        """Indices of the parameters torch.optim.Adam would hold state for (those that have received a gradient)."""
+        return sorted(self._ever_updated)
+
     def state_dict(self):
-        return {"step": self.step_num, "exp_avg": [t.clone() for t in self.exp_avg], "exp_avg_sq": [t.clone() for t in self.exp_avg_sq],
-                "hyper": {"max_lr": self.max_lr, "total_steps": self.total_steps, "pct_start": self.pct_start,
-                          "div_factor": self.div_factor, "final_div_factor": self.final_div_factor, "betas": self.betas,
-                          "eps": self.eps, "weight_decay": self.weight_decay, "clip": self.clip}}
+        """torch.optim.Adam.state_dict() layout: {"state": {index: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]},
+        so `torch.optim.Adam(model.parameters(), ...).load_state_dict(sd)` in the reference's train.py (:96) accepts it and
+        `load_state_dict` here accepts what the reference saved (:191-194).  The param group carries the keys OneCycleLR adds
+        (initial_lr / max_lr / min_lr)."""
+        state = {}
+        if self.step_num > 0:
+            for i in self._updated():
+                state[i] = {"step": torch.tensor(float(self.step_num)), "exp_avg": self.exp_avg[i].clone(),
+                            "exp_avg_sq": self.exp_avg_sq[i].clone()}
+        initial_lr = self.max_lr / self.div_factor
+        group = {"lr": self.lr_at(min(self.step_num, self.total_steps)), "betas": self.betas, "eps": self.eps,
+                 "weight_decay": self.weight_decay, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "decoupled_weight_decay": False, "initial_lr": initial_lr,
+                 "max_lr": self.max_lr, "min_lr": initial_lr / self.final_div_factor, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group],
+                "relpose": {"clip": self.clip, "pct_start": self.pct_start, "total_steps": self.total_steps,
+                            "div_factor": self.div_factor, "final_div_factor": self.final_div_factor}}
+
+    def scheduler_state_dict(self):
+        """What `OneCycleLR(...).state_dict()` holds after `step_num` scheduler steps (train.py:193), produced by torch's own
+        class on a dummy optimizer so that the key set matches the installed torch version."""
+        dummy = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=self.max_lr)
+        sch = torch.optim.lr_scheduler.OneCycleLR(dummy, self.max_lr, self.total_steps, pct_start=self.pct_start,
+                                                  div_factor=self.div_factor, final_div_factor=self.final_div_factor,
+                                                  cycle_momentum=False)
+        sd = sch.state_dict()
+        sd["last_epoch"] = self.step_num
+        sd["_step_count"] = self.step_num + 1
+        sd["_last_lr"] = [self.lr_at(min(self.step_num, self.total_steps))]
+        return sd
+
+    def load_scheduler_state_dict(self, sd):
+        self.step_num = int(sd["last_epoch"])
+        if "total_steps" in sd and int(sd["total_steps"]) != self.total_steps:
+            raise ValueError(f"scheduler total_steps {sd['total_steps']} != {self.total_steps}")
 
     def load_state_dict(self, sd):
+        """Accepts torch.optim.Adam's layout (a checkpoint written by the reference or by state_dict() above) and the
+        private layout of earlier versions of this class ({"step", "exp_avg", "exp_avg_sq", "hyper"}).  Lengths, shapes
+        and the group's hyper-parameters are validated: a mismatched parameter list is an error, not a silent partial load."""
+        if "param_groups" in sd:
+            groups = sd["param_groups"]
+            order = [i for g in groups for i in g["params"]]
+            if len(order) != len(self.params):
+                raise ValueError(f"optimizer state has {len(order)} parameters, this optimizer has {len(self.params)}")
+            g0 = groups[0]
+            for key, mine in (("betas", self.betas), ("eps", self.eps), ("weight_decay", self.weight_decay)):
+                if key in g0 and tuple(np.atleast_1d(g0[key]).tolist()) != tuple(np.atleast_1d(mine).tolist()):
+                    raise ValueError(f"optimizer state was written with {key}={g0[key]}, this optimizer uses {mine}")
+            steps = set()
+            pos = {pid: k for k, pid in enumerate(order)}
+            for pid, st in sd["state"].items():
+                k = pos[pid]
+                if tuple(st["exp_avg"].shape) != tuple(self.params[k].shape):
+                    raise ValueError(f"state of parameter {pid}: shape {tuple(st['exp_avg'].shape)} != {tuple(self.params[k].shape)}")
+                self.exp_avg[k].copy_(st["exp_avg"])
+                self.exp_avg_sq[k].copy_(st["exp_avg_sq"])
+                self._ever_updated.add(k)
+                steps.add(int(float(st["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"parameters disagree on the step count: {sorted(steps)}")
+            if steps:
+                self.step_num = steps.pop()
+            return
+        if len(sd["exp_avg"]) != len(self.params) or len(sd["exp_avg_sq"]) != len(self.params):
+            raise ValueError(f"optimizer state has {len(sd['exp_avg'])} parameters, this optimizer has {len(self.params)}")
+        hyper = sd.get("hyper", {})
+        for key in ("max_lr", "total_steps", "pct_start", "weight_decay", "eps"):
+            if key in hyper and float(hyper[key]) != float(getattr(self, key)):
+                raise ValueError(f"optimizer state was written with {key}={hyper[key]}, this optimizer uses {getattr(self, key)}")
+        for dst, src in zip(self.exp_avg, sd["exp_avg"]):
+            if tuple(dst.shape) != tuple(src.shape):
+                raise ValueError(f"moment shape {tuple(src.shape)} != {tuple(dst.shape)}")
         self.step_num = int(sd["step"])
+        if self.step_num > 0:
+            self._ever_updated.update(i for i, p in enumerate(self.params) if p.requires_grad)
         for dst, src in zip(self.exp_avg, sd["exp_avg"]):
             dst.copy_(src)
         for dst, src in zip(self.exp_avg_sq, sd["exp_avg_sq"]):

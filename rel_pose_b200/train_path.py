@@ -451,6 +451,7 @@ class BatchNormTrainFn(torch.autograd.Function):
         ws = _ws(nb, x)
         _lib.check(L.rp_bn_train_stats_f32(_p(x), _p(mean), _p(var), _p(running_mean), _p(running_var), float(momentum), M, C,
                                            _p(ws), nb, dev, st), "rp_bn_train_stats")
+        ops.bump_param_generation()          # running statistics changed behind torch's version counters
         y = torch.empty_like(x)
         res = residual.contiguous() if residual is not None else None
         _lib.check(L.rp_bn_apply_f32(_p(x), _p(mean), _p(var), _p(gamma.detach()), _p(beta.detach()), _p(res) if res is not None else None,

@@ -12,7 +12,6 @@ shift, which makes the loss learnable.  Prints one JSON line (steps/s, pairs/s, 
 import argparse
 import json
 import os
-import time
 
 import torch
 import torch.distributed as dist
@@ -37,30 +36,19 @@ def make_batch(step, rank, B, H, W, device):
     return images.to(device), poses.to(device), intr.to(device)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup_steps", type=int, default=5, help="untimed steps before the timed region")
-    ap.add_argument("--batch", type=int, default=6)                      # scripts/train_matterport.sh: --batch=6 per GPU
-    ap.add_argument("--size", type=int, nargs=2, default=[384, 512])     # the Matterport pipeline's image size
-    ap.add_argument("--lr", type=float, default=5e-4)
-    ap.add_argument("--weight_decay", type=float, default=1e-5)
-    ap.add_argument("--clip", type=float, default=2.5)
-    ap.add_argument("--w_tr", type=float, default=10.0)
-    ap.add_argument("--w_rot", type=float, default=10.0)
-    ap.add_argument("--total_steps", type=int, default=120000)
-    ap.add_argument("--warmup", type=int, default=10000)
-    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
-                    help="fused: rel_pose_b200.optim.FusedAdamOneCycle (clip + Adam + OneCycle in 3 launches, no host sync); "
-                         "torch: the reference's own calls (clip_grad_norm_, Adam.step, OneCycleLR.step)")
-    ap.add_argument("--pool", type=int, default=8, help="synthetic batches generated up front on the device and cycled")
-    a = ap.parse_args()
+def default_options(**over):
+    """The reference's Matterport training flags (scripts/train_matterport.sh:6-9, train.py:200-233)."""
+    d = dict(steps=30, warmup_steps=5, batch=6, size=[384, 512], lr=5e-4, weight_decay=1e-5, clip=2.5, w_tr=10.0, w_rot=10.0,
+             total_steps=120000, warmup=10000, optimizer="fused", pool=8, measure_allreduce=True)
+    d.update(over)
+    return argparse.Namespace(**d)
+
+
+def train_loop(a, dev, rank=0, world=1, local=0):
+    """Runs a.warmup_steps + a.steps optimizer steps of the reference's loop (train.py:140-165) and returns the result dict
+    (rank 0; None elsewhere).  The process group must already be initialised when world > 1.  Timing: CUDA events on
+    the launching stream, barrier + synchronize on both sides, max over ranks."""
     from . import ViTEss
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     margs = argparse.Namespace(noess=False, pool_size=60, fc_hidden_size=512, fusion_transformer=True, transformer_depth=6,
                                cross_features=False, use_single_softmax=False, no_pos_encoding=False, l1_pos_encoding=False)
@@ -84,38 +72,49 @@ def main():
     H, W = a.size
     # the data loader is outside the path: batches are synthesised up front on the device and cycled
     pool = [make_batch(i, rank, a.batch, H, W, dev) for i in range(max(1, a.pool))]
-    nsteps = a.warmup_steps + a.steps
-    loss_log = torch.zeros(nsteps, 2, device=dev)            # read back once at the end: no per-step host sync
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nsteps)]
-    t0 = None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for step in range(nsteps):
-        if step == a.warmup_steps:
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0.record(); t0 = time.perf_counter()
+
+    def one_step(step, evs=None, sync_grads=True):
         images, poses, intr = pool[step % len(pool)]
         intr = intr.clone()                                   # forward rescales the intrinsics in place
         opt.zero_grad()
-        ev[step][0].record()
+        if evs:
+            evs[0].record()
         Ps = SE3(poses)
         Gs = SE3.IdentityLike(Ps)
         poses_est = net(images, Gs, intrinsics=intr)
-        ltr, lrot, metrics = geodesic_loss(SE3(Ps.data.clone()), poses_est, sync_metrics=False) if a.optimizer == "fused" \
+        ltr, lrot, _ = geodesic_loss(SE3(Ps.data.clone()), poses_est, sync_metrics=False) if a.optimizer == "fused" \
             else geodesic_loss(SE3(Ps.data.clone()), poses_est)
         loss = a.w_tr * ltr + a.w_rot * lrot
-        ev[step][1].record()
-        loss.backward()
-        ev[step][2].record()
+        if evs:
+            evs[1].record()
+        if sync_grads or world == 1:
+            loss.backward()
+        else:
+            with net.no_sync():                               # same backward without the gradient exchange
+                loss.backward()
+        if evs:
+            evs[2].record()
         if a.optimizer == "fused":
             gn = opt.step()
         else:
             gn = torch.nn.utils.clip_grad_norm_(net.parameters(), a.clip)
             opt.step()
             sched.step()
-        ev[step][3].record()
-        loss_log[step, 0] = loss.detach(); loss_log[step, 1] = gn.reshape(())
+        if evs:
+            evs[3].record()
+        return loss.detach(), gn.reshape(())
+
+    nsteps = a.warmup_steps + a.steps
+    loss_log = torch.zeros(nsteps, 2, device=dev)            # read back once at the end: no per-step host sync
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nsteps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for step in range(nsteps):
+        if step == a.warmup_steps:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+        loss_log[step, 0], loss_log[step, 1] = one_step(step, ev[step])
     e1.record()
     if world > 1:
         dist.barrier()
@@ -128,16 +127,82 @@ def main():
     losses = [(float(x), float(y)) for x, y in loss_log.cpu().tolist()]
     timed = range(a.warmup_steps, nsteps)
     phase = [sum(ev[i][k].elapsed_time(ev[i][k + 1]) for i in timed) / len(timed) for k in range(3)]
+
+    # ---- the exchange step by itself (world > 1): backward with and without the gradient all-reduce, and the same
+    # payload (one flat float32 buffer of all trainable gradients) all-reduced alone on an idle GPU
+    exchange = None
+    if world > 1 and getattr(a, "measure_allreduce", True):
+        n_extra = max(3, min(8, a.steps))
+        evn = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_extra)]
+        for i in range(n_extra):
+            one_step(nsteps + i, evn[i], sync_grads=False)
+        numel = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        flat = torch.zeros(numel, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            dist.all_reduce(flat)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(flat)
+        a1.record()
+        torch.cuda.synchronize()
+        bw_nosync = sum(evn[i][1].elapsed_time(evn[i][2]) for i in range(1, n_extra)) / (n_extra - 1)
+        ar_ms = a0.elapsed_time(a1) / 5
+        tt = torch.tensor([bw_nosync, ar_ms, phase[1]], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        bw_nosync, ar_ms, bw_sync = (float(x) for x in tt.tolist())
+        exposed = max(0.0, bw_sync - bw_nosync)
+        exchange = {"payload_bytes": numel * 4, "allreduce_alone_ms": round(ar_ms, 3),
+                    "bus_bandwidth_GBps": round(2 * (world - 1) / world * numel * 4 / (ar_ms * 1e-3) / 1e9, 1),
+                    "backward_ms_with_allreduce": round(bw_sync, 3), "backward_ms_no_sync": round(bw_nosync, 3),
+                    "exposed_allreduce_ms": round(exposed, 3),
+                    "overlap_fraction": round(1.0 - min(1.0, exposed / ar_ms), 3) if ar_ms > 0 else None,
+                    "how": "DistributedDataParallel buckets (25 MB) reduced by NCCL while the backward kernels still run; "
+                           "exposed = backward with the exchange minus the same backward under no_sync(), max over ranks"}
+    if rank != 0:
+        return None
+    ls = [l for l, _ in losses]
+    return {"metric": "training steps/sec (config 5: train.py loop on synthetic pairs, fp32 operands, tensor-core + SIMT backward)",
+            "n_gpus": world, "steps": a.steps, "warmup_steps": a.warmup_steps, "pairs_per_gpu": a.batch, "image_size": [H, W],
+            "ms_per_step": ms / a.steps, "steps_per_s": a.steps / (ms * 1e-3), "pairs_per_s": world * a.batch * a.steps / (ms * 1e-3),
+            "loss_first5": [round(x, 4) for x in ls[:5]], "loss_last5": [round(x, 4) for x in ls[-5:]],
+            "grad_norm_first": round(losses[0][1], 3), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 2),
+            "ddp": world > 1, "optimizer": a.optimizer,
+            "phase_ms": {"forward+loss": round(phase[0], 3), "backward(+allreduce)": round(phase[1], 3),
+                         "clip+adam+lr": round(phase[2], 3)},
+            "exchange": exchange if exchange is not None else "single rank: no gradient exchange"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    d = default_options()
+    ap.add_argument("--steps", type=int, default=d.steps)
+    ap.add_argument("--warmup_steps", type=int, default=d.warmup_steps, help="untimed steps before the timed region")
+    ap.add_argument("--batch", type=int, default=d.batch)                # scripts/train_matterport.sh: --batch=6 per GPU
+    ap.add_argument("--size", type=int, nargs=2, default=d.size)         # the Matterport pipeline's image size
+    ap.add_argument("--lr", type=float, default=d.lr)
+    ap.add_argument("--weight_decay", type=float, default=d.weight_decay)
+    ap.add_argument("--clip", type=float, default=d.clip)
+    ap.add_argument("--w_tr", type=float, default=d.w_tr)
+    ap.add_argument("--w_rot", type=float, default=d.w_rot)
+    ap.add_argument("--total_steps", type=int, default=d.total_steps)
+    ap.add_argument("--warmup", type=int, default=d.warmup)
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: rel_pose_b200.optim.FusedAdamOneCycle (clip + Adam + OneCycle in 3 launches, no host sync); "
+                         "torch: the reference's own calls (clip_grad_norm_, Adam.step, OneCycleLR.step)")
+    ap.add_argument("--pool", type=int, default=d.pool, help="synthetic batches generated up front on the device and cycled")
+    a = ap.parse_args()
+    a.measure_allreduce = True
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    res = train_loop(a, dev, rank, world, local)
     if rank == 0:
-        ls = [l for l, _ in losses]
-        print(json.dumps({"metric": "training steps/sec (config 5, synthetic pairs, fp32 SIMT backward)", "n_gpus": world,
-                          "steps": a.steps, "pairs_per_gpu": a.batch, "image_size": [H, W], "ms_per_step": ms / a.steps,
-                          "steps_per_s": a.steps / (ms * 1e-3), "pairs_per_s": world * a.batch * a.steps / (ms * 1e-3),
-                          "loss_first5": [round(x, 4) for x in ls[:5]], "loss_last5": [round(x, 4) for x in ls[-5:]],
-                          "grad_norm_first": round(losses[0][1], 3), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 2),
-                          "ddp": world > 1, "optimizer": a.optimizer,
-                          "phase_ms": {"forward+loss": round(phase[0], 3), "backward(+allreduce)": round(phase[1], 3),
-                                       "clip+adam+lr": round(phase[2], 3)}, "allreduce": "NCCL via DistributedDataParallel (77 MB fp32 gradients per step)"}), flush=True)
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -183,6 +183,14 @@ def test_one_cycle_lr_closed_form_matches_torch():
             opt.step(); sch.step()
 
 
+def test_one_cycle_lr_refuses_to_run_past_the_schedule():
+    """torch's OneCycleLR raises once the step count exceeds total_steps; so does the closed form (no silent climb back up)."""
+    from rel_pose_b200.optim import one_cycle_lr
+    one_cycle_lr(10, 1e-3, 10, 0.3)
+    with pytest.raises(ValueError):
+        one_cycle_lr(11, 1e-3, 10, 0.3)
+
+
 def test_fused_optimizer_refuses_cpu_parameters():
     import torch
     from rel_pose_b200 import _lib
