@@ -5,13 +5,13 @@
 // (x = x0 + x1; every product is evaluated as a0 b0 + a0 b1 + a1 b0 into one fp32 TMEM accumulator, fp32 class).
 //
 // Work item = (image, head, 128-query tile); 576 = 4.5 tiles, the 5th tile is half empty (TMA zero fill, rows
-// never stored).  Keys/values stream in 6 blocks of 96.  Persistent CTAs (one per SM), 352 threads:
+// never stored).  Keys/values stream in 6 blocks of 96.  Persistent CTAs (one or two per SM), 384 threads:
 //   warp 0      TMA producer: Q tile (once per item), K and V blocks through two independent 2-stage rings
 //   warp 1      S issuer + TMEM owner:  S_j = Q K_j^T   M=128 N=96 K=64, A,B K-major SWIZZLE_128B -> TMEM S[j&1];
 //               runs up to two key blocks ahead of the softmax (s_free mbarriers)
 //   warp 2      O issuer:  O_j = P_j V_j   M=128 N=64 K=96, A = P_j read from TENSOR memory (K-major, two bf16 per
 //               column), B = V_j as loaded by TMA ([key][d] rows = MN-major SWIZZLE_128B) -> TMEM O
-//   warps 3-10  softmax: NSPLIT = 2 threads per query row (TMEM lane).  tcgen05.ld S_j, online max / sum,
+//   warps 4-11  softmax: NSPLIT = 2 threads per query row (TMEM lane).  tcgen05.ld S_j, online max / sum,
 //               p = 2^((s-m) c), P_j re-split into bf16 planes and written back to tensor memory (tcgen05.st),
 //               mbarrier arrive.  The un-normalised output is carried in registers:
 //               o = o * alpha + O_j (tcgen05.ld of the per-block product), so TMEM is never rescaled.
@@ -20,6 +20,13 @@
 // each softmax warp signals after reading O_{j-1}.
 // Measured at 64 pairs, bf16x3: 140 us (one issuer warp, P through shared memory) -> 127 us; four threads per
 // row (NSPLIT = 4, 93 registers) measured 132 us, i.e. the softmax chain is not short of warps.
+//
+// CPS = 2 (two CTAs per SM): the chain S_j -> softmax -> P_j -> PV_j -> fold of ONE query tile is latency bound (the
+// ncu capture of the CPS = 1 kernel shows the tensor pipe 41 % active and the softmax warps at ~0.3 IPC), so two
+// co-resident CTAs -- two independent tiles per SM -- hide each other's gaps.  To fit twice: the V ring drops to one
+// stage (V_{j+1} can only be used after softmax j+1 anyway), tensor memory drops to 256 columns by writing P_j over
+// S_j (the softmax threads have S_j in registers by then; the buffer is released by the PV product's commit instead
+// of by the softmax threads), and registers are capped at 88 per thread.
 #include "tc_common.cuh"
 
 namespace {
@@ -29,25 +36,26 @@ constexpr int BM = 128, BKV = 96, NBLK = NTOK / BKV, QTILES = (NTOK + BM - 1) / 
 constexpr int Q_TILE = BM * 128;          // bytes of one [128 x 64] bf16 tile
 constexpr int KV_TILE = BKV * 128;        // bytes of one [96 x 64] bf16 tile
 constexpr int P_SUB = BM * 128;           // P_j is [128 x 96] = one full and one half-used 64-wide K-major sub-tile
-constexpr int KV_STAGES = 2;
-constexpr int ATT_CTRL = 3;              // warp 0 TMA, warp 1 S = QK^T issuer, warp 2 O = PV issuer
+constexpr int K_STAGES = 2;
+constexpr int ATT_CTRL = 4;              // warp 0 TMA, warp 1 S = QK^T issuer, warp 2 O = PV issuer, warp 3 idle (fills the warpgroup: setmaxnreg)
 constexpr int NSPLIT = 2;                // softmax threads per query row (4 NSPLIT warps: NSPLIT per TMEM lane quarter)
 constexpr int ATT_THREADS = 32 * (ATT_CTRL + 4 * NSPLIT);
 constexpr int HB = BKV / NSPLIT, HO = HD / NSPLIT;  // key columns / output columns per softmax thread
 static_assert((NSPLIT == 2 || NSPLIT == 4) && HB % 8 == 0 && HO % 16 == 0, "softmax split");
-constexpr int TMEM_COLS_ATT = 512;        // S[0] 0..95, S[1] 96..191, O 192..255, P planes 256..351 (two bf16 per column)
+// CPS = 1: S[0] 0..95, S[1] 96..191, O 192..255, P planes 256..351 (two bf16 per column); 512 columns allocated
+// CPS = 2: S[0] 0..95, S[1] 96..191, O 192..255; P_j planes are written over S[j & 1]; 256 columns allocated
 constexpr int S_COL = 0, O_COL = 2 * BKV, P_COL = O_COL + HD, P_PLANE = BKV / 2;
 static_assert(NTOK % BKV == 0 && BKV % 16 == 0 && (NBLK % 2) == 0, "key blocking");
 
-template <int P>
+template <int P, int CPS>
 struct ACfg {
+    static constexpr int V_STAGES = CPS == 2 ? 1 : 2;
+    static constexpr int TMEM_COLS = CPS == 2 ? 256 : 512;
     static constexpr int Q_BYTES = P * Q_TILE;
     static constexpr int KV_BYTES = P * KV_TILE;
-    static constexpr int P_BYTES = 0;                         // P_j lives in tensor memory
     static constexpr int OFF_K = Q_BYTES;
-    static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
-    static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;
-    static constexpr int OFF_XCH = OFF_P + P_BYTES;          // float [2 parity][NSPLIT][128 rows]: row-max exchange
+    static constexpr int OFF_V = OFF_K + K_STAGES * KV_BYTES;
+    static constexpr int OFF_XCH = OFF_V + V_STAGES * KV_BYTES;   // float [2 parity][NSPLIT][128 rows]: row-max exchange
     static constexpr int OFF_BAR = OFF_XCH + 2 * NSPLIT * BM * 4;
     static constexpr int SMEM = OFF_BAR + 256 + 1024 /*align slack*/;
 };
@@ -57,12 +65,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int P>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int P, int CPS>
+__global__ void __launch_bounds__(ATT_THREADS, CPS)
 self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_planes, int p_out, int n_img,
                          float scale_log2, int kv_xor) {
-    using C = ACfg<P>;
+    using C = ACfg<P, CPS>;
+    constexpr int V_STAGES = C::V_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -92,13 +101,15 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc::mbar_init(&v_full[i], 1);
             tc::mbar_init(&v_free[i], 1);
             tc::mbar_init(&s_full[i], 1);
-            tc::mbar_init(&s_free[i], 4 * NSPLIT);     // one elected arrive per softmax warp
+            // CPS = 1: one elected arrive per softmax warp (S is in registers); CPS = 2: the commit of the PV product
+            // that read P_j out of the same columns
+            tc::mbar_init(&s_free[i], CPS == 2 ? 1 : 4 * NSPLIT);
         }
         tc::mbar_init(p_ready, 4 * NSPLIT);
         tc::mbar_init(pv_done, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS_ATT);
+    if (warp == 1) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -108,6 +119,13 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     auto k_tile = [&](int st, int p) { return smem + C::OFF_K + st * C::KV_BYTES + p * KV_TILE; };
     auto v_tile = [&](int st, int p) { return smem + C::OFF_V + st * C::KV_BYTES + p * KV_TILE; };
 
+    // CPS = 2: 2 x 384 threads share the 64 K registers of the SM = 80 each at launch; the control warpgroup hands most
+    // of its share to the two softmax warpgroups (48 S values + 32 O values + temporaries per thread live at once).
+    // The pool is per CTA: 128 x 32 + 256 x 104 = 30 720 = 384 x 80 -- a larger request would wait forever.
+    // (the instruction sits at the head of the warpgroup-uniform branch that dominates the role code, so ptxas
+    // allocates each side with its own budget)
+    if (warp < ATT_CTRL) {
+    if constexpr (CPS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
     if (warp == 0) {
         // ---------------------------------------------------------------------------- TMA producer (convergent warp)
         int ks = 0, kph = 0, vs = 0, vph = 0, it = 0;
@@ -129,7 +147,7 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         tc::tma_load_4d(k_tile(ks, p), &tmKV, &k_full[ks], EMB + h * HD, j * BKV, img ^ kv_xor, p);
                 }
                 __syncwarp();
-                if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+                if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
                 tc::mbar_wait(&v_free[vs], vph ^ 1);
                 if (tc::elect_one_sync()) {
                     tc::mbar_expect_tx(&v_full[vs], C::KV_BYTES);
@@ -138,7 +156,7 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         tc::tma_load_4d(v_tile(vs, p), &tmKV, &v_full[vs], 2 * EMB + h * HD, j * BKV, img ^ kv_xor, p);
                 }
                 __syncwarp();
-                if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
+                if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -182,7 +200,7 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     if (j + 1 == NBLK) tc::umma_commit(q_free);       // last S of this item is in flight
                 }
                 __syncwarp();
-                if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+                if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
             }
         }
     } else if (warp == 2) {
@@ -193,12 +211,13 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         int vs = 0, vph = 0;
         uint32_t g = 0;
         const uint32_t d = tmem_base + O_COL;
-        const uint32_t ap0 = tmem_base + P_COL, ap1 = tmem_base + P_COL + (P - 1) * P_PLANE;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int j = 0; j < NBLK; ++j, ++g) {
                 tc::mbar_wait(p_ready, g & 1);
                 tc::mbar_wait(&v_full[vs], vph);
                 tc::tcgen05_fence_after();
+                const uint32_t pbase = tmem_base + (CPS == 2 ? S_COL + (g & 1) * BKV : P_COL);
+                const uint32_t ap0 = pbase, ap1 = pbase + (P - 1) * P_PLANE;
                 const uint64_t dv0 = tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, 0)), 0);
                 const uint64_t dv1 = tc::make_mnmajor_sw128_desc(tc::smem_u32(v_tile(vs, P - 1)), 0);
                 if (tc::elect_one_sync()) {
@@ -219,13 +238,16 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         accum = 1u;
                     }
                     tc::umma_commit(&v_free[vs]);
+                    if (CPS == 2) tc::umma_commit(&s_free[g & 1]);      // P_j (= the S buffer) has been consumed
                     tc::umma_commit(pv_done);
                 }
                 __syncwarp();
-                if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
+                if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
             }
         }
+    }
     } else {
+        if constexpr (CPS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
         // ---------------------------------------------------------------------------- softmax warps
         // NSPLIT threads per query row: warps w, w+4, .. share a TMEM lane quarter, thread `hsel` owns key columns
         // [HB hsel, HB hsel + HB) of every block and output columns [HO hsel, HO hsel + HO).  They agree on the
@@ -246,16 +268,16 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             float o[HO];
 #pragma unroll
             for (int i = 0; i < HO; ++i) o[i] = 0.f;
-            auto fold_o = [&]() {                           // o = o * alpha_prev + O_j (this thread's 32 columns)
-                uint32_t t[HO];
-                if constexpr (HO == 32) {
-                    tc::tmem_ld_32x32b_x32(t_lane + O_COL + hsel * HO, *reinterpret_cast<uint32_t(*)[32]>(&t[0]));
-                } else {
-                    tc::tmem_ld_32x32b_x16(t_lane + O_COL + hsel * HO, *reinterpret_cast<uint32_t(*)[16]>(&t[0]));
-                }
-                tc::tmem_ld_wait();
+            auto fold_o = [&]() {                           // o = o * alpha_prev + O_j (this thread's columns)
+                // 16 columns at a time: the exponentials of the next block (HB registers) are live across this call
 #pragma unroll
-                for (int i = 0; i < HO; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(t[i]));
+                for (int c = 0; c < HO; c += 16) {
+                    uint32_t t[16];
+                    tc::tmem_ld_32x32b_x16(t_lane + O_COL + hsel * HO + c, t);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, __uint_as_float(t[i]));
+                }
             };
             for (int j = 0; j < NBLK; ++j, ++g) {
                 tc::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
@@ -272,9 +294,11 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     }
                     tc::tmem_ld_wait();
                 }
-                tc::tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&s_free[g & 1]);     // S_{g+2} may overwrite this buffer
+                if constexpr (CPS == 1) {
+                    tc::tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&s_free[g & 1]);     // S_{g+2} may overwrite this buffer
+                }
                 float bmax = __uint_as_float(s[0]);
 #pragma unroll
                 for (int i = 1; i < HB; ++i) bmax = fmaxf(bmax, __uint_as_float(s[i]));
@@ -317,7 +341,8 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                             s[2 * i + 1] = __float_as_uint(v1 - __uint_as_float(w[i] & 0xffff0000u));
                         }
                     }
-                    const uint32_t t_p = t_lane + P_COL + p * P_PLANE + hsel * (HB / 2);
+                    // CPS = 2: over S_j.  Every thread of the row loaded its S columns before the row-max barrier above.
+                    const uint32_t t_p = t_lane + (CPS == 2 ? S_COL + (g & 1) * BKV : P_COL) + p * P_PLANE + hsel * (HB / 2);
 #pragma unroll
                     for (int ci = 0; ci < HB / 16; ++ci)
                         tc::tmem_st_32x32b_x8(t_p + ci * 8, *reinterpret_cast<uint32_t(*)[8]>(&w[ci * 8]));
@@ -379,7 +404,7 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     __syncthreads();
     if (warp == 1) {
         tc::tcgen05_fence_after();
-        tc::tmem_dealloc(tmem_base, TMEM_COLS_ATT);
+        tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -405,10 +430,20 @@ int make_qkv_tmap(CUtensorMap* out, const void* base, int P, int n_img, int box_
     return RP_OK;
 }
 
-template <int P>
-int launch_attention(const void* qkv_planes, float* out_f32, void* out_planes, int p_out, int n_img, int device,
-                     cudaStream_t st, int kv_xor = 0) {
-    using C = ACfg<P>;
+// RELPOSE_ATT_CPS=1 selects the one-CTA-per-SM variant (A/B measurements); default: two CTAs per SM
+int attention_cps() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RELPOSE_ATT_CPS");
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
+
+template <int P, int CPS>
+int launch_attention_cps(const void* qkv_planes, float* out_f32, void* out_planes, int p_out, int n_img, int device,
+                         cudaStream_t st, int kv_xor) {
+    using C = ACfg<P, CPS>;
     CUtensorMap tmQ, tmKV;
     int rc = make_qkv_tmap(&tmQ, qkv_planes, P, n_img, BM);
     if (rc) return rc;
@@ -416,7 +451,7 @@ int launch_attention(const void* qkv_planes, float* out_f32, void* out_planes, i
     if (rc) return rc;
     static bool attr_set[64] = {false};
     if (device >= 0 && device < 64 && !attr_set[device]) {
-        cudaError_t e = cudaFuncSetAttribute(self_attention_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(self_attention_tc_kernel<P, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             rp::set_error("rp_self_attention_tc: cudaFuncSetAttribute(%d): %s", C::SMEM, cudaGetErrorString(e));
             return (int)e;
@@ -424,11 +459,19 @@ int launch_attention(const void* qkv_planes, float* out_f32, void* out_planes, i
         attr_set[device] = true;
     }
     const int ntiles = n_img * HEADS * QTILES;
-    const int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
+    const int slots = CPS * rp::num_sms(device);
+    const int grid = ntiles < slots ? ntiles : slots;
     const float scale_log2 = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
-    self_attention_tc_kernel<P><<<grid, ATT_THREADS, C::SMEM, st>>>(tmQ, tmKV, out_f32, static_cast<__nv_bfloat16*>(out_planes),
-                                                                  p_out, n_img, scale_log2, kv_xor);
+    self_attention_tc_kernel<P, CPS><<<grid, ATT_THREADS, C::SMEM, st>>>(tmQ, tmKV, out_f32, static_cast<__nv_bfloat16*>(out_planes),
+                                                                       p_out, n_img, scale_log2, kv_xor);
     return rp::finish_launch("rp_self_attention_tc");
+}
+
+template <int P>
+int launch_attention(const void* qkv_planes, float* out_f32, void* out_planes, int p_out, int n_img, int device,
+                     cudaStream_t st, int kv_xor = 0) {
+    if (attention_cps() == 1) return launch_attention_cps<P, 1>(qkv_planes, out_f32, out_planes, p_out, n_img, device, st, kv_xor);
+    return launch_attention_cps<P, 2>(qkv_planes, out_f32, out_planes, p_out, n_img, device, st, kv_xor);
 }
 
 }  // namespace

@@ -265,3 +265,54 @@ def test_dropin_runs_a_reference_style_script_unchanged(tmp_path):
     print(f"[parity] drop-in demo-like script: rot_err {rot.max():.3e} rad, trans_rel_err {tr.max():.3e}")
     assert rot.max() < 1e-4 and tr.max() < 1e-4
     assert np.allclose(intr_after, O.update_intrinsics(k, 384, 512).ravel(), rtol=1e-6)    # in-place rescale visible to the caller
+
+
+def test_reference_demo_py_runs_unchanged_against_the_product(tmp_path):
+    """BASELINE.json configs[0]: the reference's own demo.py (demo.py:25-98), byte for byte, on its own demo images
+    (demo/matterport_{1,2}.png), executed through `python -m rel_pose_b200.run` with a random-init checkpoint whose
+    path contains "matterport" (demo.py:52).  The printed pose must match the UNMODIFIED reference model run on the
+    CPU on the same inputs.  Needs the reference tree (/root/reference, or its copy baseline/_ref on the GPU box)."""
+    import subprocess
+    import sys
+    import cv2
+    import torch.nn.functional as F
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    ref_root = ref_loader.find_reference_root()
+    if ref_root is None:
+        pytest.skip("reference tree not present (run oracle/install_reference.py in the build container)")
+    sd = S.make_state_dict(11, "init")
+    ckpt = tmp_path / "matterport_random_init.pth"
+    torch.save({"model": {"module." + k: v for k, v in sd.items()}}, ckpt)
+    img1, img2 = (os.path.join(ref_root, "demo", f"matterport_{i}.png") for i in (1, 2))
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "rel_pose_b200.run", os.path.join(ref_root, "demo.py"), "--img1", img1, "--img2", img2,
+           "--ckpt", str(ckpt)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = r.stdout.strip().splitlines()
+    assert "predicted R&t, as quaternion, in format x,y,z,qx,qy,qz,qw:" in lines[-2] or any("predicted R&t" in ln for ln in lines)
+    txt = " ".join(lines[[i for i, ln in enumerate(lines) if "predicted R&t" in ln][0] + 1:])
+    printed = np.array([float(v) for v in txt.replace("[", " ").replace("]", " ").split()])
+    assert printed.shape == (7,)
+    # the same call sequence on the unmodified reference model, CPU fp32
+    model, SE3ref = ref_loader.load_reference_model()
+    model.load_state_dict(sd)
+    images = torch.from_numpy(np.stack([cv2.imread(img1), cv2.imread(img2)]).astype(np.float32)).permute(0, 3, 1, 2)
+    images = F.interpolate(images, size=[384, 512]).unsqueeze(0)
+    k = torch.tensor([[[517.97, 517.97, 320, 240]] * 2], dtype=torch.float32)
+    Gs = torch.zeros(1, 2, 7); Gs[..., 6] = 1
+    with torch.no_grad():
+        ref = model(images, SE3ref(Gs), intrinsics=k)[0].data[0, 1].numpy().astype(np.float64)
+    expect = np.concatenate([ref[:3] * 5, [ref[4], ref[5], ref[3], ref[6]]])       # demo.py:89-92
+    log = (f"$ {' '.join(cmd[1:])}\n{r.stdout}\n# unmodified reference model on the CPU, same inputs, demo.py's output transform:\n"
+           f"{np.array2string(expect, precision=5, suppress_small=True)}\n# max |printed - expected| = {np.abs(printed - expect).max():.2e} "
+           "(demo.py prints 5 decimals)\n")
+    print(log)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "demo_py_unchanged.log"), "w") as f:
+            f.write(log)
+    # demo.py prints 5 decimals; the translation is scaled by 5 before printing
+    assert np.abs(printed - expect).max() < 5e-4 * max(1.0, np.abs(expect).max())
