@@ -147,6 +147,9 @@ def reference_forward_factory(device="cpu", sd=None):
 
         def run(images, Gs, intr):
             with torch.no_grad():
+                if str(device) == "cpu":
+                    with ref_loader.cpu_only():       # its unconditional .cuda() (vision_transformer.py:211) stays on the CPU
+                        return model(images, SE3(Gs), intrinsics=intr.clone())[0].data
                 return model(images, SE3(Gs), intrinsics=intr.clone())[0].data
         return run, "reference", f"unmodified reference ViTEss from {root}"
     import torch_port

@@ -187,6 +187,20 @@ int rp_preprocess_stem_windows_f32(const float* images, void* planes, int n_img,
 int rp_preprocess_stem_windows_u8(const uint8_t* images, void* planes, int n_img, int H, int W, int P, int device,
                                   void* stream);
 int rp_stem_weight_windows_f32(const float* w, float* out, int O, int device, void* stream);
+/* The whole stem (src/model.py:127-130: conv1 -> bn1 -> relu -> maxpool 3x3/2/1) in one launch: tcgen05 convolution whose
+ * epilogue keeps the vertical 3-row maximum in registers and finishes the pooling through shared memory; only the pooled
+ * [n,56,56,64] map is written (float32 and/or P_out bf16 planes).  z_planes is either the window tensor of
+ * rp_preprocess_stem_windows_* (compact = 0) or the COMPACT space-to-depth image of rp_preprocess_stem_compact_*
+ * (compact = 1): bf16 planes [P][n_img][115][116][16], [yp][xs][(dy*2+dx)*3 + c] = pixel (2(yp-2)+dy, 2(xs-2)+dx) channel c
+ * of the normalised 224x224 image -- 4x smaller; the convolution reads its overlapping 64-element windows through a
+ * tensor map whose window stride (32 B) is smaller than the window (128 B).  rp_stem_compact_supported: 1 if the driver
+ * encodes that map.  w_planes [P][64][256] (rp_stem_weight_windows_f32 + rp_split_planes_bf16), scale/shift = folded bn1.
+ * Bit-identical to rp_conv2d_tc + rp_maxpool3x3s2_planes on the window tensor. */
+int rp_preprocess_stem_compact_f32(const float* images, void* planes, int n_img, int H, int W, int P, int device, void* stream);
+int rp_preprocess_stem_compact_u8(const uint8_t* images, void* planes, int n_img, int H, int W, int P, int device, void* stream);
+int rp_stem_compact_supported(int device);
+int rp_stem_pool_tc(const void* z_planes, int compact, const void* w_planes, const float* scale, const float* shift,
+                    float* out_f32, void* out_planes, int n_img, int P, int P_out, int device, void* stream);
 /* nn.MaxPool2d(3,2,1) on NHWC float32 writing float32 (y_f32, may be NULL) and/or P bf16 planes */
 int rp_maxpool3x3s2_planes(const float* x, float* y_f32, void* y_planes, int P, int n_img, int H, int W, int C,
                            int device, void* stream);

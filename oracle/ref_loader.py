@@ -96,12 +96,28 @@ def install_shims():
         _orig = tvm.resnet18
 
         def resnet18(pretrained=False, **kw):
+            kw.pop("weights", None)              # callers that already use the new API (rel_pose_b200.model) pass weights=None
             return _orig(weights=None, **kw)
 
         resnet18._relpose_offline = True
         tvm.resnet18 = resnet18
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+class cpu_only:
+    """Context manager: run the reference on the CPU of a box that HAS a CUDA device.  The reference moves its positional
+    table with an unconditional `.cuda()` (vision_transformer.py:211); for a CPU run of the model that call must be the
+    identity (exactly what install_shims() does permanently on a GPU-less box)."""
+
+    def __enter__(self):
+        self._orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self._orig
+        return False
 
 
 def default_args(**over):

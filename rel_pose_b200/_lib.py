@@ -32,6 +32,10 @@ _SIGNATURES = {
     "rp_preprocess_stem_windows_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_preprocess_stem_windows_u8": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_stem_weight_windows_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_preprocess_stem_compact_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_preprocess_stem_compact_u8": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_stem_compact_supported": (_c_int, [_c_int]),
+    "rp_stem_pool_tc": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_maxpool3x3s2_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_permute_conv_weight_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_bn_fold_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _c_int, _c_int, _ptr]),

@@ -172,6 +172,7 @@ class ViTEss(nn.Module):
         # sequence for A/B measurements
         self.fused_mlp = os.environ.get("RELPOSE_FUSED_MLP", "1") != "0"
         self.fused_ln_qkv = os.environ.get("RELPOSE_FUSED_LNQKV", "1") != "0"     # csrc/ln_linear_tc.cu
+        self.fused_stem = os.environ.get("RELPOSE_FUSED_STEM", "1") != "0"        # csrc/stem_pool_tc.cu
         self.tc_regressor = os.environ.get("RELPOSE_TC_REGRESSOR", "1") != "0"    # split-K tcgen05 GEMM for pose_regressor.0
         self.check_intrinsics = True      # reproduce the reference's assert on per-view intrinsics
         self.last_stages = None           # filled when `capture_stages` is set (parity tests)
@@ -261,8 +262,11 @@ class ViTEss(nn.Module):
                                  want_f32=f32, planes_out=P if planes else 0)
 
         _, scale, shift, _, _, wp, _ = prm["stem"]
-        stem, _ = ops.conv2d_tc(x, wp, 4, 1, scale, shift, 1, 0, R, want_f32=True, planes_out=0)
-        xf, xp = ops.maxpool3x3s2_planes(stem, P)
+        if self.fused_stem:
+            xf, xp = ops.stem_pool_tc(x, wp, scale, shift, P)         # conv1 + bn1 + relu + maxpool, one launch
+        else:
+            stem, _ = ops.conv2d_tc(x, wp, 4, 1, scale, shift, 1, 0, R, want_f32=True, planes_out=0)
+            xf, xp = ops.maxpool3x3s2_planes(stem, P)
         for blk in ("l1.0", "l1.1"):
             _, yp = tconv(blk + ".c1", xp, R)
             xf, xp = tconv(blk + ".c2", yp, R, res_pre=xf, f32=True)
@@ -470,7 +474,12 @@ class ViTEss(nn.Module):
                 if stages is not None:
                     stages["preprocessed"] = x[..., :3].permute(0, 3, 1, 2)
             if self._tc_planes():
-                x = ops.preprocess_stem_windows(images, self._tc_planes())    # A1 in the stem's window layout
+                # A1 in the stem's operand layout: the compact space-to-depth image when the fused stem runs and the
+                # driver encodes its overlapping-window tensor map, else the materialised window tensor
+                if self.fused_stem and ops.stem_compact_supported():
+                    x = ops.preprocess_stem_compact(images, self._tc_planes())
+                else:
+                    x = ops.preprocess_stem_windows(images, self._tc_planes())
             kxy = flags = None
             if intrinsics is not None:
                 intrinsics, kxy, flags = self.update_intrinsics(_orig_hw if _orig_hw is not None else images.shape, intrinsics)

@@ -183,6 +183,49 @@ def preprocess_stem_windows(images, P):
     return out
 
 
+def stem_compact_supported(device=0):
+    return bool(_lib.lib().rp_stem_compact_supported(int(device)))
+
+
+def preprocess_stem_compact(images, P):
+    """A1 into the compact space-to-depth layout: [B,2,3,H,W] -> bf16 planes [P,2B,115,116,16] (csrc/stem_pool_tc.cu)."""
+    if images.dtype == torch.uint8:
+        _req(images, "images", torch.uint8)
+        fn = _lib.lib().rp_preprocess_stem_compact_u8
+    else:
+        _req(images, "images")
+        fn = _lib.lib().rp_preprocess_stem_compact_f32
+    B, V, C, H, W = images.shape
+    assert C == 3
+    out = torch.empty((P, B * V, 115, 116, 16), dtype=torch.bfloat16, device=images.device)
+    dev, st = _ctx(images)
+    _tbegin("preprocess_stem_compact", 0.0, float(images.numel() * images.element_size()) + 2.0 * out.numel())
+    _lib.check(fn(_p(images), _p(out), B * V, H, W, P, dev, st), "rp_preprocess_stem_compact")
+    _count()
+    return out
+
+
+def stem_pool_tc(z_planes, w_planes, scale, shift, planes_out, want_f32=True):
+    """conv1 + bn1 + relu + maxpool in one launch: z_planes = window tensor [P,n,115,112,64] or compact image
+    [P,n,115,116,16]; w_planes [P,64,256] -> (float32 [n,56,56,64] | None, bf16 planes [planes_out,n,56,56,64] | None)."""
+    _req(z_planes, "z_planes", torch.bfloat16); _req(w_planes, "w_planes", torch.bfloat16)
+    _req(scale, "scale"); _req(shift, "shift")
+    P, n = z_planes.shape[0], z_planes.shape[1]
+    compact = tuple(z_planes.shape[2:]) == (115, 116, 16)
+    assert compact or tuple(z_planes.shape[2:]) == (115, 112, 64), z_planes.shape
+    assert tuple(w_planes.shape) == (P, 64, 256)
+    out = torch.empty((n, 56, 56, 64), dtype=torch.float32, device=z_planes.device) if want_f32 else None
+    outp = torch.empty((planes_out, n, 56, 56, 64), dtype=torch.bfloat16, device=z_planes.device) if planes_out else None
+    dev, st = _ctx(z_planes)
+    M = n * 112 * 112
+    _tbegin(f"stem_pool_tc{'x3' if P == 2 else ''}", 2.0 * M * 64 * 256,
+            2.0 * z_planes.numel() + (4.0 if want_f32 else 0.0) * n * 56 * 56 * 64 + 2.0 * planes_out * n * 56 * 56 * 64)
+    _lib.check(_lib.lib().rp_stem_pool_tc(_p(z_planes), int(compact), _p(w_planes), _p(scale), _p(shift), _p(out), _p(outp), n, P,
+                                          int(planes_out), dev, st), "rp_stem_pool_tc")
+    _count()
+    return out, outp
+
+
 def stem_weight_windows(w):
     """conv1.weight [O,3,7,7] -> [O,4,1,64] (the 4x4 space-to-depth kernel, KW folded into C); parameter preparation."""
     w = _req(w.detach().contiguous(), "w")

@@ -303,7 +303,7 @@ def test_reference_demo_py_runs_unchanged_against_the_product(tmp_path):
     images = F.interpolate(images, size=[384, 512]).unsqueeze(0)
     k = torch.tensor([[[517.97, 517.97, 320, 240]] * 2], dtype=torch.float32)
     Gs = torch.zeros(1, 2, 7); Gs[..., 6] = 1
-    with torch.no_grad():
+    with torch.no_grad(), ref_loader.cpu_only():
         ref = model(images, SE3ref(Gs), intrinsics=k)[0].data[0, 1].numpy().astype(np.float64)
     expect = np.concatenate([ref[:3] * 5, [ref[4], ref[5], ref[3], ref[6]]])       # demo.py:89-92
     log = (f"$ {' '.join(cmd[1:])}\n{r.stdout}\n# unmodified reference model on the CPU, same inputs, demo.py's output transform:\n"

@@ -363,6 +363,49 @@ def test_stem_windows_conv(P, B, H, W, u8):
 
 
 @pytest.mark.parametrize("P", [2, 1])
+@pytest.mark.parametrize("B,H,W,u8", [(1, 96, 128, False), (3, 384, 384, True), (37, 64, 80, False)])
+def test_stem_pool_fused(P, B, H, W, u8):
+    """conv1 + bn1 + relu + maxpool in one launch (csrc/stem_pool_tc.cu), from the window tensor and from the compact
+    space-to-depth image (overlapping-window tensor map): bit-identical to rp_conv2d_tc + rp_maxpool3x3s2_planes, and
+    within the bf16x3 bound of the oracle's conv 7x7/2 -> BN -> ReLU -> max-pool."""
+    img = S.make_images_numpy(9, B, H, W)
+    w = rnd(53, 64, 3, 7, 7, scale=1.0 / np.sqrt(147.0))
+    bn = _BN(54, 64)
+    src = cu(img.astype(np.uint8)) if u8 else cu(img)
+    wp = ops.split_planes(ops.stem_weight_windows(cu(w)).reshape(64, 256), P)
+    scale, shift = ops.bn_fold(bn, None)
+    win = ops.preprocess_stem_windows(src, P)
+    stem, _ = ops.conv2d_tc(win, wp, 4, 1, scale, shift, 1, 0, ops.ACT_RELU, want_f32=True, planes_out=0)
+    ref_f, ref_p = ops.maxpool3x3s2_planes(stem, P)
+    got_f, got_p = ops.stem_pool_tc(win, wp, scale, shift, P)
+    torch.cuda.synchronize()
+    assert torch.equal(got_f, ref_f) and torch.equal(got_p, ref_p), float((got_f - ref_f).abs().max())
+    if ops.stem_compact_supported():
+        zc = ops.preprocess_stem_compact(src, P)
+        assert tuple(zc.shape) == (P, 2 * B, 115, 116, 16)
+        # the compact image holds exactly the windows' first group: window (yp, ox) = Zc[yp, ox .. ox+3]
+        assert torch.equal(zc[:, :, :, :112], win.reshape(P, 2 * B, 115, 112, 4, 16)[:, :, :, :, 0])
+        assert torch.equal(zc[:, :, :, 3:115], win.reshape(P, 2 * B, 115, 112, 4, 16)[:, :, :, :, 3])
+        c_f, c_p = ops.stem_pool_tc(zc, wp, scale, shift, P)
+        torch.cuda.synchronize()
+        assert torch.equal(c_f, ref_f) and torch.equal(c_p, ref_p), float((c_f - ref_f).abs().max())
+        only_p = ops.stem_pool_tc(zc, wp, scale, shift, P, want_f32=False)
+        assert only_p[0] is None and torch.equal(only_p[1], ref_p)
+    else:
+        print("[stem] the driver refused the overlapping-window tensor map: compact layout not exercised")
+    x = O.preprocess(img.astype(np.float32), np.float32).astype(np.float64)
+    y = O.conv2d(x, w.astype(np.float64), None, 2, 3)
+    y = np.maximum(O.batchnorm_eval(y, {kk: v.astype(np.float64) for kk, v in bn.params("bn").items()}, "bn"), 0)
+    yp = np.full((2 * B, 64, 114, 114), -np.inf); yp[:, :, 1:113, 1:113] = y
+    ref = np.max(np.stack([yp[:, :, dy:dy + 112:2, dx:dx + 112:2] for dy in range(3) for dx in range(3)]), axis=0)
+    got = got_f.cpu().numpy().transpose(0, 3, 1, 2).astype(np.float64)
+    err = np.abs(got - ref).max()
+    tol = (4e-5 if P == 2 else 3e-2) * np.abs(ref).max()
+    print(f"[parity] stem_pool_fused P={P} B={B} {H}x{W} u8={u8}: max_abs_err={err:.3e} ratio={err / tol:.3f} compact={ops.stem_compact_supported()}")
+    assert err <= tol
+
+
+@pytest.mark.parametrize("P", [2, 1])
 @pytest.mark.parametrize("flags", [1, 2, 3])
 def test_essential_tc_ablation_flags(P, flags):
     """--use_single_softmax (1) / --cross_features (2) on the tensor-core module kernels vs the fp32 SIMT kernels of the
