@@ -131,7 +131,7 @@ def reference_inputs(batch, size, seed=0):
     return images, Gs, intr
 
 
-def reference_forward_factory(device="cpu", sd=None):
+def reference_forward_factory(device="cpu", sd=None, dtype=None):
     """Returns (fn(images, Gs, intr) -> [B,2,7] tensor on `device`, kind, description): the unmodified reference ViTEss when
     its tree is present (kind "reference"), else the pinned port (kind "port").  Test / baseline infrastructure."""
     import torch
@@ -144,6 +144,8 @@ def reference_forward_factory(device="cpu", sd=None):
         model, SE3 = ref_loader.load_reference_model()
         model.load_state_dict(sd)
         model = model.to(device).eval()
+        if dtype is not None:
+            model = model.to(dtype)
 
         def run(images, Gs, intr):
             with torch.no_grad():
@@ -153,7 +155,7 @@ def reference_forward_factory(device="cpu", sd=None):
                 return model(images, SE3(Gs), intrinsics=intr.clone())[0].data
         return run, "reference", f"unmodified reference ViTEss from {root}"
     import torch_port
-    p = {k: v.to(device) for k, v in sd.items() if v.dtype != torch.int64}
+    p = {k: (v.to(device) if dtype is None else v.to(device, dtype)) for k, v in sd.items() if v.dtype != torch.int64}
 
     def run(images, Gs, intr):
         with torch.no_grad():
@@ -732,6 +734,11 @@ def main():
             t0 = time.perf_counter()
             ref = fn(images.float().cpu(), Gs.data.cpu(), intr0.cpu()).numpy()
             r = pose_errors(timed_out, ref)
+            # the same reference in float64 = the exact result of the model: how far the float32 reference itself is from it
+            # (its own rounding, the noise floor of the 1e-4 bar) and how far this implementation is
+            fn64, _, _ = reference_forward_factory("cpu", dtype=torch.float64)
+            ref64 = fn64(images.double().cpu(), Gs.data.double().cpu(), intr0.double().cpu()).numpy()
+            r["vs_float64_reference"] = {"ours": pose_errors(timed_out, ref64), "float32_reference": pose_errors(ref, ref64)}
             r.update({"against": desc + ", CPU fp32, same inputs and weights as the timed batch", "kind": kind,
                       "bar": "1e-4 rad / 1e-4 relative translation (north_star)", "cpu_seconds": round(time.perf_counter() - t0, 2),
                       "pass": bool(r["rot_max_rad"] < 1e-4 and r["trans_max_rel"] < 1e-4) if a.precision != "bf16" else None})

@@ -27,6 +27,8 @@ CASES = [
     ("stress_b3_64x80_varied", 2, "stress", 3, 64, 80, "varied", False),
     ("stress_b1_nointr", 3, "stress", 1, 48, 48, None, True),
     ("init_b1_384x512_demo_shape", 4, "init", 1, 384, 512, "matterport", True),
+    # the benchmark's shape at a batch the CPU reference still finishes quickly (round 2)
+    ("init_b8_384x384", 5, "init", 8, 384, 384, "matterport", True),
 ]
 
 # ablation branches of the Essential Matrix Module: same generator, reference built with the flag(s)
@@ -141,6 +143,9 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only in [c[0] for c in CASES]:              # a single default-configuration case by name
+        run_case(*[c for c in CASES if c[0] == only][0])
+        sys.exit(0)
     if only not in ("ablations", "noess", "cnn_only"):
         posenc_golden()
         for c in CASES:

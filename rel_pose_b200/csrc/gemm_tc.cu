@@ -25,6 +25,7 @@
 // The two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 // Convolution tiles are R whole output rows of one image (R*Wo <= 128 pixels) so that the pixels of a
 // tile are one rectangular TMA box for every filter tap; unused accumulator rows are never stored.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace {
@@ -75,7 +76,14 @@ __device__ __forceinline__ float act_fn(float v, int act) {
     return v;
 }
 
-template <int P, int BN, bool CONV>
+// FOLD: long reductions (K > 768: the 5x5 and the 128-channel 3x3 convolutions) are cut into segments of at most
+// FOLD_KB K blocks.  tcgen05 accumulates in fp32 with TRUNCATION, so one TMEM accumulator that lives for n MMAs carries
+// a bias of ~n 2^-25 (measured 3.5e-9 K relative: 1.6e-5 at K = 4800, the largest single term of the front end's token
+// error).  Every segment gets a fresh accumulator (the two TMEM stages alternate); the epilogue warps add the finished
+// segments in fp32 registers (round to nearest) while the next segment's MMAs run, and run the usual epilogue on the sum.
+constexpr int FOLD_KB = 12;
+
+template <int P, int BN, bool CONV, bool FOLD = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams ep, Geom g) {
     using C = Cfg<P, BN>;
@@ -96,6 +104,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nsplit = (!CONV && g.ksplit > 1) ? g.ksplit : 1;
     const int ntiles = tiles_m * tiles_n * nsplit;
     const int ksteps_all = CONV ? g.taps * g.cblocks : (g.K + BK - 1) / BK;
+    const int nseg = FOLD ? (ksteps_all + FOLD_KB - 1) / FOLD_KB : 1;       // accumulator segments per tile
+    const int seg_len = (ksteps_all + nseg - 1) / nseg;
     // split-K (weight-bandwidth-bound skinny GEMMs: the 26880 -> 512 regressor layer): tile = (split, m, n), every
     // split reduces kb_per_split K blocks into its own float32 partial [split][M][N]; short accumulation chains
     auto k_range = [&](int tile, int& ks0, int& ks1) {
@@ -168,11 +178,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN);
         int stage = 0, phase = 0, acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int kt0, kt1;
+            k_range(tile, kt0, kt1);
+          for (int seg = 0; seg < nseg; ++seg) {
+            const int ks0 = FOLD ? kt0 + seg * seg_len : kt0, ks1 = FOLD ? min(kt1, ks0 + seg_len) : kt1;
             tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc::tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-            int ks0, ks1;
-            k_range(tile, ks0, ks1);
             for (int ks = ks0; ks < ks1; ++ks) {
                 tc::mbar_wait(&full[stage], phase);
                 tc::tcgen05_fence_after();
@@ -200,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..17)
@@ -231,10 +244,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row_base = tm * BM;
                 valid_rows = min(BM, M - row_base);
             }
+            // finished accumulator segments are summed in registers (FOLD): this thread's row, its CH_PER_PART chunks
+            float facc[FOLD ? CH_PER_PART * 16 : 1];
+            if constexpr (FOLD) {
+                for (int seg = 0; seg + 1 < nseg; ++seg) {
+                    tc::mbar_wait(&tfull[acc], acc_phase);
+                    tc::tcgen05_fence_after();
+                    const uint32_t t_seg = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+                    for (int ci = 0; ci < CH_PER_PART; ++ci) {
+                        uint32_t r[16];
+                        tc::tmem_ld_32x32b_x16(t_seg + (part * CH_PER_PART + ci) * 16, r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            facc[ci * 16 + i] = seg == 0 ? __uint_as_float(r[i]) : facc[ci * 16 + i] + __uint_as_float(r[i]);
+                    }
+                    tc::tcgen05_fence_before();
+                    tc::mbar_arrive(&tempty[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+            constexpr int CI_UNROLL = FOLD ? CH_PER_PART : 1;    // facc[] needs compile-time indices; otherwise keep the loop rolled
+#pragma unroll(CI_UNROLL)
             for (int ci = 0; ci < CH_PER_PART; ++ci) {
                 const int c0 = (part * CH_PER_PART + ci) * 16;
                 if (n0 + c0 >= N) break;                 // warp-uniform
@@ -262,6 +297,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t r[16];
                 tc::tmem_ld_32x32b_x16(t_row + c0, r);
                 tc::tmem_ld_wait();
+                if constexpr (FOLD) {
+                    if (nseg > 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(facc[ci * 16 + i] + __uint_as_float(r[i]));
+                    }
+                }
                 __syncwarp();                            // the previous chunk's readers are done with the patch
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -461,13 +502,13 @@ __global__ void __launch_bounds__(256) maxpool_planes_kernel(const float4* __res
     }
 }
 
-template <int P, int BN, bool CONV>
+template <int P, int BN, bool CONV, bool FOLD = false>
 int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, const Geom& g, int ntiles,
                    int device, cudaStream_t st, const char* what) {
     using C = Cfg<P, BN>;
     static bool attr_set[64] = {false};
     if (device >= 0 && device < 64 && !attr_set[device]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<P, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<P, BN, CONV, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             rp::set_error("%s: cudaFuncSetAttribute(%d): %s", what, C::SMEM, cudaGetErrorString(e));
             return (int)e;
@@ -475,7 +516,7 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiPara
         attr_set[device] = true;
     }
     int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
-    gemm_tc_kernel<P, BN, CONV><<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmB, ep, g);
+    gemm_tc_kernel<P, BN, CONV, FOLD><<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmB, ep, g);
     return rp::finish_launch(what);
 }
 
@@ -661,7 +702,13 @@ extern "C" int rp_conv2d_tc(const void* x_planes, const void* w_planes, const fl
     int ntiles = n_img * g.tiles_per_img;
     cudaStream_t st = (cudaStream_t)stream;
     const char* what = "rp_conv2d_tc";
-#define RP_CONV_DISPATCH(PP, NN) return launch_gemm_tc<PP, NN, true>(tmA, tmB, ep, g, ntiles, device, st, what)
+    // reductions longer than FOLD_KB K blocks (K > 768) sum their accumulator segments in registers (see gemm_tc_kernel);
+    // RELPOSE_CONV_FOLD=0 keeps the single-chain accumulation for A/B measurements
+    static const bool fold_enabled = !(getenv("RELPOSE_CONV_FOLD") && getenv("RELPOSE_CONV_FOLD")[0] == '0');
+    const bool fold = fold_enabled && g.taps * g.cblocks > FOLD_KB;
+#define RP_CONV_DISPATCH(PP, NN)                                                                              \
+    return fold ? launch_gemm_tc<PP, NN, true, true>(tmA, tmB, ep, g, ntiles, device, st, what)               \
+                : launch_gemm_tc<PP, NN, true, false>(tmA, tmB, ep, g, ntiles, device, st, what)
     if (P == 1) {
         if (O == 64) RP_CONV_DISPATCH(1, 64);
         if (O == 128) RP_CONV_DISPATCH(1, 128);

@@ -307,7 +307,7 @@ class ViTEss(nn.Module):
         The model without a transformer always runs on the fp32 engine: nothing between the CNN and the regressor
         normalises the tokens, and the bf16x3 front end's token error (2.7e-5 relative rms against 6e-7 in fp32,
         profiles/r01_cnn_only_error_budget.log) reaches the pose at 1.0-1.4e-4 rad on the stress golden -- over the bar."""
-        if self.cnn_only:
+        if self.cnn_only and not getattr(self, "cnn_only_tc", False):
             return 0
         return {"fp32": 0, "bf16": 1, "bf16x3": 2}[self.precision]
 

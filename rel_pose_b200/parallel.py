@@ -67,8 +67,25 @@ class StreamedInference:
         self.copy_stream = torch.cuda.Stream(self.device)
         self._bufs = [None, None]
         self._result_ring = {}
+        self._dev_ring = {}                  # (shape, dtype) -> [[device buffer, event of its last consumer] x 3, next index]
         self.row_selective = True            # copy only the rows the nearest resize reads
         self.last_image_h2d_bytes = 0
+
+    def _device_buffer(self, shape, dtype):
+        """Device staging buffer for the next batch, from a ring of three per (shape, dtype): one being consumed by the
+        kernels, one being filled by the copy engine, one spare.  The buffers are allocated once -- a per-step
+        torch.empty on the copy stream makes the caching allocator wait for / grow around blocks the compute stream still
+        holds (measured: the first end-to-end leg of a run 30 % slower than the second) -- and the copy stream waits for
+        the kernels that last read a buffer before overwriting it."""
+        key = (tuple(shape), dtype)
+        ring = self._dev_ring.get(key)
+        if ring is None:
+            ring = self._dev_ring[key] = [[[torch.empty(shape, dtype=dtype, device=self.device), None] for _ in range(3)], 0]
+        slot = ring[0][ring[1] % 3]
+        ring[1] += 1
+        if slot[1] is not None:
+            self.copy_stream.wait_event(slot[1])
+        return slot
 
     def _copy_images(self, images):
         """H2D of the image batch on the copy stream.  Pinned float32 / uint8 images taller than 224 rows are
@@ -80,16 +97,19 @@ class StreamedInference:
             from math import gcd
             from . import _lib
             if 224 // gcd(H, 224) <= 64:
-                d = torch.empty(tuple(images.shape[:-2]) + (224, W), dtype=images.dtype, device=self.device)
+                slot = self._device_buffer(tuple(images.shape[:-2]) + (224, W), images.dtype)
+                d = slot[0]
                 planes = images.numel() // (H * W)
                 dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
                 rc = _lib.lib().rp_copy_rows_h2d(ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(images.data_ptr()), planes, H,
                                                  W * images.element_size(), 224, dev,
                                                  ctypes.c_void_p(self.copy_stream.cuda_stream))
                 if rc == 0:
-                    return d, (H, W), d.numel() * d.element_size()
+                    return slot, (H, W), d.numel() * d.element_size()
                 # RP_EINVAL: the float32 row map of this height is not periodic -> plain copy of the whole tensor
-        return images.to(self.device, non_blocking=True), None, images.numel() * images.element_size()
+        slot = self._device_buffer(tuple(images.shape), images.dtype)
+        slot[0].copy_(images, non_blocking=True)
+        return slot, None, images.numel() * images.element_size()
 
     def _pinned_result(self, out):
         """Pinned host buffer for a [b,2,7] result, from a ring of three per shape (one being filled, one pending,
@@ -103,13 +123,13 @@ class StreamedInference:
     def _stage(self, slot, batch):
         images, gs, intr = batch
         with torch.cuda.stream(self.copy_stream):
-            d_img, orig_hw, nbytes = self._copy_images(images)
+            img_slot, orig_hw, nbytes = self._copy_images(images)
             self.last_image_h2d_bytes = nbytes
             d_gs = gs.to(self.device, non_blocking=True)
             d_k = intr.to(self.device, non_blocking=True) if intr is not None else None
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        self._bufs[slot] = (d_img, d_gs, d_k, ev, orig_hw)
+        self._bufs[slot] = (img_slot, d_gs, d_k, ev, orig_hw)
 
     def run(self, batches):
         from .lietorch import SE3
@@ -123,7 +143,8 @@ class StreamedInference:
         pending = None                       # (host result, event) of the previous batch
         compute = torch.cuda.current_stream(self.device)
         while True:
-            d_img, d_gs, d_k, ev, orig_hw = self._bufs[slot]
+            img_slot, d_gs, d_k, ev, orig_hw = self._bufs[slot]
+            d_img = img_slot[0]
             try:
                 nxt = next(it)
             except StopIteration:
@@ -133,9 +154,12 @@ class StreamedInference:
             compute.wait_event(ev)
             with torch.no_grad():
                 out = self.model(d_img, SE3(d_gs), intrinsics=d_k, _orig_hw=orig_hw)[0].data
-            for t in (d_img, d_gs, d_k):     # the copy stream allocated them, the compute stream used them
+            for t in (d_gs, d_k):            # the copy stream allocated them, the compute stream used them
                 if t is not None:
                     t.record_stream(compute)
+            used = torch.cuda.Event()        # the image buffer may be refilled once these kernels are done
+            used.record(compute)
+            img_slot[1] = used
             host = self._pinned_result(out)      # pinned staging ring: cudaHostAlloc per step costs ~0.1 ms
             host.copy_(out, non_blocking=True)
             done = torch.cuda.Event()

@@ -104,9 +104,8 @@ def test_forward_tensor_core_precisions(name, precision):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     seed, B, H, W, integer = (int(v) for v in g["meta"])
     profile, ikind = str(g["profile"]), str(g["intrinsics_kind"])
-    if "cnn_only" in _flags(g):
-        pytest.skip("the model without a transformer runs on the fp32 engine only (model._tc_planes)")
     m = _model(seed, profile, _flags(g))
+    m.cnn_only_tc = "cnn_only" in _flags(g)      # force the tensor-core front end for the model without a transformer
     images = torch.from_numpy(S.make_images_numpy(seed, B, H, W, bool(integer))).to(DEV)
     intr = None if ikind == "none" else torch.from_numpy(S.make_intrinsics_numpy(B, ikind, seed)).to(DEV)
     Gs = SE3.Identity(B, 2, device=DEV)
@@ -116,10 +115,15 @@ def test_forward_tensor_core_precisions(name, precision):
             poses = m(images, Gs, intrinsics=intr)[0].data.cpu().numpy()
     finally:
         m.precision = "fp32"
+        m.cnn_only_tc = False
     rot = O.rotation_error_rad(poses[:, 1, 3:], g["poses"][:, 1, 3:])
     tr = O.translation_rel_error(poses[:, 1, :3], g["poses"][:, 1, :3])
     print(f"[parity] {name} precision={precision}: rot_err max {rot.max():.3e} rad, trans_rel_err max {tr.max():.3e}")
-    if precision == "bf16x3":
+    if precision == "bf16x3" and "cnn_only" in _flags(g):
+        # no LayerNorm between the CNN and the regressor: the tensor-core front end is not the default for this variant
+        # (model._tc_planes); reported, bounded loosely
+        assert rot.max() < 3e-4 and tr.max() < 3e-4
+    elif precision == "bf16x3":
         assert rot.max() < 1e-4 and tr.max() < 1e-4
     else:
         assert rot.max() < 0.2 and tr.max() < 0.2
