@@ -295,6 +295,9 @@ int rp_se3_exp_bwd_f32(const float* dX, const float* a, float* da, int64_t n, in
  *   the unbiased variance; torchvision resnet18 / extractor.py:24-28).   rp_layernorm_*: eps inside the sqrt.
  * rp_softmax_{rows,cols}: softmax(scale * S) over dim -1 / dim -2 of [mats][n][n]; *_bwd adds into ds if accumulate.
  * rp_maxpool3x3s2_bwd: gradient to the FIRST maximum of each window (PyTorch's tie-break). */
+/* float32 [R][C] -> bf16 planes of the transpose [P][C][R] (R even): operands of the weight-gradient GEMMs
+ * dW = dY^T X on the tensor-core engine (rp_linear_tc_splitk contracts over what were the rows). */
+int rp_transpose_split_planes_bf16(const float* x, void* planes, int R, int C, int P, int device, void* stream);
 int rp_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,              int ldb, float beta, float* C, int ldc, int batch_outer, int batch_inner, int64_t sAo, int64_t sAi,              int64_t sBo, int64_t sBi, int64_t sCo, int64_t sCi, int device, void* stream);
 int rp_gelu_fwd_f32(const float* z, float* y, int64_t n, int device, void* stream);
 int rp_gelu_bwd_f32(const float* dy, const float* z, float* dz, int64_t n, int device, void* stream);

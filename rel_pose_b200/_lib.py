@@ -45,6 +45,7 @@ _SIGNATURES = {
     "rp_linear_workspace_bytes": (_c_size, [_c_int, _c_int, _c_int]),
     "rp_linear_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_split_planes_bf16": (_c_int, [_ptr, _ptr, _c_i64, _c_int, _c_int, _ptr]),
+    "rp_transpose_split_planes_bf16": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_layernorm_planes_bf16": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_f32, _c_int, _c_int, _ptr]),
     "rp_linear_tc": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_regressor_tail_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr]),

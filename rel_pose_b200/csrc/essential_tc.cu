@@ -884,10 +884,13 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             __syncwarp();
             if (++rs == RING) { rs = 0; rph ^= 1; }
         };
+        bool s0_issued = false;      // S_0 of this unit was already issued behind the previous unit's last block
         for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x, ++tt) {
-            tc::mbar_wait(q_full, tt & 1);
-            tc::tcgen05_fence_after();
-            issue_s(g);
+            if (!s0_issued) {
+                tc::mbar_wait(q_full, tt & 1);
+                tc::tcgen05_fence_after();
+                issue_s(g);
+            }
             for (int j = 0; j < NBLK; ++j, ++g) {
                 if (j + 1 < NBLK) {
                     issue_s(g + 1);
@@ -929,6 +932,16 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 __syncwarp();
                 if (++rs == RING) { rs = 0; rph ^= 1; }
+            }
+            // The next unit's first score block goes into the pipe BEFORE this unit's F step: its softmax (exponentials,
+            // A_0 into tensor memory) then overlaps the 72 small F / G products instead of waiting behind them.  S_0 of the
+            // next unit writes the S buffer whose A block was read by this unit's T_4 (issued above: in-order pipe).
+            s0_issued = false;
+            if (unit + (int)gridDim.x < nunits) {
+                tc::mbar_wait(q_full, (tt + 1) & 1);
+                tc::tcgen05_fence_after();
+                issue_s(g);
+                s0_issued = true;
             }
             // F_t = v_i^T [T_v | T_pos]  and  G_t = [T_v | T_pos]^T pos_i   (K = the 128 rows of the tile)
             tc::mbar_wait(t_ready, tt & 1);

@@ -76,12 +76,16 @@ __device__ __forceinline__ float act_fn(float v, int act) {
     return v;
 }
 
-// FOLD: long reductions (K > 768: the 5x5 and the 128-channel 3x3 convolutions) are cut into segments of at most
+// FOLD: long reductions (K > 1600: the two 5x5 convolutions that produce the tokens) are cut into segments of at most
 // FOLD_KB K blocks.  tcgen05 accumulates in fp32 with TRUNCATION, so one TMEM accumulator that lives for n MMAs carries
 // a bias of ~n 2^-25 (measured 3.5e-9 K relative: 1.6e-5 at K = 4800, the largest single term of the front end's token
 // error).  Every segment gets a fresh accumulator (the two TMEM stages alternate); the epilogue warps add the finished
 // segments in fp32 registers (round to nearest) while the next segment's MMAs run, and run the usual epilogue on the sum.
-constexpr int FOLD_KB = 12;
+// Measured (64 pairs): segments of 12 K blocks on every K > 768 layer cost 0.14 ms per step (the unrolled, spilling
+// epilogue of the FOLD variant is on the critical path of the short-K 3x3 layers) for a pose error against the float64
+// reference of 3.7e-5 rad / 2.9e-5 instead of 4.8e-5 / 4.9e-5; segments of 25 on the 5x5 layers only keep most of the
+// gain (their chains were the 1.6e-5 / 1.0e-5 terms) at a fraction of the cost.
+constexpr int FOLD_KB = 25;
 
 template <int P, int BN, bool CONV, bool FOLD = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -279,7 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (colv && ep.scale) sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col));
                 if (colv && ep.shift) sh = __ldg(reinterpret_cast<const float4*>(ep.shift + col));
                 float4 rpre[4], rpost[4];
-                if (vec4) {
+                if (vec4 && !FOLD) {          // FOLD: the partial sums occupy these registers; residuals are read at use
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
                         const int rt = q * 32 + it * 8 + rr;
@@ -317,6 +321,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (!colv || rt >= valid_rows) continue;
                         const size_t o = (size_t)(row_base + rt) * N + col;
                         const float4 a = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2));
+                        if constexpr (FOLD) {
+                            rpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            rpost[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (ep.res_pre) rpre[it] = __ldg(reinterpret_cast<const float4*>(ep.res_pre + o));
+                            if (ep.res_post) {
+                                const int rq = ep.res_post_rows > 0 ? (row_base + rt) % ep.res_post_rows : (row_base + rt);
+                                rpost[it] = __ldg(reinterpret_cast<const float4*>(ep.res_post + (size_t)rq * N + col));
+                            }
+                        }
                         float v0 = fmaf(a.x, sc.x, sh.x) + rpre[it].x, v1 = fmaf(a.y, sc.y, sh.y) + rpre[it].y;
                         float v2 = fmaf(a.z, sc.z, sh.z) + rpre[it].z, v3 = fmaf(a.w, sc.w, sh.w) + rpre[it].w;
                         if (ep.act == RP_ACT_GELU) {
@@ -408,6 +421,38 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
         } else {
             for (int j = 0; j < 8 && i + j < n; ++j) dst[j] = h[j];
+        }
+    }
+}
+
+// x [R][C] float32 -> bf16 planes of the TRANSPOSE, [P][C][R]: the weight-gradient GEMM dW = dY^T X of the training path
+// contracts over the rows of both factors, so it runs on the K-major engine above with both operands transposed
+// (train_path.py).  64 x 32 tile through shared memory: 128-byte global reads and writes (two rows per thread on the
+// store side, packed bf16x2).
+__global__ void __launch_bounds__(256) transpose_split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                                     int R, int C, int P) {
+    __shared__ float t[32][65];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + tx;
+        t[tx][ty + 8 * k] = (r < R && c < C) ? x[(size_t)r * C + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int cl = ty + 8 * m, c = c0 + cl, r = r0 + 2 * tx;
+        if (c >= C || r >= R) continue;
+        float v0 = t[cl][2 * tx], v1 = t[cl][2 * tx + 1];
+        for (int p = 0; p < P; ++p) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            const uint32_t w = *reinterpret_cast<uint32_t*>(&h);
+            __nv_bfloat16* dst = out + ((size_t)p * C + c) * R + r;
+            if (r + 1 < R) *reinterpret_cast<uint32_t*>(dst) = w;
+            else dst[0] = __ushort_as_bfloat16((unsigned short)(w & 0xffffu));
+            v0 -= __uint_as_float(w << 16);
+            v1 -= __uint_as_float(w & 0xffff0000u);
         }
     }
 }
@@ -531,6 +576,17 @@ extern "C" int rp_split_planes_bf16(const float* x, void* planes, int64_t n, int
     split_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         x, static_cast<__nv_bfloat16*>(planes), n, P);
     return rp::finish_launch("rp_split_planes");
+}
+
+extern "C" int rp_transpose_split_planes_bf16(const float* x, void* planes, int R, int C, int P, int device, void* stream) {
+    RP_REQUIRE(x && planes && R > 0 && C > 0 && (P == 1 || P == 2), RP_EINVAL, "rp_transpose_split_planes: bad argument");
+    RP_REQUIRE((R % 2) == 0 && (reinterpret_cast<uintptr_t>(planes) & 3) == 0, RP_EALIGN,
+               "rp_transpose_split_planes: R must be even and planes 4-byte aligned");
+    RP_GUARD(device);
+    dim3 grid((R + 63) / 64, (C + 31) / 32);
+    RP_REQUIRE(grid.y <= 65535, RP_EINVAL, "rp_transpose_split_planes: too many columns");
+    transpose_split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, static_cast<__nv_bfloat16*>(planes), R, C, P);
+    return rp::finish_launch("rp_transpose_split_planes");
 }
 
 extern "C" int rp_layernorm_planes_bf16(const float* x, const float* gamma, const float* beta, void* planes, int rows,

@@ -249,17 +249,30 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         partial[((size_t)blockIdx.x * 2 + 1) * cols + c] = b2;
     }
 }
-__global__ void ln_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                    int nblk, int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// 32 columns per block, 8 threads per column each summing every 8th partial (fixed order), then a fixed-order
+// shared-memory reduction: deterministic, and 8x the loads in flight of the one-thread-per-column version (which took
+// 88 us per LayerNorm at 6912 rows: 26 of them were 1.1 ms of the training step).
+__global__ void __launch_bounds__(256) ln_bwd_final_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int nblk, int cols) {
+    __shared__ float sa[8][33], sb[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < nblk; ++k) {
-        a += partial[((size_t)k * 2 + 0) * cols + c];
-        b += partial[((size_t)k * 2 + 1) * cols + c];
+    if (c < cols) {
+        for (int k = ty; k < nblk; k += 8) {
+            a += partial[((size_t)k * 2 + 0) * cols + c];
+            b += partial[((size_t)k * 2 + 1) * cols + c];
+        }
     }
-    dgamma[c] = a;
-    dbeta[c] = b;
+    sa[ty][tx] = a; sb[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float ra = 0.f, rb = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { ra += sa[r][tx]; rb += sb[r][tx]; }
+        dgamma[c] = ra;
+        dbeta[c] = rb;
+    }
 }
 
 // ============================================================================================ softmax
@@ -653,7 +666,7 @@ extern "C" int rp_layernorm_bwd_f32(const float* dy, const float* x, const float
     RP_GUARD(device);
     const int nblk = (rows + 7) / 8;
     ln_bwd_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(dy, x, gamma, mean, rstd, dx, static_cast<float*>(workspace), rows, cols);
-    ln_bwd_final_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), dgamma, dbeta, nblk, cols);
+    ln_bwd_final_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), dgamma, dbeta, nblk, cols);
     return rp::finish_launch("rp_layernorm_bwd");
 }
 

@@ -367,6 +367,19 @@ def split_planes(x, P=2):
     return out
 
 
+def transpose_split_planes(x, P=2):
+    """float32 [R, C] -> bf16 planes of the transpose [P, C, R] (R even)."""
+    _req(x, "x")
+    assert x.dim() == 2
+    R, C = x.shape
+    out = torch.empty((P, C, R), dtype=torch.bfloat16, device=x.device)
+    dev, st = _ctx(x)
+    _tbegin("transpose_split_planes", 0.0, 4.0 * R * C + 2.0 * P * R * C)
+    _lib.check(_lib.lib().rp_transpose_split_planes_bf16(_p(x), _p(out), R, C, P, dev, st), "rp_transpose_split_planes")
+    _count()
+    return out
+
+
 def layernorm_planes(x, gamma, beta, eps=1e-6, P=2):
     _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta")
     cols = x.shape[-1]

@@ -8,6 +8,7 @@ What is differentiated (reference lines): src/model.py:114-191; vision_transform
 The lietorch SE3 ops of the loss have their own kernels (rel_pose_b200/lietorch).
 """
 import ctypes
+import os
 
 import torch
 
@@ -92,6 +93,45 @@ def _ew(name, out, *args):
     return out
 
 
+# ------------------------------------------------------------------------------------------ tensor-core GEMMs of the step
+# The three products of every nn.Linear / nn.Conv2d in the step -- y = x W^T, dX = dY W, dW = dY^T X -- run on the tcgen05
+# engine of the inference path (rp_linear_tc / rp_linear_tc_splitk / rp_conv2d_tc, split-bf16 operands = fp32 class) whenever
+# the shape qualifies; all three are brought to its K-major form C = A B^T:
+#   y  = x W^T            A = planes(x)      [M,K]    B = planes(W)     [N,K]
+#   dX = dY W             A = planes(dY)     [M,N]    B = planes(W^T)   [K,N]     (re-layout copy of the small weight)
+#   dW = dY^T X           A = planes(dY^T)   [N,M]    B = planes(X^T)   [K,M]     (rp_transpose_split_planes, split-K: the
+#                                                                                 contraction runs over the M rows)
+# Convolutions: forward = the implicit-GEMM kernel; dX of a stride-1 convolution = the same kernel on dY with the
+# spatially flipped, channel-transposed filter and padding K-1-p; dW = dY^T im2col(X).  RELPOSE_TRAIN_TC=0 keeps the
+# fp32 SIMT kernels (A/B measurements); tiny problems (the pose regressor at 6 rows) always stay there.
+TRAIN_TC = os.environ.get("RELPOSE_TRAIN_TC", "1") != "0"
+_TCP = 2                                   # bf16x3
+
+
+def _lin_fwd(x2, w, b, act=ops.ACT_NONE):
+    M, K = x2.shape
+    if TRAIN_TC and M >= 64 and K % 8 == 0 and (M * K) % 8 == 0 and (w.numel() % 8) == 0:
+        return ops.linear_tc(ops.split_planes(x2, _TCP), ops.split_planes(w, _TCP), b, act=act)[0]
+    return ops.linear(x2, w, b, act=act)
+
+
+def _lin_dx(dy2, w):
+    """dy2 [M,N], w [N,K] -> dy2 @ w  [M,K]"""
+    M, N = dy2.shape
+    if TRAIN_TC and M >= 64 and N % 8 == 0 and (M * N) % 8 == 0 and (w.numel() % 8) == 0:
+        return ops.linear_tc(ops.split_planes(dy2, _TCP), ops.split_planes(w.t().contiguous(), _TCP), None)[0]
+    return mm(dy2, w)
+
+
+def _lin_dw(dy2, x2):
+    """dy2 [M,N], x2 [M,K] -> dy2^T @ x2  [N,K]"""
+    M, N = dy2.shape
+    K = x2.shape[1]
+    if TRAIN_TC and M >= 512 and M % 8 == 0 and K % 4 == 0:
+        return ops.linear_tc_splitk(ops.transpose_split_planes(dy2, _TCP), ops.transpose_split_planes(x2, _TCP))
+    return mm(dy2, x2, ta=True)
+
+
 # ------------------------------------------------------------------------------------------ autograd functions
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b   (vision_transformer.py:323,331; mlp.py:21,24; model.py:91-98)"""
@@ -100,7 +140,9 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, w, b):
         x = x.contiguous()
         ctx.save_for_backward(x, w)
-        return ops.linear(x, w.detach().contiguous(), b.detach().contiguous() if b is not None else None)
+        N, K = w.shape
+        y = _lin_fwd(x.reshape(-1, K), w.detach().contiguous(), b.detach().contiguous() if b is not None else None)
+        return y.reshape(x.shape[:-1] + (N,))
 
     @staticmethod
     def backward(ctx, dy):
@@ -108,8 +150,8 @@ class LinearFn(torch.autograd.Function):
         N, K = w.shape
         dy2 = dy.contiguous().reshape(-1, N)
         x2 = x.reshape(-1, K)
-        dx = mm(dy2, w.detach().contiguous()).reshape(x.shape) if ctx.needs_input_grad[0] else None
-        dw = mm(dy2, x2, ta=True) if ctx.needs_input_grad[1] else None
+        dx = _lin_dx(dy2, w.detach().contiguous()).reshape(x.shape) if ctx.needs_input_grad[0] else None
+        dw = _lin_dw(dy2, x2) if ctx.needs_input_grad[1] else None
         db = colsum(dy2) if ctx.needs_input_grad[2] else None
         return dx, dw, db
 
@@ -378,7 +420,8 @@ class LinearReluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
         x = x.contiguous()
-        y = ops.linear(x, w.detach().contiguous(), b.detach().contiguous(), act=ops.ACT_RELU)
+        N, K = w.shape
+        y = _lin_fwd(x.reshape(-1, K), w.detach().contiguous(), b.detach().contiguous(), act=ops.ACT_RELU).reshape(x.shape[:-1] + (N,))
         ctx.save_for_backward(x, w, y)
         return y
 
@@ -390,7 +433,7 @@ class LinearReluFn(torch.autograd.Function):
         _ew("rp_relu_bwd_f32", dz, _p(dy), _p(y), _p(dz), dy.numel())
         N, K = w.shape
         dz2 = dz.reshape(-1, N)
-        return mm(dz2, w.detach().contiguous()).reshape(x.shape), mm(dz2, x.reshape(-1, K), ta=True), colsum(dz2)
+        return _lin_dx(dz2, w.detach().contiguous()).reshape(x.shape), _lin_dw(dz2, x.reshape(-1, K)), colsum(dz2)
 
 
 class ConvFn(torch.autograd.Function):
@@ -400,8 +443,15 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad):
         x = x.contiguous()
-        wp = ops.permute_conv_weight(weight.detach(), x.shape[-1])
-        y = ops.conv2d_nhwc(x, wp, None, bias.detach().contiguous() if bias is not None else None, stride, pad, ops.ACT_NONE)
+        C = x.shape[-1]
+        wp = ops.permute_conv_weight(weight.detach(), C)
+        O, KH, KW, Cp = wp.shape
+        b = bias.detach().contiguous() if bias is not None else None
+        if TRAIN_TC and C % 64 == 0 and O in (64, 128, 192):
+            y = ops.conv2d_tc(ops.split_planes(x, _TCP), ops.split_planes(wp.reshape(O, -1), _TCP), KH, KW, None, b, stride, pad,
+                              ops.ACT_NONE, want_f32=True, planes_out=0)[0]
+        else:
+            y = ops.conv2d_nhwc(x, wp, None, b, stride, pad, ops.ACT_NONE)
         ctx.save_for_backward(x, wp)
         ctx.geom = (stride, pad, tuple(weight.shape), bias is not None)
         return y
@@ -423,14 +473,20 @@ class ConvFn(torch.autograd.Function):
             cols = _new((M, K), x)
             _lib.check(L.rp_im2col_nhwc_f32(_p(x), _p(cols), n, H, W, C, KH, KW, stride, pad, dev, st), "rp_im2col")
             ops._count()
-            dwp = mm(dy2, cols, ta=True).reshape(O, KH, KW, Cp)                   # [O, K]
+            dwp = _lin_dw(dy2, cols).reshape(O, KH, KW, Cp)                       # [O, K]
             del cols
             dwt = dwp[..., :wshape[1]].permute(0, 3, 1, 2).contiguous()          # re-layout copy back to [O,C,KH,KW]
         if ctx.needs_input_grad[0]:
-            dcols = mm(dy2, wp.reshape(O, K))                                    # [M, K]
-            dx = torch.empty_like(x)
-            _lib.check(L.rp_col2im_nhwc_f32(_p(dcols), _p(dx), n, H, W, C, KH, KW, stride, pad, dev, st), "rp_col2im")
-            ops._count()
+            if TRAIN_TC and stride == 1 and O % 64 == 0 and C in (64, 128, 192) and KH - 1 - pad >= 0:
+                # dX = "full" correlation of dY with the flipped filter, input and output channels swapped
+                wf = wp.flip(1, 2).permute(3, 1, 2, 0).contiguous()              # [C][KH][KW][O]: re-layout copy of the filter
+                dx = ops.conv2d_tc(ops.split_planes(dy, _TCP), ops.split_planes(wf.reshape(C, -1), _TCP), KH, KW, None, None, 1,
+                                   KH - 1 - pad, ops.ACT_NONE, want_f32=True, planes_out=0)[0]
+            else:
+                dcols = _lin_dx(dy2, wp.reshape(O, K))                           # [M, K]
+                dx = torch.empty_like(x)
+                _lib.check(L.rp_col2im_nhwc_f32(_p(dcols), _p(dx), n, H, W, C, KH, KW, stride, pad, dev, st), "rp_col2im")
+                ops._count()
         if has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
         return dx, dwt, db, None, None
