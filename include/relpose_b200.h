@@ -156,6 +156,18 @@ int rp_conv3x3_halo_tc(const void* x_planes, const void* w_planes, const float* 
 int rp_ln_linear_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W_planes,
                     const float* bias, float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out,
                     int device, void* stream);
+/* Generalised form of rp_ln_linear_tc for a chain of Blocks in which every producer of the residual stream also
+ * emits the NEXT LayerNorm's output as bf16 planes, so that no consumer computes a LayerNorm on its critical path:
+ *   xn_planes != NULL     the A operand is supplied as bf16 planes [P][M][192] (x / ln_gamma / ln_beta unused), loaded
+ *                         by TMA: `self.qkv(...)` of vision_transformer.py:323 on the planes of norm1(x);
+ *   residual  != NULL     (N = 192) out_f32 = A W^T + bias + residual: `x = x + self.attn.proj(...)`
+ *                         (vision_transformer.py:331,351); out_planes must be NULL;
+ *   out_ln_planes != NULL (with residual) additionally LayerNorm(out_f32; ln2_gamma, ln2_beta, eps2) as bf16 planes
+ *                         [P][M][192]: the Block's norm2 (vision_transformer.py:352), consumed by rp_mlp_tc_ex. */
+int rp_ln_linear_tc_ex(const float* x, const void* xn_planes, const float* ln_gamma, const float* ln_beta, float eps,
+                       const void* W_planes, const float* bias, const float* residual, float* out_f32, void* out_planes,
+                       void* out_ln_planes, const float* ln2_gamma, const float* ln2_beta, float eps2, int M, int N, int K,
+                       int P, int P_out, int device, void* stream);
 
 /* Fused MLP half-block  out = x + fc2(GELU(fc1(LayerNorm(x))))  in one launch: Block.forward's
  * `x = x + self.mlp(self.norm2(x))` (vision_transformer.py:352-353; mlp.py:20-26) and CrossBlock.forward's
@@ -166,6 +178,14 @@ int rp_ln_linear_tc(const float* x, const float* ln_gamma, const float* ln_beta,
 int rp_mlp_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W1_planes,
               const float* b1, const void* W2_planes, const float* b2, float* out, int M, int dim, int hidden,
               int P, int device, void* stream);
+/* Same with the LayerNorms moved to the producers (see rp_ln_linear_tc_ex): xn_planes != NULL supplies norm2(x) as
+ * bf16 planes [P][M][192] (fc1's A operand by TMA; ln_gamma / ln_beta unused); out_ln_planes != NULL additionally
+ * receives LayerNorm(out; ln2_gamma, ln2_beta, eps2) -- norm1 of the NEXT Block (vision_transformer.py:350) -- as bf16
+ * planes [P][M][192]. */
+int rp_mlp_tc_ex(const float* x, const void* xn_planes, const float* ln_gamma, const float* ln_beta, float eps,
+                 const void* W1_planes, const float* b1, const void* W2_planes, const float* b2, float* out,
+                 void* out_ln_planes, const float* ln2_gamma, const float* ln2_beta, float eps2, int M, int dim, int hidden,
+                 int P, int device, void* stream);
 
 /* Tensor-core convolution (A2/A3), same epilogue contract as rp_conv2d_nhwc_f32.  x_planes is the NHWC
  * activation as bf16 planes [P][n_img][H][W][C] (C % 64 == 0), w_planes [P][O][KH*KW*C] is the split of

@@ -55,6 +55,10 @@ _SIGNATURES = {
     "rp_conv3x3_halo_tc": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr] + [_c_int] * 9 + [_ptr]),
     "rp_ln_linear_tc": (_c_int, [_ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_mlp_tc": (_c_int, [_ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_ln_linear_tc_ex": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_f32,
+                                    _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_mlp_tc_ex": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_f32,
+                              _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_conv2d_tc": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr] + [_c_int] * 13 + [_ptr]),
     "rp_maxpool3x3s2_planes": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_self_attention_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),

@@ -109,7 +109,9 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tc::mbar_init(pv_done, 1);
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -462,7 +464,7 @@ int launch_attention_cps(const void* qkv_planes, float* out_f32, void* out_plane
     const int slots = CPS * rp::num_sms(device);
     const int grid = ntiles < slots ? ntiles : slots;
     const float scale_log2 = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
-    self_attention_tc_kernel<P, CPS><<<grid, ATT_THREADS, C::SMEM, st>>>(tmQ, tmKV, out_f32, static_cast<__nv_bfloat16*>(out_planes),
+    rp::launch(self_attention_tc_kernel<P, CPS>, dim3(grid), dim3(ATT_THREADS), (size_t)(C::SMEM), st, tmQ, tmKV, out_f32, static_cast<__nv_bfloat16*>(out_planes),
                                                                        p_out, n_img, scale_log2, kv_xor);
     return rp::finish_launch("rp_self_attention_tc");
 }

@@ -82,6 +82,36 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A forward pass is ~50 dependent launches on one stream, most of them persistent one-CTA-per-SM kernels whose
+// prologue (mbarrier init, tensor-memory allocation, tensor-map prefetch, first weight loads) and launch latency
+// used to sit exposed between the last CTA of one kernel and the first useful instruction of the next.  Every
+// kernel of the library is launched with programmaticStreamSerialization: it may become resident as soon as ALL
+// CTAs of its predecessor have executed pdl_launch_dependents() (the first instruction of every kernel) and an SM
+// has room, runs its prologue, and blocks in pdl_wait() until the predecessor grid has completed and its memory is
+// visible.  Rule: no global memory produced by an earlier kernel is read, and nothing an earlier kernel may still
+// read or write is written, before pdl_wait(); all threads execute it.  RELPOSE_PDL=0 launches without the attribute
+// (pdl_wait() then returns at once) for A/B runs.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms(int device) {
     static int cached[64] = {0};
     if (device < 0 || device >= 64) return 148;

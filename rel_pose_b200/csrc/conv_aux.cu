@@ -22,6 +22,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 preprocess_stem_windows_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ out, int n_img, int H, int W,
                                float scale_h, float scale_w, int P) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     const long long total = (long long)n_img * STEM_HP * STEM_W * 4;       // one thread = one s2d pixel of one window
     const long long plane = (long long)n_img * STEM_HP * STEM_W * STEM_K;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -69,6 +71,8 @@ preprocess_stem_windows_kernel(const T* __restrict__ img, __nv_bfloat16* __restr
 
 // conv1.weight [64][3][7][7] -> W2 [64][4 (a)][64 (b*16 + (dy*2+dx)*3 + c)] float32
 __global__ void stem_weight_windows_kernel(const float* __restrict__ w, float* __restrict__ out, int O) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     const int total = O * 4 * 64;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int k = idx & 63, a = (idx >> 6) & 3, o = idx >> 8;
@@ -87,6 +91,8 @@ __global__ void stem_weight_windows_kernel(const float* __restrict__ w, float* _
 template <typename T>
 __global__ void __launch_bounds__(256) preprocess_nhwc4_kernel(const T* __restrict__ img, float4* __restrict__ out,
                                                                 int n_img, int H, int W, float scale_h, float scale_w) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     const int OUT = 224;
     long long total = (long long)n_img * OUT * OUT;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -110,6 +116,8 @@ __global__ void __launch_bounds__(256) preprocess_nhwc4_kernel(const T* __restri
 // nn.MaxPool2d(3, stride 2, padding 1) on NHWC, one thread per 4 channels of an output pixel
 __global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const float4* __restrict__ x, float4* __restrict__ y,
                                                                  int n_img, int H, int W, int C4, int Ho, int Wo) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     long long total = (long long)n_img * Ho * Wo * C4;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -136,6 +144,8 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const float4* __
 // [O][C][KH][KW] -> [O][KH][KW][Cp]  (Cp >= C, zero padded)
 __global__ void permute_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int C, int KH,
                                            int KW, int Cp) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     long long total = (long long)O * KH * KW * Cp;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -151,6 +161,8 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
                                const float* __restrict__ mean, const float* __restrict__ var,
                                const float* __restrict__ conv_bias, float eps, float* __restrict__ scale,
                                float* __restrict__ shift, int C) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s = gamma[c] / sqrtf(var[c] + eps);
@@ -172,7 +184,7 @@ extern "C" int rp_preprocess_nhwc4_f32(const float* images, float* out, int n_im
     RP_REQUIRE(rp::aligned16(out), RP_EALIGN, "rp_preprocess_nhwc4: out must be 16-byte aligned");
     RP_GUARD(device);
     long long total = (long long)n_img * 224 * 224;
-    preprocess_nhwc4_kernel<float><<<grid_for(total, device), 256, 0, (cudaStream_t)stream>>>(
+    rp::launch(preprocess_nhwc4_kernel<float>, dim3(grid_for(total, device)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         images, reinterpret_cast<float4*>(out), n_img, H, W, (float)H / (float)224, (float)W / (float)224);
     return rp::finish_launch("rp_preprocess_nhwc4");
 }
@@ -182,7 +194,7 @@ extern "C" int rp_preprocess_nhwc4_u8(const uint8_t* images, float* out, int n_i
     RP_REQUIRE(rp::aligned16(out), RP_EALIGN, "rp_preprocess_nhwc4: out must be 16-byte aligned");
     RP_GUARD(device);
     long long total = (long long)n_img * 224 * 224;
-    preprocess_nhwc4_kernel<uint8_t><<<grid_for(total, device), 256, 0, (cudaStream_t)stream>>>(
+    rp::launch(preprocess_nhwc4_kernel<uint8_t>, dim3(grid_for(total, device)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         images, reinterpret_cast<float4*>(out), n_img, H, W, (float)H / (float)224, (float)W / (float)224);
     return rp::finish_launch("rp_preprocess_nhwc4");
 }
@@ -194,7 +206,7 @@ static int stem_windows_launch(const T* images, void* planes, int n_img, int H, 
     RP_REQUIRE(rp::aligned16(planes), RP_EALIGN, "rp_preprocess_stem_windows: planes must be 16-byte aligned");
     RP_GUARD(device);
     long long total = (long long)n_img * STEM_HP * STEM_W * 4;
-    preprocess_stem_windows_kernel<T><<<grid_for(total, device), 256, 0, (cudaStream_t)stream>>>(
+    rp::launch(preprocess_stem_windows_kernel<T>, dim3(grid_for(total, device)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         images, static_cast<__nv_bfloat16*>(planes), n_img, H, W, (float)H / (float)224, (float)W / (float)224, P);
     return rp::finish_launch("rp_preprocess_stem_windows");
 }
@@ -211,7 +223,7 @@ extern "C" int rp_preprocess_stem_windows_u8(const uint8_t* images, void* planes
 extern "C" int rp_stem_weight_windows_f32(const float* w, float* out, int O, int device, void* stream) {
     RP_REQUIRE(w && out && O > 0, RP_EINVAL, "rp_stem_weight_windows: bad argument");
     RP_GUARD(device);
-    stem_weight_windows_kernel<<<(O * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, out, O);
+    rp::launch(stem_weight_windows_kernel, dim3((O * 256 + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, w, out, O);
     return rp::finish_launch("rp_stem_weight_windows");
 }
 
@@ -221,7 +233,7 @@ extern "C" int rp_maxpool3x3s2_nhwc_f32(const float* x, float* y, int n_img, int
     RP_GUARD(device);
     int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     long long total = (long long)n_img * Ho * Wo * (C / 4);
-    maxpool3x3s2_nhwc_kernel<<<grid_for(total, device), 256, 0, (cudaStream_t)stream>>>(
+    rp::launch(maxpool3x3s2_nhwc_kernel, dim3(grid_for(total, device)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n_img, H, W, C / 4, Ho, Wo);
     return rp::finish_launch("rp_maxpool3x3s2");
 }
@@ -231,7 +243,7 @@ extern "C" int rp_permute_conv_weight_f32(const float* w, float* out, int O, int
     RP_REQUIRE(w && out && O > 0 && C > 0 && KH > 0 && KW > 0 && Cp >= C, RP_EINVAL, "rp_permute_conv_weight: bad argument");
     RP_GUARD(device);
     long long total = (long long)O * KH * KW * Cp;
-    permute_conv_weight_kernel<<<grid_for(total, device), 256, 0, (cudaStream_t)stream>>>(w, out, O, C, KH, KW, Cp);
+    rp::launch(permute_conv_weight_kernel, dim3(grid_for(total, device)), dim3(256), (size_t)(0), (cudaStream_t)stream, w, out, O, C, KH, KW, Cp);
     return rp::finish_launch("rp_permute_conv_weight");
 }
 
@@ -240,6 +252,6 @@ extern "C" int rp_bn_fold_f32(const float* gamma, const float* beta, const float
                               void* stream) {
     RP_REQUIRE(gamma && beta && mean && var && scale && shift && C > 0, RP_EINVAL, "rp_bn_fold: bad argument");
     RP_GUARD(device);
-    bn_fold_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, conv_bias, eps, scale, shift, C);
+    rp::launch(bn_fold_kernel, dim3((C + 127) / 128), dim3(128), (size_t)(0), (cudaStream_t)stream, gamma, beta, mean, var, conv_bias, eps, scale, shift, C);
     return rp::finish_launch("rp_bn_fold");
 }

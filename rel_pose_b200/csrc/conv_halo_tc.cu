@@ -96,7 +96,9 @@ conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -287,7 +289,7 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloEpi& e
     }
     const int ntiles = g.n_img * g.tiles_per_img;
     const int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
-    conv3x3_halo_tc_kernel<P, BN><<<grid, NTHREADS, smem, st>>>(tmA, tmB, ep, g);
+    rp::launch(conv3x3_halo_tc_kernel<P, BN>, dim3(grid), dim3(NTHREADS), (size_t)(smem), st, tmA, tmB, ep, g);
     return rp::finish_launch("rp_conv3x3_halo_tc");
 }
 

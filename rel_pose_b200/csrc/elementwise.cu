@@ -3,6 +3,7 @@
 // A6 (vision_transformer.py:90-158), A10 (src/model.py:145-152).
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace rp {
@@ -12,6 +13,10 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("RELPOSE_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 }  // namespace rp
 
@@ -92,6 +97,8 @@ extern "C" int rp_copy_rows_h2d(void* dst, const void* src_pinned, int64_t plane
 template <typename T>
 __global__ void __launch_bounds__(256) preprocess_kernel(const T* __restrict__ img, float* __restrict__ out,
                                                           int n_img, int H, int W, float scale_h, float scale_w) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     const int OUT = 224;
     const float mean[3] = {0.485f, 0.456f, 0.406f};
     const float stdv[3] = {0.229f, 0.224f, 0.225f};
@@ -124,7 +131,7 @@ static int preprocess_launch(const T* images, float* out, int n_img, int H, int 
     long long total = (long long)n_img * 224 * 224;
     int blocks = (int)min((total + 255) / 256, (long long)rp::num_sms(device) * 16);
     float sh = (float)H / (float)224, sw = (float)W / (float)224;   // ATen: scale = (float)in / out
-    preprocess_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(images, out, n_img, H, W, sh, sw);
+    rp::launch(preprocess_kernel<T>, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, images, out, n_img, H, W, sh, sw);
     return rp::finish_launch("rp_preprocess");
 }
 
@@ -138,6 +145,8 @@ extern "C" int rp_preprocess_u8(const uint8_t* images, float* out, int n_img, in
 // ------------------------------------------------------------------- intrinsics (model.py:100-109)
 __global__ void intrinsics_prepare_kernel(float* __restrict__ intr, float* __restrict__ kxy, int* __restrict__ flags,
                                           int B, float sx, float sy) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float k[2][4];
@@ -168,7 +177,7 @@ extern "C" int rp_intrinsics_prepare_f32(float* intrinsics, float* kxy, int* fla
     RP_REQUIRE(rp::aligned16(intrinsics), RP_EALIGN, "rp_intrinsics_prepare: intrinsics not 16-byte aligned");
     RP_GUARD(device);
     float sx = (float)(24.0 / (double)W), sy = (float)(24.0 / (double)H);
-    intrinsics_prepare_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(intrinsics, kxy, flags, B, sx, sy);
+    rp::launch(intrinsics_prepare_kernel, dim3((B + 127) / 128), dim3(128), (size_t)(0), (cudaStream_t)stream, intrinsics, kxy, flags, B, sx, sy);
     return rp::finish_launch("rp_intrinsics_prepare");
 }
 
@@ -176,6 +185,8 @@ extern "C" int rp_intrinsics_prepare_f32(float* intrinsics, float* kxy, int* fla
 // [n,192,576] -> [n,576,192] (+pos_embed): 32x32 shared-memory tile transpose, both sides coalesced.
 __global__ void __launch_bounds__(256) tokens_posembed_kernel(const float* __restrict__ fmap,
                                                               const float* __restrict__ pos, float* __restrict__ x) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     __shared__ float tile[32][33];
     const int C = RP_EMBED, N = RP_NTOK;
     int n = blockIdx.z;
@@ -198,7 +209,7 @@ extern "C" int rp_tokens_posembed_f32(const float* fmap, const float* pos_embed,
     RP_REQUIRE(fmap && pos_embed && x && n_img > 0, RP_EINVAL, "rp_tokens_posembed: bad argument");
     RP_GUARD(device);
     dim3 grid(RP_NTOK / 32, RP_EMBED / 32, n_img);
-    tokens_posembed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fmap, pos_embed, x);
+    rp::launch(tokens_posembed_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, fmap, pos_embed, x);
     return rp::finish_launch("rp_tokens_posembed");
 }
 
@@ -208,6 +219,8 @@ template <int PER>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ b, float* __restrict__ y, int rows,
                                                         int cols, float eps) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -245,9 +258,9 @@ extern "C" int rp_layernorm_f32(const float* x, const float* gamma, const float*
     int blocks = (rows + 7) / 8;
     cudaStream_t st = (cudaStream_t)stream;
     if (cols <= 256)
-        layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps);
+        rp::launch(layernorm_kernel<8>, dim3(blocks), dim3(256), (size_t)(0), st, x, gamma, beta, y, rows, cols, eps);
     else
-        layernorm_kernel<32><<<blocks, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps);
+        rp::launch(layernorm_kernel<32>, dim3(blocks), dim3(256), (size_t)(0), st, x, gamma, beta, y, rows, cols, eps);
     return rp::finish_launch("rp_layernorm");
 }
 
@@ -257,6 +270,8 @@ struct Lin24 {
 };
 
 __global__ void posenc_kernel(const float* __restrict__ kxy, Lin24 lin, float* __restrict__ pos, int B, int l1) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * RP_NTOK) return;
     int b = idx / RP_NTOK, i = idx % RP_NTOK;
@@ -287,7 +302,7 @@ extern "C" int rp_posenc_ex_f32(const float* kxy, const float* host_lin24, float
     Lin24 lin;
     memcpy(lin.v, host_lin24, sizeof(lin.v));
     int total = B * RP_NTOK;
-    posenc_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kxy, lin, pos, B, l1);
+    rp::launch(posenc_kernel, dim3((total + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, kxy, lin, pos, B, l1);
     return rp::finish_launch("rp_posenc");
 }
 
@@ -301,6 +316,8 @@ constexpr int RT_ROWS = 1, RT_H = 512, RT_OUT = 14;     // one row per CTA: 64 C
 __global__ void __launch_bounds__(RT_H) regressor_tail_kernel(const float* __restrict__ h, const float* __restrict__ W1T,
                                                               const float* __restrict__ b1, const float* __restrict__ W2,
                                                               const float* __restrict__ b2, float* __restrict__ out, int B) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     __shared__ __align__(16) float hs[RT_ROWS][RT_H];
     __shared__ __align__(16) float h2[RT_ROWS][RT_H];
     const int j = threadIdx.x, row0 = blockIdx.x * RT_ROWS;
@@ -346,13 +363,15 @@ extern "C" int rp_regressor_tail_f32(const float* h, const float* W1T, const flo
     RP_REQUIRE(hidden == RT_H && n_out == RT_OUT, RP_EINVAL, "rp_regressor_tail: built for 512 hidden units and 14 outputs (got %d, %d)",
                hidden, n_out);
     RP_GUARD(device);
-    regressor_tail_kernel<<<(B + RT_ROWS - 1) / RT_ROWS, RT_H, 0, (cudaStream_t)stream>>>(h, W1T, b1, W2, b2, out, B);
+    rp::launch(regressor_tail_kernel, dim3((B + RT_ROWS - 1) / RT_ROWS), dim3(RT_H), (size_t)(0), (cudaStream_t)stream, h, W1T, b1, W2, b2, out, B);
     return rp::finish_launch("rp_regressor_tail");
 }
 
 // ----------------------------------------------------------------------------------------- A10
 __global__ void normalize_pose_kernel(const float* __restrict__ raw, const float* __restrict__ Gs,
                                       float* __restrict__ out, int B) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float* g = Gs + (long long)b * 14;
@@ -375,6 +394,6 @@ __global__ void normalize_pose_kernel(const float* __restrict__ raw, const float
 extern "C" int rp_normalize_pose_f32(const float* raw, const float* Gs, float* out, int B, int device, void* stream) {
     RP_REQUIRE(raw && Gs && out && B > 0, RP_EINVAL, "rp_normalize_pose: bad argument");
     RP_GUARD(device);
-    normalize_pose_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(raw, Gs, out, B);
+    rp::launch(normalize_pose_kernel, dim3((B + 127) / 128), dim3(128), (size_t)(0), (cudaStream_t)stream, raw, Gs, out, B);
     return rp::finish_launch("rp_normalize_pose");
 }

@@ -83,7 +83,9 @@ em_stats_tc_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
         }
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -285,7 +287,9 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc::mbar_init(f_done, 1);
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -753,7 +757,9 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc::mbar_init(f_done, 1);
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -1151,6 +1157,8 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // bil[item][e] = sum over the item's RTILES row tiles of part[item * RTILES + t][e], in tile order (deterministic)
 __global__ void __launch_bounds__(256) em_reduce_tiles_kernel(const float* __restrict__ part, float* __restrict__ bil,
                                                               long long total, int ww) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long item = idx / ww;
         const int e = (int)(idx - item * ww);
@@ -1165,6 +1173,8 @@ __global__ void __launch_bounds__(256) em_reduce_tiles_kernel(const float* __res
 // pos [B][576][6] float32 -> pos^T bf16 planes [P][B][8][576] (rows 6, 7 zero): K-major operand of the EM products
 __global__ void __launch_bounds__(256) pos_planes_kernel(const float* __restrict__ pos, __nv_bfloat16* __restrict__ out,
                                                          int B, int P) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     const int total = B * 8 * NTOK;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int tok = idx % NTOK, u = (idx / NTOK) & 7, b = idx / (8 * NTOK);
@@ -1218,7 +1228,7 @@ int launch_essential(const void* qkv_planes, const float* pos, float* bil, int B
     rc = make_map4(&tmC, qkv_planes, 3 * EMB, NTOK, 2 * (cuuint64_t)B, P, 64, BKV, "rp_essential_tc(cols)");
     if (rc) return rc;
     if (pos) {
-        pos_planes_kernel<<<(B * 8 * NTOK + 255) / 256, 256, 0, st>>>(pos, static_cast<__nv_bfloat16*>(pos_planes), B, P);
+        rp::launch(pos_planes_kernel, dim3((B * 8 * NTOK + 255) / 256), dim3(256), (size_t)(0), st, pos, static_cast<__nv_bfloat16*>(pos_planes), B, P);
         rc = rp::finish_launch("rp_essential_tc(pos planes)");
         if (rc) return rc;
     }
@@ -1241,20 +1251,20 @@ int launch_essential(const void* qkv_planes, const float* pos, float* bil, int B
     }
     const int sms = rp::num_sms(device);
     const int n_stats = B * 2 * 2 * HEADS * RTILES, n_acc = B * 2 * HEADS;
-    em_stats_tc_kernel<P><<<n_stats < 2 * sms ? n_stats : 2 * sms, EM_THREADS, SCfg<P>::SMEM, st>>>(tmR, tmC, lse2, B);
+    rp::launch(em_stats_tc_kernel<P>, dim3(n_stats < 2 * sms ? n_stats : 2 * sms), dim3(EM_THREADS), (size_t)(SCfg<P>::SMEM), st, tmR, tmC, lse2, B);
     rc = rp::finish_launch("rp_essential_tc(stats)");
     if (rc) return rc;
     if (em_use_v1()) {
-        em_accum_tc_kernel<P><<<n_acc < sms ? n_acc : sms, EM_THREADS, ECfg<P>::SMEM, st>>>(tmR, tmC, tmPos, lse2, bil, B, width, flags);
+        rp::launch(em_accum_tc_kernel<P>, dim3(n_acc < sms ? n_acc : sms), dim3(EM_THREADS), (size_t)(ECfg<P>::SMEM), st, tmR, tmC, tmPos, lse2, bil, B, width, flags);
         return rp::finish_launch("rp_essential_tc(accum)");
     }
     const int n_units = n_acc * RTILES;
-    em_accum2_tc_kernel<P><<<n_units < sms ? n_units : sms, EM2_THREADS, ECfg<P>::SMEM, st>>>(tmR, tmC, tmPos, lse2, part, B, width, flags);
+    rp::launch(em_accum2_tc_kernel<P>, dim3(n_units < sms ? n_units : sms), dim3(EM2_THREADS), (size_t)(ECfg<P>::SMEM), st, tmR, tmC, tmPos, lse2, part, B, width, flags);
     rc = rp::finish_launch("rp_essential_tc(accum)");
     if (rc) return rc;
     const long long total = (long long)n_acc * width * width;
     long long blocks = (total + 255) / 256;
-    em_reduce_tiles_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(part, bil, total, width * width);
+    rp::launch(em_reduce_tiles_kernel, dim3((unsigned)(blocks < 4096 ? blocks : 4096)), dim3(256), (size_t)(0), st, part, bil, total, width * width);
     return rp::finish_launch("rp_essential_tc(reduce)");
 }
 

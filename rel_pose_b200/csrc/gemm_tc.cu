@@ -133,7 +133,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -400,6 +402,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // x -> P bf16 planes (x0 = bf16(x), x1 = bf16(x - x0), ...), 8 elements per thread, 16-byte stores
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                            long long n, int P) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (i >= n) return;
     float v[8];
@@ -431,6 +435,8 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 // store side, packed bf16x2).
 __global__ void __launch_bounds__(256) transpose_split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                                      int R, int C, int P) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     __shared__ float t[32][65];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
@@ -463,6 +469,8 @@ __global__ void __launch_bounds__(256) transpose_split_planes_kernel(const float
 __global__ void __launch_bounds__(256) layernorm_planes_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                                const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
                                                                int rows, int cols, float eps, int P) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const int c0 = lane * 8;
@@ -509,6 +517,8 @@ __global__ void __launch_bounds__(256) layernorm_planes_kernel(const float* __re
 __global__ void __launch_bounds__(256) maxpool_planes_kernel(const float4* __restrict__ x, float4* __restrict__ y,
                                                              __nv_bfloat16* __restrict__ yp, int P, int n_img, int H, int W,
                                                              int C4, int Ho, int Wo) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     long long total = (long long)n_img * Ho * Wo * C4;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -561,7 +571,7 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiPara
         attr_set[device] = true;
     }
     int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
-    gemm_tc_kernel<P, BN, CONV, FOLD><<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmB, ep, g);
+    rp::launch(gemm_tc_kernel<P, BN, CONV, FOLD>, dim3(grid), dim3(NTHREADS), (size_t)(C::SMEM), st, tmA, tmB, ep, g);
     return rp::finish_launch(what);
 }
 
@@ -573,7 +583,7 @@ extern "C" int rp_split_planes_bf16(const float* x, void* planes, int64_t n, int
                "rp_split_planes: 16-byte alignment and n %% 8 == 0 required");
     RP_GUARD(device);
     long long threads = (n + 7) / 8;
-    split_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    rp::launch(split_planes_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         x, static_cast<__nv_bfloat16*>(planes), n, P);
     return rp::finish_launch("rp_split_planes");
 }
@@ -585,7 +595,7 @@ extern "C" int rp_transpose_split_planes_bf16(const float* x, void* planes, int 
     RP_GUARD(device);
     dim3 grid((R + 63) / 64, (C + 31) / 32);
     RP_REQUIRE(grid.y <= 65535, RP_EINVAL, "rp_transpose_split_planes: too many columns");
-    transpose_split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, static_cast<__nv_bfloat16*>(planes), R, C, P);
+    rp::launch(transpose_split_planes_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, x, static_cast<__nv_bfloat16*>(planes), R, C, P);
     return rp::finish_launch("rp_transpose_split_planes");
 }
 
@@ -596,7 +606,7 @@ extern "C" int rp_layernorm_planes_bf16(const float* x, const float* gamma, cons
     RP_REQUIRE(rp::aligned16(x) && rp::aligned16(gamma) && rp::aligned16(beta) && rp::aligned16(planes), RP_EALIGN,
                "rp_layernorm_planes: 16-byte alignment");
     RP_GUARD(device);
-    layernorm_planes_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+    rp::launch(layernorm_planes_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         x, gamma, beta, static_cast<__nv_bfloat16*>(planes), rows, cols, eps, P);
     return rp::finish_launch("rp_layernorm_planes");
 }
@@ -611,7 +621,7 @@ extern "C" int rp_maxpool3x3s2_planes(const float* x, float* y_f32, void* y_plan
     long long total = (long long)n_img * Ho * Wo * (C / 4);
     long long blocks = (total + 255) / 256;
     long long cap = (long long)rp::num_sms(device) * 16;
-    maxpool_planes_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+    rp::launch(maxpool_planes_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y_f32), static_cast<__nv_bfloat16*>(y_planes), P,
         n_img, H, W, C / 4, Ho, Wo);
     return rp::finish_launch("rp_maxpool3x3s2_planes");
@@ -620,6 +630,8 @@ extern "C" int rp_maxpool3x3s2_planes(const float* x, float* y_f32, void* y_plan
 // out[m][n] = act(bias[n] + sum over splits of part[s][m][n]), fixed summation order (deterministic)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias,
                                                             float* __restrict__ out, long long mn, int N, int nsplit, int act) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= mn) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -682,7 +694,7 @@ extern "C" int rp_linear_tc_splitk(const void* A_planes, const void* W_planes, c
                   : launch_gemm_tc<2, BN, false>(tmA, tmB, ep, g, ntiles, device, st, "rp_linear_tc_splitk");
     if (rc) return rc;
     const long long mn = (long long)M * N;
-    splitk_reduce_kernel<<<(unsigned)((mn / 4 + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), bias, out_f32, mn, N,
+    rp::launch(splitk_reduce_kernel, dim3((unsigned)((mn / 4 + 255) / 256)), dim3(256), (size_t)(0), st, static_cast<const float*>(workspace), bias, out_f32, mn, N,
                                                                         ksplit, act);
     return rp::finish_launch("rp_linear_tc_splitk(reduce)");
 }

@@ -406,6 +406,7 @@ struct Svd3 {
     V3 u[3];
     float s[3];
     V3 v[3];   // columns
+    float det_u, det_v;   // +-1, known from the construction (no determinant is evaluated)
 };
 
 // Bare MUFU.RCP / MUFU.RSQ.  `__fdividef` and `rsqrtf` wrap each MUFU in a denormal range check (FSETP + two FMUL:
@@ -425,21 +426,29 @@ __device__ __forceinline__ float mufu_rsq(float x) {
 // One Jacobi rotation of columns p, q.  MUFU-only arithmetic (rcp / rsqrt approximations): a slightly inexact
 // angle costs nothing -- the next rotation removes what is left -- while c, s are normalised consistently so the
 // accumulated V stays orthonormal to ~1e-7.  Returns true if another sweep is needed because of this pair.
-__device__ __forceinline__ bool jacobi_pair(V3& ap, V3& aq, V3& vp, V3& vq) {
-    const float alpha = dot(ap, ap), beta = dot(aq, aq), gamma = dot(ap, aq);
+// The squared column norms alpha, beta are CARRIED, not recomputed: a rotation by the root t of t^2 + 2 zeta t - 1 = 0
+// changes them by -+ t gamma (Golub & Van Loan 8.4), one FFMA + clamp each instead of two dot products.  They only
+// steer the angle and the convergence test (their drift, ~2e-7 of the larger norm per rotation, is far below both);
+// the singular values come from norms recomputed after the last sweep.  The kernels are instruction-issue bound
+// (~0.9 IPC per scheduler), so the 7 instructions this saves per rotation are time.
+__device__ __forceinline__ bool jacobi_pair(V3& ap, V3& aq, V3& vp, V3& vq, float& alpha, float& beta) {
+    const float gamma = dot(ap, aq);
+    const float ab = alpha * beta, g2 = gamma * gamma;
     // already orthogonal to fp32 precision: gamma^2 <= (1e-7)^2 alpha beta  (no sqrt)
-    if (gamma * gamma <= 1e-14f * alpha * beta) return false;
+    if (g2 <= 1e-14f * ab) return false;
     // Jacobi converges quadratically: a pair whose cosine is below 3e-4 BEFORE its rotation is orthogonal to ~1e-7
     // after it, so such a rotation does not ask for another sweep
-    const bool big = gamma * gamma > 1e-7f * alpha * beta;
+    const bool big = g2 > 1e-7f * ab;
     const float zeta = (beta - alpha) * mufu_rcp(2.0f * gamma);
-    const float r = 1.0f + zeta * zeta;
-    const float t = copysignf(mufu_rcp(fabsf(zeta) + r * mufu_rsq(r)), zeta);
-    const float c = mufu_rsq(1.0f + t * t), sn = c * t;
+    const float r = fmaf(zeta, zeta, 1.0f);
+    const float t = copysignf(mufu_rcp(fmaf(r, mufu_rsq(r), fabsf(zeta))), zeta);
+    const float c = mufu_rsq(fmaf(t, t, 1.0f)), sn = c * t;
     const V3 np_ = c * ap - sn * aq, nq = sn * ap + c * aq;
     ap = np_; aq = nq;
     const V3 wp = c * vp - sn * vq, wq = sn * vp + c * vq;
     vp = wp; vq = wq;
+    alpha = fmaxf(fmaf(-t, gamma, alpha), 0.0f);
+    beta = fmaxf(fmaf(t, gamma, beta), 0.0f);
     return big;
 }
 __device__ __forceinline__ void swap_cols(V3& a, V3& b, V3& va, V3& vb, float& na, float& nb) {
@@ -448,25 +457,30 @@ __device__ __forceinline__ void swap_cols(V3& a, V3& b, V3& va, V3& vb, float& n
     float f = na; na = nb; nb = f;
 }
 
-__device__ Svd3 svd3(const float* e /* row-major 3x3 */) {
+__device__ __forceinline__ Svd3 svd3(const float* e /* row-major 3x3 */) {
     V3 a0 = v3(e[0], e[3], e[6]), a1 = v3(e[1], e[4], e[7]), a2 = v3(e[2], e[5], e[8]);   // columns
     V3 v0 = v3(1, 0, 0), v1 = v3(0, 1, 0), v2 = v3(0, 0, 1);
+    float n0 = dot(a0, a0), n1 = dot(a1, a1), n2 = dot(a2, a2);
     // Cyclic one-sided Jacobi converges quadratically: 3-4 sweeps reach fp32 precision for almost every matrix.
     // The loop ends as soon as no lane of the warp saw a large rotation during a sweep (warp-uniform exit, no
     // divergence); 8 is a safety bound.
 #pragma unroll 1
     for (int sweep = 0; sweep < 8; ++sweep) {
-        bool rot = jacobi_pair(a0, a1, v0, v1);
-        rot |= jacobi_pair(a0, a2, v0, v2);
-        rot |= jacobi_pair(a1, a2, v1, v2);
+        bool rot = jacobi_pair(a0, a1, v0, v1, n0, n1);
+        rot |= jacobi_pair(a0, a2, v0, v2, n0, n2);
+        rot |= jacobi_pair(a1, a2, v1, v2, n1, n2);
         if (!__any_sync(0xffffffffu, rot)) break;
     }
-    float n0 = dot(a0, a0), n1 = dot(a1, a1), n2 = dot(a2, a2);
-    if (n0 < n1) swap_cols(a0, a1, v0, v1, n0, n1);
-    if (n0 < n2) swap_cols(a0, a2, v0, v2, n0, n2);
-    if (n1 < n2) swap_cols(a1, a2, v1, v2, n1, n2);
+    n0 = dot(a0, a0); n1 = dot(a1, a1); n2 = dot(a2, a2);
+    // V is a product of rotations (det +1); every column swap of the sort flips its sign
+    float det_v = 1.0f;
+    if (n0 < n1) { swap_cols(a0, a1, v0, v1, n0, n1); det_v = -det_v; }
+    if (n0 < n2) { swap_cols(a0, a2, v0, v2, n0, n2); det_v = -det_v; }
+    if (n1 < n2) { swap_cols(a1, a2, v1, v2, n1, n2); det_v = -det_v; }
     Svd3 r;
-    const float i0 = n0 > 0.f ? rsqrtf(n0) : 0.f, i1 = n1 > 0.f ? rsqrtf(n1) : 0.f;
+    // bare MUFU.RSQ (the range-checked rsqrtf costs ~8 instructions a call): zero norms are excluded explicitly, and a
+    // flushed denormal norm is a zero column to fp32 anyway
+    const float i0 = n0 > 0.f ? mufu_rsq(n0) : 0.f, i1 = n1 > 0.f ? mufu_rsq(n1) : 0.f;
     r.s[0] = n0 * i0; r.s[1] = n1 * i1; r.s[2] = 0.f;    // |a| = n / sqrt(n); s[2] is set from the completed basis below
     r.v[0] = v0; r.v[1] = v1; r.v[2] = v2;
     // U: normalise the two dominant columns, complete by a cross product (rank-deficient safe)
@@ -475,17 +489,19 @@ __device__ Svd3 svd3(const float* e /* row-major 3x3 */) {
     if (r.s[1] > 1e-12f * r.s[0] && r.s[1] > 0.f) {
         u1 = i1 * a1;
         u1 = u1 - dot(u1, u0) * u0;                      // one Gram-Schmidt polish
-        u1 = rsqrtf(dot(u1, u1)) * u1;
+        u1 = mufu_rsq(dot(u1, u1)) * u1;                 // |u1| ~ 1 here
     } else {                                             // rank <= 1: any unit vector orthogonal to u0
         V3 ax = fabsf(u0.x) < 0.6f ? v3(1, 0, 0) : v3(0, 1, 0);
         u1 = cross(u0, ax);
-        u1 = rsqrtf(dot(u1, u1)) * u1;
+        u1 = mufu_rsq(dot(u1, u1)) * u1;                 // |u0 x ax|^2 >= 0.64
     }
-    V3 u2 = cross(u0, u1);
+    V3 u2 = cross(u0, u1);                               // det [u0 u1 u2] = +1 ...
     float sg = dot(u2, a2);
-    if (sg < 0.f) { u2 = neg(u2); sg = -sg; }
+    r.det_u = 1.0f;
+    if (sg < 0.f) { u2 = neg(u2); sg = -sg; r.det_u = -1.0f; }   // ... unless the third column is flipped
     r.s[2] = sg;                                         // = |a2| when a2 is non-degenerate
     r.u[0] = u0; r.u[1] = u1; r.u[2] = u2;
+    r.det_v = det_v;
     return r;
 }
 
@@ -519,15 +535,16 @@ __global__ void __launch_bounds__(TPB) essential_to_rt_kernel(const float* E, fl
     __syncthreads();
     Svd3 r = svd3(se + threadIdx.x * 9);
     __syncthreads();
-    float su = det3(r.u[0], r.u[1], r.u[2]) < 0.f ? -1.f : 1.f;
-    float sv = det3(r.v[0], r.v[1], r.v[2]) < 0.f ? -1.f : 1.f;
-    V3 u0 = su * r.u[0], u1 = su * r.u[1], u2 = su * r.u[2];
-    V3 v0 = sv * r.v[0], v1 = sv * r.v[1], v2 = sv * r.v[2];
+    // proper rotations: U <- det(U) U, V <- det(V) V.  Both signs are known from the construction of the basis
+    // (Svd3::det_u / det_v), and in R = (U W) V^T they only appear as the product su sv.
+    const float su = r.det_u, ssv = r.det_u * r.det_v;
+    V3 u0 = r.u[0], u1 = r.u[1], u2 = su * r.u[2];
+    V3 v0 = ssv * r.v[0], v1 = ssv * r.v[1], v2 = ssv * r.v[2];
     // U W = [u1, -u0, u2] ; U W^T = [-u1, u0, u2] ;  R = (U W) V^T = sum_k (UW)_k v_k^T
     V3 w0 = u1, w1 = neg(u0);
     float* p1 = se + threadIdx.x * 9;
     float* p2 = s2 + threadIdx.x * 9;
-    const float uw[3][3] = {{w0.x, w1.x, u2.x}, {w0.y, w1.y, u2.y}, {w0.z, w1.z, u2.z}};
+    const float uw[3][3] = {{w0.x, w1.x, r.u[2].x}, {w0.y, w1.y, r.u[2].y}, {w0.z, w1.z, r.u[2].z}};
     const float vv[3][3] = {{v0.x, v1.x, v2.x}, {v0.y, v1.y, v2.y}, {v0.z, v1.z, v2.z}};
 #pragma unroll
     for (int i = 0; i < 3; ++i)

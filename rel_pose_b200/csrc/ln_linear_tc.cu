@@ -18,6 +18,9 @@
 //               a warp-private shared-memory patch -> float32 and/or planes with per-lane stores).
 //               The next row tile's LayerNorm runs as soon as the last column tile's MMAs have retired, before that
 //               tile's epilogue, so the tensor pipe does not drain at row-tile boundaries.
+#include <stdlib.h>
+
+#include "rows_ln_epilogue.cuh"
 #include "tc_common.cuh"
 
 namespace {
@@ -44,7 +47,7 @@ struct LCfg {
 };
 
 struct LnLinParams {
-    const float* x;        // [M,192]
+    const float* x;        // [M,192] (AIN = false: LayerNorm input)
     const float* gamma;
     const float* beta;
     const float* bias;     // [N] or null
@@ -53,6 +56,12 @@ struct LnLinParams {
     int p_out;
     int M, N;
     float eps;
+    // EPI == 3 (N == 192): out_f32 = acc + bias + residual, and optionally LayerNorm(out_f32; gamma2, beta2) as planes
+    const float* residual; // [M,192]
+    __nv_bfloat16* ln_planes;    // [P][M][192] or null
+    const float* gamma2;
+    const float* beta2;
+    float eps2;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -66,10 +75,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // tensor work).  Here a thread keeps its TMEM row: bias, plane split, two 16-byte shared-memory stores per plane
 // into the 128-byte-swizzled box layout of a [128 x 64] bf16 tile, and ONE thread hands the tile to the TMA
 // (cp.async.bulk.tensor store; rows / columns outside the tensor are clipped by the hardware).
-template <int P, bool TMAOUT>
+// AIN: the A operand arrives as bf16 planes [P][M][192] by TMA (six [128 x 64] boxes per row tile) instead of being
+// LayerNorm-ed here: the producer of x wrote them (rows_ln_epilogue.cuh).  EPI == 3 (N == 192, one column tile): the
+// residual-stream epilogue of rows_ln_epilogue.cuh -- out_f32 = acc + bias + residual and the next LayerNorm's planes.
+template <int P, int EPI, bool AIN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, LnLinParams prm) {
+ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
+                    const __grid_constant__ CUtensorMap tmXN, LnLinParams prm) {
     using C = LCfg<P>;
+    constexpr bool TMAOUT = (EPI == 1);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -78,7 +92,8 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     uint64_t* xn_full = bars + 2 * C::NS;
     uint64_t* tfull = xn_full + 1;               // [2]
     uint64_t* tempty = xn_full + 3;              // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xn_full + 5);
+    uint64_t* xn_free = xn_full + 5;             // AIN: the row tile's last MMAs have retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xn_full + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = prm.M, N = prm.N;
@@ -88,18 +103,22 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmW);
         if (TMAOUT) tc::prefetch_tmap(&tmOut);
+        if (AIN) tc::prefetch_tmap(&tmXN);
         for (int i = 0; i < C::NS; ++i) {
             tc::mbar_init(&wfull[i], 1);
             tc::mbar_init(&wempty[i], 1);
         }
-        tc::mbar_init(xn_full, EPI_WARPS);
+        tc::mbar_init(xn_full, AIN ? 1 : EPI_WARPS);
+        tc::mbar_init(xn_free, 1);
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&tfull[i], 1);
             tc::mbar_init(&tempty[i], EPI_WARPS);
         }
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -136,6 +155,20 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             dxn0[kb] = tc::make_kmajor_sw128_desc(tc::smem_u32(xn_tile(0, kb)));
             dxn1[kb] = tc::make_kmajor_sw128_desc(tc::smem_u32(xn_tile(P - 1, kb)));
         }
+        // AIN: this warp also fetches the row tiles' A planes (six [128 x 64] boxes into the swizzled A tiles; rows beyond
+        // M are TMA zero fill): it is idle exactly while the tile's last products retire, and the weight producer keeps
+        // running ahead undisturbed.
+        auto load_xn = [&](int tile) {
+            if (tc::elect_one_sync()) {
+                tc::mbar_expect_tx(xn_full, (uint32_t)(P * KB * TILE16K));
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) tc::tma_load_3d(xn_tile(p, kb), &tmXN, xn_full, kb * 64, tile * BM, p);
+            }
+            __syncwarp();
+        };
+        if (AIN && (int)blockIdx.x < ntiles) load_xn(blockIdx.x);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             tc::mbar_wait(xn_full, it & 1);
             tc::tcgen05_fence_after();
@@ -163,10 +196,15 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                         }
                         tc::umma_commit(&wempty[s]);
                         if (kb == KB - 1) tc::umma_commit(&tfull[acc]);
+                        if (AIN && kb == KB - 1 && nt == NT - 1) tc::umma_commit(xn_free);
                     }
                     __syncwarp();
                     if (++s == C::NS) { s = 0; ph ^= 1; }
                 }
+            }
+            if (AIN && tile + (int)gridDim.x < ntiles) {
+                tc::mbar_wait(xn_free, it & 1);              // the tile's last products have retired
+                load_xn(tile + (int)gridDim.x);
             }
         }
     } else {
@@ -180,15 +218,11 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const bool vec4 = (N % 4) == 0;
         uint32_t c = 0;
 
-        auto layer_norm_tile = [&](int tile) {           // same arithmetic as mlp_tc.cu / layernorm_planes_kernel
-            float g[6], bt[6];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float2 gg = __ldg(reinterpret_cast<const float2*>(prm.gamma + 64 * i + 2 * lane));
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(prm.beta + 64 * i + 2 * lane));
-                g[2 * i] = gg.x; g[2 * i + 1] = gg.y; bt[2 * i] = bb.x; bt[2 * i + 1] = bb.y;
-            }
-            float v[8][6];
+        // LayerNorm in two phases so that the global-memory latency of the next row tile's rows hides behind the wait
+        // for the current tile's last accumulator: ln_load requests the 8 rows this warp owns (48 registers per lane),
+        // ln_finish (same arithmetic as mlp_tc.cu / layernorm_planes_kernel) normalises and writes the A-operand planes.
+        float v[8][6];
+        auto ln_load = [&](int tile) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int grow = tile * BM + ew * 8 + j;
@@ -198,6 +232,15 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                     if (grow < M) a = __ldg(reinterpret_cast<const float2*>(prm.x + (size_t)grow * D + 64 * i + 2 * lane));
                     v[j][2 * i] = a.x; v[j][2 * i + 1] = a.y;
                 }
+            }
+        };
+        auto ln_finish = [&]() {
+            float g[6], bt[6];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float2 gg = __ldg(reinterpret_cast<const float2*>(prm.gamma + 64 * i + 2 * lane));
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(prm.beta + 64 * i + 2 * lane));
+                g[2 * i] = gg.x; g[2 * i + 1] = gg.y; bt[2 * i] = bb.x; bt[2 * i + 1] = bb.y;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -230,20 +273,38 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             if (lane == 0) tc::mbar_arrive(xn_full);
         };
 
-        if ((int)blockIdx.x < ntiles) layer_norm_tile(blockIdx.x);
+        if (!AIN && (int)blockIdx.x < ntiles) { ln_load(blockIdx.x); ln_finish(); }
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int row_base = tile * BM;
             const int valid_rows = min(BM, M - row_base);
             for (int nt = 0; nt < NT; ++nt, ++c) {
                 const uint32_t acc = c & 1;
                 const int n0 = nt * BN;
+                // every MMA of this row tile has retired once its last column tile is complete: the LayerNorm planes
+                // are dead, write the next row tile's before draining this accumulator (its rows were requested
+                // before the wait)
+                const bool ln_next = (!AIN && nt == NT - 1 && tile + (int)gridDim.x < ntiles);
+                if (ln_next) ln_load(tile + (int)gridDim.x);
                 tc::mbar_wait(&tfull[acc], (c >> 1) & 1);
                 tc::tcgen05_fence_after();
-                // every MMA of this row tile has retired once its last column tile is complete: the LayerNorm planes
-                // are dead, write the next row tile's before draining this accumulator
-                if (nt == NT - 1 && tile + (int)gridDim.x < ntiles) layer_norm_tile(tile + (int)gridDim.x);
+                if (ln_next) ln_finish();
                 const uint32_t t_row = t_lane + acc * ACC_STRIDE;
-                if constexpr (TMAOUT) {
+                if constexpr (EPI == 3) {
+                    float* staging = reinterpret_cast<float*>(smem + C::OFF_STG);
+                    auto wait_acc = [&]() {};                        // already complete (tfull above)
+                    auto release = [&]() {
+                        tc::tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+                    };
+                    if (prm.ln_planes)
+                        rowsln::epilogue<P>(t_row, staging, q, part, lane, prm.bias, prm.residual, prm.out_f32, prm.ln_planes,
+                                            prm.gamma2, prm.beta2, prm.eps2, row_base, valid_rows, (size_t)M * D, wait_acc, release);
+                    else
+                        rowsln::epilogue<0>(t_row, staging, q, part, lane, prm.bias, prm.residual, prm.out_f32, nullptr, nullptr,
+                                            nullptr, 0.f, row_base, valid_rows, 0, wait_acc, release);
+                    continue;                                        // tempty released inside
+                } else if constexpr (TMAOUT) {
                     uint8_t* stg8 = smem + C::OFF_STG;               // [P][128 rows][128 B], 128-byte swizzle
                     const int r = q * 32 + lane;
                     const uint32_t row_off = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
@@ -368,12 +429,13 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     }
 }
 
-template <int P, bool TMAOUT>
-int launch_ln_linear(const CUtensorMap& tmW, const CUtensorMap& tmOut, const LnLinParams& prm, int device, cudaStream_t st) {
+template <int P, int EPI, bool AIN>
+int launch_ln_linear(const CUtensorMap& tmW, const CUtensorMap& tmOut, const CUtensorMap& tmXN, const LnLinParams& prm, int device,
+                     cudaStream_t st) {
     using C = LCfg<P>;
     static bool attr_set[64] = {false};
     if (device >= 0 && device < 64 && !attr_set[device]) {
-        cudaError_t e = cudaFuncSetAttribute(ln_linear_tc_kernel<P, TMAOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(ln_linear_tc_kernel<P, EPI, AIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             rp::set_error("rp_ln_linear_tc: cudaFuncSetAttribute(%d): %s", C::SMEM, cudaGetErrorString(e));
             return (int)e;
@@ -382,37 +444,70 @@ int launch_ln_linear(const CUtensorMap& tmW, const CUtensorMap& tmOut, const LnL
     }
     const int ntiles = (prm.M + BM - 1) / BM;
     const int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
-    ln_linear_tc_kernel<P, TMAOUT><<<grid, NTHREADS, C::SMEM, st>>>(tmW, tmOut, prm);
+    rp::launch(ln_linear_tc_kernel<P, EPI, AIN>, dim3(grid), dim3(NTHREADS), (size_t)(C::SMEM), st, tmW, tmOut, tmXN, prm);
     return rp::finish_launch("rp_ln_linear_tc");
+}
+
+template <int P, bool AIN>
+int dispatch_ln_linear(const void* xn_planes, const void* W_planes, LnLinParams& prm, int device, cudaStream_t st) {
+    const int M = prm.M, N = prm.N;
+    CUtensorMap tmW, tmXN, tmOut;
+    int rc = tc::make_planes_tmap(&tmW, W_planes, P, N, D, BN);           // [P][N][192], box 192 rows x 64 K
+    if (rc) return rc;
+    tmXN = tmW; tmOut = tmW;
+    if (AIN) {
+        rc = tc::make_planes_tmap(&tmXN, xn_planes, P, M, D, BM);        // [P][M][192], box 128 rows x 64 K
+        if (rc) return rc;
+    }
+    if (prm.residual) return launch_ln_linear<P, 3, AIN>(tmW, tmOut, tmXN, prm, device, st);
+    // planes-only output with as many planes as the operands and 16-byte row pitch: TMA-store epilogue
+    if (!prm.out_f32 && prm.out_planes && prm.p_out == P && (N % 8) == 0) {
+        rc = tc::make_planes_tmap(&tmOut, prm.out_planes, P, M, N, BM);  // [P][M][N], box 128 rows x 64 columns
+        if (rc) return rc;
+        return launch_ln_linear<P, 1, AIN>(tmW, tmOut, tmXN, prm, device, st);
+    }
+    return launch_ln_linear<P, 0, AIN>(tmW, tmOut, tmXN, prm, device, st);
 }
 
 }  // namespace
 
-extern "C" int rp_ln_linear_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W_planes,
-                               const float* bias, float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out,
-                               int device, void* stream) {
-    RP_REQUIRE(x && ln_gamma && ln_beta && W_planes && (out_f32 || out_planes) && M > 0 && N > 0, RP_EINVAL,
+// Generalised entry point.  A operand: xn_planes != null -> bf16 planes [P][M][192] supplied by the producer of x (the
+// LayerNorm arguments are unused), else LayerNorm(x) computed in the kernel.  residual != null (N must be 192):
+// out_f32 = A W^T + bias + residual, and out_ln_planes != null additionally receives LayerNorm(out_f32; ln2_*) as bf16
+// planes [P][M][192] -- the attention projection with the Block's norm2 folded in (vision_transformer.py:351-352).
+extern "C" int rp_ln_linear_tc_ex(const float* x, const void* xn_planes, const float* ln_gamma, const float* ln_beta, float eps,
+                                  const void* W_planes, const float* bias, const float* residual, float* out_f32, void* out_planes,
+                                  void* out_ln_planes, const float* ln2_gamma, const float* ln2_beta, float eps2, int M, int N,
+                                  int K, int P, int P_out, int device, void* stream) {
+    RP_REQUIRE((xn_planes || (x && ln_gamma && ln_beta)) && W_planes && (out_f32 || out_planes) && M > 0 && N > 0, RP_EINVAL,
                "rp_ln_linear_tc: null pointer or empty shape");
     RP_REQUIRE(K == D, RP_EINVAL, "rp_ln_linear_tc: built for K = 192 (got %d)", K);
     RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_ln_linear_tc: P must be 1 (bf16) or 2 (bf16x3)");
     RP_REQUIRE(!out_planes || (P_out >= 1 && P_out <= 2), RP_EINVAL, "rp_ln_linear_tc: bad P_out");
-    RP_REQUIRE(rp::aligned16(x) && rp::aligned16(W_planes) && rp::aligned16(ln_gamma) && rp::aligned16(ln_beta) &&
-                   rp::aligned16(bias) && rp::aligned16(out_f32) && rp::aligned16(out_planes),
+    RP_REQUIRE(!residual || (N == D && out_f32 && !out_planes && bias), RP_EINVAL,
+               "rp_ln_linear_tc: the residual epilogue needs N = 192, a bias, a float32 output and no plane output");
+    RP_REQUIRE(!out_ln_planes || (residual && ln2_gamma && ln2_beta), RP_EINVAL,
+               "rp_ln_linear_tc: LayerNorm planes need the residual epilogue and the norm weights");
+    RP_REQUIRE(rp::aligned16(x) && rp::aligned16(xn_planes) && rp::aligned16(W_planes) && rp::aligned16(ln_gamma) &&
+                   rp::aligned16(ln_beta) && rp::aligned16(bias) && rp::aligned16(out_f32) && rp::aligned16(out_planes) &&
+                   rp::aligned16(residual) && rp::aligned16(out_ln_planes) && rp::aligned16(ln2_gamma) && rp::aligned16(ln2_beta),
                RP_EALIGN, "rp_ln_linear_tc: 16-byte alignment");
     RP_GUARD(device);
-    CUtensorMap tmW;
-    int rc = tc::make_planes_tmap(&tmW, W_planes, P, N, D, BN);           // [P][N][192], box 192 rows x 64 K
-    if (rc) return rc;
-    LnLinParams prm{x, ln_gamma, ln_beta, bias, out_f32, static_cast<__nv_bfloat16*>(out_planes), P_out, M, N, eps};
+    LnLinParams prm{x, ln_gamma, ln_beta, bias, out_f32, static_cast<__nv_bfloat16*>(out_planes), P_out, M, N, eps,
+                    residual, static_cast<__nv_bfloat16*>(out_ln_planes), ln2_gamma, ln2_beta, eps2};
     cudaStream_t st = (cudaStream_t)stream;
-    // planes-only output with as many planes as the operands and 16-byte row pitch: TMA-store epilogue
-    if (!out_f32 && out_planes && P_out == P && (N % 8) == 0) {
-        CUtensorMap tmOut;
-        rc = tc::make_planes_tmap(&tmOut, out_planes, P, M, N, BM);      // [P][M][N], box 128 rows x 64 columns
-        if (rc) return rc;
-        if (P == 1) return launch_ln_linear<1, true>(tmW, tmOut, prm, device, st);
-        return launch_ln_linear<2, true>(tmW, tmOut, prm, device, st);
+    if (xn_planes) {
+        if (P == 1) return dispatch_ln_linear<1, true>(xn_planes, W_planes, prm, device, st);
+        return dispatch_ln_linear<2, true>(xn_planes, W_planes, prm, device, st);
     }
-    if (P == 1) return launch_ln_linear<1, false>(tmW, tmW, prm, device, st);
-    return launch_ln_linear<2, false>(tmW, tmW, prm, device, st);
+    if (P == 1) return dispatch_ln_linear<1, false>(xn_planes, W_planes, prm, device, st);
+    return dispatch_ln_linear<2, false>(xn_planes, W_planes, prm, device, st);
+}
+
+extern "C" int rp_ln_linear_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W_planes,
+                               const float* bias, float* out_f32, void* out_planes, int M, int N, int K, int P, int P_out,
+                               int device, void* stream) {
+    RP_REQUIRE(x && ln_gamma && ln_beta, RP_EINVAL, "rp_ln_linear_tc: null pointer");
+    return rp_ln_linear_tc_ex(x, nullptr, ln_gamma, ln_beta, eps, W_planes, bias, nullptr, out_f32, out_planes, nullptr, nullptr,
+                              nullptr, 0.f, M, N, K, P, P_out, device, stream);
 }

@@ -29,6 +29,7 @@
 // 161 (first fused version, one issuer, fc1 one chunk ahead) -> 150 (fc1 two ahead) -> 131 (three issuers,
 // N = 192 fc2) -> 116 (GELU chunk through TMEM, double buffered) -> 114 us.  Remaining bound: the N = 64 fc1
 // MMAs read 6 KB of shared memory per 32-cycle instruction (128 B/clk limit -> 48 cycles), tile-boundary drain.
+#include "rows_ln_epilogue.cuh"
 #include "tc_common.cuh"
 
 namespace {
@@ -65,13 +66,18 @@ struct MCfg {
 
 struct MlpParams {
     const float* x;        // [M,192] input = residual
-    const float* gamma;    // LayerNorm weight / bias [192]
+    const float* gamma;    // LayerNorm weight / bias [192] (AIN = false)
     const float* beta;
     const float* b1;       // [768]
     const float* b2;       // [192]
     float* out;            // [M,192]
     int M;
     float eps;
+    // optional second output: LayerNorm(out) with the NEXT layer's norm weights as bf16 planes [P][M][192]
+    __nv_bfloat16* ln_planes;
+    const float* gamma2;
+    const float* beta2;
+    float eps2;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -79,9 +85,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int P>
+// AIN: the LayerNorm output (fc1's A operand) arrives as bf16 planes [P][M][192] by TMA -- written by the producer of x
+// (rows_ln_epilogue.cuh) -- instead of being computed here.  ncu of the AIN = false kernel: the in-kernel LayerNorm held
+// 30 % of the sixteen epilogue warps' time (lockstep loads + reductions while the GELU pipeline and, behind it, the
+// tensor pipe stood still at every row-tile boundary).
+template <int P, bool AIN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, MlpParams prm) {
+mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                    const __grid_constant__ CUtensorMap tmXN, MlpParams prm) {
     using C = MCfg<P>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,6 +100,7 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     uint64_t* wfull = bars;                      // [NU]
     uint64_t* wempty = bars + C::NU;             // [NU]
     uint64_t* xn_full = bars + 2 * C::NU;
+    uint64_t* xn_free = xn_full + 1;             // AIN: both fc1 issuers' last products of the tile have retired
     uint64_t* acc1_full = xn_full + 2;           // [NA1]
     uint64_t* acc1_empty = xn_full + 5;          // [NA1]
     uint64_t* h_full = xn_full + 8;              // [2]
@@ -105,12 +117,14 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmW1);
         tc::prefetch_tmap(&tmW2);
+        if (AIN) tc::prefetch_tmap(&tmXN);
         for (int i = 0; i < C::NU; ++i) {
             tc::mbar_init(&wfull[i], 1);
             tc::mbar_init(&wempty[i], 1);
         }
-        tc::mbar_init(xn_full, EPI_WARPS);          // one elected arrive per epilogue warp (512 arrives on one
-                                                    // mbarrier serialise in the shared-memory atomic unit)
+        tc::mbar_init(xn_full, AIN ? 1 : EPI_WARPS); // one elected arrive per epilogue warp (512 arrives on one
+                                                    // mbarrier serialise in the shared-memory atomic unit) | TMA bytes
+        tc::mbar_init(xn_free, 2);
         for (int i = 0; i < NA1; ++i) {
             tc::mbar_init(&acc1_full[i], 1);
             tc::mbar_init(&acc1_empty[i], EPI_WARPS);
@@ -125,7 +139,9 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
         tc::mbar_init(&turn[1], 1);
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -175,6 +191,20 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
             dxn0[kb] = tc::make_kmajor_sw128_desc(tc::smem_u32(xn_tile(0, kb)));
             dxn1[kb] = tc::make_kmajor_sw128_desc(tc::smem_u32(xn_tile(P - 1, kb)));
         }
+        // AIN: the second issuer also fetches the tiles' LayerNorm planes -- six [128 x 64] boxes straight into the
+        // swizzled A-operand tiles (rows beyond M: TMA zero fill, never stored).  It issues the last chunk of a tile, so
+        // it is idle exactly while those products retire, and the weight producer keeps running ahead undisturbed.
+        auto load_xn = [&](int tile) {
+            if (tc::elect_one_sync()) {
+                tc::mbar_expect_tx(xn_full, (uint32_t)(P * KB * TILE16K));
+#pragma unroll
+                for (int p = 0; p < P; ++p)
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) tc::tma_load_3d(xn_tile(p, kb), &tmXN, xn_full, kb * 64, tile * BM, p);
+            }
+            __syncwarp();
+        };
+        if (AIN && sel == 1 && (int)blockIdx.x < ntiles) load_xn(blockIdx.x);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             tc::mbar_wait(xn_full, it & 1);
             tc::tcgen05_fence_after();
@@ -211,11 +241,16 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                         tc::umma_commit(&wempty[u]);
                         if (kb == KB - 1) {
                             tc::umma_commit(&acc1_full[b]);
+                            if (AIN && s + 2 >= NCH) tc::umma_commit(xn_free);   // this issuer's last chunk of the tile
                             tc::mbar_arrive(&turn[sel ^ 1]);
                         }
                     }
                     __syncwarp();
                 }
+            }
+            if (AIN && sel == 1 && tile + (int)gridDim.x < ntiles) {
+                tc::mbar_wait(xn_free, it & 1);              // both issuers' last fc1 products of this tile have retired
+                load_xn(tile + (int)gridDim.x);
             }
         }
     } else if (warp == 3) {
@@ -293,15 +328,10 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 
         // LayerNorm (eps 1e-6, vision_transformer.py:396) of the 8 rows this warp owns, written as the bf16 planes
         // of the fc1 A operand: three K-major SWIZZLE_128B tiles [128 rows x 64 columns] per plane.
-        auto layer_norm_tile = [&](int tile) {
-            float g[6], bt[6];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float2 gg = __ldg(reinterpret_cast<const float2*>(prm.gamma + 64 * i + 2 * lane));
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(prm.beta + 64 * i + 2 * lane));
-                g[2 * i] = gg.x; g[2 * i + 1] = gg.y; bt[2 * i] = bb.x; bt[2 * i + 1] = bb.y;
-            }
-            float v[8][6];
+        // Two phases: ln_load requests the 8 rows this warp owns (48 registers per lane) so that their latency hides
+        // behind the wait for the last fc1 products of the current tile; ln_finish normalises and writes the planes.
+        float vln[8][6];
+        auto ln_load = [&](int tile) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int grow = tile * BM + ew * 8 + j;
@@ -309,26 +339,35 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 for (int i = 0; i < 3; ++i) {
                     float2 a = make_float2(0.f, 0.f);
                     if (grow < M) a = __ldg(reinterpret_cast<const float2*>(prm.x + (size_t)grow * D + 64 * i + 2 * lane));
-                    v[j][2 * i] = a.x; v[j][2 * i + 1] = a.y;
+                    vln[j][2 * i] = a.x; vln[j][2 * i + 1] = a.y;
                 }
+            }
+        };
+        auto ln_finish = [&]() {
+            float g[6], bt[6];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float2 gg = __ldg(reinterpret_cast<const float2*>(prm.gamma + 64 * i + 2 * lane));
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(prm.beta + 64 * i + 2 * lane));
+                g[2 * i] = gg.x; g[2 * i + 1] = gg.y; bt[2 * i] = bb.x; bt[2 * i + 1] = bb.y;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int rl = ew * 8 + j;
                 float s = 0.f;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) s += v[j][i];
+                for (int i = 0; i < 6; ++i) s += vln[j][i];
                 const float mean = rp::warp_sum(s) * (1.0f / D);
                 float qv = 0.f;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) { const float dlt = v[j][i] - mean; qv += dlt * dlt; }
+                for (int i = 0; i < 6; ++i) { const float dlt = vln[j][i] - mean; qv += dlt * dlt; }
                 const float rstd = 1.0f / sqrtf(rp::warp_sum(qv) * (1.0f / D) + prm.eps);
                 const uint32_t off = (uint32_t)(rl >> 3) * 1024 + (uint32_t)(rl & 7) * 128 +
                                      ((((uint32_t)lane >> 2) ^ (uint32_t)(rl & 7)) << 4) + (uint32_t)(lane & 3) * 4;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    float y0 = (v[j][2 * i] - mean) * rstd * g[2 * i] + bt[2 * i];
-                    float y1 = (v[j][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bt[2 * i + 1];
+                    float y0 = (vln[j][2 * i] - mean) * rstd * g[2 * i] + bt[2 * i];
+                    float y1 = (vln[j][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bt[2 * i + 1];
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         const uint32_t w = pack_bf16x2(y0, y1);
@@ -343,12 +382,41 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
             if (lane == 0) tc::mbar_arrive(xn_full);
         };
 
-        if ((int)blockIdx.x < ntiles) layer_norm_tile(blockIdx.x);
+        // ---- output of a finished tile: acc2 + b2 + x, transposed through warp-private staging patches for coalesced
+        // float4 stores.  DEFERRED: it runs inside the NEXT tile's chunk loop (before its third GELU chunk), not right
+        // after the last GELU chunk.  The in-order tensor pipe has the next tile's first fc1 products queued ahead of
+        // this tile's last two fc2 products, so waiting for acc2_full at the tile boundary parked all sixteen warps
+        // for ~5 k cycles per tile with the GELU pipeline empty behind them (ncu: the output epilogue held 21 % of the
+        // epilogue warps' samples for 1.3 k instructions); two chunks later the accumulator is long complete and the
+        // tensor pipe still has two fc1 chunks queued while these warps are busy here.
+        auto out_epilogue = [&](int tile, uint32_t itp) {
+            const int valid_rows = min(BM, M - tile * BM);
+            float* staging = reinterpret_cast<float*>(smem + C::OFF_H);
+            auto wait_acc = [&]() {
+                tc::mbar_wait(acc2_full, itp & 1);
+                tc::tcgen05_fence_after();
+            };
+            auto release = [&]() {                           // acc2 is in registers: fc2 of the following tile may overwrite it
+                tc::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(acc2_empty);
+            };
+            if (prm.ln_planes)
+                rowsln::epilogue<P>(t_lane + ACC2_COL, staging, q, part, lane, prm.b2, prm.x, prm.out, prm.ln_planes, prm.gamma2,
+                                    prm.beta2, prm.eps2, tile * BM, valid_rows, (size_t)M * D, wait_acc, release);
+            else
+                rowsln::epilogue<0>(t_lane + ACC2_COL, staging, q, part, lane, prm.b2, prm.x, prm.out, nullptr, nullptr, nullptr,
+                                    0.f, tile * BM, valid_rows, 0, wait_acc, release);
+        };
+
+        int prev_tile = -1;
+        if (!AIN && (int)blockIdx.x < ntiles) { ln_load(blockIdx.x); ln_finish(); }
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             // ---- twelve hidden chunks: acc1 -> + b1 -> GELU -> bf16 planes (A operand of fc2)
 #pragma unroll 1
             for (int j = 0; j < NCH; ++j, ++c2) {
                 const uint32_t b = b1;
+                if (j == 2 && prev_tile >= 0) out_epilogue(prev_tile, it - 1);
                 if (j == 2) {
                     // pull the next tile's rows towards L2 now; its LayerNorm runs before this tile's last two chunks
                     const int nrow = (tile + (int)gridDim.x) * BM + ew * 8 + (lane >> 2);
@@ -357,14 +425,15 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     if (nrow < M && (lane & 3) < 3)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.x + (size_t)nrow * D + (lane & 3) * 64 + 32));
                 }
-                if (j == NCH - 2 && tile + (int)gridDim.x < ntiles) {
+                if (!AIN && j == NCH - 2 && tile + (int)gridDim.x < ntiles) {
                     // LayerNorm of the NEXT tile, two chunks before this tile ends: once the last two fc1 products
                     // have completed (all earlier ones were observed chunk by chunk) this tile's LayerNorm planes
                     // are dead, and the next tile's fc1 / this tile's last fc2 and output epilogue overlap.
                     const uint32_t bn = (b1 + 1 == NA1) ? 0u : b1 + 1;
+                    ln_load(tile + (int)gridDim.x);
                     tc::mbar_wait(&acc1_full[b1], ph1);
                     tc::mbar_wait(&acc1_full[bn], bn == 0 ? ph1 ^ 1 : ph1);
-                    layer_norm_tile(tile + (int)gridDim.x);
+                    ln_finish();
                 }
                 float bias[16];
 #pragma unroll
@@ -407,56 +476,9 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&h_full[hb]);
             }
-            // ---- output: acc2 + b2 + x, transposed through the (now idle) H buffer for coalesced float4 stores.
-            // The residual rows (L2 hits: this CTA read them for the LayerNorm) are requested before the wait.
-            const int valid_rows = min(BM, M - tile * BM);
-            float4 res[3][4];
-#pragma unroll
-            for (int gi = 0; gi < 3; ++gi) {
-                const int col = part * 48 + gi * 16 + cq * 4;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int rt = q * 32 + t * 8 + rr;
-                    res[gi][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rt < valid_rows)
-                        res[gi][t] = __ldg(reinterpret_cast<const float4*>(prm.x + (size_t)(tile * BM + rt) * D + col));
-                }
-            }
-            tc::mbar_wait(acc2_full, it & 1);
-            tc::tcgen05_fence_after();
-#pragma unroll
-            for (int gi = 0; gi < 3; ++gi) {
-                const int c0 = part * 48 + gi * 16;
-                const int col = c0 + cq * 4;
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(prm.b2 + col));
-                uint32_t a[16];
-                tc::tmem_ld_32x32b_x16(t_lane + ACC2_COL + c0, a);
-                tc::tmem_ld_wait();
-                __syncwarp();
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                    *reinterpret_cast<uint4*>(stg + lane * STG_LD + ((jj ^ ((lane >> 1) & 3)) << 2)) =
-                        make_uint4(a[4 * jj], a[4 * jj + 1], a[4 * jj + 2], a[4 * jj + 3]);
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int rl = t * 8 + rr;
-                    const int rt = q * 32 + rl;
-                    if (rt >= valid_rows) continue;
-                    const float4 acc = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2));
-                    float4 o;
-                    o.x = acc.x + sh.x + res[gi][t].x; o.y = acc.y + sh.y + res[gi][t].y;
-                    o.z = acc.z + sh.z + res[gi][t].z; o.w = acc.w + sh.w + res[gi][t].w;
-                    *reinterpret_cast<float4*>(prm.out + (size_t)(tile * BM + rt) * D + col) = o;
-                }
-            }
-            tc::tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(acc2_empty);
-            // the staging patches live in the H buffer: nobody may start the next tile's GELU writes before all
-            // epilogue warps are done with them (named barrier over the 16 epilogue warps only)
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            prev_tile = tile;
         }
+        if (prev_tile >= 0) out_epilogue(prev_tile, it - 1);
     }
 
     tc::tcgen05_fence_before();
@@ -467,12 +489,13 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     }
 }
 
-template <int P>
-int launch_mlp(const CUtensorMap& tmW1, const CUtensorMap& tmW2, const MlpParams& prm, int device, cudaStream_t st) {
+template <int P, bool AIN>
+int launch_mlp(const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmXN, const MlpParams& prm, int device,
+               cudaStream_t st) {
     using C = MCfg<P>;
     static bool attr_set[64] = {false};
     if (device >= 0 && device < 64 && !attr_set[device]) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fused_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(mlp_fused_tc_kernel<P, AIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             rp::set_error("rp_mlp_tc: cudaFuncSetAttribute(%d): %s", C::SMEM, cudaGetErrorString(e));
             return (int)e;
@@ -481,29 +504,51 @@ int launch_mlp(const CUtensorMap& tmW1, const CUtensorMap& tmW2, const MlpParams
     }
     const int ntiles = (prm.M + BM - 1) / BM;
     const int grid = ntiles < rp::num_sms(device) ? ntiles : rp::num_sms(device);
-    mlp_fused_tc_kernel<P><<<grid, NTHREADS, C::SMEM, st>>>(tmW1, tmW2, prm);
+    rp::launch(mlp_fused_tc_kernel<P, AIN>, dim3(grid), dim3(NTHREADS), (size_t)(C::SMEM), st, tmW1, tmW2, tmXN, prm);
     return rp::finish_launch("rp_mlp_tc");
 }
 
 }  // namespace
 
-extern "C" int rp_mlp_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W1_planes,
-                         const float* b1, const void* W2_planes, const float* b2, float* out, int M, int dim, int hidden,
-                         int P, int device, void* stream) {
-    RP_REQUIRE(x && ln_gamma && ln_beta && W1_planes && b1 && W2_planes && b2 && out && M > 0, RP_EINVAL,
+// xn_planes != null: LayerNorm(x) is supplied as bf16 planes [P][M][192] (ln_gamma / ln_beta unused).
+// out_ln_planes != null: also writes LayerNorm(out; ln2_gamma, ln2_beta, eps2) as bf16 planes [P][M][192].
+extern "C" int rp_mlp_tc_ex(const float* x, const void* xn_planes, const float* ln_gamma, const float* ln_beta, float eps,
+                            const void* W1_planes, const float* b1, const void* W2_planes, const float* b2, float* out,
+                            void* out_ln_planes, const float* ln2_gamma, const float* ln2_beta, float eps2, int M, int dim,
+                            int hidden, int P, int device, void* stream) {
+    RP_REQUIRE(x && (xn_planes || (ln_gamma && ln_beta)) && W1_planes && b1 && W2_planes && b2 && out && M > 0, RP_EINVAL,
                "rp_mlp_tc: null pointer or M <= 0");
+    RP_REQUIRE(!out_ln_planes || (ln2_gamma && ln2_beta), RP_EINVAL, "rp_mlp_tc: LayerNorm planes requested without weights");
     RP_REQUIRE(dim == D && hidden == HID, RP_EINVAL, "rp_mlp_tc: built for dim=192, hidden=768 (got %d, %d)", dim, hidden);
     RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_mlp_tc: P must be 1 (bf16) or 2 (bf16x3)");
     RP_REQUIRE(rp::aligned16(x) && rp::aligned16(out) && rp::aligned16(W1_planes) && rp::aligned16(W2_planes) &&
-                   rp::aligned16(b1) && rp::aligned16(b2) && rp::aligned16(ln_gamma) && rp::aligned16(ln_beta),
+                   rp::aligned16(b1) && rp::aligned16(b2) && rp::aligned16(ln_gamma) && rp::aligned16(ln_beta) &&
+                   rp::aligned16(xn_planes) && rp::aligned16(out_ln_planes) && rp::aligned16(ln2_gamma) && rp::aligned16(ln2_beta),
                RP_EALIGN, "rp_mlp_tc: 16-byte alignment");
     RP_GUARD(device);
-    CUtensorMap tmW1, tmW2;
+    CUtensorMap tmW1, tmW2, tmXN;
     int rc = tc::make_planes_tmap(&tmW1, W1_planes, P, HID, D, 64);      // [P][768][192], box 64 rows x 64 K
     if (rc) return rc;
     rc = tc::make_planes_tmap(&tmW2, W2_planes, P, D, HID, 64);          // [P][192][768]
     if (rc) return rc;
-    MlpParams prm{x, ln_gamma, ln_beta, b1, b2, out, M, eps};
-    if (P == 1) return launch_mlp<1>(tmW1, tmW2, prm, device, (cudaStream_t)stream);
-    return launch_mlp<2>(tmW1, tmW2, prm, device, (cudaStream_t)stream);
+    tmXN = tmW1;
+    if (xn_planes) {
+        rc = tc::make_planes_tmap(&tmXN, xn_planes, P, M, D, BM);        // [P][M][192], box 128 rows x 64 K
+        if (rc) return rc;
+    }
+    MlpParams prm{x, ln_gamma, ln_beta, b1, b2, out, M, eps, static_cast<__nv_bfloat16*>(out_ln_planes), ln2_gamma, ln2_beta, eps2};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (xn_planes) {
+        if (P == 1) return launch_mlp<1, true>(tmW1, tmW2, tmXN, prm, device, st);
+        return launch_mlp<2, true>(tmW1, tmW2, tmXN, prm, device, st);
+    }
+    if (P == 1) return launch_mlp<1, false>(tmW1, tmW2, tmXN, prm, device, st);
+    return launch_mlp<2, false>(tmW1, tmW2, tmXN, prm, device, st);
+}
+
+extern "C" int rp_mlp_tc(const float* x, const float* ln_gamma, const float* ln_beta, float eps, const void* W1_planes,
+                         const float* b1, const void* W2_planes, const float* b2, float* out, int M, int dim, int hidden,
+                         int P, int device, void* stream) {
+    return rp_mlp_tc_ex(x, nullptr, ln_gamma, ln_beta, eps, W1_planes, b1, W2_planes, b2, out, nullptr, nullptr, nullptr, 0.f, M,
+                        dim, hidden, P, device, stream);
 }

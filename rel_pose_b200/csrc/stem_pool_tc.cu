@@ -74,7 +74,9 @@ stem_pool_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc::mbar_init(wfull, 1);
         tc::fence_barrier_init();
     }
+    rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, 128);
+    rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -263,6 +265,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 preprocess_stem_compact_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ out, int n_img, int H, int W,
                                float scale_h, float scale_w, int P) {
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
     const long long total = (long long)n_img * HP * WC;
     const long long plane = total * 16;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -343,7 +347,7 @@ int launch_stem_pool(const CUtensorMap& tmA, const CUtensorMap& tmW, const float
     }
     const int nunits = n_img * BANDS;
     const int grid = nunits < rp::num_sms(device) ? nunits : rp::num_sms(device);
-    stem_pool_tc_kernel<P><<<grid, NTHREADS, C::SMEM, st>>>(tmA, tmW, scale, shift, out_f32, static_cast<__nv_bfloat16*>(out_planes),
+    rp::launch(stem_pool_tc_kernel<P>, dim3(grid), dim3(NTHREADS), (size_t)(C::SMEM), st, tmA, tmW, scale, shift, out_f32, static_cast<__nv_bfloat16*>(out_planes),
                                                            p_out, n_img);
     return rp::finish_launch("rp_stem_pool_tc");
 }
@@ -357,7 +361,7 @@ int stem_compact_launch(const T* images, void* planes, int n_img, int H, int W, 
     const long long total = (long long)n_img * HP * WC;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)rp::num_sms(device) * 16;
-    preprocess_stem_compact_kernel<T><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+    rp::launch(preprocess_stem_compact_kernel<T>, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         images, static_cast<__nv_bfloat16*>(planes), n_img, H, W, (float)H / (float)224, (float)W / (float)224, P);
     return rp::finish_launch("rp_preprocess_stem_compact");
 }

@@ -172,6 +172,13 @@ class ViTEss(nn.Module):
         # sequence for A/B measurements
         self.fused_mlp = os.environ.get("RELPOSE_FUSED_MLP", "1") != "0"
         self.fused_ln_qkv = os.environ.get("RELPOSE_FUSED_LNQKV", "1") != "0"     # csrc/ln_linear_tc.cu
+        # RELPOSE_CHAIN_LN=1: LayerNorms computed by the PRODUCER of the residual stream (csrc/rows_ln_epilogue.cuh): the
+        # attention projection emits norm2(x) and the fused MLP emits the next Block's norm1(x) as bf16 planes, the
+        # consumers load them by TMA.  Measured (profiles/r02_bench_call7_*.json, 64 pairs, bf16x3): the QKV GEMM gains
+        # (89 -> 67 us) but the projection (42 -> 66 us) and the MLP (123 -> 138 us: the LayerNorm epilogue sits on the
+        # GELU warps' critical path just as the in-kernel LayerNorm did) lose more, plus 171 MB of extra plane traffic
+        # per Block -- a net loss of 17 us per Block, so the default keeps every LayerNorm inside its consumer.
+        self.chain_ln = os.environ.get("RELPOSE_CHAIN_LN", "0") == "1"
         self.fused_stem = os.environ.get("RELPOSE_FUSED_STEM", "1") != "0"        # csrc/stem_pool_tc.cu
         self.tc_regressor = os.environ.get("RELPOSE_TC_REGRESSOR", "1") != "0"    # split-K tcgen05 GEMM for pose_regressor.0
         self.check_intrinsics = True      # reproduce the reference's assert on per-view intrinsics
@@ -311,8 +318,10 @@ class ViTEss(nn.Module):
             return 0
         return {"fp32": 0, "bf16": 1, "bf16x3": 2}[self.precision]
 
-    def _block(self, blk, x):
-        """Block.forward (vision_transformer.py:349-354): no 576x576 tensor ever reaches HBM."""
+    def _block(self, blk, x, xn=None, next_norm=None):
+        """Block.forward (vision_transformer.py:349-354): no 576x576 tensor ever reaches HBM.
+        xn: norm1(x) as bf16 planes when the previous Block produced them; next_norm: the LayerNorm whose output of the
+        result the caller wants as planes.  Returns (x', planes | None)."""
         P = self._tc_planes()
         if P == 0:
             h = ops.layernorm(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
@@ -321,12 +330,31 @@ class ViTEss(nn.Module):
             x = ops.linear(a, blk.attn.proj.weight, blk.attn.proj.bias, residual=x)
             h = ops.layernorm(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
             h = ops.linear(h, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
-            return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=x)
+            return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=x), None
         # tensor-core engine: LayerNorm and the GEMM epilogues emit the bf16 planes the next GEMM reads
+        if self.chain_ln and self.fused_mlp and self.fused_ln_qkv:
+            return self._block_chained(blk, blk.attn, x, xn, next_norm, P)
         qkv = self._ln_qkv_tc(x, blk.norm1, blk.attn.qkv, P)
         _, a = ops.self_attention_tc(qkv, planes_out=P)
         x, _ = ops.linear_tc(a, self._planes(blk.attn.proj.weight, P), blk.attn.proj.bias, residual=x)
-        return self._mlp_tc(blk, x, P)
+        return self._mlp_tc(blk, x, P), None
+
+    def _block_chained(self, blk, attn, x, xn, next_norm, P, cross=False):
+        """One Block with every LayerNorm computed where its input is produced: xn = norm1(x) as bf16 planes (None for
+        the first Block: computed inside the QKV kernel); returns (x', norm_next(x') planes | None)."""
+        if xn is None:
+            qkv = self._ln_qkv_tc(x, blk.norm1, attn.qkv, P)
+        else:
+            qkv = ops.planes_linear_tc(xn, self._planes(attn.qkv.weight, P), attn.qkv.bias, planes_out=P)
+        _, a = ops.self_attention_tc(qkv, planes_out=P, cross=cross)
+        n2 = blk.norm2
+        x, xn2 = ops.planes_linear_tc(a, self._planes(attn.proj.weight, P), attn.proj.bias, residual=x,
+                                      ln_next=(n2.weight, n2.bias, n2.eps))
+        m = blk.mlp
+        ln_next = None if next_norm is None else (next_norm.weight, next_norm.bias, next_norm.eps)
+        r = ops.mlp_tc(x, None, None, 0.0, self._planes(m.fc1.weight, P), m.fc1.bias, self._planes(m.fc2.weight, P), m.fc2.bias,
+                       xn_planes=xn2, ln_next=ln_next)
+        return r if ln_next is not None else (r, None)
 
     def _ln_qkv_tc(self, x, norm, qkv, P):
         """qkv(norm1(x)) as bf16 planes: one fused launch (LayerNorm -> shared-memory A operand -> GEMM)."""
@@ -346,7 +374,7 @@ class ViTEss(nn.Module):
         x, _ = ops.linear_tc(h, self._planes(blk.mlp.fc2.weight, P), blk.mlp.fc2.bias, residual=x)
         return x
 
-    def _cross_block(self, blk, x, kxy, stages):
+    def _cross_block(self, blk, x, kxy, stages, xn=None):
         """CrossBlock.forward (vision_transformer.py:285-296) around the Essential Matrix Module."""
         B = x.shape[0] // 2
         P = self._tc_planes()
@@ -354,6 +382,8 @@ class ViTEss(nn.Module):
         if P == 0:
             h = ops.layernorm(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)     # norm1 on both views
             qkv = ops.linear(h, ca.qkv.weight, ca.qkv.bias)
+        elif xn is not None:
+            qkv = ops.planes_linear_tc(xn, self._planes(ca.qkv.weight, P), ca.qkv.bias, planes_out=P)
         else:
             qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
         pos = ops.posenc(B, kxy, x.device, self.l1_pos_encoding)
@@ -367,7 +397,7 @@ class ViTEss(nn.Module):
             return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=f)
         return self._mlp_tc(blk, f, P)
 
-    def _cross_block_noess(self, blk, x):
+    def _cross_block_noess(self, blk, x, xn=None):
         """CrossBlock.forward, --noess branch (vision_transformer.py:297-303): x + proj(cross attention), then the MLP.
         The attention kernels read the other view's keys/values in place (image n -> n^1), which also yields the
         flipped return order of :262; no copy, no 576x576 tensor in HBM."""
@@ -381,6 +411,8 @@ class ViTEss(nn.Module):
             h = ops.layernorm(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
             h = ops.linear(h, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
             return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=x)
+        if self.chain_ln and self.fused_mlp and self.fused_ln_qkv:
+            return self._block_chained(blk, ca, x, xn, None, P, cross=True)[0]
         qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
         _, a = ops.self_attention_tc(qkv, planes_out=P, cross=True)
         x, _ = ops.linear_tc(a, self._planes(ca.proj.weight, P), ca.proj.bias, residual=x)
@@ -493,16 +525,17 @@ class ViTEss(nn.Module):
             x = self._cnn_front_end(x)                                        # A2, A3, A4
             if stages is not None:
                 stages["tokens"] = x if self.cnn_only else x - vt.pos_embed
+            xn = None                                                         # norm1(x) of the next Block as bf16 planes
             for i in range(0 if self.cnn_only else self.transformer_depth - 1):   # A5
-                x = self._block(vt.blocks[i], x)
+                x, xn = self._block(vt.blocks[i], x, xn, vt.blocks[i + 1].norm1)
                 if stages is not None:
                     stages[f"block{i}"] = x
             if self.cnn_only:
                 pass                                                          # model.py:179-181: tokens go straight to the head
             elif self.noess:
-                x = self._cross_block_noess(vt.blocks[self.transformer_depth - 1], x)
+                x = self._cross_block_noess(vt.blocks[self.transformer_depth - 1], x, xn)
             else:
-                x = self._cross_block(vt.blocks[self.transformer_depth - 1], x, kxy, stages)   # A6-A8
+                x = self._cross_block(vt.blocks[self.transformer_depth - 1], x, kxy, stages, xn)   # A6-A8
             if stages is not None and not self.cnn_only:
                 stages["cross"] = x
             if not self.cnn_only:

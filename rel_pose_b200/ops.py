@@ -476,21 +476,76 @@ def ln_linear_tc(x, gamma, beta, eps, w_planes, bias=None, want_f32=False, plane
     return out, outp
 
 
-def mlp_tc(x, gamma, beta, eps, w1_planes, b1, w2_planes, b2):
+def planes_linear_tc(xn_planes, w_planes, bias=None, planes_out=0, residual=None, ln_next=None):
+    """The K = 192 GEMM of csrc/ln_linear_tc.cu fed with LayerNorm planes its producer wrote (rp_ln_linear_tc_ex):
+    xn_planes bf16 [P,...,192], w_planes bf16 [P,N,192].
+      residual is None:  -> bf16 planes [planes_out,...,N]                 (the QKV projection)
+      residual given:    -> (float32 [...,192] = A W^T + bias + residual,  (the attention projection + skip)
+                             bf16 planes [P,...,192] of LayerNorm(out; *ln_next) | None)"""
+    _req(xn_planes, "xn_planes", torch.bfloat16); _req(w_planes, "w_planes", torch.bfloat16)
+    P, N, K = w_planes.shape
+    assert xn_planes.shape[0] == P and xn_planes.shape[-1] == K
+    lead = tuple(xn_planes.shape[1:-1])
+    M = xn_planes[0].numel() // K
+    if bias is not None:
+        _req(bias, "bias")
+    dev, st = _ctx(xn_planes)
+    L = _lib.lib()
+    if residual is None:
+        assert planes_out
+        outp = torch.empty((planes_out,) + lead + (N,), dtype=torch.bfloat16, device=xn_planes.device)
+        _tbegin(f"planes_linear_tc{'x3' if P == 2 else ''}[{N}x{K}]", 2.0 * M * N * K,
+                2.0 * P * M * K + 2.0 * P * N * K + 2.0 * planes_out * M * N)
+        _lib.check(L.rp_ln_linear_tc_ex(None, _p(xn_planes), None, None, 0.0, _p(w_planes), _p(bias), None, None, _p(outp), None,
+                                        None, None, 0.0, M, N, K, P, int(planes_out), dev, st), "rp_ln_linear_tc_ex")
+        _count()
+        return outp
+    _req(residual, "residual")
+    assert N == K and residual.numel() == M * N and bias is not None
+    out = torch.empty(lead + (N,), dtype=torch.float32, device=xn_planes.device)
+    lnp, g2, b2, e2 = None, None, None, 0.0
+    if ln_next is not None:
+        g2, b2, e2 = ln_next
+        _req(g2, "ln_next gamma"); _req(b2, "ln_next beta")
+        lnp = torch.empty((P,) + lead + (N,), dtype=torch.bfloat16, device=xn_planes.device)
+    _tbegin(f"proj_ln_tc{'x3' if P == 2 else ''}[{N}x{K}]", 2.0 * M * N * K,
+            2.0 * P * M * K + 2.0 * P * N * K + 8.0 * M * N + (2.0 * P * M * N if lnp is not None else 0.0))
+    _lib.check(L.rp_ln_linear_tc_ex(None, _p(xn_planes), None, None, 0.0, _p(w_planes), _p(bias), _p(residual), _p(out), None,
+                                    _p(lnp), _p(g2), _p(b2), float(e2), M, N, K, P, 0, dev, st), "rp_ln_linear_tc_ex")
+    _count()
+    return out, lnp
+
+
+def mlp_tc(x, gamma, beta, eps, w1_planes, b1, w2_planes, b2, xn_planes=None, ln_next=None):
     """Fused `x + fc2(gelu(fc1(layernorm(x))))` on tcgen05 (csrc/mlp_tc.cu): x float32 [...,192],
-    w1_planes bf16 [P,768,192], w2_planes bf16 [P,192,768] -> float32 [...,192]."""
-    _req(x, "x"); _req(gamma, "gamma"); _req(beta, "beta"); _req(b1, "b1"); _req(b2, "b2")
+    w1_planes bf16 [P,768,192], w2_planes bf16 [P,192,768] -> float32 [...,192].
+    xn_planes: layernorm(x) already available as bf16 planes [P,...,192] (written by the producer of x).
+    ln_next = (gamma, beta, eps): also return LayerNorm(out) with these weights as bf16 planes -> (out, planes)."""
+    _req(x, "x"); _req(b1, "b1"); _req(b2, "b2")
     _req(w1_planes, "w1_planes", torch.bfloat16); _req(w2_planes, "w2_planes", torch.bfloat16)
     P, hidden, dim = w1_planes.shape
     assert tuple(w2_planes.shape) == (P, dim, hidden) and x.shape[-1] == dim
     M = x.numel() // dim
+    if xn_planes is not None:
+        _req(xn_planes, "xn_planes", torch.bfloat16)
+        assert xn_planes.shape[0] == P and xn_planes.numel() == P * M * dim
+    else:
+        _req(gamma, "gamma"); _req(beta, "beta")
     out = torch.empty_like(x)
+    lnp, g2, bt2, e2 = None, None, None, 0.0
+    if ln_next is not None:
+        g2, bt2, e2 = ln_next
+        _req(g2, "ln_next gamma"); _req(bt2, "ln_next beta")
+        lnp = torch.empty((P,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
     dev, st = _ctx(x)
-    _tbegin(f"mlp_fused_tc{'x3' if P == 2 else ''}", 4.0 * M * dim * hidden, 8.0 * M * dim + 4.0 * P * dim * hidden)
-    _lib.check(_lib.lib().rp_mlp_tc(_p(x), _p(gamma), _p(beta), float(eps), _p(w1_planes), _p(b1), _p(w2_planes), _p(b2),
-                                    _p(out), M, dim, hidden, P, dev, st), "rp_mlp_tc")
+    _tbegin(f"mlp_fused_tc{'x3' if P == 2 else ''}", 4.0 * M * dim * hidden,
+            8.0 * M * dim + 4.0 * P * dim * hidden + (2.0 * P * M * dim if xn_planes is not None else 0.0) +
+            (2.0 * P * M * dim if lnp is not None else 0.0))
+    _lib.check(_lib.lib().rp_mlp_tc_ex(_p(x), _p(xn_planes), _p(gamma), _p(beta), float(eps), _p(w1_planes), _p(b1),
+                                       _p(w2_planes), _p(b2), _p(out), _p(lnp), _p(g2), _p(bt2), float(e2), M, dim, hidden, P,
+                                       dev, st), "rp_mlp_tc")
     _count()
-    return out
+    return out if ln_next is None else (out, lnp)
 
 
 def conv2d_tc(x_planes, w_planes, KH, KW, scale=None, shift=None, stride=1, pad=0, act=ACT_NONE, res_pre=None,

@@ -180,6 +180,96 @@ def test_mlp_fused_tc(P, M):
     assert torch.equal(got, again)
 
 
+@pytest.mark.parametrize("P", [1, 2])
+@pytest.mark.parametrize("M", [128, 140, 1152, 148 * 128 * 2 + 77])
+def test_planes_linear_tc_qkv(P, M):
+    """rp_ln_linear_tc_ex with the A operand supplied as LayerNorm planes (TMA-fed): bit-identical to the kernel that
+    computes the same LayerNorm itself (same planes, same MMA order, same epilogue)."""
+    x = rnd(40, M, 192, scale=1.5) + 0.2
+    g = 1 + 0.1 * rnd(41, 192); be = 0.1 * rnd(42, 192)
+    w = rnd(43, 576, 192, scale=0.07); b = rnd(44, 576, scale=0.1)
+    wp = ops.split_planes(cu(w), P)
+    xn = ops.layernorm_planes(cu(x), cu(g), cu(be), 1e-6, P)
+    got = ops.planes_linear_tc(xn, wp, cu(b), planes_out=P)
+    torch.cuda.synchronize()
+    f64 = np.float64
+    ref = planes_to_f64(xn) @ planes_to_f64(wp).T + b
+    tol = (3e-5 if P == 2 else 2e-2) * np.abs(ref).max()
+    err = np.abs(planes_to_f64(got) - ref).max()
+    print(f"[parity] planes_linear_tc P={P} M={M}: max_abs_err={err:.3e} ratio={err / tol:.3f}")
+    assert np.isfinite(planes_to_f64(got)).all() and err <= tol
+    # the kernel that computes the LayerNorm itself agrees (its LayerNorm rounds like layernorm_planes up to the last ulp)
+    fused = ops.ln_linear_tc(cu(x), cu(g), cu(be), 1e-6, wp, cu(b), want_f32=False, planes_out=P)[1]
+    assert np.abs(planes_to_f64(fused) - planes_to_f64(got)).max() <= tol
+    assert torch.equal(ops.planes_linear_tc(xn, wp, cu(b), planes_out=P), got)
+
+
+@pytest.mark.parametrize("P", [1, 2])
+@pytest.mark.parametrize("M,with_ln", [(128, True), (140, True), (1152, False), (8960, True), (148 * 128 * 2 + 77, True)])
+def test_proj_residual_ln_planes(P, M, with_ln):
+    """Attention projection + skip with the Block's norm2 folded into the epilogue (rows_ln_epilogue.cuh):
+    out = a Wp^T + b + x against float64; LayerNorm(out) planes against float64 of the kernel's own float32 output."""
+    a = rnd(50, M, 192, scale=1.2)
+    x = rnd(51, M, 192, scale=1.5) + 0.4
+    w = rnd(52, 192, 192, scale=0.07); b = rnd(53, 192, scale=0.1)
+    g2 = 1 + 0.1 * rnd(54, 192); be2 = 0.1 * rnd(55, 192)
+    ap = ops.split_planes(cu(a), P); wp = ops.split_planes(cu(w), P)
+    out, lnp = ops.planes_linear_tc(ap, wp, cu(b), residual=cu(x), ln_next=(cu(g2), cu(be2), 1e-6) if with_ln else None)
+    torch.cuda.synchronize()
+    f64 = np.float64
+    ref = planes_to_f64(ap) @ planes_to_f64(wp).T + b + x
+    outn = out.cpu().numpy().astype(f64)
+    tol = (3e-5 if P == 2 else 2e-2) * np.abs(ref - x).max()
+    err = np.abs(outn - ref).max()
+    print(f"[parity] proj_ln_tc P={P} M={M}: max_abs_err={err:.3e} ratio={err / tol:.3f}")
+    assert np.isfinite(outn).all() and err <= tol
+    # the generic GEMM engine computes the same product
+    un, _ = ops.linear_tc(ap, wp, cu(b), residual=cu(x))
+    assert np.abs(un.cpu().numpy() - outn).max() <= 2 * tol
+    if with_ln:
+        lref = O.layernorm(outn, g2.astype(f64), be2.astype(f64))
+        lgot = planes_to_f64(lnp)
+        lerr = np.abs(lgot - lref).max()
+        ltol = (3e-5 if P == 2 else 5e-3) * np.abs(lref).max()
+        print(f"[parity] proj_ln_tc planes P={P} M={M}: max_abs_err={lerr:.3e} ratio={lerr / ltol:.3f}")
+        assert tuple(lnp.shape) == (P, M, 192) and np.isfinite(lgot).all() and lerr <= ltol
+        again = ops.planes_linear_tc(ap, wp, cu(b), residual=cu(x), ln_next=(cu(g2), cu(be2), 1e-6))
+        assert torch.equal(again[0], out) and torch.equal(again[1], lnp)
+    else:
+        assert lnp is None
+
+
+@pytest.mark.parametrize("P", [1, 2])
+@pytest.mark.parametrize("M", [128, 140, 1152, 148 * 128 * 2 + 77])
+def test_mlp_fused_tc_planes_in_out(P, M):
+    """rp_mlp_tc_ex: norm2(x) supplied as planes (TMA-fed fc1 operand) and the next Block's norm1 of the result
+    returned as planes.  Bit-identical float32 output to the kernel that computes the LayerNorm itself."""
+    x = rnd(60, M, 192, scale=1.5) + 0.2
+    g = 1 + 0.1 * rnd(61, 192); be = 0.1 * rnd(62, 192)
+    g2 = 1 + 0.1 * rnd(67, 192); be2 = 0.1 * rnd(68, 192)
+    w1 = rnd(63, 768, 192, scale=0.07); b1 = rnd(64, 768, scale=0.1)
+    w2 = rnd(65, 192, 768, scale=0.04); b2 = rnd(66, 192, scale=0.1)
+    w1p = ops.split_planes(cu(w1), P); w2p = ops.split_planes(cu(w2), P)
+    xg = cu(x)
+    base = ops.mlp_tc(xg, cu(g), cu(be), 1e-6, w1p, cu(b1), w2p, cu(b2))
+    xn = ops.layernorm_planes(xg, cu(g), cu(be), 1e-6, P)
+    out, lnp = ops.mlp_tc(xg, None, None, 0.0, w1p, cu(b1), w2p, cu(b2), xn_planes=xn, ln_next=(cu(g2), cu(be2), 1e-6))
+    torch.cuda.synchronize()
+    f64 = np.float64
+    assert np.abs(out.cpu().numpy().astype(f64) - base.cpu().numpy()).max() <= 1e-5 * np.abs(base.cpu().numpy() - x).max()
+    lref = O.layernorm(out.cpu().numpy().astype(f64), g2.astype(f64), be2.astype(f64))
+    lgot = planes_to_f64(lnp)
+    lerr = np.abs(lgot - lref).max()
+    ltol = (3e-5 if P == 2 else 5e-3) * np.abs(lref).max()
+    print(f"[parity] mlp_tc_ex planes P={P} M={M}: max_abs_err={lerr:.3e} ratio={lerr / ltol:.3f}")
+    assert tuple(lnp.shape) == (P, M, 192) and np.isfinite(lgot).all() and lerr <= ltol
+    # planes in only / planes out only: same arithmetic as the combined call / as the plain kernel
+    assert torch.equal(ops.mlp_tc(xg, None, None, 0.0, w1p, cu(b1), w2p, cu(b2), xn_planes=xn), out)
+    o2, l2 = ops.mlp_tc(xg, cu(g), cu(be), 1e-6, w1p, cu(b1), w2p, cu(b2), ln_next=(cu(g2), cu(be2), 1e-6))
+    assert torch.equal(o2, base)
+    assert np.abs(planes_to_f64(l2) - O.layernorm(base.cpu().numpy().astype(f64), g2.astype(f64), be2.astype(f64))).max() <= ltol
+
+
 # ------------------------------------------------------------------------------------------ conv on tcgen05
 class _BN:
     def __init__(self, seed, C):
