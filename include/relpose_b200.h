@@ -366,6 +366,12 @@ int rp_grad_norm_multi(const void* descs, const int* blk_tensor, const int64_t* 
 int rp_adam_clip_step_multi(const void* descs, const int* blk_tensor, const int64_t* blk_off, int nblk, int chunk,
                             const float* total_norm, double max_norm, double lr, double beta1, double beta2, double eps,
                             double weight_decay, int step, int device, void* stream);
+/* rp_adam_clip_step_multi for CUDA-graph replays: the two scalars that change every step, step_hyper[0] = lr_t /
+ * (1 - beta1^t) and step_hyper[1] = sqrt(1 - beta2^t) (float32, DEVICE memory), are read by the kernel instead of
+ * being passed by value, so one captured launch serves every optimizer step (train.py:161-165 as a replayed graph). */
+int rp_adam_clip_step_multi_dev(const void* descs, const int* blk_tensor, const int64_t* blk_off, int nblk, int chunk,
+                                const float* total_norm, double max_norm, const float* step_hyper, double beta1,
+                                double beta2, double eps, double weight_decay, int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,8 @@ _SIGNATURES = {
     "rp_scatter_dv_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_grad_norm_multi": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr, _c_int, _ptr]),
     "rp_adam_clip_step_multi": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr] + [ctypes.c_double] * 6 + [_c_int, _c_int, _ptr]),
+    "rp_adam_clip_step_multi_dev": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, ctypes.c_double, _ptr] + [ctypes.c_double] * 4 +
+                                    [_c_int, _ptr]),
     "rp_svd3_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
     "rp_essential_to_rt_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr]),
 }

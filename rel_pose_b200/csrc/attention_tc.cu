@@ -73,7 +73,7 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     using C = ACfg<P, CPS>;
     constexpr int V_STAGES = C::V_STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* q_full = bars + 0;
     uint64_t* q_free = bars + 1;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_halo_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, HaloEpi ep, HaloGeom g) {
     using C = HCfg<P, BN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
     // layout: halo[2][P][halo_bytes] | filter ring [NSTAGE][P][B_TILE] | staging | barriers.  Operand reads that run
     // past a halo buffer (junk accumulator rows) land in the next halo buffer / the ring: valid shared memory.
     const int halo_buf = P * g.halo_bytes;

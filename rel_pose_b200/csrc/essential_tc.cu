@@ -58,7 +58,7 @@ em_stats_tc_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
                    float* __restrict__ lse2, int B) {
     using C = SCfg<P>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* r_full = bars + 0;
     uint64_t* r_free = bars + 1;
@@ -248,7 +248,7 @@ em_accum_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    int B, int width, int em_flags) {
     using C = ECfg<P>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
     float* cl = reinterpret_cast<float*>(smem + C::OFF_CL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* q_full = bars + 0;
@@ -718,7 +718,7 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     int B, int width, int em_flags) {
     using C = ECfg<P>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
     float* cl = reinterpret_cast<float*>(smem + C::OFF_CL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* q_full = bars + 0;

@@ -423,33 +423,53 @@ __device__ __forceinline__ float mufu_rsq(float x) {
     return y;
 }
 
-// One Jacobi rotation of columns p, q.  MUFU-only arithmetic (rcp / rsqrt approximations): a slightly inexact
-// angle costs nothing -- the next rotation removes what is left -- while c, s are normalised consistently so the
-// accumulated V stays orthonormal to ~1e-7.  Returns true if another sweep is needed because of this pair.
+__device__ __forceinline__ float mufu_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One Jacobi rotation of columns p, q of A.  MUFU-only arithmetic (rcp / rsqrt / sqrt approximations): a slightly
+// inexact angle costs nothing -- the next rotation removes what is left -- while c, s are normalised consistently so
+// the accumulated V stays orthonormal to ~1e-7.  Returns false if the pair is already orthogonal (c = 1, s = 0).
+// `flags`: bit 0 = another sweep is needed because of this pair, bit 1 = the carried norms are inconsistent.
+//
 // The squared column norms alpha, beta are CARRIED, not recomputed: a rotation by the root t of t^2 + 2 zeta t - 1 = 0
 // changes them by -+ t gamma (Golub & Van Loan 8.4), one FFMA + clamp each instead of two dot products.  They only
 // steer the angle and the convergence test (their drift, ~2e-7 of the larger norm per rotation, is far below both);
-// the singular values come from norms recomputed after the last sweep.  The kernels are instruction-issue bound
-// (~0.9 IPC per scheduler), so the 7 instructions this saves per rotation are time.
-__device__ __forceinline__ bool jacobi_pair(V3& ap, V3& aq, V3& vp, V3& vq, float& alpha, float& beta) {
+// the singular values come from norms recomputed after the last sweep.  A carried norm that has drifted BELOW what
+// Cauchy-Schwarz allows (gamma^2 > alpha beta: the clamped norm of a (near-)null column, i.e. every essential matrix)
+// must not reach the tests: the product is raised to gamma^2 here (one FMNMX, the rotation then proceeds and asks for
+// another sweep) and the sweep loop recomputes the three norms before that sweep.  |zeta| may overflow to inf for
+// columns 19 orders of magnitude apart; sqrt.approx keeps that an identity rotation (t = 1 / inf = 0) where
+// r * rsqrt(r) would be inf * 0.  The kernels are instruction-issue bound (~0.9 IPC per scheduler): every
+// instruction saved per rotation is time.
+__device__ __forceinline__ bool jacobi_rot(V3& ap, V3& aq, float& alpha, float& beta, float& c, float& sn, unsigned& flags) {
     const float gamma = dot(ap, aq);
-    const float ab = alpha * beta, g2 = gamma * gamma;
+    const float g2 = gamma * gamma, ab0 = alpha * beta;
+    const float ab = fmaxf(ab0, g2);
+    if (g2 > ab0) flags |= 2u;
     // already orthogonal to fp32 precision: gamma^2 <= (1e-7)^2 alpha beta  (no sqrt)
     if (g2 <= 1e-14f * ab) return false;
     // Jacobi converges quadratically: a pair whose cosine is below 3e-4 BEFORE its rotation is orthogonal to ~1e-7
     // after it, so such a rotation does not ask for another sweep
-    const bool big = g2 > 1e-7f * ab;
+    if (g2 > 1e-7f * ab) flags |= 1u;
     const float zeta = (beta - alpha) * mufu_rcp(2.0f * gamma);
-    const float r = fmaf(zeta, zeta, 1.0f);
-    const float t = copysignf(mufu_rcp(fmaf(r, mufu_rsq(r), fabsf(zeta))), zeta);
-    const float c = mufu_rsq(fmaf(t, t, 1.0f)), sn = c * t;
+    const float t = copysignf(mufu_rcp(fabsf(zeta) + mufu_sqrt(fmaf(zeta, zeta, 1.0f))), zeta);
+    c = mufu_rsq(fmaf(t, t, 1.0f));
+    sn = c * t;
     const V3 np_ = c * ap - sn * aq, nq = sn * ap + c * aq;
     ap = np_; aq = nq;
-    const V3 wp = c * vp - sn * vq, wq = sn * vp + c * vq;
-    vp = wp; vq = wq;
     alpha = fmaxf(fmaf(-t, gamma, alpha), 0.0f);
     beta = fmaxf(fmaf(t, gamma, beta), 0.0f);
-    return big;
+    return true;
+}
+__device__ __forceinline__ void jacobi_pair(V3& ap, V3& aq, V3& vp, V3& vq, float& alpha, float& beta, unsigned& flags) {
+    float c, sn;
+    if (jacobi_rot(ap, aq, alpha, beta, c, sn, flags)) {
+        const V3 wp = c * vp - sn * vq, wq = sn * vp + c * vq;
+        vp = wp; vq = wq;
+    }
 }
 __device__ __forceinline__ void swap_cols(V3& a, V3& b, V3& va, V3& vb, float& na, float& nb) {
     V3 t = a; a = b; b = t;
@@ -459,17 +479,32 @@ __device__ __forceinline__ void swap_cols(V3& a, V3& b, V3& va, V3& vb, float& n
 
 __device__ __forceinline__ Svd3 svd3(const float* e /* row-major 3x3 */) {
     V3 a0 = v3(e[0], e[3], e[6]), a1 = v3(e[1], e[4], e[7]), a2 = v3(e[2], e[5], e[8]);   // columns
-    V3 v0 = v3(1, 0, 0), v1 = v3(0, 1, 0), v2 = v3(0, 0, 1);
     float n0 = dot(a0, a0), n1 = dot(a1, a1), n2 = dot(a2, a2);
+    // First sweep with V = I written out: the three rotations of the identity need 14 multiplications instead of 36
+    // (a skipped rotation is c = 1, s = 0).
+    V3 v0, v1, v2;
+    unsigned flags = 0;
+    {
+        float c1 = 1.0f, s1 = 0.0f, c2 = 1.0f, s2 = 0.0f, c3 = 1.0f, s3 = 0.0f;
+        jacobi_rot(a0, a1, n0, n1, c1, s1, flags);        // v0 = (c1, -s1, 0), v1 = (s1, c1, 0), v2 = e2
+        jacobi_rot(a0, a2, n0, n2, c2, s2, flags);        // v0 <- c2 v0 - s2 e2,  v2 = s2 v0 + c2 e2
+        v0 = v3(c2 * c1, -(c2 * s1), -s2);
+        v2 = v3(s2 * c1, -(s2 * s1), c2);
+        jacobi_rot(a1, a2, n1, n2, c3, s3, flags);        // v1 <- c3 v1 - s3 v2,  v2 <- s3 v1 + c3 v2
+        v1 = v3(fmaf(c3, s1, -(s3 * v2.x)), fmaf(c3, c1, -(s3 * v2.y)), -(s3 * v2.z));
+        v2 = v3(fmaf(s3, s1, c3 * v2.x), fmaf(s3, c1, c3 * v2.y), c3 * v2.z);
+    }
     // Cyclic one-sided Jacobi converges quadratically: 3-4 sweeps reach fp32 precision for almost every matrix.
     // The loop ends as soon as no lane of the warp saw a large rotation during a sweep (warp-uniform exit, no
-    // divergence); 8 is a safety bound.
+    // divergence); 8 sweeps in all is a safety bound.
 #pragma unroll 1
-    for (int sweep = 0; sweep < 8; ++sweep) {
-        bool rot = jacobi_pair(a0, a1, v0, v1, n0, n1);
-        rot |= jacobi_pair(a0, a2, v0, v2, n0, n2);
-        rot |= jacobi_pair(a1, a2, v1, v2, n1, n2);
-        if (!__any_sync(0xffffffffu, rot)) break;
+    for (int sweep = 1; sweep < 8; ++sweep) {
+        if (!__any_sync(0xffffffffu, flags != 0)) break;
+        if (flags & 2u) { n0 = dot(a0, a0); n1 = dot(a1, a1); n2 = dot(a2, a2); }   // a carried norm drifted: refresh
+        flags = 0;
+        jacobi_pair(a0, a1, v0, v1, n0, n1, flags);
+        jacobi_pair(a0, a2, v0, v2, n0, n2, flags);
+        jacobi_pair(a1, a2, v1, v2, n1, n2, flags);
     }
     n0 = dot(a0, a0); n1 = dot(a1, a1); n2 = dot(a2, a2);
     // V is a product of rotations (det +1); every column swap of the sort flips its sign
@@ -550,10 +585,9 @@ __global__ void __launch_bounds__(TPB) essential_to_rt_kernel(const float* E, fl
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            float a = uw[i][0] * vv[j][0] + uw[i][1] * vv[j][1];
-            float b = uw[i][2] * vv[j][2];
-            p1[i * 3 + j] = a + b;      // U W V^T
-            p2[i * 3 + j] = -a + b;     // U W^T V^T
+            const float a = fmaf(uw[i][0], vv[j][0], uw[i][1] * vv[j][1]);
+            p1[i * 3 + j] = fmaf(uw[i][2], vv[j][2], a);       // U W V^T
+            p2[i * 3 + j] = fmaf(uw[i][2], vv[j][2], -a);      // U W^T V^T
         }
     st[threadIdx.x * 3 + 0] = u2.x; st[threadIdx.x * 3 + 1] = u2.y; st[threadIdx.x * 3 + 2] = u2.z;
     __syncthreads();

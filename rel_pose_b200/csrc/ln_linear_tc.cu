@@ -85,7 +85,7 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     using C = LCfg<P>;
     constexpr bool TMAOUT = (EPI == 1);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* wfull = bars;                      // [NS]
     uint64_t* wempty = bars + C::NS;             // [NS]

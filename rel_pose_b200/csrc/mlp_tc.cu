@@ -95,7 +95,7 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     const __grid_constant__ CUtensorMap tmXN, MlpParams prm) {
     using C = MCfg<P>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* wfull = bars;                      // [NU]
     uint64_t* wempty = bars + C::NU;             // [NU]
@@ -425,16 +425,9 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     if (nrow < M && (lane & 3) < 3)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.x + (size_t)nrow * D + (lane & 3) * 64 + 32));
                 }
-                if (!AIN && j == NCH - 2 && tile + (int)gridDim.x < ntiles) {
-                    // LayerNorm of the NEXT tile, two chunks before this tile ends: once the last two fc1 products
-                    // have completed (all earlier ones were observed chunk by chunk) this tile's LayerNorm planes
-                    // are dead, and the next tile's fc1 / this tile's last fc2 and output epilogue overlap.
-                    const uint32_t bn = (b1 + 1 == NA1) ? 0u : b1 + 1;
-                    ln_load(tile + (int)gridDim.x);
-                    tc::mbar_wait(&acc1_full[b1], ph1);
-                    tc::mbar_wait(&acc1_full[bn], bn == 0 ? ph1 ^ 1 : ph1);
-                    ln_finish();
-                }
+                // the next tile's rows are requested before the last GELU chunk's wait (their latency hides behind it);
+                // they are normalised after that chunk -- see below
+                const bool ln_next = !AIN && j == NCH - 1 && tile + (int)gridDim.x < ntiles;
                 float bias[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -475,6 +468,14 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 tc::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&h_full[hb]);
+                if (ln_next) {
+                    // LayerNorm of the NEXT tile right after the last GELU chunk: every fc1 product of this tile has
+                    // been observed complete (chunk by chunk), so the LayerNorm planes are dead; while these warps are
+                    // busy here the tensor pipe still has this tile's last three fc2 products queued (one more than
+                    // when the LayerNorm ran before the last two chunks).
+                    ln_load(tile + (int)gridDim.x);
+                    ln_finish();
+                }
             }
             prev_tile = tile;
         }

@@ -89,7 +89,10 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(OPT_TPB) adam_clip_multi_kernel(const TensorDesc* __restrict__ td,
                                                                  const int* __restrict__ blk_tensor,
                                                                  const long long* __restrict__ blk_off, int chunk,
-                                                                 const float* __restrict__ total_norm, AdamArgs a) {
+                                                                 const float* __restrict__ total_norm, AdamArgs a,
+                                                                 const float* __restrict__ step_hyper) {
+    // CUDA-graph replays: the two per-step scalars come from device memory (written by a copy that precedes the replay)
+    if (step_hyper) { a.lr_over_bc1 = __ldg(step_hyper); a.bc2_sqrt = __ldg(step_hyper + 1); }
     const TensorDesc t = td[blk_tensor[blockIdx.x]];
     const long long off = blk_off[blockIdx.x];
     const long long end = (off + chunk < t.n) ? off + chunk : t.n;
@@ -152,6 +155,27 @@ extern "C" int rp_adam_clip_step_multi(const void* descs, const int* blk_tensor,
     a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
     adam_clip_multi_kernel<<<nblk, OPT_TPB, 0, (cudaStream_t)stream>>>(static_cast<const TensorDesc*>(descs), blk_tensor,
                                                                       reinterpret_cast<const long long*>(blk_off), chunk,
-                                                                      total_norm, a);
+                                                                      total_norm, a, nullptr);
     return rp::finish_launch("rp_adam_clip_step_multi");
+}
+
+// Same update with the two per-step scalars {lr / (1 - beta1^t), sqrt(1 - beta2^t)} read from DEVICE memory
+// (step_hyper[2], float32), so that the launch can be captured in a CUDA graph once and replayed every step: the
+// host writes the pair for step t into pinned memory and enqueues a 8-byte copy in front of the replay.
+extern "C" int rp_adam_clip_step_multi_dev(const void* descs, const int* blk_tensor, const int64_t* blk_off, int nblk, int chunk,
+                                           const float* total_norm, double max_norm, const float* step_hyper, double beta1,
+                                           double beta2, double eps, double weight_decay, int device, void* stream) {
+    RP_REQUIRE(descs && blk_tensor && blk_off && step_hyper && nblk > 0 && chunk > 0 && (chunk % 4) == 0, RP_EINVAL,
+               "rp_adam_clip_step_multi_dev: bad argument");
+    RP_REQUIRE(max_norm <= 0.f || total_norm, RP_EINVAL, "rp_adam_clip_step_multi_dev: clipping needs the total norm");
+    RP_GUARD(device);
+    AdamArgs a;
+    a.max_norm = (float)max_norm;
+    a.lr_over_bc1 = 0.f; a.bc2_sqrt = 1.f;
+    a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.weight_decay = (float)weight_decay;
+    a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+    adam_clip_multi_kernel<<<nblk, OPT_TPB, 0, (cudaStream_t)stream>>>(static_cast<const TensorDesc*>(descs), blk_tensor,
+                                                                      reinterpret_cast<const long long*>(blk_off), chunk,
+                                                                      total_norm, a, step_hyper);
+    return rp::finish_launch("rp_adam_clip_step_multi_dev");
 }

@@ -28,8 +28,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 
 // t_acc: tensor-memory address of the accumulator's column 0 in this warp's lane quarter.
-// staging: base of the 16 patches (patch index = 4 part + q).  wait_acc(): blocks until the accumulator is complete
-// (called after the residual loads have been issued).  release(): called once the accumulator is in registers.
+// staging: base of the 16 patches (patch index = 4 part + q).  wait_acc(): blocks until the accumulator is complete.
+// release(): called once the accumulator is in registers.
 // P_ln = 0: no LayerNorm planes.
 template <int P_LN, typename WaitFn, typename ReleaseFn>
 __device__ __forceinline__ void epilogue(uint32_t t_acc, float* staging, int q, int part, int lane, const float* __restrict__ bias,
@@ -39,22 +39,14 @@ __device__ __forceinline__ void epilogue(uint32_t t_acc, float* staging, int q, 
                                          size_t plane_stride, WaitFn wait_acc, ReleaseFn release) {
     const int rr = lane >> 2, cq = lane & 3;
     float* stg = staging + (part * 4 + q) * PATCH;
+    // Phase 1: accumulator -> registers (transposed), then release it at once.  The residual rows are requested only
+    // afterwards: their L2 / HBM latency used to sit between the wait and the release, i.e. on the tensor pipe's
+    // critical path (the next tile's products wait for this accumulator), now it overlaps with those products.
     float4 o[3][4];
-#pragma unroll
-    for (int gi = 0; gi < 3; ++gi) {
-        const int col = part * 48 + gi * 16 + cq * 4;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int rt = q * 32 + t * 8 + rr;
-            o[gi][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rt < valid_rows) o[gi][t] = __ldg(reinterpret_cast<const float4*>(res + (size_t)(row_base + rt) * D + col));
-        }
-    }
     wait_acc();
 #pragma unroll
     for (int gi = 0; gi < 3; ++gi) {
         const int c0 = part * 48 + gi * 16;
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(bias + c0 + cq * 4));
         uint32_t a[16];
         tc::tmem_ld_32x32b_x16(t_acc + c0, a);
         tc::tmem_ld_wait();
@@ -68,17 +60,26 @@ __device__ __forceinline__ void epilogue(uint32_t t_acc, float* staging, int q, 
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int rl = t * 8 + rr;
-            const float4 acc = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2));
-            o[gi][t].x += acc.x + sh.x; o[gi][t].y += acc.y + sh.y;
-            o[gi][t].z += acc.z + sh.z; o[gi][t].w += acc.w + sh.w;
+            o[gi][t] = *reinterpret_cast<const float4*>(stg + rl * STG_LD + ((cq ^ ((rl >> 1) & 3)) << 2));
         }
     }
+    // Phase 2: + bias + residual, float32 output (coalesced 128-byte row segments)
 #pragma unroll
     for (int gi = 0; gi < 3; ++gi) {
         const int col = part * 48 + gi * 16 + cq * 4;
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(bias + col));
+        float4 r4[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int rt = q * 32 + t * 8 + rr;
+            r4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rt < valid_rows) r4[t] = __ldg(reinterpret_cast<const float4*>(res + (size_t)(row_base + rt) * D + col));
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int rt = q * 32 + t * 8 + rr;
+            o[gi][t].x = (o[gi][t].x + sh.x) + r4[t].x; o[gi][t].y = (o[gi][t].y + sh.y) + r4[t].y;
+            o[gi][t].z = (o[gi][t].z + sh.z) + r4[t].z; o[gi][t].w = (o[gi][t].w + sh.w) + r4[t].w;
             if (rt < valid_rows) *reinterpret_cast<float4*>(out + (size_t)(row_base + rt) * D + col) = o[gi][t];
         }
     }

@@ -48,7 +48,7 @@ stem_pool_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __nv_bfloat16* __restrict__ out_planes, int p_out, int n_img) {
     using C = SCfg<P>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
     float* vbuf = reinterpret_cast<float*>(smem + C::OFF_VBUF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* full = bars;                      // [STAGES]

@@ -118,9 +118,41 @@ class FusedAdamOneCycle:
         self._key, self._tables = key, (d_desc, d_t, d_o, partial, len(blk_t))
         return self._tables
 
+    # ---- CUDA-graph support: the per-step scalars live in device memory --------------------------------------
+    def step_scalars(self, step_num=None):
+        """(lr_t / (1 - beta1^t), sqrt(1 - beta2^t)) for optimizer step `step_num` (0-based; default: the next one)."""
+        k = self.step_num if step_num is None else step_num
+        t = k + 1
+        return (self.lr_at(k) / (1.0 - self.betas[0] ** t), math.sqrt(1.0 - self.betas[1] ** t))
+
+    def enable_device_scalars(self):
+        """After this call step() reads the learning rate / bias corrections from a 2-float device buffer, so a step
+        captured in a CUDA graph can be replayed: call `upload_step_scalars()` (an 8-byte async copy) before each replay
+        and `advance()` after it.  Eager `step()` keeps working (it uploads and advances by itself)."""
+        if getattr(self, "_hyper_dev", None) is None:
+            # a RING of pinned slots: the host runs many steps ahead of the device, and a slot must not be rewritten
+            # before its asynchronous copy has executed (the launch queue is far shorter than the ring)
+            self._hyper_host = torch.zeros((self._HYPER_RING, 2), dtype=torch.float32).pin_memory()
+            self._hyper_dev = torch.zeros(2, dtype=torch.float32, device=self.device)
+        return self
+
+    _HYPER_RING = 4096
+
+    def upload_step_scalars(self):
+        a, b = self.step_scalars()
+        slot = self._hyper_host[self.step_num % self._HYPER_RING]
+        slot[0] = a; slot[1] = b
+        self._hyper_dev.copy_(slot, non_blocking=True)
+
+    def advance(self):
+        """Book-keeping of one replayed step (the kernels ran inside the graph)."""
+        ops.bump_param_generation()
+        self.step_num += 1
+
     @torch.no_grad()
-    def step(self):
-        """clip -> Adam -> advance the schedule.  Returns the device tensor holding the pre-clip gradient norm."""
+    def step(self, _captured=False):
+        """clip -> Adam -> advance the schedule.  Returns the device tensor holding the pre-clip gradient norm.
+        _captured: called while a CUDA graph is being recorded -- launches only, no host-side state changes."""
         active = [(i, p) for i, p in enumerate(self.params) if p.grad is not None]
         if not active:
             self.step_num += 1
@@ -135,6 +167,16 @@ class FusedAdamOneCycle:
         if self.clip is not None:
             _lib.check(L.rp_grad_norm_multi(P(d_desc), P(d_t), P(d_o), nblk, self.chunk, P(partial), P(self.grad_norm), dev,
                                             ctypes.c_void_p(st)), "rp_grad_norm_multi")
+        if getattr(self, "_hyper_dev", None) is not None:
+            if not _captured:
+                self.upload_step_scalars()
+            _lib.check(L.rp_adam_clip_step_multi_dev(P(d_desc), P(d_t), P(d_o), nblk, self.chunk, P(self.grad_norm),
+                                                     self.clip if self.clip is not None else 0.0, P(self._hyper_dev),
+                                                     self.betas[0], self.betas[1], self.eps, self.weight_decay, dev,
+                                                     ctypes.c_void_p(st)), "rp_adam_clip_step_multi_dev")
+            if not _captured:
+                self.advance()
+            return self.grad_norm
         lr = self.lr_at(self.step_num)
         _lib.check(L.rp_adam_clip_step_multi(P(d_desc), P(d_t), P(d_o), nblk, self.chunk, P(self.grad_norm),
                                              self.clip if self.clip is not None else 0.0, lr, self.betas[0], self.betas[1],

@@ -597,7 +597,13 @@ def forward_train(model, images, Gs, intrinsics):
     kxy = None
     if intrinsics is not None:
         intrinsics, kxy, flags = model.update_intrinsics(images.shape, intrinsics)
-        f = int(flags.item())
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture (train_synthetic.GraphedStep): no host read inside the graph; the caller checks the flag
+            # word after each replay (GraphedStep.check_flags)
+            model.__dict__["_train_flags"] = flags
+            f = 0
+        else:
+            f = int(flags.item())
         if f & 1:
             raise AssertionError("intrinsics must be identical for both views of a pair (vision_transformer.py:117)")
         if f & 2:

@@ -39,7 +39,7 @@ def make_batch(step, rank, B, H, W, device):
 def default_options(**over):
     """The reference's Matterport training flags (scripts/train_matterport.sh:6-9, train.py:200-233)."""
     d = dict(steps=30, warmup_steps=5, batch=6, size=[384, 512], lr=5e-4, weight_decay=1e-5, clip=2.5, w_tr=10.0, w_rot=10.0,
-             total_steps=120000, warmup=10000, optimizer="fused", pool=8, measure_allreduce=True)
+             total_steps=120000, warmup=10000, optimizer="fused", pool=8, measure_allreduce=True, graph=True)
     d.update(over)
     return argparse.Namespace(**d)
 
@@ -104,17 +104,90 @@ def train_loop(a, dev, rank=0, world=1, local=0):
             evs[3].record()
         return loss.detach(), gn.reshape(())
 
+    # ---- the whole step as ONE CUDA graph (forward + loss + backward [+ DDP all-reduce] + clip + Adam): a step is ~700
+    # kernel launches of 5-30 us each, so issued one by one from Python it is bound by the host (17 ms per step for 11 ms
+    # of kernels).  Captured once after the eager warm-up steps and replayed; the batch is copied into static buffers,
+    # the two per-step optimizer scalars into a 2-float device buffer, in front of each replay.
+    graph = None
+    graph_note = "off"
+    if getattr(a, "graph", False) and a.optimizer == "fused":
+        opt.enable_device_scalars()
+        static = [t.clone() for t in pool[0]]
+        g_out = {}
+
+        def captured_step():
+            images, poses, intr = static
+            intr_w = intr.clone()
+            opt.zero_grad()
+            Ps = SE3(poses)
+            poses_est = net(images, SE3.IdentityLike(Ps), intrinsics=intr_w)
+            ltr, lrot, _ = geodesic_loss(SE3(Ps.data.clone()), poses_est, sync_metrics=False)
+            loss = a.w_tr * ltr + a.w_rot * lrot
+            loss.backward()
+            gn = opt.step(_captured=True)
+            g_out["loss"], g_out["gn"] = loss.detach(), gn.reshape(())
+
+        # the first n_pre steps of the run are issued eagerly on a side stream (the allocator / DDP warm-up a capture
+        # needs), the graph is recorded after them and replayed for every later step: same batches, same number of
+        # optimizer steps as the eager loop
+        n_pre = max(1, min(a.warmup_steps, 11 if world > 1 else 2))
+        pre_log = []
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for i in range(n_pre):
+                    for dst, src in zip(static, pool[i % len(pool)]):
+                        dst.copy_(src)
+                    opt.upload_step_scalars()
+                    captured_step()
+                    opt.advance()
+                    pre_log.append((g_out["loss"].clone(), g_out["gn"].clone()))
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            opt.upload_step_scalars()
+            with torch.cuda.graph(graph):
+                captured_step()
+            graph_note = "forward + loss + backward" + (" + DDP all-reduce" if world > 1 else "") + \
+                         f" + clip + Adam in one CUDA graph (first {n_pre} steps eager)"
+        except Exception as ex:                               # e.g. a collective that cannot be captured: stay eager
+            graph = None
+            graph_note = f"capture failed, eager: {type(ex).__name__}: {str(ex)[:160]}"
+            torch.cuda.synchronize()
+
+    def graphed_step(step, evs=None):
+        for dst, src in zip(static, pool[step % len(pool)]):
+            dst.copy_(src, non_blocking=True)
+        opt.upload_step_scalars()
+        if evs:
+            evs[0].record()
+        graph.replay()
+        if evs:
+            evs[1].record(); evs[2].record(); evs[3].record()
+        opt.advance()
+        return g_out["loss"], g_out["gn"]
+
     nsteps = a.warmup_steps + a.steps
     loss_log = torch.zeros(nsteps, 2, device=dev)            # read back once at the end: no per-step host sync
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(nsteps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for step in range(nsteps):
-        if step == a.warmup_steps:
+    first = 0
+    if graph is not None:                                     # steps already taken while warming up for the capture
+        first = n_pre
+        for i, (l_, g_) in enumerate(pre_log):
+            loss_log[i, 0].copy_(l_); loss_log[i, 1].copy_(g_)
+    for step in range(first, nsteps):
+        if step == max(a.warmup_steps, first):
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             e0.record()
-        loss_log[step, 0], loss_log[step, 1] = one_step(step, ev[step])
+        if graph is not None:
+            l_, g_ = graphed_step(step, ev[step])
+            loss_log[step, 0].copy_(l_); loss_log[step, 1].copy_(g_)
+        else:
+            loss_log[step, 0], loss_log[step, 1] = one_step(step, ev[step])
     e1.record()
     if world > 1:
         dist.barrier()
@@ -125,13 +198,13 @@ def train_loop(a, dev, rank=0, world=1, local=0):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     losses = [(float(x), float(y)) for x, y in loss_log.cpu().tolist()]
-    timed = range(a.warmup_steps, nsteps)
+    timed = range(max(a.warmup_steps, first), nsteps)
     phase = [sum(ev[i][k].elapsed_time(ev[i][k + 1]) for i in timed) / len(timed) for k in range(3)]
 
     # ---- the exchange step by itself (world > 1): backward with and without the gradient all-reduce, and the same
     # payload (one flat float32 buffer of all trainable gradients) all-reduced alone on an idle GPU
     exchange = None
-    if world > 1 and getattr(a, "measure_allreduce", True):
+    if world > 1 and getattr(a, "measure_allreduce", True) and graph is None:
         n_extra = max(3, min(8, a.steps))
         evn = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_extra)]
         for i in range(n_extra):
@@ -166,10 +239,11 @@ def train_loop(a, dev, rank=0, world=1, local=0):
     ls = [l for l, _ in losses]
     return {"metric": "training steps/sec (config 5: train.py loop on synthetic pairs, fp32 operands, tensor-core + SIMT backward)",
             "n_gpus": world, "steps": a.steps, "warmup_steps": a.warmup_steps, "pairs_per_gpu": a.batch, "image_size": [H, W],
-            "ms_per_step": ms / a.steps, "steps_per_s": a.steps / (ms * 1e-3), "pairs_per_s": world * a.batch * a.steps / (ms * 1e-3),
+            "ms_per_step": ms / len(timed), "steps_per_s": len(timed) / (ms * 1e-3),
+            "pairs_per_s": world * a.batch * len(timed) / (ms * 1e-3),
             "loss_first5": [round(x, 4) for x in ls[:5]], "loss_last5": [round(x, 4) for x in ls[-5:]],
             "grad_norm_first": round(losses[0][1], 3), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 2),
-            "ddp": world > 1, "optimizer": a.optimizer,
+            "ddp": world > 1, "optimizer": a.optimizer, "cuda_graph": graph_note,
             "phase_ms": {"forward+loss": round(phase[0], 3), "backward(+allreduce)": round(phase[1], 3),
                          "clip+adam+lr": round(phase[2], 3)},
             "exchange": exchange if exchange is not None else "single rank: no gradient exchange"}
@@ -193,8 +267,10 @@ def main():
                     help="fused: rel_pose_b200.optim.FusedAdamOneCycle (clip + Adam + OneCycle in 3 launches, no host sync); "
                          "torch: the reference's own calls (clip_grad_norm_, Adam.step, OneCycleLR.step)")
     ap.add_argument("--pool", type=int, default=d.pool, help="synthetic batches generated up front on the device and cycled")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the whole step as one CUDA graph (fused optimizer only); 0: eager")
     a = ap.parse_args()
     a.measure_allreduce = True
+    a.graph = bool(a.graph)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
