@@ -58,7 +58,8 @@ def train_loop(a, dev, rank=0, world=1, local=0):
     for p in list(model.resnet.layer4.parameters()) + list(model.resnet.layer3.parameters()):
         p.requires_grad = False
     net = model
-    if world > 1:
+    use_graph = bool(getattr(a, "graph", False)) and a.optimizer == "fused"
+    if world > 1 and not use_graph:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
     if a.optimizer == "fused":
         from .optim import FusedAdamOneCycle
@@ -87,8 +88,10 @@ def train_loop(a, dev, rank=0, world=1, local=0):
         loss = a.w_tr * ltr + a.w_rot * lrot
         if evs:
             evs[1].record()
-        if sync_grads or world == 1:
+        if sync_grads or world == 1 or net is model:
             loss.backward()
+            if world > 1 and net is model and sync_grads:     # graph path that fell back to eager: same flat all-reduce
+                dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
         else:
             with net.no_sync():                               # same backward without the gradient exchange
                 loss.backward()
@@ -104,18 +107,30 @@ def train_loop(a, dev, rank=0, world=1, local=0):
             evs[3].record()
         return loss.detach(), gn.reshape(())
 
-    # ---- the whole step as ONE CUDA graph (forward + loss + backward [+ DDP all-reduce] + clip + Adam): a step is ~700
-    # kernel launches of 5-30 us each, so issued one by one from Python it is bound by the host (17 ms per step for 11 ms
-    # of kernels).  Captured once after the eager warm-up steps and replayed; the batch is copied into static buffers,
-    # the two per-step optimizer scalars into a 2-float device buffer, in front of each replay.
+    # ---- the step as CUDA graphs: a step is ~700 kernel launches of 5-30 us each, so issued one by one from Python it is
+    # bound by the host (17 ms per step for 11 ms of kernels).  Two graphs are recorded once after a few eager steps and
+    # replayed: G1 = zero_grad + forward + loss + backward, G2 = gradient norm + clipped Adam.  Between them, on more than
+    # one rank, ONE NCCL all-reduce (average) of the flat gradient buffer -- every parameter's .grad is a view of it.
+    # It is the whole exchange step of train.py:66-67 in one call: 77 MB take 0.18 ms over NVLink, 1-2 % of the step, so
+    # there is nothing to gain from bucketing it into the backward the way DistributedDataParallel does (whose reducer
+    # cannot be captured: the attempt invalidated the capture, profiles/r02_train_2gpu_ddp_capture_attempt.json).
+    # The batch is copied into static buffers and the two per-step optimizer scalars into a 2-float device buffer in
+    # front of each replay.
     graph = None
     graph_note = "off"
-    if getattr(a, "graph", False) and a.optimizer == "fused":
+    if use_graph:
         opt.enable_device_scalars()
+        trainable = [p for p in model.parameters() if p.requires_grad]
+        offs, o = [], 0
+        for p in trainable:
+            offs.append(o); o += (p.numel() + 3) // 4 * 4
+        flat_grad = torch.zeros(o, dtype=torch.float32, device=dev)
+        for p, off in zip(trainable, offs):
+            p.grad = flat_grad[off:off + p.numel()].view_as(p)
         static = [t.clone() for t in pool[0]]
         g_out = {}
 
-        def captured_step():
+        def fwd_bwd():
             images, poses, intr = static
             intr_w = intr.clone()
             opt.zero_grad()
@@ -124,13 +139,19 @@ def train_loop(a, dev, rank=0, world=1, local=0):
             ltr, lrot, _ = geodesic_loss(SE3(Ps.data.clone()), poses_est, sync_metrics=False)
             loss = a.w_tr * ltr + a.w_rot * lrot
             loss.backward()
-            gn = opt.step(_captured=True)
-            g_out["loss"], g_out["gn"] = loss.detach(), gn.reshape(())
+            g_out["loss"] = loss.detach()
 
-        # the first n_pre steps of the run are issued eagerly on a side stream (the allocator / DDP warm-up a capture
-        # needs), the graph is recorded after them and replayed for every later step: same batches, same number of
+        def exchange_grads():
+            if world > 1:
+                dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+
+        def opt_part():
+            g_out["gn"] = opt.step(_captured=True).reshape(())
+
+        # the first n_pre steps of the run are issued eagerly on a side stream (the allocator warm-up a capture needs),
+        # the graphs are recorded after them and replayed for every later step: same batches, same number of
         # optimizer steps as the eager loop
-        n_pre = max(1, min(a.warmup_steps, 11 if world > 1 else 2))
+        n_pre = max(1, min(a.warmup_steps, 2))
         pre_log = []
         try:
             side = torch.cuda.Stream(device=dev)
@@ -140,18 +161,23 @@ def train_loop(a, dev, rank=0, world=1, local=0):
                     for dst, src in zip(static, pool[i % len(pool)]):
                         dst.copy_(src)
                     opt.upload_step_scalars()
-                    captured_step()
+                    fwd_bwd(); exchange_grads(); opt_part()
                     opt.advance()
                     pre_log.append((g_out["loss"].clone(), g_out["gn"].clone()))
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            graph2 = torch.cuda.CUDAGraph()
             opt.upload_step_scalars()
             with torch.cuda.graph(graph):
-                captured_step()
-            graph_note = "forward + loss + backward" + (" + DDP all-reduce" if world > 1 else "") + \
-                         f" + clip + Adam in one CUDA graph (first {n_pre} steps eager)"
-        except Exception as ex:                               # e.g. a collective that cannot be captured: stay eager
+                fwd_bwd()
+            with torch.cuda.graph(graph2, pool=graph.pool()):
+                opt_part()
+            assert all(p.grad.data_ptr() == flat_grad.data_ptr() + 4 * off for p, off in zip(trainable, offs)), \
+                "a gradient left the flat buffer"
+            graph_note = ("G1 = forward + loss + backward, " + ("one NCCL all-reduce (AVG) of the flat gradient buffer, "
+                          if world > 1 else "") + f"G2 = clip + Adam: CUDA graphs (first {n_pre} steps eager)")
+        except Exception as ex:
             graph = None
             graph_note = f"capture failed, eager: {type(ex).__name__}: {str(ex)[:160]}"
             torch.cuda.synchronize()
@@ -164,7 +190,13 @@ def train_loop(a, dev, rank=0, world=1, local=0):
             evs[0].record()
         graph.replay()
         if evs:
-            evs[1].record(); evs[2].record(); evs[3].record()
+            evs[1].record()
+        exchange_grads()
+        if evs:
+            evs[2].record()
+        graph2.replay()
+        if evs:
+            evs[3].record()
         opt.advance()
         return g_out["loss"], g_out["gn"]
 
@@ -204,7 +236,7 @@ def train_loop(a, dev, rank=0, world=1, local=0):
     # ---- the exchange step by itself (world > 1): backward with and without the gradient all-reduce, and the same
     # payload (one flat float32 buffer of all trainable gradients) all-reduced alone on an idle GPU
     exchange = None
-    if world > 1 and getattr(a, "measure_allreduce", True) and graph is None:
+    if world > 1 and getattr(a, "measure_allreduce", True) and graph is None and net is not model:
         n_extra = max(3, min(8, a.steps))
         evn = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_extra)]
         for i in range(n_extra):
@@ -243,10 +275,15 @@ def train_loop(a, dev, rank=0, world=1, local=0):
             "pairs_per_s": world * a.batch * len(timed) / (ms * 1e-3),
             "loss_first5": [round(x, 4) for x in ls[:5]], "loss_last5": [round(x, 4) for x in ls[-5:]],
             "grad_norm_first": round(losses[0][1], 3), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2**30, 2),
-            "ddp": world > 1, "optimizer": a.optimizer, "cuda_graph": graph_note,
-            "phase_ms": {"forward+loss": round(phase[0], 3), "backward(+allreduce)": round(phase[1], 3),
-                         "clip+adam+lr": round(phase[2], 3)},
-            "exchange": exchange if exchange is not None else "single rank: no gradient exchange"}
+            "ddp": world > 1 and graph is None, "optimizer": a.optimizer, "cuda_graph": graph_note,
+            "phase_ms": ({"forward+loss+backward (G1)": round(phase[0], 3), "gradient all-reduce": round(phase[1], 3),
+                          "clip+adam+lr (G2)": round(phase[2], 3)} if graph is not None else
+                         {"forward+loss": round(phase[0], 3), "backward(+allreduce)": round(phase[1], 3),
+                          "clip+adam+lr": round(phase[2], 3)}),
+            "exchange": exchange if exchange is not None else (
+                "single rank: no gradient exchange" if world == 1 else
+                {"payload_bytes": int(flat_grad.numel()) * 4, "how": "one NCCL all-reduce (average) of the flat gradient buffer "
+                 "between the two graphs; its time is phase_ms['gradient all-reduce'] (CUDA events, max over ranks not taken)"})}
 
 
 def main():
