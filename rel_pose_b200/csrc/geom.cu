@@ -464,83 +464,82 @@ __device__ __forceinline__ bool jacobi_rot(V3& ap, V3& aq, float& alpha, float& 
     beta = fmaxf(fmaf(t, gamma, beta), 0.0f);
     return true;
 }
-__device__ __forceinline__ void jacobi_pair(V3& ap, V3& aq, V3& vp, V3& vq, float& alpha, float& beta, unsigned& flags) {
-    float c, sn;
-    if (jacobi_rot(ap, aq, alpha, beta, c, sn, flags)) {
-        const V3 wp = c * vp - sn * vq, wq = sn * vp + c * vq;
-        vp = wp; vq = wq;
-    }
-}
-__device__ __forceinline__ void swap_cols(V3& a, V3& b, V3& va, V3& vb, float& na, float& nb) {
-    V3 t = a; a = b; b = t;
-    t = va; va = vb; vb = t;
-    float f = na; na = nb; nb = f;
-}
-
+// A V = U Sigma: the sweeps orthogonalise the COLUMNS of A only (6 of the 12 rotated vectors' multiply-adds per
+// rotation; V is not accumulated).  Afterwards U comes from the normalised columns and V from V = A^T U Sigma^-1:
+// v0 = normalise(A^T u0), v1 = normalise(A^T u1 - (.,v0) v0), v2 = +-(v0 x v1) with the sign that makes sigma_2 =
+// u2 . A v2 non-negative.  V is orthonormal by construction; the direction of v1 carries an error ~eps sigma_0 / sigma_1
+// (instead of Jacobi's high relative accuracy), which reaches U Sigma V^T only multiplied by sigma_1, i.e. at eps
+// sigma_0 like every other rounding error of the factorisation -- and essential matrices have sigma_0 = sigma_1.
+// Saves ~90 of ~920 instructions per matrix in kernels that are instruction-issue bound.
 __device__ __forceinline__ Svd3 svd3(const float* e /* row-major 3x3 */) {
     V3 a0 = v3(e[0], e[3], e[6]), a1 = v3(e[1], e[4], e[7]), a2 = v3(e[2], e[5], e[8]);   // columns
     float n0 = dot(a0, a0), n1 = dot(a1, a1), n2 = dot(a2, a2);
-    // First sweep with V = I written out: the three rotations of the identity need 14 multiplications instead of 36
-    // (a skipped rotation is c = 1, s = 0).
-    V3 v0, v1, v2;
-    unsigned flags = 0;
-    {
-        float c1 = 1.0f, s1 = 0.0f, c2 = 1.0f, s2 = 0.0f, c3 = 1.0f, s3 = 0.0f;
-        jacobi_rot(a0, a1, n0, n1, c1, s1, flags);        // v0 = (c1, -s1, 0), v1 = (s1, c1, 0), v2 = e2
-        jacobi_rot(a0, a2, n0, n2, c2, s2, flags);        // v0 <- c2 v0 - s2 e2,  v2 = s2 v0 + c2 e2
-        v0 = v3(c2 * c1, -(c2 * s1), -s2);
-        v2 = v3(s2 * c1, -(s2 * s1), c2);
-        jacobi_rot(a1, a2, n1, n2, c3, s3, flags);        // v1 <- c3 v1 - s3 v2,  v2 <- s3 v1 + c3 v2
-        v1 = v3(fmaf(c3, s1, -(s3 * v2.x)), fmaf(c3, c1, -(s3 * v2.y)), -(s3 * v2.z));
-        v2 = v3(fmaf(s3, s1, c3 * v2.x), fmaf(s3, c1, c3 * v2.y), c3 * v2.z);
-    }
     // Cyclic one-sided Jacobi converges quadratically: 3-4 sweeps reach fp32 precision for almost every matrix.
     // The loop ends as soon as no lane of the warp saw a large rotation during a sweep (warp-uniform exit, no
-    // divergence); 8 sweeps in all is a safety bound.
+    // divergence); 8 sweeps is a safety bound.
+    unsigned flags = 1u;
 #pragma unroll 1
-    for (int sweep = 1; sweep < 8; ++sweep) {
+    for (int sweep = 0; sweep < 8; ++sweep) {
         if (!__any_sync(0xffffffffu, flags != 0)) break;
         if (flags & 2u) { n0 = dot(a0, a0); n1 = dot(a1, a1); n2 = dot(a2, a2); }   // a carried norm drifted: refresh
         flags = 0;
-        jacobi_pair(a0, a1, v0, v1, n0, n1, flags);
-        jacobi_pair(a0, a2, v0, v2, n0, n2, flags);
-        jacobi_pair(a1, a2, v1, v2, n1, n2, flags);
+        float c, sn;
+        jacobi_rot(a0, a1, n0, n1, c, sn, flags);
+        jacobi_rot(a0, a2, n0, n2, c, sn, flags);
+        jacobi_rot(a1, a2, n1, n2, c, sn, flags);
     }
     n0 = dot(a0, a0); n1 = dot(a1, a1); n2 = dot(a2, a2);
-    // V is a product of rotations (det +1); every column swap of the sort flips its sign
-    float det_v = 1.0f;
-    if (n0 < n1) { swap_cols(a0, a1, v0, v1, n0, n1); det_v = -det_v; }
-    if (n0 < n2) { swap_cols(a0, a2, v0, v2, n0, n2); det_v = -det_v; }
-    if (n1 < n2) { swap_cols(a1, a2, v1, v2, n1, n2); det_v = -det_v; }
+    // the two dominant columns, in order (the third is only needed through sigma_2 below)
+    if (n0 < n1) { V3 t = a0; a0 = a1; a1 = t; float f = n0; n0 = n1; n1 = f; }
+    if (n0 < n2) { V3 t = a0; a0 = a2; a2 = t; float f = n0; n0 = n2; n2 = f; }
+    if (n1 < n2) { a1 = a2; n1 = n2; }
     Svd3 r;
     // bare MUFU.RSQ (the range-checked rsqrtf costs ~8 instructions a call): zero norms are excluded explicitly, and a
     // flushed denormal norm is a zero column to fp32 anyway
     const float i0 = n0 > 0.f ? mufu_rsq(n0) : 0.f, i1 = n1 > 0.f ? mufu_rsq(n1) : 0.f;
-    r.s[0] = n0 * i0; r.s[1] = n1 * i1; r.s[2] = 0.f;    // |a| = n / sqrt(n); s[2] is set from the completed basis below
-    r.v[0] = v0; r.v[1] = v1; r.v[2] = v2;
+    r.s[0] = n0 * i0; r.s[1] = n1 * i1;                  // |a| = n / sqrt(n)
+    const bool rank2 = r.s[1] > 1e-12f * r.s[0] && r.s[1] > 0.f;
     // U: normalise the two dominant columns, complete by a cross product (rank-deficient safe)
-    V3 u0 = r.s[0] > 0.f ? i0 * a0 : v3(1, 0, 0);
+    const V3 u0 = r.s[0] > 0.f ? i0 * a0 : v3(1, 0, 0);
     V3 u1;
-    if (r.s[1] > 1e-12f * r.s[0] && r.s[1] > 0.f) {
+    if (rank2) {
         u1 = i1 * a1;
         u1 = u1 - dot(u1, u0) * u0;                      // one Gram-Schmidt polish
         u1 = mufu_rsq(dot(u1, u1)) * u1;                 // |u1| ~ 1 here
     } else {                                             // rank <= 1: any unit vector orthogonal to u0
-        V3 ax = fabsf(u0.x) < 0.6f ? v3(1, 0, 0) : v3(0, 1, 0);
+        const V3 ax = fabsf(u0.x) < 0.6f ? v3(1, 0, 0) : v3(0, 1, 0);
         u1 = cross(u0, ax);
         u1 = mufu_rsq(dot(u1, u1)) * u1;                 // |u0 x ax|^2 >= 0.64
     }
-    V3 u2 = cross(u0, u1);                               // det [u0 u1 u2] = +1 ...
-    float sg = dot(u2, a2);
-    r.det_u = 1.0f;
-    if (sg < 0.f) { u2 = neg(u2); sg = -sg; r.det_u = -1.0f; }   // ... unless the third column is flipped
-    r.s[2] = sg;                                         // = |a2| when a2 is non-degenerate
+    const V3 u2 = cross(u0, u1);                         // det [u0 u1 u2] = +1
+    // V = A^T U Sigma^-1, orthonormalised.  The original columns are read again here (shared memory) instead of being
+    // kept in nine registers through the sweeps: 32 registers per thread = 16 resident blocks per SM instead of 12.
+    const V3 A0 = v3(e[0], e[3], e[6]), A1 = v3(e[1], e[4], e[7]), A2 = v3(e[2], e[5], e[8]);
+    V3 v0 = v3(dot(A0, u0), dot(A1, u0), dot(A2, u0));   // = sigma_0 v0
+    const float q0 = dot(v0, v0);
+    v0 = q0 > 0.f ? mufu_rsq(q0) * v0 : v3(1, 0, 0);
+    V3 v1 = v3(dot(A0, u1), dot(A1, u1), dot(A2, u1));   // = sigma_1 v1 (+ rounding noise ~eps sigma_0)
+    v1 = v1 - dot(v1, v0) * v0;
+    const float q1 = dot(v1, v1);
+    if (rank2 && q1 > 0.f) {
+        v1 = mufu_rsq(q1) * v1;
+    } else {                                             // sigma_1 = 0 to fp32: any unit vector orthogonal to v0
+        const V3 ax = fabsf(v0.x) < 0.6f ? v3(1, 0, 0) : v3(0, 1, 0);
+        v1 = cross(v0, ax);
+        v1 = mufu_rsq(dot(v1, v1)) * v1;
+    }
+    V3 v2 = cross(v0, v1);                               // det [v0 v1 v2] = +1 ...
+    const V3 av2 = v2.x * A0 + v2.y * A1 + v2.z * A2;    // A v2 = sigma_2 u2
+    float sg = dot(u2, av2);
+    r.det_u = 1.0f; r.det_v = 1.0f;
+    if (sg < 0.f) { v2 = neg(v2); sg = -sg; r.det_v = -1.0f; }   // ... unless the third column is flipped
+    r.s[2] = sg;
     r.u[0] = u0; r.u[1] = u1; r.u[2] = u2;
-    r.det_v = det_v;
+    r.v[0] = v0; r.v[1] = v1; r.v[2] = v2;
     return r;
 }
 
-__global__ void __launch_bounds__(TPB) svd3_kernel(const float* E, float* U, float* S, float* V, int64_t n) {
+__global__ void __launch_bounds__(TPB, 16) svd3_kernel(const float* E, float* U, float* S, float* V, int64_t n) {
     __shared__ __align__(16) float se[TPB * 9], sv[TPB * 9], ss[TPB * 3];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<9, true>(E, se, base, n);
@@ -563,23 +562,23 @@ __global__ void __launch_bounds__(TPB) svd3_kernel(const float* E, float* U, flo
 
 __device__ __forceinline__ float det3(V3 a, V3 b, V3 c) { return dot(a, cross(b, c)); }
 
-__global__ void __launch_bounds__(TPB) essential_to_rt_kernel(const float* E, float* R1, float* R2, float* T, int64_t n) {
+__global__ void __launch_bounds__(TPB, 16) essential_to_rt_kernel(const float* E, float* R1, float* R2, float* T, int64_t n) {
     __shared__ __align__(16) float se[TPB * 9], s2[TPB * 9], st[TPB * 3];
     int64_t base = (int64_t)blockIdx.x * TPB;
     stage_in<9, true>(E, se, base, n);
     __syncthreads();
     Svd3 r = svd3(se + threadIdx.x * 9);
     __syncthreads();
-    // proper rotations: U <- det(U) U, V <- det(V) V.  Both signs are known from the construction of the basis
-    // (Svd3::det_u / det_v), and in R = (U W) V^T they only appear as the product su sv.
-    const float su = r.det_u, ssv = r.det_u * r.det_v;
-    V3 u0 = r.u[0], u1 = r.u[1], u2 = su * r.u[2];
-    V3 v0 = ssv * r.v[0], v1 = ssv * r.v[1], v2 = ssv * r.v[2];
+    // The decomposition needs PROPER rotations U, V with E = U diag(s, s, ~0) V^T.  svd3 builds u2 = u0 x u1, so U is
+    // proper; taking v2 = v0 x v1 makes V proper as well -- the sign svd3 may have put on its v2 belongs to sigma_2,
+    // which the decomposition discards.  (Reading only v0, v1 here lets the compiler drop svd3's sigma_2 / sign code.)
+    const V3 u0 = r.u[0], u1 = r.u[1], u2 = r.u[2];
+    const V3 v0 = r.v[0], v1 = r.v[1], v2 = cross(r.v[0], r.v[1]);
     // U W = [u1, -u0, u2] ; U W^T = [-u1, u0, u2] ;  R = (U W) V^T = sum_k (UW)_k v_k^T
     V3 w0 = u1, w1 = neg(u0);
     float* p1 = se + threadIdx.x * 9;
     float* p2 = s2 + threadIdx.x * 9;
-    const float uw[3][3] = {{w0.x, w1.x, r.u[2].x}, {w0.y, w1.y, r.u[2].y}, {w0.z, w1.z, r.u[2].z}};
+    const float uw[3][3] = {{w0.x, w1.x, u2.x}, {w0.y, w1.y, u2.y}, {w0.z, w1.z, u2.z}};
     const float vv[3][3] = {{v0.x, v1.x, v2.x}, {v0.y, v1.y, v2.y}, {v0.z, v1.z, v2.z}};
 #pragma unroll
     for (int i = 0; i < 3; ++i)

@@ -20,6 +20,7 @@
 //               tile's epilogue, so the tensor pipe does not drain at row-tile boundaries.
 #include <stdlib.h>
 
+#include "ln_rows.cuh"
 #include "rows_ln_epilogue.cuh"
 #include "tc_common.cuh"
 
@@ -218,57 +219,13 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const bool vec4 = (N % 4) == 0;
         uint32_t c = 0;
 
-        // LayerNorm in two phases so that the global-memory latency of the next row tile's rows hides behind the wait
-        // for the current tile's last accumulator: ln_load requests the 8 rows this warp owns (48 registers per lane),
-        // ln_finish (same arithmetic as mlp_tc.cu / layernorm_planes_kernel) normalises and writes the A-operand planes.
-        float v[8][6];
-        auto ln_load = [&](int tile) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int grow = tile * BM + ew * 8 + j;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    float2 a = make_float2(0.f, 0.f);
-                    if (grow < M) a = __ldg(reinterpret_cast<const float2*>(prm.x + (size_t)grow * D + 64 * i + 2 * lane));
-                    v[j][2 * i] = a.x; v[j][2 * i + 1] = a.y;
-                }
-            }
-        };
+        // LayerNorm of the 8 rows this warp owns, straight into the swizzled A-operand planes (ln_rows.cuh): two phases,
+        // so that the rows' global-memory latency can hide behind a wait
+        float vln[4][12];
+        auto ln_load = [&](int tile) { lnrows::load8(prm.x, M, tile * BM, ew, lane, vln); };
         auto ln_finish = [&]() {
-            float g[6], bt[6];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float2 gg = __ldg(reinterpret_cast<const float2*>(prm.gamma + 64 * i + 2 * lane));
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(prm.beta + 64 * i + 2 * lane));
-                g[2 * i] = gg.x; g[2 * i + 1] = gg.y; bt[2 * i] = bb.x; bt[2 * i + 1] = bb.y;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int rl = ew * 8 + j;
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) s += v[j][i];
-                const float mean = rp::warp_sum(s) * (1.0f / D);
-                float qv = 0.f;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) { const float dlt = v[j][i] - mean; qv += dlt * dlt; }
-                const float rstd = 1.0f / sqrtf(rp::warp_sum(qv) * (1.0f / D) + prm.eps);
-                const uint32_t off = (uint32_t)(rl >> 3) * 1024 + (uint32_t)(rl & 7) * 128 +
-                                     ((((uint32_t)lane >> 2) ^ (uint32_t)(rl & 7)) << 4) + (uint32_t)(lane & 3) * 4;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    float y0 = (v[j][2 * i] - mean) * rstd * g[2 * i] + bt[2 * i];
-                    float y1 = (v[j][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bt[2 * i + 1];
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const uint32_t w = pack_bf16x2(y0, y1);
-                        *reinterpret_cast<uint32_t*>(xn_tile(p, i) + off) = w;
-                        y0 -= __uint_as_float(w << 16);
-                        y1 -= __uint_as_float(w & 0xffff0000u);
-                    }
-                }
-            }
-            tc::fence_proxy_async_smem();
+            lnrows::finish8<P>(vln, prm.gamma, prm.beta, prm.eps, smem + C::OFF_XN, ew, lane);
+            tc::fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(xn_full);
         };
@@ -309,7 +266,12 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                     const int r = q * 32 + lane;
                     const uint32_t row_off = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
                     const uint32_t sw = (uint32_t)(r & 7);
-                    const bool leader = (ew == 0 && lane == 0);
+                    // one store pipeline per TMEM lane quarter: its four warps (the 64-column round split four ways) own
+                    // rows 32 q .. 32 q + 31 = a [32 x 128 B] slice of each plane's staging tile, synchronise among
+                    // themselves (128-thread named barriers; they sit on one scheduler) and issue their own bulk stores,
+                    // so a quarter waiting for its previous store's read does not hold the other three
+                    const bool leader = (part == 0 && lane == 0);
+                    const int qbar = 1 + q;
 #pragma unroll 1
                     for (int rd = 0; rd < BN / 64; ++rd) {             // 64-column rounds of the 192-column tile
                         const int c0 = n0 + rd * 64;
@@ -330,7 +292,7 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[i]) + bia[i];
                         // the previous round's TMA store has finished reading the staging tile
                         if (leader) tc::tma_store_wait_read();
-                        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
 #pragma unroll
                         for (int p = 0; p < P; ++p) {
 #pragma unroll
@@ -351,10 +313,11 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                             }
                         }
                         tc::fence_proxy_async_smem();                // generic-proxy writes -> visible to the TMA
-                        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
                         if (leader) {
 #pragma unroll
-                            for (int p = 0; p < P; ++p) tc::tma_store_3d(&tmOut, stg8 + p * TILE16K, c0, row_base, p);
+                            for (int p = 0; p < P; ++p)
+                                tc::tma_store_3d(&tmOut, stg8 + p * TILE16K + q * 4096, c0, row_base + 32 * q, p);
                             tc::tma_store_commit();
                         }
                     }
@@ -420,7 +383,7 @@ ln_linear_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         }
     }
 
-    if (TMAOUT && warp == 2 && lane == 0) tc::tma_store_wait_all();   // the leader's bulk stores are complete
+    if (TMAOUT && warp >= 2 && warp < 6 && lane == 0) tc::tma_store_wait_all();   // the quarter leaders' bulk stores are complete
     tc::tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -462,7 +425,7 @@ int dispatch_ln_linear(const void* xn_planes, const void* W_planes, LnLinParams&
     if (prm.residual) return launch_ln_linear<P, 3, AIN>(tmW, tmOut, tmXN, prm, device, st);
     // planes-only output with as many planes as the operands and 16-byte row pitch: TMA-store epilogue
     if (!prm.out_f32 && prm.out_planes && prm.p_out == P && (N % 8) == 0) {
-        rc = tc::make_planes_tmap(&tmOut, prm.out_planes, P, M, N, BM);  // [P][M][N], box 128 rows x 64 columns
+        rc = tc::make_planes_tmap(&tmOut, prm.out_planes, P, M, N, 32);  // [P][M][N], box 32 rows x 64 columns (one lane quarter)
         if (rc) return rc;
         return launch_ln_linear<P, 1, AIN>(tmW, tmOut, tmXN, prm, device, st);
     }

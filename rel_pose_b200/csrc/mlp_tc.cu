@@ -29,6 +29,7 @@
 // 161 (first fused version, one issuer, fc1 one chunk ahead) -> 150 (fc1 two ahead) -> 131 (three issuers,
 // N = 192 fc2) -> 116 (GELU chunk through TMEM, double buffered) -> 114 us.  Remaining bound: the N = 64 fc1
 // MMAs read 6 KB of shared memory per 32-cycle instruction (128 B/clk limit -> 48 cycles), tile-boundary drain.
+#include "ln_rows.cuh"
 #include "rows_ln_epilogue.cuh"
 #include "tc_common.cuh"
 
@@ -328,55 +329,12 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 
         // LayerNorm (eps 1e-6, vision_transformer.py:396) of the 8 rows this warp owns, written as the bf16 planes
         // of the fc1 A operand: three K-major SWIZZLE_128B tiles [128 rows x 64 columns] per plane.
-        // Two phases: ln_load requests the 8 rows this warp owns (48 registers per lane) so that their latency hides
-        // behind the wait for the last fc1 products of the current tile; ln_finish normalises and writes the planes.
-        float vln[8][6];
-        auto ln_load = [&](int tile) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int grow = tile * BM + ew * 8 + j;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    float2 a = make_float2(0.f, 0.f);
-                    if (grow < M) a = __ldg(reinterpret_cast<const float2*>(prm.x + (size_t)grow * D + 64 * i + 2 * lane));
-                    vln[j][2 * i] = a.x; vln[j][2 * i + 1] = a.y;
-                }
-            }
-        };
+        // LayerNorm of the 8 rows this warp owns, straight into the swizzled A-operand planes (ln_rows.cuh): two phases,
+        // so that the rows' global-memory latency can hide behind a wait
+        float vln[4][12];
+        auto ln_load = [&](int tile) { lnrows::load8(prm.x, M, tile * BM, ew, lane, vln); };
         auto ln_finish = [&]() {
-            float g[6], bt[6];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float2 gg = __ldg(reinterpret_cast<const float2*>(prm.gamma + 64 * i + 2 * lane));
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(prm.beta + 64 * i + 2 * lane));
-                g[2 * i] = gg.x; g[2 * i + 1] = gg.y; bt[2 * i] = bb.x; bt[2 * i + 1] = bb.y;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int rl = ew * 8 + j;
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) s += vln[j][i];
-                const float mean = rp::warp_sum(s) * (1.0f / D);
-                float qv = 0.f;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) { const float dlt = vln[j][i] - mean; qv += dlt * dlt; }
-                const float rstd = 1.0f / sqrtf(rp::warp_sum(qv) * (1.0f / D) + prm.eps);
-                const uint32_t off = (uint32_t)(rl >> 3) * 1024 + (uint32_t)(rl & 7) * 128 +
-                                     ((((uint32_t)lane >> 2) ^ (uint32_t)(rl & 7)) << 4) + (uint32_t)(lane & 3) * 4;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    float y0 = (vln[j][2 * i] - mean) * rstd * g[2 * i] + bt[2 * i];
-                    float y1 = (vln[j][2 * i + 1] - mean) * rstd * g[2 * i + 1] + bt[2 * i + 1];
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const uint32_t w = pack_bf16x2(y0, y1);
-                        *reinterpret_cast<uint32_t*>(xn_tile(p, i) + off) = w;
-                        y0 -= __uint_as_float(w << 16);
-                        y1 -= __uint_as_float(w & 0xffff0000u);
-                    }
-                }
-            }
+            lnrows::finish8<P>(vln, prm.gamma, prm.beta, prm.eps, smem + C::OFF_XN, ew, lane);
             tc::fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(xn_full);
