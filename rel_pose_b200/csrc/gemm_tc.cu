@@ -129,7 +129,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&tfull[i], 1);
-            tc::mbar_init(&tempty[i], EPI_WARPS * 32);
+            tc::mbar_init(&tempty[i], EPI_WARPS);     // one elected arrive per epilogue warp (512 arrives on one mbarrier
+                                                      // serialise in the shared-memory atomic unit)
         }
         tc::fence_barrier_init();
     }
@@ -267,7 +268,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             facc[ci * 16 + i] = seg == 0 ? __uint_as_float(r[i]) : facc[ci * 16 + i] + __uint_as_float(r[i]);
                     }
                     tc::tcgen05_fence_before();
-                    tc::mbar_arrive(&tempty[acc]);
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&tempty[acc]);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
@@ -385,7 +387,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             tc::tcgen05_fence_before();
-            tc::mbar_arrive(&tempty[acc]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
