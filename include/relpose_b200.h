@@ -343,6 +343,18 @@ int rp_im2col_nhwc_f32(const float* x, float* cols, int n, int H, int W, int C, 
 int rp_col2im_nhwc_f32(const float* dcols, float* dx, int n, int H, int W, int C, int KH, int KW, int stride, int pad,                  int device, void* stream);
 int rp_maxpool3x3s2_bwd_f32(const float* dy, const float* x, float* dx, int n, int H, int W, int C, int device, void* stream);
 int rp_normalize_pose_bwd_f32(const float* dout, const float* raw, float* draw, int B, int device, void* stream);
+/* Flash-style attention for the training step (autograd of vision_transformer.py:321-329 without the 576x576 tensors):
+ * rp_self_attention_tc_lse = rp_self_attention_tc that also writes lse [n_img][3][576], the log2-sum-exp of every
+ *   scaled score row (P_ij = 2^(s_ij 0.125 log2 e - lse_i)).
+ * rp_attention_bwd_prep: d_out, out float32 [n_img,576,192] -> bf16 planes of d_out [2][n_img][576][192] and
+ *   delta [n_img][3][576] = <d_out, out> per row and head.
+ * rp_attention_bwd_tc: qkv planes [2][n_img][576][576], d_out planes, lse, delta -> d_qkv float32 [n_img,576,576]
+ *   (every element written once).  tcgen05: S, dP recomputed per tile; dv = P^T dO, dk = dS^T q, dq = dS k. */
+int rp_self_attention_tc_lse(const void* qkv_planes, float* out_f32, float* lse, int n_img, int P, int device, void* stream);
+int rp_attention_bwd_prep(const float* d_out, const float* out, void* d_out_planes, float* delta, int n_img, int device,
+                          void* stream);
+int rp_attention_bwd_tc(const void* qkv_planes, const void* d_out_planes, const float* lse, const float* delta,
+                        float* d_qkv, int n_img, int device, void* stream);
 int rp_concat_vpos_f32(const float* qkv, const float* pos, float* vp, int n_img, int device, void* stream);
 int rp_scatter_dv_f32(const float* dvp, float* dqkv, int n_img, int device, void* stream);
 

@@ -110,6 +110,9 @@ _SIGNATURES = {
     "rp_normalize_pose_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_concat_vpos_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_scatter_dv_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_self_attention_tc_lse": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _ptr]),
+    "rp_attention_bwd_prep": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
+    "rp_attention_bwd_tc": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_grad_norm_multi": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr, _c_int, _ptr]),
     "rp_adam_clip_step_multi": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr] + [ctypes.c_double] * 6 + [_c_int, _c_int, _ptr]),
     "rp_adam_clip_step_multi_dev": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, ctypes.c_double, _ptr] + [ctypes.c_double] * 4 +

@@ -69,7 +69,7 @@ template <int P, int CPS>
 __global__ void __launch_bounds__(ATT_THREADS, CPS)
 self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_planes, int p_out, int n_img,
-                         float scale_log2, int kv_xor) {
+                         float scale_log2, int kv_xor, float* __restrict__ lse_out) {
     using C = ACfg<P, CPS>;
     constexpr int V_STAGES = C::V_STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -370,6 +370,10 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const float inv = 1.0f / lsum;
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * NSPLIT) : "memory");      // slot parity g&1 is reused by the next tile's block 0
             const int row = qt * BM + r;
+            // training: log2-sum-exp of the scaled row, L = m c + log2(sum), so that P = 2^(s c - L) can be recomputed
+            // by the backward kernel (attention_bwd_tc.cu) instead of being stored
+            if (lse_out && hsel == 0 && row < NTOK)
+                lse_out[((size_t)img * HEADS + h) * NTOK + row] = fmaf(m, scale_log2, log2f(lsum));
             if (row < NTOK) {
                 // out[n, row, h*64 + d]  ((attn @ v).transpose(1,2).reshape(B,N,C), vision_transformer.py:329)
                 const size_t o_idx = ((size_t)img * NTOK + row) * EMB + h * HD + hsel * HO;
@@ -444,7 +448,7 @@ int attention_cps() {
 
 template <int P, int CPS>
 int launch_attention_cps(const void* qkv_planes, float* out_f32, void* out_planes, int p_out, int n_img, int device,
-                         cudaStream_t st, int kv_xor) {
+                         cudaStream_t st, int kv_xor, float* lse_out) {
     using C = ACfg<P, CPS>;
     CUtensorMap tmQ, tmKV;
     int rc = make_qkv_tmap(&tmQ, qkv_planes, P, n_img, BM);
@@ -465,15 +469,15 @@ int launch_attention_cps(const void* qkv_planes, float* out_f32, void* out_plane
     const int grid = ntiles < slots ? ntiles : slots;
     const float scale_log2 = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
     rp::launch(self_attention_tc_kernel<P, CPS>, dim3(grid), dim3(ATT_THREADS), (size_t)(C::SMEM), st, tmQ, tmKV, out_f32, static_cast<__nv_bfloat16*>(out_planes),
-                                                                       p_out, n_img, scale_log2, kv_xor);
+                                                                       p_out, n_img, scale_log2, kv_xor, lse_out);
     return rp::finish_launch("rp_self_attention_tc");
 }
 
 template <int P>
 int launch_attention(const void* qkv_planes, float* out_f32, void* out_planes, int p_out, int n_img, int device,
-                     cudaStream_t st, int kv_xor = 0) {
-    if (attention_cps() == 1) return launch_attention_cps<P, 1>(qkv_planes, out_f32, out_planes, p_out, n_img, device, st, kv_xor);
-    return launch_attention_cps<P, 2>(qkv_planes, out_f32, out_planes, p_out, n_img, device, st, kv_xor);
+                     cudaStream_t st, int kv_xor = 0, float* lse_out = nullptr) {
+    if (attention_cps() == 1) return launch_attention_cps<P, 1>(qkv_planes, out_f32, out_planes, p_out, n_img, device, st, kv_xor, lse_out);
+    return launch_attention_cps<P, 2>(qkv_planes, out_f32, out_planes, p_out, n_img, device, st, kv_xor, lse_out);
 }
 
 }  // namespace
@@ -488,6 +492,18 @@ extern "C" int rp_self_attention_tc(const void* qkv_planes, float* out_f32, void
     RP_GUARD(device);
     if (P == 1) return launch_attention<1>(qkv_planes, out_f32, out_planes, P_out, n_img, device, (cudaStream_t)stream);
     return launch_attention<2>(qkv_planes, out_f32, out_planes, P_out, n_img, device, (cudaStream_t)stream);
+}
+
+// Training forward (A11): the same kernel, which also writes the log2-sum-exp of every scaled score row,
+// lse [n_img][3][576] -- all the backward kernel (rp_attention_bwd_tc) needs to recompute the probabilities.
+extern "C" int rp_self_attention_tc_lse(const void* qkv_planes, float* out_f32, float* lse, int n_img, int P, int device,
+                                        void* stream) {
+    RP_REQUIRE(qkv_planes && out_f32 && lse && n_img > 0, RP_EINVAL, "rp_self_attention_tc_lse: bad argument");
+    RP_REQUIRE(P == 1 || P == 2, RP_EINVAL, "rp_self_attention_tc_lse: P must be 1 (bf16) or 2 (bf16x3)");
+    RP_REQUIRE(rp::aligned16(qkv_planes) && rp::aligned16(out_f32), RP_EALIGN, "rp_self_attention_tc_lse: 16-byte alignment");
+    RP_GUARD(device);
+    if (P == 1) return launch_attention<1>(qkv_planes, out_f32, nullptr, 0, n_img, device, (cudaStream_t)stream, 0, lse);
+    return launch_attention<2>(qkv_planes, out_f32, nullptr, 0, n_img, device, (cudaStream_t)stream, 0, lse);
 }
 
 // Plain cross attention between the two views of each pair (--noess ablation, vision_transformer.py:239-253):

@@ -611,6 +611,38 @@ def self_attention(qkv, cross=False):
     return out
 
 
+def self_attention_tc_lse(qkv_planes):
+    """Training forward: qkv_planes bf16 [P,n,576,576] -> (float32 out [n,576,192], float32 lse [n,3,576])."""
+    _req(qkv_planes, "qkv_planes", torch.bfloat16)
+    P, n = qkv_planes.shape[0], qkv_planes.shape[1]
+    assert tuple(qkv_planes.shape[2:]) == (NTOK, 3 * EMBED)
+    out = torch.empty((n, NTOK, EMBED), dtype=torch.float32, device=qkv_planes.device)
+    lse = torch.empty((n, HEADS, NTOK), dtype=torch.float32, device=qkv_planes.device)
+    dev, st = _ctx(qkv_planes)
+    _tbegin(f"self_attention_tc{'x3' if P == 2 else ''}", 4.0 * n * HEADS * NTOK * NTOK * HDIM,
+            2.0 * P * n * NTOK * 3 * EMBED + 4.0 * n * NTOK * EMBED)
+    _lib.check(_lib.lib().rp_self_attention_tc_lse(_p(qkv_planes), _p(out), _p(lse), n, P, dev, st), "rp_self_attention_tc_lse")
+    _count()
+    return out, lse
+
+
+def attention_bwd_tc(qkv_planes, d_out, out, lse):
+    """Flash-style backward of the attention core: -> d_qkv float32 [n,576,576] (two launches, no 576x576 tensor)."""
+    _req(qkv_planes, "qkv_planes", torch.bfloat16); _req(d_out, "d_out"); _req(out, "out"); _req(lse, "lse")
+    P, n = qkv_planes.shape[0], qkv_planes.shape[1]
+    assert P == 2 and tuple(d_out.shape) == (n, NTOK, EMBED) == tuple(out.shape) and tuple(lse.shape) == (n, HEADS, NTOK)
+    dop = torch.empty((2, n, NTOK, EMBED), dtype=torch.bfloat16, device=d_out.device)
+    delta = torch.empty((n, HEADS, NTOK), dtype=torch.float32, device=d_out.device)
+    dqkv = torch.empty((n, NTOK, 3 * EMBED), dtype=torch.float32, device=d_out.device)
+    dev, st = _ctx(d_out)
+    L = _lib.lib()
+    _lib.check(L.rp_attention_bwd_prep(_p(d_out), _p(out), _p(dop), _p(delta), n, dev, st), "rp_attention_bwd_prep")
+    _tbegin("attention_bwd_tcx3", 14.0 * n * HEADS * NTOK * NTOK * HDIM, 2.0 * 2 * n * NTOK * 4 * EMBED + 4.0 * n * NTOK * 3 * EMBED)
+    _lib.check(L.rp_attention_bwd_tc(_p(qkv_planes), _p(dop), _p(lse), _p(delta), _p(dqkv), n, dev, st), "rp_attention_bwd_tc")
+    _count(2)
+    return dqkv
+
+
 def self_attention_tc(qkv_planes, want_f32=False, planes_out=0, cross=False):
     """qkv_planes bf16 [P,n,576,576] -> (float32 [n,576,192] | None, bf16 planes [planes_out,n,576,192] | None).
     cross=True: image i attends to the keys/values of image i^1 (--noess)."""

@@ -105,6 +105,7 @@ def _ew(name, out, *args):
 # spatially flipped, channel-transposed filter and padding K-1-p; dW = dY^T im2col(X).  RELPOSE_TRAIN_TC=0 keeps the
 # fp32 SIMT kernels (A/B measurements); tiny problems (the pose regressor at 6 rows) always stay there.
 TRAIN_TC = os.environ.get("RELPOSE_TRAIN_TC", "1") != "0"
+TRAIN_FLASH = TRAIN_TC and os.environ.get("RELPOSE_TRAIN_FLASH", "1") != "0"      # attention gradients without 576 x 576 tensors
 _TCP = 2                                   # bf16x3
 
 
@@ -235,9 +236,9 @@ class LayerNormFn(torch.autograd.Function):
         return dx, dg, db, None
 
 
-class AttentionFn(torch.autograd.Function):
-    """softmax(q k^T / 8) v per image and head on qkv [n,576,576]   (vision_transformer.py:323-329).
-    The probabilities are materialised (training batches are small: 12 images = 48 MB per block)."""
+class AttentionMaterialisedFn(torch.autograd.Function):
+    """softmax(q k^T / 8) v per image and head on qkv [n,576,576]   (vision_transformer.py:323-329), fp32 SIMT with the
+    probabilities materialised (12 images = 48 MB per block): the A/B partner of AttentionFn (RELPOSE_TRAIN_FLASH=0)."""
 
     @staticmethod
     def forward(ctx, qkv):
@@ -279,6 +280,29 @@ class AttentionFn(torch.autograd.Function):
         gemm(True, False, NTOK, HDIM, NTOK, dS, 0, NTOK, qkv, 0, 3 * EMBED, dqkv, EMBED, 3 * EMBED,
              bo=n, bi=HEADS, sA=(HEADS * SS, SS), sB=(IMG, HDIM), sC=(IMG, HDIM))
         return dqkv
+
+
+class AttentionFn(torch.autograd.Function):
+    """softmax(q k^T / 8) v per image and head on qkv [n,576,576]   (vision_transformer.py:323-329), flash style in both
+    directions: the forward is the inference kernel (tcgen05, split-bf16 operands) which also saves the log-sum-exp of
+    every score row; the backward recomputes the probabilities tile by tile (csrc/attention_bwd_tc.cu).  Saved for the
+    backward: the bf16 planes of qkv, the output and 3 x 576 floats per image -- no 576 x 576 tensor exists."""
+
+    @staticmethod
+    def forward(ctx, qkv):
+        planes = ops.split_planes(qkv.contiguous(), _TCP)
+        out, lse = ops.self_attention_tc_lse(planes)
+        ctx.save_for_backward(planes, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, dO):
+        planes, out, lse = ctx.saved_tensors
+        return ops.attention_bwd_tc(planes, dO.contiguous(), out, lse)
+
+
+def attention(qkv):
+    return (AttentionFn if TRAIN_FLASH else AttentionMaterialisedFn).apply(qkv)
 
 
 class EssentialFn(torch.autograd.Function):
@@ -622,7 +646,7 @@ def forward_train(model, images, Gs, intrinsics):
     for i in range(depth - 1):                                        # A5
         blk = vt.blocks[i]
         qkv = LinearFn.apply(_ln(x, blk.norm1), blk.attn.qkv.weight, blk.attn.qkv.bias)
-        a = AttentionFn.apply(qkv)
+        a = attention(qkv)
         x = AddFn.apply(x, LinearFn.apply(a, blk.attn.proj.weight, blk.attn.proj.bias))
         x = AddFn.apply(x, _mlp(_ln(x, blk.norm2), blk.mlp))
     blk = vt.blocks[depth - 1]                                        # A6-A8
