@@ -355,6 +355,14 @@ int rp_attention_bwd_prep(const float* d_out, const float* out, void* d_out_plan
                           void* stream);
 int rp_attention_bwd_tc(const void* qkv_planes, const void* d_out_planes, const float* lse, const float* delta,
                         float* d_qkv, int n_img, int device, void* stream);
+/* Weight gradient of a stride-1 nn.Conv2d as an implicit GEMM on tcgen05 (no im2col matrix, no transposed copies):
+ * x_planes bf16 [2][n][H][W][C], dy_planes bf16 [2][n][OH][OW][O] (OH = H + 2 pad - KH + 1) -> dw float32 [O][KH][KW][C].
+ * Both operands are read as MN-major tiles straight from the NHWC planes; the taps are shifted views of one halo
+ * tile; per-pixel-slice partial sums are reduced in a fixed order (deterministic).  C % 64 == 0, O in {64,128,192}. */
+int rp_conv_dw_tc_supported(int C, int O, int KH, int KW, int stride);
+size_t rp_conv_dw_tc_workspace_bytes(int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int device);
+int rp_conv_dw_tc(const void* x_planes, const void* dy_planes, float* dw, int n_img, int H, int W, int C, int O, int KH,
+                  int KW, int pad, void* workspace, size_t workspace_bytes, int device, void* stream);
 int rp_concat_vpos_f32(const float* qkv, const float* pos, float* vp, int n_img, int device, void* stream);
 int rp_scatter_dv_f32(const float* dvp, float* dqkv, int n_img, int device, void* stream);
 

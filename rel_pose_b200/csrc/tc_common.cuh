@@ -131,6 +131,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "r"((uint32_t)adesc), "r"((uint32_t)bdesc), "r"(idesc), "r"(accumulate), "n"(DESC_HI)
         : "memory");
 }
+// Same with both 64-bit descriptors given in full (operands whose stride byte offset is not 1024 B: the shifted halo
+// views of conv_dw_tc.cu)
+__device__ __forceinline__ void umma_bf16_desc64(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Same with the A operand read from TENSOR MEMORY (K-major only): lane = row, 16-bit elements packed two per
 // 32-bit column (element k in column k/2, even k in the low half) -- the layout tcgen05.st.32x32b of packed
 // bf16x2 registers produces (cute/atom/mma_traits_sm100.hpp, tmem_frg: dense A, M = 128).  A K step of 16

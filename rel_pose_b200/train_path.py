@@ -105,6 +105,7 @@ def _ew(name, out, *args):
 # spatially flipped, channel-transposed filter and padding K-1-p; dW = dY^T im2col(X).  RELPOSE_TRAIN_TC=0 keeps the
 # fp32 SIMT kernels (A/B measurements); tiny problems (the pose regressor at 6 rows) always stay there.
 TRAIN_TC = os.environ.get("RELPOSE_TRAIN_TC", "1") != "0"
+TRAIN_DW_TC = TRAIN_TC and os.environ.get("RELPOSE_TRAIN_DW_TC", "1") != "0"         # implicit-GEMM conv weight gradients
 TRAIN_FLASH = TRAIN_TC and os.environ.get("RELPOSE_TRAIN_FLASH", "1") != "0"      # attention gradients without 576 x 576 tensors
 _TCP = 2                                   # bf16x3
 
@@ -471,44 +472,53 @@ class ConvFn(torch.autograd.Function):
         wp = ops.permute_conv_weight(weight.detach(), C)
         O, KH, KW, Cp = wp.shape
         b = bias.detach().contiguous() if bias is not None else None
-        if TRAIN_TC and C % 64 == 0 and O in (64, 128, 192):
-            y = ops.conv2d_tc(ops.split_planes(x, _TCP), ops.split_planes(wp.reshape(O, -1), _TCP), KH, KW, None, b, stride, pad,
+        use_tc = TRAIN_TC and C % 64 == 0 and O in (64, 128, 192)
+        xp = ops.split_planes(x, _TCP) if use_tc else None
+        if use_tc:
+            y = ops.conv2d_tc(xp, ops.split_planes(wp.reshape(O, -1), _TCP), KH, KW, None, b, stride, pad,
                               ops.ACT_NONE, want_f32=True, planes_out=0)[0]
         else:
             y = ops.conv2d_nhwc(x, wp, None, b, stride, pad, ops.ACT_NONE)
-        ctx.save_for_backward(x, wp)
-        ctx.geom = (stride, pad, tuple(weight.shape), bias is not None)
+        # the implicit-GEMM weight gradient reads the bf16 planes the forward made anyway: the float32 input is not kept
+        dw_tc = use_tc and TRAIN_DW_TC and ops.conv_dw_tc_supported(C, O, KH, KW, stride)
+        ctx.save_for_backward(xp if dw_tc else x, wp)
+        ctx.geom = (stride, pad, tuple(weight.shape), bias is not None, dw_tc, tuple(x.shape))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, wp = ctx.saved_tensors
-        stride, pad, wshape, has_bias = ctx.geom
+        stride, pad, wshape, has_bias, dw_tc, xshape = ctx.geom
         dy = dy.contiguous()
-        n, H, W, C = x.shape
+        n, H, W, C = xshape
         O, KH, KW, Cp = wp.shape
         M = dy.numel() // O
         K = KH * KW * Cp
         dy2 = dy.reshape(M, O)
-        dev, st = _ctx(x)
+        dev, st = _ctx(dy)
         L = _lib.lib()
         dx = dwt = db = None
+        dx_tc = ctx.needs_input_grad[0] and TRAIN_TC and stride == 1 and O % 64 == 0 and C in (64, 128, 192) and KH - 1 - pad >= 0
+        dyp = ops.split_planes(dy, _TCP) if (dx_tc or (dw_tc and ctx.needs_input_grad[1])) else None
         if ctx.needs_input_grad[1]:
-            cols = _new((M, K), x)
-            _lib.check(L.rp_im2col_nhwc_f32(_p(x), _p(cols), n, H, W, C, KH, KW, stride, pad, dev, st), "rp_im2col")
-            ops._count()
-            dwp = _lin_dw(dy2, cols).reshape(O, KH, KW, Cp)                       # [O, K]
-            del cols
+            if dw_tc:
+                dwp = ops.conv_dw_tc(x, dyp, KH, KW, pad)                         # [O,KH,KW,C], no im2col
+            else:
+                cols = _new((M, K), x)
+                _lib.check(L.rp_im2col_nhwc_f32(_p(x), _p(cols), n, H, W, C, KH, KW, stride, pad, dev, st), "rp_im2col")
+                ops._count()
+                dwp = _lin_dw(dy2, cols).reshape(O, KH, KW, Cp)                   # [O, K]
+                del cols
             dwt = dwp[..., :wshape[1]].permute(0, 3, 1, 2).contiguous()          # re-layout copy back to [O,C,KH,KW]
         if ctx.needs_input_grad[0]:
-            if TRAIN_TC and stride == 1 and O % 64 == 0 and C in (64, 128, 192) and KH - 1 - pad >= 0:
+            if dx_tc:
                 # dX = "full" correlation of dY with the flipped filter, input and output channels swapped
                 wf = wp.flip(1, 2).permute(3, 1, 2, 0).contiguous()              # [C][KH][KW][O]: re-layout copy of the filter
-                dx = ops.conv2d_tc(ops.split_planes(dy, _TCP), ops.split_planes(wf.reshape(C, -1), _TCP), KH, KW, None, None, 1,
+                dx = ops.conv2d_tc(dyp, ops.split_planes(wf.reshape(C, -1), _TCP), KH, KW, None, None, 1,
                                    KH - 1 - pad, ops.ACT_NONE, want_f32=True, planes_out=0)[0]
             else:
                 dcols = _lin_dx(dy2, wp.reshape(O, K))                           # [M, K]
-                dx = torch.empty_like(x)
+                dx = torch.empty(xshape, dtype=torch.float32, device=dy.device)
                 _lib.check(L.rp_col2im_nhwc_f32(_p(dcols), _p(dx), n, H, W, C, KH, KW, stride, pad, dev, st), "rp_col2im")
                 ops._count()
         if has_bias and ctx.needs_input_grad[2]:
