@@ -312,7 +312,9 @@ int rp_se3_exp_bwd_f32(const float* dX, const float* a, float* da, int64_t n, in
  *   Matrix Module products on materialised 576x576 matrices (autograd of vision_transformer.py:198-223,325-329).
  * rp_im2col / rp_col2im: NHWC convolution gradients as GEMMs (column = (ky*KW+kx)*C + c).
  * rp_bn_*: nn.BatchNorm2d in training mode on [M][C] (batch statistics, biased variance, running-stat update with
- *   the unbiased variance; torchvision resnet18 / extractor.py:24-28).   rp_layernorm_*: eps inside the sqrt.
+ *   the unbiased variance; torchvision resnet18 / extractor.py:24-28), C % 4 == 0.  rp_bn_bwd: y_relu (may be NULL) = the
+ *   block's output when a ReLU followed (dz = dy .* (y > 0) is formed on the fly); dz_out (may be NULL) receives dz, the
+ *   gradient of the residual branch.   rp_layernorm_*: eps inside the sqrt.
  * rp_softmax_{rows,cols}: softmax(scale * S) over dim -1 / dim -2 of [mats][n][n]; *_bwd adds into ds if accumulate.
  * rp_maxpool3x3s2_bwd: gradient to the FIRST maximum of each window (PyTorch's tie-break). */
 /* float32 [R][C] -> bf16 planes of the transpose [P][C][R] (R even): operands of the weight-gradient GEMMs
@@ -338,8 +340,14 @@ int rp_softmax_cols_bwd_f32(const float* dp, const float* p, float* ds, int mats
 size_t rp_bn_workspace_bytes(int64_t M, int C);
 int rp_bn_train_stats_f32(const float* x, float* mean, float* var, float* running_mean, float* running_var,                   float momentum, int64_t M, int C, void* workspace, size_t workspace_bytes, int device,                   void* stream);
 int rp_bn_apply_f32(const float* x, const float* mean, const float* var, const float* gamma, const float* beta,                const float* residual, float* y, int64_t M, int C, float eps, int relu, int device, void* stream);
-int rp_bn_bwd_f32(const float* dy, const float* x, const float* mean, const float* var, const float* gamma, float eps,               float* dx, float* dgamma, float* dbeta, int64_t M, int C, void* workspace, size_t workspace_bytes,               int device, void* stream);
+int rp_bn_bwd_f32(const float* dy, const float* y_relu, const float* x, const float* mean, const float* var, const float* gamma,
+                  float eps, float* dx, float* dz_out, float* dgamma, float* dbeta, int64_t M, int C, void* workspace,
+                  size_t workspace_bytes, int device, void* stream);
 int rp_im2col_nhwc_f32(const float* x, float* cols, int n, int H, int W, int C, int KH, int KW, int stride, int pad,                  int device, void* stream);
+/* im2col written as the bf16 planes of cols^T, planes [P][KH*KW*C][n*Ho*Wo] (the B operand of the split-K weight-gradient
+ * GEMM), for the convolutions rp_conv_dw_tc does not take (C % 64 != 0: the stem). */
+int rp_im2col_t_planes_bf16(const float* x, void* planes, int P, int n, int H, int W, int C, int KH, int KW, int stride, int pad,
+                            int device, void* stream);
 int rp_col2im_nhwc_f32(const float* dcols, float* dx, int n, int H, int W, int C, int KH, int KW, int stride, int pad,                  int device, void* stream);
 int rp_maxpool3x3s2_bwd_f32(const float* dy, const float* x, float* dx, int n, int H, int W, int C, int device, void* stream);
 int rp_normalize_pose_bwd_f32(const float* dout, const float* raw, float* draw, int B, int device, void* stream);
@@ -355,14 +363,14 @@ int rp_attention_bwd_prep(const float* d_out, const float* out, void* d_out_plan
                           void* stream);
 int rp_attention_bwd_tc(const void* qkv_planes, const void* d_out_planes, const float* lse, const float* delta,
                         float* d_qkv, int n_img, int device, void* stream);
-/* Weight gradient of a stride-1 nn.Conv2d as an implicit GEMM on tcgen05 (no im2col matrix, no transposed copies):
- * x_planes bf16 [2][n][H][W][C], dy_planes bf16 [2][n][OH][OW][O] (OH = H + 2 pad - KH + 1) -> dw float32 [O][KH][KW][C].
+/* Weight gradient of nn.Conv2d (stride 1 or 2) as an implicit GEMM on tcgen05 (no im2col matrix, no transposed copies):
+ * x_planes bf16 [2][n][H][W][C], dy_planes bf16 [2][n][OH][OW][O] (OH = (H + 2 pad - KH) / stride + 1) -> dw float32 [O][KH][KW][C].
  * Both operands are read as MN-major tiles straight from the NHWC planes; the taps are shifted views of one halo
- * tile; per-pixel-slice partial sums are reduced in a fixed order (deterministic).  C % 64 == 0, O in {64,128,192}. */
+ * tile (stride 1; one box per tap for stride 2); per-pixel-slice partial sums are reduced in a fixed order (deterministic).  C % 64 == 0, O in {64,128,192}. */
 int rp_conv_dw_tc_supported(int C, int O, int KH, int KW, int stride);
-size_t rp_conv_dw_tc_workspace_bytes(int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int device);
+size_t rp_conv_dw_tc_workspace_bytes(int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int stride, int device);
 int rp_conv_dw_tc(const void* x_planes, const void* dy_planes, float* dw, int n_img, int H, int W, int C, int O, int KH,
-                  int KW, int pad, void* workspace, size_t workspace_bytes, int device, void* stream);
+                  int KW, int pad, int stride, void* workspace, size_t workspace_bytes, int device, void* stream);
 int rp_concat_vpos_f32(const float* qkv, const float* pos, float* vp, int n_img, int device, void* stream);
 int rp_scatter_dv_f32(const float* dvp, float* dqkv, int n_img, int device, void* stream);
 

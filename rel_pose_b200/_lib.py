@@ -103,8 +103,9 @@ _SIGNATURES = {
     "rp_bn_workspace_bytes": (_c_size, [_c_i64, _c_int]),
     "rp_bn_train_stats_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _c_i64, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_bn_apply_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_f32, _c_int, _c_int, _ptr]),
-    "rp_bn_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr, _c_size, _c_int, _ptr]),
+    "rp_bn_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_im2col_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_im2col_t_planes_bf16": (_c_int, [_ptr, _ptr] + [_c_int] * 10 + [_ptr]),
     "rp_col2im_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_maxpool3x3s2_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_normalize_pose_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
@@ -114,8 +115,8 @@ _SIGNATURES = {
     "rp_attention_bwd_prep": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_attention_bwd_tc": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_conv_dw_tc_supported": (_c_int, [_c_int] * 5),
-    "rp_conv_dw_tc_workspace_bytes": (_c_size, [_c_int] * 9),
-    "rp_conv_dw_tc": (_c_int, [_ptr, _ptr, _ptr] + [_c_int] * 8 + [_ptr, _c_size, _c_int, _ptr]),
+    "rp_conv_dw_tc_workspace_bytes": (_c_size, [_c_int] * 10),
+    "rp_conv_dw_tc": (_c_int, [_ptr, _ptr, _ptr] + [_c_int] * 9 + [_ptr, _c_size, _c_int, _ptr]),
     "rp_grad_norm_multi": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr, _c_int, _ptr]),
     "rp_adam_clip_step_multi": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr] + [ctypes.c_double] * 6 + [_c_int, _c_int, _ptr]),
     "rp_adam_clip_step_multi_dev": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, ctypes.c_double, _ptr] + [ctypes.c_double] * 4 +

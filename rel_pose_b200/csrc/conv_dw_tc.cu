@@ -1,4 +1,4 @@
-// Weight gradient of a stride-1 convolution (A11: autograd of nn.Conv2d in torchvision BasicBlock / extractor.py:9-13)
+// Weight gradient of a convolution (stride 1 or 2) (A11: autograd of nn.Conv2d in torchvision BasicBlock / extractor.py:9-13)
 // as an IMPLICIT GEMM on tcgen05 -- no im2col matrix, no transposed copies:
 //
 //   dW[o][kh][kw][c] = sum over (img, oy, ox) of  dy[img][oy][ox][o] * x[img][oy + kh - pad][ox + kw - pad][c]
@@ -11,7 +11,8 @@
 //   D[(tap, c)][o] (+)= A^T B    M = 128, N = O, K = 16 pixels per instruction, split-bf16 (a1 b0 + a0 b1 + a0 b0)
 // HALO mode: ONE box per pixel tile brings the (8 + KH - 1) x (8 + KW - 1) halo of the 64 input channels; every tap
 // is a shifted view of it (start address + ((kh) * halo_width + kw) rows of 128 bytes, stride byte offset = one halo
-// row): the input tile is read once, not KH * KW times.  RELPOSE_DW_HALO=0 loads one 8 x 8 box per tap instead (A/B).
+// row): the input tile is read once, not KH * KW times.  Stride-2 convolutions (and RELPOSE_DW_HALO=0, for A/B runs)
+// load one 8 x 8 box per tap instead (element stride 2 in the tensor map).
 //
 // Work item (one CTA) = (64-channel chunk of C, group of G taps, slice of the pixel tiles): accumulators stay in
 // tensor memory for the whole slice (ceil(G / 2) x O <= 512 columns), then go to a per-slice partial buffer; a
@@ -28,7 +29,7 @@ constexpr int THREADS = 256;
 constexpr int MAX_STAGES = 4;
 
 struct DwGeom {
-    int n_img, OH, OW, C, O, KH, KW, pad;
+    int n_img, OH, OW, C, O, KH, KW, pad, stride;
     int HW, HH, halo_bytes;                // halo box (pixels) and its 1024-rounded size in shared memory
     int tiles_x, tiles_y, ntiles;
     int ncc, ntg, G, nps;                  // 64-channel chunks of C, tap groups, taps per group, pixel slices
@@ -108,8 +109,8 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     for (int t = 0; t < gcur; ++t) {
                         const int kh = (tap0 + t) / g.KW, kw = (tap0 + t) % g.KW;
                         for (int p = 0; p < P; ++p)
-                            tc::tma_load_5d(sb + g.dy_bytes + (t * P + p) * TILE_B, &tmX, &full[stage], cc * 64, ox0 + kw - g.pad,
-                                            oy0 + kh - g.pad, img, p);
+                            tc::tma_load_5d(sb + g.dy_bytes + (t * P + p) * TILE_B, &tmX, &full[stage], cc * 64,
+                                            ox0 * g.stride + kw - g.pad, oy0 * g.stride + kh - g.pad, img, p);
                     }
                 }
             }
@@ -219,10 +220,10 @@ bool dw_halo_enabled() {
     return v == 1;
 }
 
-int make_geom(DwGeom& g, int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int device, bool halo) {
-    g.n_img = n_img; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.pad = pad;
-    g.OH = H + 2 * pad - KH + 1;
-    g.OW = W + 2 * pad - KW + 1;
+int make_geom(DwGeom& g, int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int stride, int device, bool halo) {
+    g.n_img = n_img; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.pad = pad; g.stride = stride;
+    g.OH = (H + 2 * pad - KH) / stride + 1;
+    g.OW = (W + 2 * pad - KW) / stride + 1;
     g.HW = TP + KW - 1; g.HH = TP + KH - 1;
     g.halo_bytes = (g.HH * g.HW * 128 + 1023) / 1024 * 1024;
     g.tiles_x = (g.OW + TP - 1) / TP; g.tiles_y = (g.OH + TP - 1) / TP;
@@ -252,25 +253,29 @@ int make_geom(DwGeom& g, int n_img, int H, int W, int C, int O, int KH, int KW, 
 }  // namespace
 
 extern "C" int rp_conv_dw_tc_supported(int C, int O, int KH, int KW, int stride) {
-    return stride == 1 && C % 64 == 0 && C >= 64 && (O == 64 || O == 128 || O == 192) && KH >= 1 && KW >= 1 && KH <= 7 && KW <= 7;
+    return (stride == 1 || stride == 2) && C % 64 == 0 && C >= 64 && (O == 64 || O == 128 || O == 192) && KH >= 1 && KW >= 1 && KH <= 7 && KW <= 7;
 }
 
-extern "C" size_t rp_conv_dw_tc_workspace_bytes(int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int device) {
+extern "C" size_t rp_conv_dw_tc_workspace_bytes(int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int stride,
+                                                int device) {
     DwGeom g;
-    if (!rp_conv_dw_tc_supported(C, O, KH, KW, 1) || make_geom(g, n_img, H, W, C, O, KH, KW, pad, device, dw_halo_enabled())) return 0;
+    if (!rp_conv_dw_tc_supported(C, O, KH, KW, stride) ||
+        make_geom(g, n_img, H, W, C, O, KH, KW, pad, stride, device, stride == 1 && dw_halo_enabled()))
+        return 0;
     return (size_t)g.nps * O * KH * KW * C * sizeof(float);
 }
 
 extern "C" int rp_conv_dw_tc(const void* x_planes, const void* dy_planes, float* dw, int n_img, int H, int W, int C, int O,
-                             int KH, int KW, int pad, void* workspace, size_t workspace_bytes, int device, void* stream) {
+                             int KH, int KW, int pad, int stride, void* workspace, size_t workspace_bytes, int device,
+                             void* stream) {
     RP_REQUIRE(x_planes && dy_planes && dw && workspace && n_img > 0, RP_EINVAL, "rp_conv_dw_tc: bad argument");
-    RP_REQUIRE(rp_conv_dw_tc_supported(C, O, KH, KW, 1), RP_EINVAL, "rp_conv_dw_tc: unsupported shape C=%d O=%d %dx%d", C, O, KH, KW);
+    RP_REQUIRE(rp_conv_dw_tc_supported(C, O, KH, KW, stride), RP_EINVAL, "rp_conv_dw_tc: unsupported shape C=%d O=%d %dx%d/%d", C, O, KH, KW, stride);
     RP_REQUIRE(rp::aligned16(x_planes) && rp::aligned16(dy_planes) && rp::aligned16(dw) && rp::aligned16(workspace), RP_EALIGN,
                "rp_conv_dw_tc: 16-byte alignment");
     RP_GUARD(device);
-    const bool halo = dw_halo_enabled();
+    const bool halo = stride == 1 && dw_halo_enabled();      // a strided tap is not a shifted view of a dense halo
     DwGeom g;
-    RP_REQUIRE(make_geom(g, n_img, H, W, C, O, KH, KW, pad, device, halo) == RP_OK && g.OH > 0 && g.OW > 0, RP_EINVAL,
+    RP_REQUIRE(make_geom(g, n_img, H, W, C, O, KH, KW, pad, stride, device, halo) == RP_OK && g.OH > 0 && g.OW > 0, RP_EINVAL,
                "rp_conv_dw_tc: geometry does not fit");
     const size_t need = (size_t)g.nps * O * KH * KW * C * sizeof(float);
     RP_REQUIRE(workspace_bytes >= need, RP_EINVAL, "rp_conv_dw_tc: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -280,8 +285,8 @@ extern "C" int rp_conv_dw_tc(const void* x_planes, const void* dy_planes, float*
     {
         cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img, (cuuint64_t)P};
         cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)n_img * H * W * C * 2};
-        cuuint32_t box[5] = {64, (cuuint32_t)(halo ? g.HW : TP), (cuuint32_t)(halo ? g.HH : TP), 1, 1};
-        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        cuuint32_t box[5] = {64, (cuuint32_t)(halo ? g.HW : TP * stride), (cuuint32_t)(halo ? g.HH : TP * stride), 1, 1};
+        cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
         CUresult r = fn(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_planes), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

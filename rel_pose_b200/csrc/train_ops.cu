@@ -10,6 +10,7 @@
 //   rp_gelu_{fwd,bwd}, rp_relu_bwd, rp_mul, rp_axpby, rp_colsum, rp_maxpool3x3s2_bwd, rp_normalize_pose_bwd ...
 // Reference semantics being differentiated: src/model.py:114-191, src/modules/vision_transformer.py:188-354,
 // src/modules/extractor.py:51-65, torchvision BasicBlock; autograd does the rest in the reference.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -355,32 +356,92 @@ __global__ void __launch_bounds__(256) softmax_cols_bwd_kernel(const float* __re
 }
 
 // ============================================================================================ BatchNorm (train)
-// x [M][C] (NHWC flattened).  Stage 1: per-block partial sum / sum of squares; stage 2: mean, biased var.
-constexpr int BN_ROWS = 512;
-__global__ void bn_stats_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, long long M, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(M, r0 + BN_ROWS);
-    float s = 0.f, q = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-        const float v = x[r * C + c];
-        s += v;
-        q += v * v;
+// x [M][C] (NHWC flattened), C % 4 == 0.  Stage 1: per-block partial sums over BN_ROWS rows (256 threads = C/4 float4
+// columns x 256/(C/4) row lanes, four loads in flight per thread, lanes combined through shared memory in a fixed
+// order); stage 2: the blocks' partials in double (four lanes per channel), mean / biased variance / running statistics.
+// Round 1's version walked 512 rows per 64-thread block with one scalar load in flight: 76 us for the 38 MB stem tensor.
+constexpr int BN_ROWS = 128;
+constexpr int BN_THREADS = 256;
+
+// one block's partial sums of (a, b) per channel: a = f0(row), b = f1(row), written to partial[blk][2][C]
+template <typename F>
+__device__ __forceinline__ void bn_block_sums(float* __restrict__ partial, long long M, int C, F&& load) {
+    __shared__ float4 sm[2][BN_THREADS];
+    const int c4n = C >> 2;
+    const int nl = BN_THREADS / c4n;                                  // row lanes (C = 64: 16, 128: 8, 192: 5)
+    const int col4 = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+    const long long r0 = (long long)blockIdx.x * BN_ROWS, r1 = min(M, r0 + BN_ROWS);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (rl < nl) {
+        long long r = r0 + rl;
+        for (; r + 3 * nl < r1; r += 4 * nl) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load((r + u * nl) * c4n + col4, col4, a[u], b[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s.x += a[u].x; s.y += a[u].y; s.z += a[u].z; s.w += a[u].w;
+                q.x += b[u].x; q.y += b[u].y; q.z += b[u].z; q.w += b[u].w;
+            }
+        }
+        for (; r < r1; r += nl) {
+            float4 a, b;
+            load(r * c4n + col4, col4, a, b);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+        }
     }
-    partial[((long long)blockIdx.y * 2 + 0) * C + c] = s;
-    partial[((long long)blockIdx.y * 2 + 1) * C + c] = q;
+    sm[0][threadIdx.x] = s;
+    sm[1][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x < 2 * c4n) {                                     // threads [0,c4n): sums, [c4n,2 c4n): second sums
+        const int which = threadIdx.x / c4n, c = threadIdx.x % c4n;
+        float4 t = sm[which][c];
+        for (int l = 1; l < nl; ++l) {
+            const float4 v = sm[which][l * c4n + c];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 2 + which) * C)[c] = t;
+    }
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const float* __restrict__ x, float* __restrict__ partial,
+                                                                       long long M, int C) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    bn_block_sums(partial, M, C, [&](long long i, int, float4& a, float4& b) {
+        a = x4[i];
+        b = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
+    });
+}
+// partial [nblk][2][C] -> sums in double: thread = (channel, one of four lanes over the blocks), fixed combination order
+__device__ __forceinline__ void bn_final_sums(const float* __restrict__ partial, int nblk, int C, double& s, double& q, int& c,
+                                              bool& writer) {
+    __shared__ double sm[2][4][64];
+    const int cl = threadIdx.x & 63, l = threadIdx.x >> 6;
+    c = blockIdx.x * 64 + cl;
+    double ss = 0.0, qq = 0.0;
+    if (c < C)
+        for (int b = l; b < nblk; b += 4) {
+            ss += (double)partial[((long long)b * 2 + 0) * C + c];
+            qq += (double)partial[((long long)b * 2 + 1) * C + c];
+        }
+    sm[0][l][cl] = ss;
+    sm[1][l][cl] = qq;
+    __syncthreads();
+    writer = l == 0 && c < C;
+    s = sm[0][0][cl] + sm[0][1][cl] + sm[0][2][cl] + sm[0][3][cl];
+    q = sm[1][0][cl] + sm[1][1][cl] + sm[1][2][cl] + sm[1][3][cl];
 }
 // mean / biased var in double (the one-pass sum of squares is safe there); also the running-stat update
-__global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nblk, long long M, int C, float* __restrict__ mean,
-                                      float* __restrict__ var, float* __restrict__ running_mean, float* __restrict__ running_var,
-                                      float momentum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-        s += (double)partial[((long long)b * 2 + 0) * C + c];
-        q += (double)partial[((long long)b * 2 + 1) * C + c];
-    }
+__global__ void __launch_bounds__(256) bn_stats_final_kernel(const float* __restrict__ partial, int nblk, long long M, int C,
+                                                              float* __restrict__ mean, float* __restrict__ var,
+                                                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                              float momentum) {
+    double s, q;
+    int c;
+    bool writer;
+    bn_final_sums(partial, nblk, C, s, q, c, writer);
+    if (!writer) return;
     const double m = s / (double)M;
     double v = q / (double)M - m * m;
     if (v < 0.0) v = 0.0;
@@ -392,57 +453,90 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nbl
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
 }
-// y = act(gamma * (x - mean) * rstd + beta + residual)
-__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ residual,
-                                float* __restrict__ y, long long M, int C, float eps, int relu) {
-    const long long n = M * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        float v = (x[i] - mean[c]) * (1.0f / sqrtf(var[c] + eps)) * gamma[c] + beta[c];
-        if (residual) v += residual[i];
-        y[i] = relu ? fmaxf(v, 0.f) : v;
+// y = act(gamma * (x - mean) * rstd + beta + residual), float4 per thread
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                        const float* __restrict__ var, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ residual,
+                                                        float* __restrict__ y, long long M, int C, float eps, int relu) {
+    const long long n4 = M * C / 4;
+    const int c4n = C >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4;
+        const float4 xv = reinterpret_cast<const float4*>(x)[i];
+        const float4 mv = *reinterpret_cast<const float4*>(mean + c), vv = *reinterpret_cast<const float4*>(var + c);
+        const float4 gv = *reinterpret_cast<const float4*>(gamma + c), bv = *reinterpret_cast<const float4*>(beta + c);
+        float4 o;
+        o.x = (xv.x - mv.x) * (1.0f / sqrtf(vv.x + eps)) * gv.x + bv.x;
+        o.y = (xv.y - mv.y) * (1.0f / sqrtf(vv.y + eps)) * gv.y + bv.y;
+        o.z = (xv.z - mv.z) * (1.0f / sqrtf(vv.z + eps)) * gv.z + bv.z;
+        o.w = (xv.w - mv.w) * (1.0f / sqrtf(vv.w + eps)) * gv.w + bv.w;
+        if (residual) {
+            const float4 r = reinterpret_cast<const float4*>(residual)[i];
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        reinterpret_cast<float4*>(y)[i] = o;
     }
 }
-// partial [nblk][2][C]: sum(dy), sum(dy * xhat)
-__global__ void bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                                      const float* __restrict__ var, float eps, float* __restrict__ partial, long long M, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const long long r0 = (long long)blockIdx.y * BN_ROWS, r1 = min(M, r0 + BN_ROWS);
-    const float m = mean[c], rs = 1.0f / sqrtf(var[c] + eps);
-    float s = 0.f, q = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-        const float d = dy[r * C + c];
-        s += d;
-        q += d * (x[r * C + c] - m) * rs;
-    }
-    partial[((long long)blockIdx.y * 2 + 0) * C + c] = s;
-    partial[((long long)blockIdx.y * 2 + 1) * C + c] = q;
+// partial [nblk][2][C]: sum(dz), sum(dz * xhat) with dz = dy .* (y > 0) when the block ended in a ReLU (y != NULL)
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                                     const float* __restrict__ x, const float* __restrict__ mean,
+                                                                     const float* __restrict__ var, float eps,
+                                                                     float* __restrict__ partial, long long M, int C) {
+    const float4* dy4 = reinterpret_cast<const float4*>(dy);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const int col4 = threadIdx.x % (C >> 2);
+    const float4 m = *reinterpret_cast<const float4*>(mean + 4 * col4), v = *reinterpret_cast<const float4*>(var + 4 * col4);
+    const float4 rs = make_float4(1.0f / sqrtf(v.x + eps), 1.0f / sqrtf(v.y + eps), 1.0f / sqrtf(v.z + eps), 1.0f / sqrtf(v.w + eps));
+    bn_block_sums(partial, M, C, [&](long long i, int, float4& a, float4& b) {
+        a = dy4[i];
+        if (y4) {
+            const float4 yv = y4[i];
+            a.x = yv.x > 0.f ? a.x : 0.f; a.y = yv.y > 0.f ? a.y : 0.f; a.z = yv.z > 0.f ? a.z : 0.f; a.w = yv.w > 0.f ? a.w : 0.f;
+        }
+        const float4 xv = x4[i];
+        b = make_float4(a.x * (xv.x - m.x) * rs.x, a.y * (xv.y - m.y) * rs.y, a.z * (xv.z - m.z) * rs.z, a.w * (xv.w - m.w) * rs.w);
+    });
 }
-__global__ void bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-        s += (double)partial[((long long)b * 2 + 0) * C + c];
-        q += (double)partial[((long long)b * 2 + 1) * C + c];
-    }
+__global__ void __launch_bounds__(256) bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int C,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    double s, q;
+    int c;
+    bool writer;
+    bn_final_sums(partial, nblk, C, s, q, c, writer);
+    if (!writer) return;
     dbeta[c] = (float)s;
     dgamma[c] = (float)q;
 }
-// dx = gamma * rstd * (dy - dbeta / M - xhat * dgamma / M)
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                                    const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ dgamma,
-                                    const float* __restrict__ dbeta, float eps, float* __restrict__ dx, long long M, int C) {
-    const long long n = M * C;
+// dx = gamma * rstd * (dz - dbeta / M - xhat * dgamma / M); dz (the gradient of the residual branch) is written out on request
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                            const float* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ var, const float* __restrict__ gamma,
+                                                            const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                                            float eps, float* __restrict__ dx, float* __restrict__ dz_out,
+                                                            long long M, int C) {
+    const long long n4 = M * C / 4;
+    const int c4n = C >> 2;
     const float invM = 1.0f / (float)M;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const float rs = 1.0f / sqrtf(var[c] + eps);
-        const float xh = (x[i] - mean[c]) * rs;
-        dx[i] = gamma[c] * rs * (dy[i] - dbeta[c] * invM - xh * dgamma[c] * invM);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4;
+        float4 d = reinterpret_cast<const float4*>(dy)[i];
+        if (y) {
+            const float4 yv = reinterpret_cast<const float4*>(y)[i];
+            d.x = yv.x > 0.f ? d.x : 0.f; d.y = yv.y > 0.f ? d.y : 0.f; d.z = yv.z > 0.f ? d.z : 0.f; d.w = yv.w > 0.f ? d.w : 0.f;
+        }
+        if (dz_out) reinterpret_cast<float4*>(dz_out)[i] = d;
+        const float4 xv = reinterpret_cast<const float4*>(x)[i];
+        const float d4[4] = {d.x, d.y, d.z, d.w}, x4[4] = {xv.x, xv.y, xv.z, xv.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float rs = 1.0f / sqrtf(var[c + k] + eps);
+            const float xh = (x4[k] - mean[c + k]) * rs;
+            o[k] = gamma[c + k] * rs * (d4[k] - dbeta[c + k] * invM - xh * dgamma[c + k] * invM);
+        }
+        reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -458,6 +552,32 @@ __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ c
         const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho), im = (int)(row / ((long long)Wo * Ho));
         const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
         cols[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long long)im * H + iy) * W + ix) * C + c] : 0.f;
+    }
+}
+// The same gather written straight into the operand layout of the weight-gradient GEMM: bf16 planes of cols^T,
+// planes[p][k][m] (m = output pixel, two per thread), for the convolutions rp_conv_dw_tc does not take (the 7x7 / 2 stem on
+// 4 input channels): no float32 cols matrix, no separate transposing split pass.
+__global__ void __launch_bounds__(256) im2col_t_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, int P,
+                                                               int n, int H, int W, int C, int KH, int KW, int stride, int pad,
+                                                               int Ho, int Wo) {
+    const long long M = (long long)n * Ho * Wo, m0 = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (m0 >= M) return;
+    const int k = blockIdx.y;
+    const int c = k % C, t = k / C, kx = t % KW, ky = t / KW;
+    float v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const long long row = m0 + j;
+        const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho), im = (int)(row / ((long long)Wo * Ho));
+        const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
+        v[j] = (row < M && iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long long)im * H + iy) * W + ix) * C + c] : 0.f;
+    }
+    const long long K = (long long)KH * KW * C;
+    for (int p = 0; p < P; ++p) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(planes + ((long long)p * K + k) * M + m0) = h;
+        v[0] -= __bfloat162float(h.x);
+        v[1] -= __bfloat162float(h.y);
     }
 }
 // dx[n][iy][ix][c] = sum over (ky,kx) with a valid output pixel of dcols[(oy,ox)][(ky,kx,c)]   (gather: no atomics)
@@ -707,29 +827,33 @@ extern "C" int rp_bn_train_stats_f32(const float* x, float* mean, float* var, fl
     RP_REQUIRE(x && mean && var && M > 0 && C > 0, RP_EINVAL, "rp_bn_train_stats: bad argument");
     RP_REQUIRE(workspace && workspace_bytes >= rp_bn_workspace_bytes(M, C), RP_EWORKSPACE, "rp_bn_train_stats: workspace too small");
     RP_GUARD(device);
+    RP_REQUIRE(C % 4 == 0 && C <= 2 * BN_THREADS && rp::aligned16(x), RP_EINVAL, "rp_bn_train_stats: C must be a multiple of 4 (<= 512)");
     const int nblk = (int)((M + BN_ROWS - 1) / BN_ROWS);
-    bn_stats_partial_kernel<<<dim3((C + 63) / 64, nblk), 64, 0, (cudaStream_t)stream>>>(x, static_cast<float*>(workspace), M, C);
-    bn_stats_final_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), nblk, M, C, mean, var,
-                                                                        running_mean, running_var, momentum);
+    bn_stats_partial_kernel<<<nblk, BN_THREADS, 0, (cudaStream_t)stream>>>(x, static_cast<float*>(workspace), M, C);
+    bn_stats_final_kernel<<<(C + 63) / 64, 256, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), nblk, M, C, mean, var,
+                                                                         running_mean, running_var, momentum);
     return rp::finish_launch("rp_bn_train_stats");
 }
 extern "C" int rp_bn_apply_f32(const float* x, const float* mean, const float* var, const float* gamma, const float* beta,
                                const float* residual, float* y, int64_t M, int C, float eps, int relu, int device, void* stream) {
     RP_REQUIRE(x && mean && var && gamma && beta && y && M > 0 && C > 0, RP_EINVAL, "rp_bn_apply: bad argument");
     RP_GUARD(device);
-    RP_LAUNCH1D(bn_apply_kernel, M * C, x, mean, var, gamma, beta, residual, y, M, C, eps, relu);
+    RP_REQUIRE(C % 4 == 0 && rp::aligned16(x) && rp::aligned16(y) && rp::aligned16(residual), RP_EINVAL, "rp_bn_apply: C % 4, 16-byte alignment");
+    RP_LAUNCH1D(bn_apply_kernel, M * C / 4, x, mean, var, gamma, beta, residual, y, M, C, eps, relu);
     return rp::finish_launch("rp_bn_apply");
 }
-extern "C" int rp_bn_bwd_f32(const float* dy, const float* x, const float* mean, const float* var, const float* gamma, float eps,
-                             float* dx, float* dgamma, float* dbeta, int64_t M, int C, void* workspace, size_t workspace_bytes,
-                             int device, void* stream) {
+extern "C" int rp_bn_bwd_f32(const float* dy, const float* y_relu, const float* x, const float* mean, const float* var,
+                             const float* gamma, float eps, float* dx, float* dz_out, float* dgamma, float* dbeta, int64_t M, int C,
+                             void* workspace, size_t workspace_bytes, int device, void* stream) {
     RP_REQUIRE(dy && x && mean && var && gamma && dx && dgamma && dbeta && M > 0 && C > 0, RP_EINVAL, "rp_bn_bwd: bad argument");
     RP_REQUIRE(workspace && workspace_bytes >= rp_bn_workspace_bytes(M, C), RP_EWORKSPACE, "rp_bn_bwd: workspace too small");
     RP_GUARD(device);
+    RP_REQUIRE(C % 4 == 0 && C <= 2 * BN_THREADS && rp::aligned16(dy) && rp::aligned16(x) && rp::aligned16(dx) && rp::aligned16(y_relu) &&
+                   rp::aligned16(dz_out), RP_EINVAL, "rp_bn_bwd: C must be a multiple of 4 (<= 512), 16-byte alignment");
     const int nblk = (int)((M + BN_ROWS - 1) / BN_ROWS);
-    bn_bwd_partial_kernel<<<dim3((C + 63) / 64, nblk), 64, 0, (cudaStream_t)stream>>>(dy, x, mean, var, eps, static_cast<float*>(workspace), M, C);
-    bn_bwd_final_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), nblk, C, dgamma, dbeta);
-    RP_LAUNCH1D(bn_bwd_apply_kernel, M * C, dy, x, mean, var, gamma, dgamma, dbeta, eps, dx, M, C);
+    bn_bwd_partial_kernel<<<nblk, BN_THREADS, 0, (cudaStream_t)stream>>>(dy, y_relu, x, mean, var, eps, static_cast<float*>(workspace), M, C);
+    bn_bwd_final_kernel<<<(C + 63) / 64, 256, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), nblk, C, dgamma, dbeta);
+    RP_LAUNCH1D(bn_bwd_apply_kernel, M * C / 4, dy, y_relu, x, mean, var, gamma, dgamma, dbeta, eps, dx, dz_out, M, C);
     return rp::finish_launch("rp_bn_bwd");
 }
 
@@ -740,6 +864,18 @@ extern "C" int rp_im2col_nhwc_f32(const float* x, float* cols, int n, int H, int
     const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
     RP_LAUNCH1D(im2col_kernel, (long long)n * Ho * Wo * KH * KW * C, x, cols, n, H, W, C, KH, KW, stride, pad, Ho, Wo);
     return rp::finish_launch("rp_im2col");
+}
+extern "C" int rp_im2col_t_planes_bf16(const float* x, void* planes, int P, int n, int H, int W, int C, int KH, int KW, int stride,
+                                       int pad, int device, void* stream) {
+    RP_REQUIRE(x && planes && n > 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0 && P >= 1 && P <= 2,
+               RP_EINVAL, "rp_im2col_t_planes: bad argument");
+    RP_GUARD(device);
+    const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+    const long long M = (long long)n * Ho * Wo;
+    RP_REQUIRE(M % 2 == 0 && KH * KW * C <= 65535, RP_EINVAL, "rp_im2col_t_planes: even pixel count, K <= 65535");
+    im2col_t_planes_kernel<<<dim3((unsigned)((M / 2 + 255) / 256), KH * KW * C), 256, 0, (cudaStream_t)stream>>>(
+        x, static_cast<__nv_bfloat16*>(planes), P, n, H, W, C, KH, KW, stride, pad, Ho, Wo);
+    return rp::finish_launch("rp_im2col_t_planes");
 }
 extern "C" int rp_col2im_nhwc_f32(const float* dcols, float* dx, int n, int H, int W, int C, int KH, int KW, int stride, int pad,
                                   int device, void* stream) {

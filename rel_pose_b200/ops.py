@@ -615,22 +615,22 @@ def conv_dw_tc_supported(C, O, KH, KW, stride):
     return bool(_lib.lib().rp_conv_dw_tc_supported(int(C), int(O), int(KH), int(KW), int(stride)))
 
 
-def conv_dw_tc(x_planes, dy_planes, KH, KW, pad):
-    """Weight gradient of a stride-1 convolution, implicit GEMM on tcgen05: x_planes bf16 [2,n,H,W,C], dy_planes bf16
+def conv_dw_tc(x_planes, dy_planes, KH, KW, pad, stride=1):
+    """Weight gradient of a convolution (stride 1 or 2), implicit GEMM on tcgen05: x_planes bf16 [2,n,H,W,C], dy_planes bf16
     [2,n,OH,OW,O] -> float32 [O,KH,KW,C]."""
     _req(x_planes, "x_planes", torch.bfloat16); _req(dy_planes, "dy_planes", torch.bfloat16)
     P, n, H, W, C = x_planes.shape
     O = dy_planes.shape[-1]
-    assert P == 2 and tuple(dy_planes.shape) == (2, n, H + 2 * pad - KH + 1, W + 2 * pad - KW + 1, O)
+    assert P == 2 and tuple(dy_planes.shape) == (2, n, (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1, O)
     dev, st = _ctx(x_planes)
     L = _lib.lib()
-    nb = L.rp_conv_dw_tc_workspace_bytes(n, H, W, C, O, KH, KW, pad, dev)
+    nb = L.rp_conv_dw_tc_workspace_bytes(n, H, W, C, O, KH, KW, pad, stride, dev)
     assert nb > 0
     ws = torch.empty((nb // 4,), dtype=torch.float32, device=x_planes.device)
     dw = torch.empty((O, KH, KW, C), dtype=torch.float32, device=x_planes.device)
     M = dy_planes[0].numel() // O
-    _tbegin(f"conv_dw_tcx3[{O}x{KH}x{KW}x{C}]", 2.0 * M * O * KH * KW * C, 2.0 * 2 * (x_planes[0].numel() + dy_planes[0].numel()) + 2.0 * nb)
-    _lib.check(L.rp_conv_dw_tc(_p(x_planes), _p(dy_planes), _p(dw), n, H, W, C, O, KH, KW, pad, _p(ws), nb, dev, st), "rp_conv_dw_tc")
+    _tbegin(f"conv_dw_tcx3[{O}x{KH}x{KW}x{C}/s{stride}]", 2.0 * M * O * KH * KW * C, 2.0 * 2 * (x_planes[0].numel() + dy_planes[0].numel()) + 2.0 * nb)
+    _lib.check(L.rp_conv_dw_tc(_p(x_planes), _p(dy_planes), _p(dw), n, H, W, C, O, KH, KW, pad, stride, _p(ws), nb, dev, st), "rp_conv_dw_tc")
     _count(2)
     return dw
 

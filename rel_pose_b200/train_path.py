@@ -114,6 +114,9 @@ def _lin_fwd(x2, w, b, act=ops.ACT_NONE):
     M, K = x2.shape
     if TRAIN_TC and M >= 64 and K % 8 == 0 and (M * K) % 8 == 0 and (w.numel() % 8) == 0:
         return ops.linear_tc(ops.split_planes(x2, _TCP), ops.split_planes(w, _TCP), b, act=act)[0]
+    if TRAIN_TC and K >= 4096 and K % 64 == 0 and w.shape[0] % 64 == 0:
+        # pose_regressor.0 at a handful of rows (26 880 -> 512): weight-bandwidth bound, the split-K kernel of the inference path
+        return ops.linear_tc_splitk(ops.split_planes(x2, _TCP), ops.split_planes(w, _TCP), b, act=act)
     return ops.linear(x2, w, b, act=act)
 
 
@@ -502,7 +505,14 @@ class ConvFn(torch.autograd.Function):
         dyp = ops.split_planes(dy, _TCP) if (dx_tc or (dw_tc and ctx.needs_input_grad[1])) else None
         if ctx.needs_input_grad[1]:
             if dw_tc:
-                dwp = ops.conv_dw_tc(x, dyp, KH, KW, pad)                         # [O,KH,KW,C], no im2col
+                dwp = ops.conv_dw_tc(x, dyp, KH, KW, pad, stride)                         # [O,KH,KW,C], no im2col
+            elif TRAIN_TC and M >= 512 and M % 8 == 0:
+                # the stem (4 input channels): im2col written directly as the transposed bf16 planes the split-K GEMM reads
+                colsT = torch.empty((_TCP, K, M), dtype=torch.bfloat16, device=x.device)
+                _lib.check(L.rp_im2col_t_planes_bf16(_p(x), _p(colsT), _TCP, n, H, W, C, KH, KW, stride, pad, dev, st), "rp_im2col_t_planes")
+                ops._count()
+                dwp = ops.linear_tc_splitk(ops.transpose_split_planes(dy2, _TCP), colsT).reshape(O, KH, KW, Cp)
+                del colsT
             else:
                 cols = _new((M, K), x)
                 _lib.check(L.rp_im2col_nhwc_f32(_p(x), _p(cols), n, H, W, C, KH, KW, stride, pad, dev, st), "rp_im2col")
@@ -560,20 +570,16 @@ class BatchNormTrainFn(torch.autograd.Function):
         M = x.numel() // C
         L = _lib.lib()
         dev, st = _ctx(x)
-        if relu:
-            dz = torch.empty_like(dy)
-            _lib.check(L.rp_relu_bwd_f32(_p(dy), _p(y), _p(dz), dy.numel(), dev, st), "rp_relu_bwd")
-            ops._count()
-        else:
-            dz = dy
+        # dz = dy .* (y > 0) is formed inside the two BatchNorm passes; it is only written out for the residual branch
+        dz = torch.empty_like(dy) if (relu and has_res) else (dy if has_res else None)
         dx = torch.empty_like(x)
         dg = _new((C,), x); db = _new((C,), x)
         nb = L.rp_bn_workspace_bytes(M, C)
         ws = _ws(nb, x)
-        _lib.check(L.rp_bn_bwd_f32(_p(dz), _p(x), _p(mean), _p(var), _p(gamma.detach()), eps, _p(dx), _p(dg), _p(db), M, C, _p(ws), nb,
-                                   dev, st), "rp_bn_bwd")
+        _lib.check(L.rp_bn_bwd_f32(_p(dy), _p(y) if relu else None, _p(x), _p(mean), _p(var), _p(gamma.detach()), eps, _p(dx),
+                                   _p(dz) if (relu and has_res) else None, _p(dg), _p(db), M, C, _p(ws), nb, dev, st), "rp_bn_bwd")
         ops._count(3)
-        return dx, dg, db, None, None, None, None, (dz if has_res else None), None
+        return dx, dg, db, None, None, None, None, dz, None
 
 
 class MaxPoolFn(torch.autograd.Function):
