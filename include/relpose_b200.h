@@ -371,6 +371,14 @@ int rp_conv_dw_tc_supported(int C, int O, int KH, int KW, int stride);
 size_t rp_conv_dw_tc_workspace_bytes(int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int stride, int device);
 int rp_conv_dw_tc(const void* x_planes, const void* dy_planes, float* dw, int n_img, int H, int W, int C, int O, int KH,
                   int KW, int pad, int stride, void* workspace, size_t workspace_bytes, int device, void* stream);
+/* Flash-style backward of the Essential Matrix Module core (autograd of vision_transformer.py:198-223 without the
+ * 576x576 tensors).  Forward = rp_essential_tc, whose workspace begins with lse2 [B][2][2][3][576] (row / column
+ * log2-sum-exp of the scaled scores): keep it.  d_bil [B,2,3,70,70] -> d_qkv float32 [2B,576,576] (every element written
+ * once; the positional encodings receive no gradient).  Four launches: dT = V' dF, pass A (row / column sums of A .* dA,
+ * T = A V', A^T dT), dv, pass B (dq = dS k, dk = dS^T q); S and A are recomputed per tile on tcgen05. */
+size_t rp_em_bwd_tc_workspace_bytes(int B);
+int rp_em_bwd_tc(const void* qkv_planes, const float* pos, const float* lse2, const float* d_bil, float* d_qkv, int B,
+                 void* workspace, size_t workspace_bytes, int device, void* stream);
 int rp_concat_vpos_f32(const float* qkv, const float* pos, float* vp, int n_img, int device, void* stream);
 int rp_scatter_dv_f32(const float* dvp, float* dqkv, int n_img, int device, void* stream);
 

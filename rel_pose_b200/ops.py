@@ -759,6 +759,43 @@ def essential_tc(qkv_planes, pos, flags=0):
     return bil
 
 
+def essential_tc_train(qkv_planes, pos):
+    """Training forward of the module core: (bil [B,2,3,70,70], lse2 [B,2,2,3,576]) -- the row / column log2-sum-exp
+    vectors are the head of rp_essential_tc's workspace and all the flash-style backward needs besides q, k, v."""
+    _req(qkv_planes, "qkv_planes", torch.bfloat16); _req(pos, "pos")
+    P, n = qkv_planes.shape[0], qkv_planes.shape[1]
+    B = n // 2
+    assert n == 2 * B and tuple(qkv_planes.shape[2:]) == (NTOK, 3 * EMBED) and tuple(pos.shape) == (B, NTOK, NPOS)
+    bil = torch.empty((B, 2, HEADS, EMW, EMW), dtype=torch.float32, device=qkv_planes.device)
+    L = _lib.lib()
+    ws_bytes = L.rp_essential_tc_workspace_bytes(B, P)
+    ws = torch.empty((ws_bytes // 4 + 4,), dtype=torch.float32, device=qkv_planes.device)
+    dev, st = _ctx(qkv_planes)
+    _tbegin(f"essential_tc{'x3' if P == 2 else ''}",
+            B * 2.0 * HEADS * (3 * 2.0 * NTOK * NTOK * HDIM + 2.0 * NTOK * NTOK * EMW + 2.0 * NTOK * EMW * EMW),
+            2.0 * P * n * NTOK * 3 * EMBED + 4.0 * B * 2 * HEADS * EMW * EMW)
+    _lib.check(L.rp_essential_ex_tc(_p(qkv_planes), _p(pos), _p(bil), B, P, 0, _p(ws), ws_bytes, dev, st), "rp_essential_tc")
+    _count(3)
+    return bil, ws[:B * 2 * 2 * HEADS * NTOK].clone().reshape(B, 2, 2, HEADS, NTOK)
+
+
+def em_bwd_tc(qkv_planes, pos, lse2, d_bil):
+    """Flash-style backward of the module core -> d_qkv float32 [2B,576,576]."""
+    _req(qkv_planes, "qkv_planes", torch.bfloat16); _req(pos, "pos"); _req(lse2, "lse2"); _req(d_bil, "d_bil")
+    P, n = qkv_planes.shape[0], qkv_planes.shape[1]
+    B = n // 2
+    assert P == 2 and tuple(d_bil.shape) == (B, 2, HEADS, EMW, EMW) and tuple(lse2.shape) == (B, 2, 2, HEADS, NTOK)
+    L = _lib.lib()
+    nb = L.rp_em_bwd_tc_workspace_bytes(B)
+    ws = torch.empty((nb // 4 + 4,), dtype=torch.float32, device=d_bil.device)
+    dqkv = torch.empty((n, NTOK, 3 * EMBED), dtype=torch.float32, device=d_bil.device)
+    dev, st = _ctx(d_bil)
+    _tbegin("em_bwd_tcx3", B * 2.0 * HEADS * (7 * 2.0 * NTOK * NTOK * HDIM), 2.0 * P * n * NTOK * 3 * EMBED + 4.0 * n * NTOK * 3 * EMBED)
+    _lib.check(L.rp_em_bwd_tc(_p(qkv_planes), _p(pos), _p(lse2), _p(d_bil), _p(dqkv), B, _p(ws), nb, dev, st), "rp_em_bwd_tc")
+    _count(4)
+    return dqkv
+
+
 def em_project(bil, weight, bias):
     """bil [B,2,3,70,70] -> [2B,70,192] (proj_fundamental + the reference's output flip)."""
     _req(bil, "bil"); _req(weight, "weight"); _req(bias, "bias")

@@ -309,8 +309,9 @@ def attention(qkv):
     return (AttentionFn if TRAIN_FLASH else AttentionMaterialisedFn).apply(qkv)
 
 
-class EssentialFn(torch.autograd.Function):
-    """Essential Matrix Module core (vision_transformer.py:198-223): qkv [2B,576,576], pos [B,576,6] -> F [B,2,3,70,70].
+class EssentialMaterialisedFn(torch.autograd.Function):
+    """Essential Matrix Module core on materialised 576 x 576 matrices, fp32 SIMT: the A/B partner of EssentialFn
+    (RELPOSE_TRAIN_FLASH=0).  (vision_transformer.py:198-223): qkv [2B,576,576], pos [B,576,6] -> F [B,2,3,70,70].
     dir 0: S = q2 k1^T/8, V' = [v1|pos];  dir 1: S = q1 k2^T/8, V' = [v2|pos];  A = softmax(S,-1)*softmax(S,-2);
     F = V'^T A V'.  The positional columns receive no gradient (9.2)."""
 
@@ -388,6 +389,30 @@ class EssentialFn(torch.autograd.Function):
         _lib.check(L.rp_scatter_dv_f32(_p(dVp), _p(dqkv), n, dev, st), "rp_scatter_dv")
         ops._count()
         return dqkv, None
+
+
+class EssentialFn(torch.autograd.Function):
+    """Essential Matrix Module core (vision_transformer.py:198-223), flash style in both directions: qkv [2B,576,576],
+    pos [B,576,6] -> F [B,2,3,70,70].  Forward = the inference kernels (rp_essential_tc); saved for the backward: the bf16
+    planes of qkv, pos and the row / column log-sum-exp vectors; csrc/em_bwd_tc.cu recomputes S and the dual-softmax matrix
+    per tile.  The positional columns receive no gradient."""
+
+    @staticmethod
+    def forward(ctx, qkv, pos):
+        planes = ops.split_planes(qkv.contiguous(), _TCP)
+        pos = pos.contiguous()
+        bil, lse2 = ops.essential_tc_train(planes, pos)
+        ctx.save_for_backward(planes, pos, lse2)
+        return bil
+
+    @staticmethod
+    def backward(ctx, dF):
+        planes, pos, lse2 = ctx.saved_tensors
+        return ops.em_bwd_tc(planes, pos, lse2, dF.contiguous()), None
+
+
+def essential(qkv, pos):
+    return (EssentialFn if TRAIN_FLASH else EssentialMaterialisedFn).apply(qkv, pos)
 
 
 class EmProjectFn(torch.autograd.Function):
@@ -536,6 +561,46 @@ class ConvFn(torch.autograd.Function):
         return dx, dwt, db, None, None
 
 
+_stem_idx_cache = {}
+
+
+def _stem_window_index(device):
+    """position of conv1.weight[o, c, ky, kx] inside the [4 x 64] space-to-depth window filter of rp_stem_weight_windows_f32
+    (conv_aux.cu): row a = (ky + 1) // 2, column b * 16 + (dy * 2 + dx) * 3 + c with b = (kx + 1) // 2"""
+    key = str(device)
+    if key not in _stem_idx_cache:
+        c, ky, kx = torch.meshgrid(torch.arange(3), torch.arange(7), torch.arange(7), indexing="ij")
+        a, dy, b, dx = (ky + 1) // 2, (ky + 1) % 2, (kx + 1) // 2, (kx + 1) % 2
+        _stem_idx_cache[key] = (a * 64 + b * 16 + (dy * 2 + dx) * 3 + c).reshape(-1).to(device)
+    return _stem_idx_cache[key]
+
+
+class StemConvFn(torch.autograd.Function):
+    """resnet.conv1 (7x7 / 2 on 3 channels, model.py:127) on the tensor cores in both directions: the images go straight
+    into the space-to-depth window planes of the inference path (A1 fused, rp_preprocess_stem_windows_*), where the stem is
+    a 4 x 1 convolution over 64 'channels'; its weight gradient is the implicit-GEMM kernel on the same planes, gathered
+    back to [64,3,7,7].  No gradient flows to the images."""
+
+    @staticmethod
+    def forward(ctx, images, weight):
+        O = weight.shape[0]
+        xw = ops.preprocess_stem_windows(images, _TCP)                                   # [P, 2B, 115, 112, 64]
+        w2 = ops.stem_weight_windows(weight.detach())                                    # [O, 4, 1, 64]
+        y = ops.conv2d_tc(xw, ops.split_planes(w2.reshape(O, -1), _TCP), 4, 1, None, None, 1, 0, ops.ACT_NONE,
+                          want_f32=True, planes_out=0)[0]
+        ctx.save_for_backward(xw)
+        ctx.O = O
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xw,) = ctx.saved_tensors
+        O = ctx.O
+        dw2 = ops.conv_dw_tc(xw, ops.split_planes(dy.contiguous(), _TCP), 4, 1, 0, 1)    # [O, 4, 1, 64]
+        dw = dw2.reshape(O, 256).index_select(1, _stem_window_index(dy.device)).reshape(O, 3, 7, 7)
+        return None, dw
+
+
 class BatchNormTrainFn(torch.autograd.Function):
     """y = act(BN_train(x) + residual) on NHWC [.., C]; updates the running statistics like nn.BatchNorm2d.train()."""
 
@@ -633,7 +698,6 @@ def forward_train(model, images, Gs, intrinsics):
     images = images.contiguous()
     if images.dtype != torch.uint8:
         images = images.float()
-    x = ops.preprocess_nhwc4(images)                                  # A1 (no gradient w.r.t. the images)
     kxy = None
     if intrinsics is not None:
         intrinsics, kxy, flags = model.update_intrinsics(images.shape, intrinsics)
@@ -649,7 +713,11 @@ def forward_train(model, images, Gs, intrinsics):
         if f & 2:
             raise ValueError("principal point is in upper left, not setup for this right now (vision_transformer.py:124-126)")
     r, e, vt = model.resnet, model.extractor_final_conv, model.fusion_transformer
-    x = _bn(_conv(x, r.conv1), r.bn1)                                 # A2
+    if TRAIN_DW_TC and tuple(r.conv1.weight.shape) == (64, 3, 7, 7) and r.conv1.bias is None:
+        x = StemConvFn.apply(images, r.conv1.weight)                  # A1 + conv1 (no gradient w.r.t. the images)
+    else:
+        x = _conv(ops.preprocess_nhwc4(images), r.conv1)
+    x = _bn(x, r.bn1)                                                 # A2
     x = MaxPoolFn.apply(x)
     for blk in (r.layer1[0], r.layer1[1], r.layer2[0], r.layer2[1]):
         x = _basic_block(x, blk)
@@ -669,7 +737,7 @@ def forward_train(model, images, Gs, intrinsics):
     ca = blk.cross_attn
     qkv = LinearFn.apply(_ln(x, blk.norm1), ca.qkv.weight, ca.qkv.bias)
     pos = ops.posenc(B, kxy, x.device)
-    bil = EssentialFn.apply(qkv, pos)
+    bil = essential(qkv, pos)
     f = EmProjectFn.apply(bil, ca.proj_fundamental.weight, ca.proj_fundamental.bias)
     f = AddFn.apply(f, _mlp(_ln(f, blk.norm2), blk.mlp))
     feat = _ln(f, vt.norm).reshape(B, -1)                             # A9
