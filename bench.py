@@ -391,10 +391,82 @@ def leg_config4(model, dev, rank, world, size, total_pairs, micro, passes):
             "frac_of_sustained_bf16_peak_all_gpus": val * FLOP_PER_PAIR / 1e12 / (pk["bf16_tflops_sustained"] * world)}
 
 
+def reference_train_eager(dev, a, steps, warm):
+    """The GPU bar of config 5: the UNMODIFIED reference model in .train() on this B200 under torch eager (cuDNN / cuBLAS
+    forward, torch autograd backward), with the optimizer stack train.py builds (Adam + OneCycleLR + clip_grad_norm_, train.py:69-73,
+    161-165).  lietorch is absent, so the loss backward -- a few hundred FLOPs on [B,2,7] -- is replaced by a fixed upstream pose
+    gradient injected at poses_est[0].data (what make_golden_train.py does); everything that costs time is the reference's own.
+    Returns ms per step for fp32 (TF32 off) / TF32 / bf16 autocast, or None when the reference tree is not present."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    if ref_loader.find_reference_root() is None:
+        return None
+    from rel_pose_b200 import synthetic as S, train_synthetic as T
+    out = {"what": "unmodified reference ViTEss.train() + torch autograd + Adam/OneCycleLR/clip_grad_norm_, torch eager on cuda",
+           "pairs_per_gpu": a.batch, "image_size": list(a.size), "steps": steps, "warmup_steps": warm,
+           "timing": "CUDA events around the timed steps, device-resident batches"}
+    batches = [T.make_batch(i, 0, a.batch, a.size[0], a.size[1], dev) for i in range(2)]
+    g = torch.Generator().manual_seed(5)
+    gpose = (torch.randn(a.batch, 2, 7, generator=g) * 0.1).to(dev)
+    tf32_state = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def run(mode):
+        model, SE3 = ref_loader.load_reference_model()
+        model.load_state_dict(S.make_state_dict(0, "init"))
+        model = model.to(dev).train()
+        for q in list(model.resnet.layer3.parameters()) + list(model.resnet.layer4.parameters()):
+            q.requires_grad = False                                                  # train.py:60-64
+        params = [q for q in model.parameters() if q.requires_grad]
+        opt = torch.optim.Adam(params, lr=a.lr, weight_decay=a.weight_decay)
+        sch = torch.optim.lr_scheduler.OneCycleLR(opt, a.lr, a.total_steps, pct_start=a.warmup / a.total_steps, div_factor=25,
+                                                  anneal_strategy="cos")
+        tf = mode == "tf32"
+        torch.backends.cuda.matmul.allow_tf32 = tf
+        torch.backends.cudnn.allow_tf32 = tf
+
+        def step(i):
+            images, poses, intr = batches[i % 2]
+            Gs = torch.zeros(a.batch, 2, 7, device=dev); Gs[..., 6] = 1
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
+                est = model(images, SE3(Gs), intrinsics=intr.clone())[0].data
+            est.backward(gpose.to(est.dtype))
+            torch.nn.utils.clip_grad_norm_(params, a.clip)
+            opt.step()
+            sch.step()
+        for i in range(warm):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / steps
+        del model, opt, sch
+        torch.cuda.empty_cache()
+        return ms
+    try:
+        for mode in ("fp32", "tf32", "bf16_autocast"):
+            out["ms_per_step_" + mode] = run(mode)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32_state
+    return out
+
+
 def leg_config5(dev, rank, world, local, steps, warm):
     from rel_pose_b200 import train_synthetic as T
     a = T.default_options(steps=steps, warmup_steps=warm, pool=4)
-    return T.train_loop(a, dev, rank, world, local)
+    res = T.train_loop(a, dev, rank, world, local)
+    if rank == 0 and res is not None and world == 1:
+        try:
+            res["gpu_eager_baseline"] = reference_train_eager(dev, a, min(steps, 10), 3)
+        except Exception as e:                                                       # baseline leg: never takes the line down
+            res["gpu_eager_baseline"] = {"error": repr(e)[:300]}
+    return res
 
 
 def leg_geometry(dev):

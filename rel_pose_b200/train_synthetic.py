@@ -269,7 +269,7 @@ def train_loop(a, dev, rank=0, world=1, local=0):
     if rank != 0:
         return None
     ls = [l for l, _ in losses]
-    return {"metric": "training steps/sec (config 5: train.py loop on synthetic pairs, fp32 operands, tensor-core + SIMT backward)",
+    return {"metric": "training steps/sec (config 5: train.py loop on synthetic pairs; fp32-class split-bf16 products on tcgen05 in forward and backward, flash-style attention / Essential-Matrix-Module gradients, implicit-GEMM weight gradients)",
             "n_gpus": world, "steps": a.steps, "warmup_steps": a.warmup_steps, "pairs_per_gpu": a.batch, "image_size": [H, W],
             "ms_per_step": ms / len(timed), "steps_per_s": len(timed) / (ms * 1e-3),
             "pairs_per_s": world * a.batch * len(timed) / (ms * 1e-3),
