@@ -349,7 +349,9 @@ int rp_im2col_nhwc_f32(const float* x, float* cols, int n, int H, int W, int C, 
 int rp_im2col_t_planes_bf16(const float* x, void* planes, int P, int n, int H, int W, int C, int KH, int KW, int stride, int pad,
                             int device, void* stream);
 int rp_col2im_nhwc_f32(const float* dcols, float* dx, int n, int H, int W, int C, int KH, int KW, int stride, int pad,                  int device, void* stream);
-int rp_maxpool3x3s2_bwd_f32(const float* dy, const float* x, float* dx, int n, int H, int W, int C, int device, void* stream);
+size_t rp_maxpool3x3s2_bwd_workspace_bytes(int n, int H, int W, int C);
+int rp_maxpool3x3s2_bwd_f32(const float* dy, const float* x, float* dx, int n, int H, int W, int C, void* workspace,
+                            size_t workspace_bytes, int device, void* stream);
 int rp_normalize_pose_bwd_f32(const float* dout, const float* raw, float* draw, int B, int device, void* stream);
 /* Flash-style attention for the training step (autograd of vision_transformer.py:321-329 without the 576x576 tensors):
  * rp_self_attention_tc_lse = rp_self_attention_tc that also writes lse [n_img][3][576], the log2-sum-exp of every

@@ -107,7 +107,8 @@ _SIGNATURES = {
     "rp_im2col_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
     "rp_im2col_t_planes_bf16": (_c_int, [_ptr, _ptr] + [_c_int] * 10 + [_ptr]),
     "rp_col2im_nhwc_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
-    "rp_maxpool3x3s2_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr]),
+    "rp_maxpool3x3s2_bwd_workspace_bytes": (_c_size, [_c_int] * 4),
+    "rp_maxpool3x3s2_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_normalize_pose_bwd_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_concat_vpos_f32": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr]),
     "rp_scatter_dv_f32": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr]),

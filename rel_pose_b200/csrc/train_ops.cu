@@ -138,7 +138,7 @@ __global__ void add_bcast_rows_kernel(const float* __restrict__ a, const float* 
 }
 
 // column sums of A (optionally of A .* B) over rows: two deterministic stages.  partial [nblk][cols]
-constexpr int CS_ROWS = 256;
+constexpr int CS_ROWS = 64;
 __global__ void colsum_partial_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ partial,
                                       long long rows, int cols, int period) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +152,36 @@ __global__ void colsum_partial_kernel(const float* __restrict__ A, const float* 
     }
     (void)period;
     partial[(long long)blockIdx.y * cols + c] = s;
+}
+// cols % 4 == 0: 256 threads = CW float4 columns x 256 / CW row lanes, lanes combined through shared memory in a fixed order
+// (the scalar kernel above walked 256 rows per thread with one load in flight: 17 us per bias gradient)
+__global__ void __launch_bounds__(256) colsum_partial_v4_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                float* __restrict__ partial, long long rows, int cols, int CW) {
+    __shared__ float4 sm[256];
+    const int c4n = cols >> 2, nl = 256 / CW;
+    const int cl = threadIdx.x % CW, rl = threadIdx.x / CW, col4 = blockIdx.x * CW + cl;
+    const long long r0 = (long long)blockIdx.y * CS_ROWS, r1 = min(rows, r0 + CS_ROWS);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < nl && col4 < c4n) {
+        for (long long r = r0 + rl; r < r1; r += nl) {
+            float4 v = reinterpret_cast<const float4*>(A)[r * c4n + col4];
+            if (B) {
+                const float4 b = reinterpret_cast<const float4*>(B)[r * c4n + col4];
+                v.x *= b.x; v.y *= b.y; v.z *= b.z; v.w *= b.w;
+            }
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < CW && col4 < c4n) {
+        float4 t = sm[threadIdx.x];
+        for (int l = 1; l < nl; ++l) {
+            const float4 v = sm[l * CW + threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        reinterpret_cast<float4*>(partial + (long long)blockIdx.y * cols)[col4] = t;
+    }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblk, int cols) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,23 +232,27 @@ __global__ void __launch_bounds__(256) ln_train_fwd_kernel(const float* __restri
     }
     if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
-// dx per row; per-block partial dgamma / dbeta (block = 8 rows) -> partial [nblk][2][cols]
+// dx per row; per-block partial dgamma / dbeta (block = LN_BWD_ROWS rows, four per warp) -> partial [nblk][2][cols]
+constexpr int LN_BWD_ROWS = 32;
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ g, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, float* __restrict__ dx,
                                                      float* __restrict__ partial, int rows, int cols) {
     __shared__ float sg[8][256], sb[8][256];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + w;
-    float dyv[8], xh[8];
+    float ga[8], ba[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dyv[i] = 0.f; xh[i] = 0.f; }
-    if (row < rows) {
+    for (int i = 0; i < 8; ++i) { ga[i] = 0.f; ba[i] = 0.f; }
+    for (int j = 0; j < LN_BWD_ROWS / 8; ++j) {
+        const int row = blockIdx.x * LN_BWD_ROWS + j * 8 + w;
+        if (row >= rows) break;
+        float dyv[8], xh[8];
         const float m = mean[row], rs = rstd[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c = lane + 32 * i;
+            dyv[i] = 0.f; xh[i] = 0.f;
             if (c < cols) {
                 dyv[i] = dy[(size_t)row * cols + c];
                 xh[i] = (x[(size_t)row * cols + c] - m) * rs;
@@ -233,12 +267,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         for (int i = 0; i < 8; ++i) {
             const int c = lane + 32 * i;
             if (c < cols) dx[(size_t)row * cols + c] = rs * (dyv[i] * g[c] - s1 - xh[i] * s2);
+            ga[i] = fmaf(dyv[i], xh[i], ga[i]);
+            ba[i] += dyv[i];
         }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = lane + 32 * i;
-        if (c < 256) { sg[w][c] = dyv[i] * xh[i]; sb[w][c] = dyv[i]; }
+        if (c < 256) { sg[w][c] = ga[i]; sb[w][c] = ba[i]; }
     }
     __syncthreads();
     const int c = threadIdx.x;
@@ -362,6 +398,7 @@ __global__ void __launch_bounds__(256) softmax_cols_bwd_kernel(const float* __re
 // Round 1's version walked 512 rows per 64-thread block with one scalar load in flight: 76 us for the 38 MB stem tensor.
 constexpr int BN_ROWS = 128;
 constexpr int BN_THREADS = 256;
+constexpr int BN_FINAL_LANES = 16;                                   // threads per channel in the second stage (block = 64 channels x 16)
 
 // one block's partial sums of (a, b) per channel: a = f0(row), b = f1(row), written to partial[blk][2][C]
 template <typename F>
@@ -413,15 +450,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_partial_kernel(const floa
         b = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
     });
 }
-// partial [nblk][2][C] -> sums in double: thread = (channel, one of four lanes over the blocks), fixed combination order
+// partial [nblk][2][C] -> sums in double: thread = (channel, one of BN_FINAL_LANES lanes over the blocks), fixed combination order
 __device__ __forceinline__ void bn_final_sums(const float* __restrict__ partial, int nblk, int C, double& s, double& q, int& c,
                                               bool& writer) {
-    __shared__ double sm[2][4][64];
+    __shared__ double sm[2][BN_FINAL_LANES][64];
     const int cl = threadIdx.x & 63, l = threadIdx.x >> 6;
     c = blockIdx.x * 64 + cl;
     double ss = 0.0, qq = 0.0;
     if (c < C)
-        for (int b = l; b < nblk; b += 4) {
+        for (int b = l; b < nblk; b += BN_FINAL_LANES) {
             ss += (double)partial[((long long)b * 2 + 0) * C + c];
             qq += (double)partial[((long long)b * 2 + 1) * C + c];
         }
@@ -429,11 +466,12 @@ __device__ __forceinline__ void bn_final_sums(const float* __restrict__ partial,
     sm[1][l][cl] = qq;
     __syncthreads();
     writer = l == 0 && c < C;
-    s = sm[0][0][cl] + sm[0][1][cl] + sm[0][2][cl] + sm[0][3][cl];
-    q = sm[1][0][cl] + sm[1][1][cl] + sm[1][2][cl] + sm[1][3][cl];
+    s = 0.0; q = 0.0;
+    if (writer)
+        for (int k = 0; k < BN_FINAL_LANES; ++k) { s += sm[0][k][cl]; q += sm[1][k][cl]; }
 }
 // mean / biased var in double (the one-pass sum of squares is safe there); also the running-stat update
-__global__ void __launch_bounds__(256) bn_stats_final_kernel(const float* __restrict__ partial, int nblk, long long M, int C,
+__global__ void __launch_bounds__(64 * BN_FINAL_LANES) bn_stats_final_kernel(const float* __restrict__ partial, int nblk, long long M, int C,
                                                               float* __restrict__ mean, float* __restrict__ var,
                                                               float* __restrict__ running_mean, float* __restrict__ running_var,
                                                               float momentum) {
@@ -499,7 +537,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_partial_kernel(const float*
         b = make_float4(a.x * (xv.x - m.x) * rs.x, a.y * (xv.y - m.y) * rs.y, a.z * (xv.z - m.z) * rs.z, a.w * (xv.w - m.w) * rs.w);
     });
 }
-__global__ void __launch_bounds__(256) bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int C,
+__global__ void __launch_bounds__(64 * BN_FINAL_LANES) bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int C,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
     double s, q;
     int c;
@@ -607,38 +645,63 @@ __global__ void col2im_kernel(const float* __restrict__ dcols, float* __restrict
 }
 // nn.MaxPool2d(3,2,1) backward, NHWC.  PyTorch routes the gradient of a window to its FIRST maximum in (ky,kx)
 // scan order; an input pixel gathers from the <= 4 windows that contain it.
-__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int n, int H,
-                                   int W, int C, int Ho, int Wo) {
-    const long long total = (long long)n * H * W * C;
+// Two passes (the one-pass version re-scanned up to four 3x3 windows per input element: 36 loads each, 277 us for the stem):
+//  1. arg[window][c] = position 0..8 of the FIRST maximum of the window (PyTorch's tie-break), 4 channels per thread
+//  2. dx[pixel][c] = sum of dy over the <= 4 windows that contain the pixel and whose arg points at it (fixed order)
+__global__ void __launch_bounds__(256) maxpool_arg_kernel(const float* __restrict__ x, uchar4* __restrict__ arg, int n, int H, int W,
+                                                          int C4, int Ho, int Wo) {
+    const long long total = (long long)n * Ho * Wo * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const long long pix = i / C;
-        const int ix = (int)(pix % W), iy = (int)((pix / W) % H), im = (int)(pix / ((long long)W * H));
-        const float xv = x[i];
-        float s = 0.f;
-        for (int oy = (iy + 1 - 2 + 1) / 2; oy <= (iy + 1) / 2; ++oy) {          // windows rows with 2*oy-1 <= iy <= 2*oy+1
-            if (oy < 0 || oy >= Ho) continue;
-            for (int ox = (ix + 1 - 2 + 1) / 2; ox <= (ix + 1) / 2; ++ox) {
-                if (ox < 0 || ox >= Wo) continue;
-                // is (iy,ix) the first maximum of window (oy,ox)?
-                bool first = true;
-                float mx = -INFINITY;
-                int ay = -1, ax = -1;
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int yy = 2 * oy - 1 + ky;
-                    if (yy < 0 || yy >= H) continue;
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int xx = 2 * ox - 1 + kx;
-                        if (xx < 0 || xx >= W) continue;
-                        const float v = x[(((long long)im * H + yy) * W + xx) * C + c];
-                        if (v > mx) { mx = v; ay = yy; ax = xx; }
-                    }
-                }
-                (void)first;
-                if (ay == iy && ax == ix && xv == mx) s += dy[(((long long)im * Ho + oy) * Wo + ox) * C + c];
+        const int c4 = (int)(i % C4);
+        const long long win = i / C4;
+        const int ox = (int)(win % Wo), oy = (int)((win / Wo) % Ho), im = (int)(win / ((long long)Wo * Ho));
+        float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        uchar4 a = make_uchar4(255, 255, 255, 255);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = 2 * oy - 1 + ky;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = 2 * ox - 1 + kx;
+                if (xx < 0 || xx >= W) continue;
+                const float4 v = reinterpret_cast<const float4*>(x)[(((long long)im * H + yy) * W + xx) * C4 + c4];
+                const unsigned char k = (unsigned char)(ky * 3 + kx);
+                if (v.x > mx.x) { mx.x = v.x; a.x = k; }
+                if (v.y > mx.y) { mx.y = v.y; a.y = k; }
+                if (v.z > mx.z) { mx.z = v.z; a.z = k; }
+                if (v.w > mx.w) { mx.w = v.w; a.w = k; }
             }
         }
-        dx[i] = s;
+        arg[i] = a;
+    }
+}
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, const uchar4* __restrict__ arg,
+                                                          float* __restrict__ dx, int n, int H, int W, int C4, int Ho, int Wo) {
+    const long long total = (long long)n * H * W * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const long long pix = i / C4;
+        const int ix = (int)(pix % W), iy = (int)((pix / W) % H), im = (int)(pix / ((long long)W * H));
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {                        // windows with 2 oy - 1 <= iy <= 2 oy + 1
+            if (oy >= Ho) continue;
+            const int ky = iy - (2 * oy - 1);
+            for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
+                if (ox >= Wo) continue;
+                const unsigned char k = (unsigned char)(ky * 3 + (ix - (2 * ox - 1)));
+                const long long w = (((long long)im * Ho + oy) * Wo + ox) * C4 + c4;
+                const uchar4 a = arg[w];
+                if (a.x == k || a.y == k || a.z == k || a.w == k) {
+                    const float4 d = reinterpret_cast<const float4*>(dy)[w];
+                    if (a.x == k) s.x += d.x;
+                    if (a.y == k) s.y += d.y;
+                    if (a.z == k) s.z += d.z;
+                    if (a.w == k) s.w += d.w;
+                }
+            }
+        }
+        reinterpret_cast<float4*>(dx)[i] = s;
     }
 }
 
@@ -760,8 +823,14 @@ extern "C" int rp_colsum_f32(const float* A, const float* B, float* out, int64_t
     RP_REQUIRE(workspace && workspace_bytes >= rp_colsum_workspace_bytes(rows, cols), RP_EWORKSPACE, "rp_colsum: workspace too small");
     RP_GUARD(device);
     const int nblk = (int)((rows + CS_ROWS - 1) / CS_ROWS);
-    dim3 grid((cols + 127) / 128, nblk);
-    colsum_partial_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(A, B, static_cast<float*>(workspace), rows, cols, 0);
+    if (cols % 4 == 0 && rp::aligned16(A) && rp::aligned16(B) && rp::aligned16(workspace)) {
+        const int c4n = cols / 4, CW = c4n < 64 ? c4n : 64;
+        colsum_partial_v4_kernel<<<dim3((c4n + CW - 1) / CW, nblk), 256, 0, (cudaStream_t)stream>>>(A, B, static_cast<float*>(workspace),
+                                                                                                  rows, cols, CW);
+    } else {
+        dim3 grid((cols + 127) / 128, nblk);
+        colsum_partial_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(A, B, static_cast<float*>(workspace), rows, cols, 0);
+    }
     colsum_final_kernel<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), out, nblk, cols);
     return rp::finish_launch("rp_colsum");
 }
@@ -784,7 +853,7 @@ extern "C" int rp_layernorm_bwd_f32(const float* dy, const float* x, const float
                "rp_layernorm_bwd: bad argument");
     RP_REQUIRE(workspace && workspace_bytes >= rp_layernorm_bwd_workspace_bytes(rows, cols), RP_EWORKSPACE, "rp_layernorm_bwd: workspace too small");
     RP_GUARD(device);
-    const int nblk = (rows + 7) / 8;
+    const int nblk = (rows + LN_BWD_ROWS - 1) / LN_BWD_ROWS;
     ln_bwd_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(dy, x, gamma, mean, rstd, dx, static_cast<float*>(workspace), rows, cols);
     ln_bwd_final_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), dgamma, dbeta, nblk, cols);
     return rp::finish_launch("rp_layernorm_bwd");
@@ -830,7 +899,7 @@ extern "C" int rp_bn_train_stats_f32(const float* x, float* mean, float* var, fl
     RP_REQUIRE(C % 4 == 0 && C <= 2 * BN_THREADS && rp::aligned16(x), RP_EINVAL, "rp_bn_train_stats: C must be a multiple of 4 (<= 512)");
     const int nblk = (int)((M + BN_ROWS - 1) / BN_ROWS);
     bn_stats_partial_kernel<<<nblk, BN_THREADS, 0, (cudaStream_t)stream>>>(x, static_cast<float*>(workspace), M, C);
-    bn_stats_final_kernel<<<(C + 63) / 64, 256, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), nblk, M, C, mean, var,
+    bn_stats_final_kernel<<<(C + 63) / 64, 64 * BN_FINAL_LANES, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), nblk, M, C, mean, var,
                                                                          running_mean, running_var, momentum);
     return rp::finish_launch("rp_bn_train_stats");
 }
@@ -852,7 +921,7 @@ extern "C" int rp_bn_bwd_f32(const float* dy, const float* y_relu, const float* 
                    rp::aligned16(dz_out), RP_EINVAL, "rp_bn_bwd: C must be a multiple of 4 (<= 512), 16-byte alignment");
     const int nblk = (int)((M + BN_ROWS - 1) / BN_ROWS);
     bn_bwd_partial_kernel<<<nblk, BN_THREADS, 0, (cudaStream_t)stream>>>(dy, y_relu, x, mean, var, eps, static_cast<float*>(workspace), M, C);
-    bn_bwd_final_kernel<<<(C + 63) / 64, 256, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), nblk, C, dgamma, dbeta);
+    bn_bwd_final_kernel<<<(C + 63) / 64, 64 * BN_FINAL_LANES, 0, (cudaStream_t)stream>>>(static_cast<float*>(workspace), nblk, C, dgamma, dbeta);
     RP_LAUNCH1D(bn_bwd_apply_kernel, M * C / 4, dy, y_relu, x, mean, var, gamma, dgamma, dbeta, eps, dx, dz_out, M, C);
     return rp::finish_launch("rp_bn_bwd");
 }
@@ -885,11 +954,20 @@ extern "C" int rp_col2im_nhwc_f32(const float* dcols, float* dx, int n, int H, i
     RP_LAUNCH1D(col2im_kernel, (long long)n * H * W * C, dcols, dx, n, H, W, C, KH, KW, stride, pad, Ho, Wo);
     return rp::finish_launch("rp_col2im");
 }
-extern "C" int rp_maxpool3x3s2_bwd_f32(const float* dy, const float* x, float* dx, int n, int H, int W, int C, int device, void* stream) {
-    RP_REQUIRE(dy && x && dx && n > 0 && H > 0 && W > 0 && C > 0, RP_EINVAL, "rp_maxpool3x3s2_bwd: bad argument");
+extern "C" size_t rp_maxpool3x3s2_bwd_workspace_bytes(int n, int H, int W, int C) {
+    if (n <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
+    return (size_t)n * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * C;               // one byte per (window, channel)
+}
+extern "C" int rp_maxpool3x3s2_bwd_f32(const float* dy, const float* x, float* dx, int n, int H, int W, int C, void* workspace,
+                                       size_t workspace_bytes, int device, void* stream) {
+    RP_REQUIRE(dy && x && dx && workspace && n > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, RP_EINVAL, "rp_maxpool3x3s2_bwd: bad argument");
+    RP_REQUIRE(workspace_bytes >= rp_maxpool3x3s2_bwd_workspace_bytes(n, H, W, C), RP_EWORKSPACE, "rp_maxpool3x3s2_bwd: workspace too small");
+    RP_REQUIRE(rp::aligned16(dy) && rp::aligned16(x) && rp::aligned16(dx) && rp::aligned16(workspace), RP_EALIGN, "rp_maxpool3x3s2_bwd: 16-byte alignment");
     RP_GUARD(device);
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    RP_LAUNCH1D(maxpool_bwd_kernel, (long long)n * H * W * C, dy, x, dx, n, H, W, C, Ho, Wo);
+    uchar4* arg = static_cast<uchar4*>(workspace);
+    RP_LAUNCH1D(maxpool_arg_kernel, (long long)n * Ho * Wo * (C / 4), x, arg, n, H, W, C / 4, Ho, Wo);
+    RP_LAUNCH1D(maxpool_bwd_kernel, (long long)n * H * W * (C / 4), dy, arg, dx, n, H, W, C / 4, Ho, Wo);
     return rp::finish_launch("rp_maxpool3x3s2_bwd");
 }
 extern "C" int rp_normalize_pose_bwd_f32(const float* dout, const float* raw, float* draw, int B, int device, void* stream) {

@@ -661,8 +661,11 @@ class MaxPoolFn(torch.autograd.Function):
         n, H, W, C = x.shape
         dx = torch.empty_like(x)
         dev, st = _ctx(x)
-        _lib.check(_lib.lib().rp_maxpool3x3s2_bwd_f32(_p(dy), _p(x), _p(dx), n, H, W, C, dev, st), "rp_maxpool3x3s2_bwd")
-        ops._count()
+        L = _lib.lib()
+        nb = L.rp_maxpool3x3s2_bwd_workspace_bytes(n, H, W, C)
+        ws = _ws(nb, x)
+        _lib.check(L.rp_maxpool3x3s2_bwd_f32(_p(dy), _p(x), _p(dx), n, H, W, C, _p(ws), nb, dev, st), "rp_maxpool3x3s2_bwd")
+        ops._count(2)
         return dx
 
 
