@@ -373,6 +373,15 @@ int rp_conv_dw_tc_supported(int C, int O, int KH, int KW, int stride);
 size_t rp_conv_dw_tc_workspace_bytes(int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int stride, int device);
 int rp_conv_dw_tc(const void* x_planes, const void* dy_planes, float* dw, int n_img, int H, int W, int C, int O, int KH,
                   int KW, int pad, int stride, void* workspace, size_t workspace_bytes, int device, void* stream);
+/* Weight gradient of nn.Linear (autograd of vision_transformer.py:323,331, vit_layers/mlp.py:21,24), dW [N][K] = dY^T X,
+ * through the same implicit-GEMM kernel: the M rows are the "pixels", the K / 64 column blocks of X the "taps" of a
+ * 1 x (K/64) convolution over 64 channels, so x_planes bf16 [2][M][K] and dy_planes bf16 [2][M][N] are read in place as
+ * MN-major operands (no transposed copies).  M % 8 == 0, M >= 64, K % 64 == 0, K <= 4096, N in {64,128,192} or a
+ * multiple of 192 / 128.  Deterministic (fixed-order slice reduction). */
+int rp_linear_dw_tc_supported(int M, int N, int K);
+size_t rp_linear_dw_tc_workspace_bytes(int M, int N, int K, int device);
+int rp_linear_dw_tc(const void* x_planes, const void* dy_planes, float* dw, int M, int N, int K, void* workspace,
+                    size_t workspace_bytes, int device, void* stream);
 /* Flash-style backward of the Essential Matrix Module core (autograd of vision_transformer.py:198-223 without the
  * 576x576 tensors).  Forward = rp_essential_tc, whose workspace begins with lse2 [B][2][2][3][576] (row / column
  * log2-sum-exp of the scaled scores): keep it.  d_bil [B,2,3,70,70] -> d_qkv float32 [2B,576,576] (every element written

@@ -118,6 +118,9 @@ _SIGNATURES = {
     "rp_conv_dw_tc_supported": (_c_int, [_c_int] * 5),
     "rp_conv_dw_tc_workspace_bytes": (_c_size, [_c_int] * 10),
     "rp_conv_dw_tc": (_c_int, [_ptr, _ptr, _ptr] + [_c_int] * 9 + [_ptr, _c_size, _c_int, _ptr]),
+    "rp_linear_dw_tc_supported": (_c_int, [_c_int] * 3),
+    "rp_linear_dw_tc_workspace_bytes": (_c_size, [_c_int] * 4),
+    "rp_linear_dw_tc": (_c_int, [_ptr, _ptr, _ptr] + [_c_int] * 3 + [_ptr, _c_size, _c_int, _ptr]),
     "rp_em_bwd_tc_workspace_bytes": (_c_size, [_c_int]),
     "rp_em_bwd_tc": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _c_size, _c_int, _ptr]),
     "rp_grad_norm_multi": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr, _c_int, _ptr]),

@@ -29,7 +29,9 @@ constexpr int THREADS = 256;
 constexpr int MAX_STAGES = 4;
 
 struct DwGeom {
-    int n_img, OH, OW, C, O, KH, KW, pad, stride;
+    int n_img, OH, OW, C, O, KH, KW, pad, stride_x, stride_y;
+    int Osub, nog;                         // output channels per work item (<= 192) and number of such groups
+    int tap_c;                             // 0: a tap shifts the pixel window (convolution); 64: a tap is the next 64-column block (nn.Linear)
     int HW, HH, halo_bytes;                // halo box (pixels) and its 1024-rounded size in shared memory
     int tiles_x, tiles_y, ntiles;
     int ncc, ntg, G, nps;                  // 64-channel chunks of C, tap groups, taps per group, pixel slices
@@ -64,7 +66,8 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // item -> (pixel slice, tap group, channel chunk)
     const int ps = blockIdx.x % g.nps;
     const int tg = (blockIdx.x / g.nps) % g.ntg;
-    const int cc = blockIdx.x / (g.nps * g.ntg);
+    const int cc = (blockIdx.x / (g.nps * g.ntg)) % g.ncc;
+    const int og = blockIdx.x / (g.nps * g.ntg * g.ncc);
     const int tap0 = tg * g.G;
     const int gcur = min(g.G, T - tap0);                     // taps of this group
     const int npairs = (gcur + 1) >> 1;
@@ -101,7 +104,7 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 tc::mbar_expect_tx(&full[stage], tx_bytes);
                 for (int p = 0; p < P; ++p)
                     for (int oc = 0; oc < g.noc; ++oc)
-                        tc::tma_load_5d(sb + (p * g.noc + oc) * TILE_B, &tmDY, &full[stage], oc * 64, ox0, oy0, img, p);
+                        tc::tma_load_5d(sb + (p * g.noc + oc) * TILE_B, &tmDY, &full[stage], og * g.Osub + oc * 64, ox0, oy0, img, p);
                 if (HALO) {
                     for (int p = 0; p < P; ++p)
                         tc::tma_load_5d(sb + g.dy_bytes + p * g.halo_bytes, &tmX, &full[stage], cc * 64, ox0 - g.pad, oy0 - g.pad, img, p);
@@ -109,8 +112,8 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     for (int t = 0; t < gcur; ++t) {
                         const int kh = (tap0 + t) / g.KW, kw = (tap0 + t) % g.KW;
                         for (int p = 0; p < P; ++p)
-                            tc::tma_load_5d(sb + g.dy_bytes + (t * P + p) * TILE_B, &tmX, &full[stage], cc * 64,
-                                            ox0 * g.stride + kw - g.pad, oy0 * g.stride + kh - g.pad, img, p);
+                            tc::tma_load_5d(sb + g.dy_bytes + (t * P + p) * TILE_B, &tmX, &full[stage], cc * 64 + kw * g.tap_c,
+                                            ox0 * g.stride_x + (g.tap_c ? 0 : kw) - g.pad, oy0 * g.stride_y + kh - g.pad, img, p);
                     }
                 }
             }
@@ -119,7 +122,7 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------------------- MMA issuer (convergent warp)
-        const uint32_t idesc = tc::make_idesc_bf16(128, g.O) | tc::IDESC_A_MN | tc::IDESC_B_MN;
+        const uint32_t idesc = tc::make_idesc_bf16(128, g.Osub) | tc::IDESC_A_MN | tc::IDESC_B_MN;
         int stage = 0, phase = 0;
         for (int tile = t_begin; tile < t_end; ++tile) {
             tc::mbar_wait(&full[stage], phase);
@@ -145,7 +148,7 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     const uint32_t a_kstep = HALO ? 2u * sbo : 2048u;    // 16 pixels = two rows of the tile
                     const uint32_t a0 = sb + g.dy_bytes + a_off0, a1 = a0 + a_plane;
                     const uint32_t b0 = sb, b1 = sb + g.noc * TILE_B;
-                    const uint32_t d = tmem_base + (uint32_t)(q * g.O);
+                    const uint32_t d = tmem_base + (uint32_t)(q * g.Osub);
                     uint32_t accum = first;
                     // correction terms of all four K steps first, main terms last (truncating fp32 accumulation)
 #pragma unroll
@@ -171,16 +174,16 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int span = r >> 6, c = r & 63;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const size_t KC = (size_t)T * g.C;
-        float* dst0 = partial + (size_t)ps * g.O * KC + (size_t)cc * 64 + c;
+        float* dst0 = partial + ((size_t)ps * g.O + (size_t)og * g.Osub) * KC + (size_t)cc * 64 + c;
         tc::mbar_wait(acc_full, 0);
         tc::tcgen05_fence_after();
         for (int q = 0; q < npairs; ++q) {
             const int t = 2 * q + span;
             const bool valid = t < gcur;                   // the odd group's last pair carries a duplicate second span
             float* dst = dst0 + (size_t)(tap0 + (valid ? t : 0)) * g.C;
-            for (int o0 = 0; o0 < g.O; o0 += 32) {
+            for (int o0 = 0; o0 < g.Osub; o0 += 32) {
                 uint32_t v[32];
-                tc::tmem_ld_32x32b_x32(t_lane + (uint32_t)(q * g.O + o0), v);
+                tc::tmem_ld_32x32b_x32(t_lane + (uint32_t)(q * g.Osub + o0), v);
                 tc::tmem_ld_wait();
                 if (valid) {
 #pragma unroll
@@ -220,34 +223,91 @@ bool dw_halo_enabled() {
     return v == 1;
 }
 
-int make_geom(DwGeom& g, int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int stride, int device, bool halo) {
-    g.n_img = n_img; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.pad = pad; g.stride = stride;
-    g.OH = (H + 2 * pad - KH) / stride + 1;
-    g.OW = (W + 2 * pad - KW) / stride + 1;
+int make_geom(DwGeom& g, int n_img, int H, int W, int C, int O, int KH, int KW, int pad, int stride_x, int stride_y, int device,
+              bool halo, bool linear = false) {
+    g.n_img = n_img; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.pad = pad; g.stride_x = stride_x; g.stride_y = stride_y;
+    g.tap_c = linear ? 64 : 0;
+    g.OH = (H + 2 * pad - KH) / stride_y + 1;
+    g.OW = linear ? W : (W + 2 * pad - KW) / stride_x + 1;
     g.HW = TP + KW - 1; g.HH = TP + KH - 1;
     g.halo_bytes = (g.HH * g.HW * 128 + 1023) / 1024 * 1024;
     g.tiles_x = (g.OW + TP - 1) / TP; g.tiles_y = (g.OH + TP - 1) / TP;
     g.ntiles = n_img * g.tiles_x * g.tiles_y;
-    g.ncc = C / 64; g.noc = O / 64;
+    g.Osub = O <= 192 ? O : (O % 192 == 0 ? 192 : 128);
+    g.nog = O / g.Osub;
+    g.ncc = C / 64; g.noc = g.Osub / 64;
     const int T = KH * KW;
-    const int maxpairs = 512 / O;
+    const int maxpairs = 512 / g.Osub;
     int G = T < 2 * maxpairs ? T : 2 * maxpairs;
+    if (linear)                                                 // two stages in flight: the taps are not views of one halo tile
+        while (G > 2 && 2 * (P * g.noc * TILE_B + P * G * TILE_B) > 200 * 1024) G -= 2;
     g.ntg = (T + G - 1) / G;
     g.G = (T + g.ntg - 1) / g.ntg;
-    const int groups = g.ncc * g.ntg;
+    const int groups = g.ncc * g.ntg * g.nog;
     const int sms = rp::num_sms(device);
     int nps = (sms + groups / 2) / groups;
+    if (nps > (g.ntiles + 3) / 4) nps = (g.ntiles + 3) / 4;      // at least ~4 pixel tiles per slice: the partial buffers are the traffic
     if (nps < 1) nps = 1;
-    if (nps > g.ntiles) nps = g.ntiles;
     g.nps = nps;
     g.dy_bytes = P * g.noc * TILE_B;
     g.stage_bytes = g.dy_bytes + (halo ? P * g.halo_bytes : P * g.G * TILE_B);
     int stages = (200 * 1024) / g.stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     g.stages = stages;
-    const int cols = ((g.G + 1) / 2) * O;
+    const int cols = ((g.G + 1) / 2) * g.Osub;
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     return stages >= 1 ? RP_OK : RP_EINVAL;
+}
+
+// shared by the convolution and the linear entry points: tensor maps, launch, slice reduction
+int launch_dw(const void* x_planes, const void* dy_planes, float* dw, const DwGeom& g, int H, int W, bool halo, void* workspace,
+              size_t workspace_bytes, int device, cudaStream_t st, const char* what) {
+    const int T = g.KH * g.KW;
+    const size_t need = (size_t)g.nps * g.O * T * g.C * sizeof(float);
+    RP_REQUIRE(workspace_bytes >= need, RP_EWORKSPACE, "%s: workspace too small (%zu < %zu)", what, workspace_bytes, need);
+    tc::EncodeTiledFn fn = tc::get_encode_fn();
+    RP_REQUIRE(fn != nullptr, RP_EINVAL, "%s: cuTensorMapEncodeTiled entry point unavailable", what);
+    CUtensorMap tmX, tmDY;
+    {
+        const cuuint64_t Cm = g.tap_c ? (cuuint64_t)64 * g.KW : (cuuint64_t)g.C;     // nn.Linear: a "pixel" is a whole row of X
+        cuuint64_t gdim[5] = {Cm, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)g.n_img, (cuuint64_t)P};
+        cuuint64_t gstr[4] = {Cm * 2, (cuuint64_t)W * Cm * 2, (cuuint64_t)H * W * Cm * 2, (cuuint64_t)g.n_img * H * W * Cm * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)(halo ? g.HW : TP * g.stride_x), (cuuint32_t)(halo ? g.HH : TP * g.stride_y), 1, 1};
+        cuuint32_t estr[5] = {1, (cuuint32_t)g.stride_x, (cuuint32_t)g.stride_y, 1, 1};
+        CUresult r = fn(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_planes), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RP_REQUIRE(r == CUDA_SUCCESS, RP_EINVAL, "%s: input tensor map failed (CUresult %d)", what, (int)r);
+    }
+    {
+        cuuint64_t gdim[5] = {(cuuint64_t)g.O, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.n_img, (cuuint64_t)P};
+        cuuint64_t gstr[4] = {(cuuint64_t)g.O * 2, (cuuint64_t)g.OW * g.O * 2, (cuuint64_t)g.OH * g.OW * g.O * 2,
+                              (cuuint64_t)g.n_img * g.OH * g.OW * g.O * 2};
+        cuuint32_t box[5] = {64, TP, TP, 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = fn(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy_planes), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RP_REQUIRE(r == CUDA_SUCCESS, RP_EINVAL, "%s: gradient tensor map failed (CUresult %d)", what, (int)r);
+    }
+    const size_t smem = (size_t)g.stages * g.stage_bytes + 256 + 1024;
+    auto kern = halo ? conv_dw_tc_kernel<true> : conv_dw_tc_kernel<false>;
+    static bool attr_set[2][64] = {{false}};
+    if (device >= 0 && device < 64 && !attr_set[halo][device]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            rp::set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_set[halo][device] = true;
+    }
+    const int grid = g.ncc * g.ntg * g.nog * g.nps;
+    rp::launch(kern, dim3(grid), dim3(THREADS), smem, st, tmX, tmDY, static_cast<float*>(workspace), g);
+    int rc = rp::finish_launch(what);
+    if (rc) return rc;
+    const long long n4 = (long long)g.O * T * g.C / 4;
+    conv_dw_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), dw, n4, g.nps);
+    return rp::finish_launch(what);
 }
 
 }  // namespace
@@ -260,7 +320,7 @@ extern "C" size_t rp_conv_dw_tc_workspace_bytes(int n_img, int H, int W, int C, 
                                                 int device) {
     DwGeom g;
     if (!rp_conv_dw_tc_supported(C, O, KH, KW, stride) ||
-        make_geom(g, n_img, H, W, C, O, KH, KW, pad, stride, device, stride == 1 && dw_halo_enabled()))
+        make_geom(g, n_img, H, W, C, O, KH, KW, pad, stride, stride, device, stride == 1 && dw_halo_enabled()))
         return 0;
     return (size_t)g.nps * O * KH * KW * C * sizeof(float);
 }
@@ -275,51 +335,37 @@ extern "C" int rp_conv_dw_tc(const void* x_planes, const void* dy_planes, float*
     RP_GUARD(device);
     const bool halo = stride == 1 && dw_halo_enabled();      // a strided tap is not a shifted view of a dense halo
     DwGeom g;
-    RP_REQUIRE(make_geom(g, n_img, H, W, C, O, KH, KW, pad, stride, device, halo) == RP_OK && g.OH > 0 && g.OW > 0, RP_EINVAL,
+    RP_REQUIRE(make_geom(g, n_img, H, W, C, O, KH, KW, pad, stride, stride, device, halo) == RP_OK && g.OH > 0 && g.OW > 0, RP_EINVAL,
                "rp_conv_dw_tc: geometry does not fit");
-    const size_t need = (size_t)g.nps * O * KH * KW * C * sizeof(float);
-    RP_REQUIRE(workspace_bytes >= need, RP_EINVAL, "rp_conv_dw_tc: workspace too small (%zu < %zu)", workspace_bytes, need);
-    tc::EncodeTiledFn fn = tc::get_encode_fn();
-    RP_REQUIRE(fn != nullptr, RP_EINVAL, "rp_conv_dw_tc: cuTensorMapEncodeTiled entry point unavailable");
-    CUtensorMap tmX, tmDY;
-    {
-        cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img, (cuuint64_t)P};
-        cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)n_img * H * W * C * 2};
-        cuuint32_t box[5] = {64, (cuuint32_t)(halo ? g.HW : TP * stride), (cuuint32_t)(halo ? g.HH : TP * stride), 1, 1};
-        cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
-        CUresult r = fn(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x_planes), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        RP_REQUIRE(r == CUDA_SUCCESS, RP_EINVAL, "rp_conv_dw_tc: input tensor map failed (CUresult %d)", (int)r);
-    }
-    {
-        cuuint64_t gdim[5] = {(cuuint64_t)O, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)n_img, (cuuint64_t)P};
-        cuuint64_t gstr[4] = {(cuuint64_t)O * 2, (cuuint64_t)g.OW * O * 2, (cuuint64_t)g.OH * g.OW * O * 2,
-                              (cuuint64_t)n_img * g.OH * g.OW * O * 2};
-        cuuint32_t box[5] = {64, TP, TP, 1, 1};
-        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        CUresult r = fn(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy_planes), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        RP_REQUIRE(r == CUDA_SUCCESS, RP_EINVAL, "rp_conv_dw_tc: gradient tensor map failed (CUresult %d)", (int)r);
-    }
-    const size_t smem = (size_t)g.stages * g.stage_bytes + 256 + 1024;
-    auto kern = halo ? conv_dw_tc_kernel<true> : conv_dw_tc_kernel<false>;
-    static size_t attr_set[2][64] = {{0}};
-    if (device >= 0 && device < 64 && attr_set[halo][device] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) {
-            rp::set_error("rp_conv_dw_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr_set[halo][device] = 227 * 1024;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int grid = g.ncc * g.ntg * g.nps;
-    rp::launch(kern, dim3(grid), dim3(THREADS), smem, st, tmX, tmDY, static_cast<float*>(workspace), g);
-    int rc = rp::finish_launch("rp_conv_dw_tc");
-    if (rc) return rc;
-    const long long n4 = (long long)O * KH * KW * C / 4;
-    conv_dw_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), dw, n4, g.nps);
-    return rp::finish_launch("rp_conv_dw_tc (reduce)");
+    return launch_dw(x_planes, dy_planes, dw, g, H, W, halo, workspace, workspace_bytes, device, (cudaStream_t)stream, "rp_conv_dw_tc");
+}
+
+// Weight gradient of nn.Linear, dW [N][K] = dY^T X with X [M][K], dY [M][N] (bf16 planes, row-major): the same kernel.  The
+// rows are the "pixels" (an image of M / 8 rows of 8 pixels, a pixel = one row of X), the K / 64 column blocks of X are
+// the "taps": tap t reads channels [64 t, 64 t + 64) of the same pixel window (tap_c = 64) -- so X and dY are read in
+// place as MN-major operands and neither is transposed (the split-K path needed rp_transpose_split_planes_bf16 of both).
+static bool linear_dw_geom(DwGeom& g, int M, int N, int K, int device) {
+    if (M < 64 || M % 8 != 0 || K % 64 != 0 || K / 64 > 64) return false;
+    if (!(N == 64 || N == 128 || N == 192 || (N > 192 && (N % 192 == 0 || N % 128 == 0)))) return false;
+    return make_geom(g, 1, M / 8, 8, 64, N, 1, K / 64, 0, 1, 1, device, false, true) == RP_OK;
+}
+extern "C" int rp_linear_dw_tc_supported(int M, int N, int K) {
+    DwGeom g;
+    return linear_dw_geom(g, M, N, K, 0) ? 1 : 0;
+}
+extern "C" size_t rp_linear_dw_tc_workspace_bytes(int M, int N, int K, int device) {
+    DwGeom g;
+    if (!linear_dw_geom(g, M, N, K, device)) return 0;
+    return (size_t)g.nps * N * K * sizeof(float);
+}
+extern "C" int rp_linear_dw_tc(const void* x_planes, const void* dy_planes, float* dw, int M, int N, int K, void* workspace,
+                               size_t workspace_bytes, int device, void* stream) {
+    RP_REQUIRE(x_planes && dy_planes && dw && workspace, RP_EINVAL, "rp_linear_dw_tc: bad argument");
+    RP_REQUIRE(rp::aligned16(x_planes) && rp::aligned16(dy_planes) && rp::aligned16(dw) && rp::aligned16(workspace), RP_EALIGN,
+               "rp_linear_dw_tc: 16-byte alignment");
+    RP_GUARD(device);
+    DwGeom g;
+    RP_REQUIRE(linear_dw_geom(g, M, N, K, device), RP_EINVAL, "rp_linear_dw_tc: unsupported shape M=%d N=%d K=%d", M, N, K);
+    return launch_dw(x_planes, dy_planes, dw, g, M / 8, 8, false, workspace, workspace_bytes, device, (cudaStream_t)stream,
+                     "rp_linear_dw_tc");
 }

@@ -635,6 +635,29 @@ def conv_dw_tc(x_planes, dy_planes, KH, KW, pad, stride=1):
     return dw
 
 
+def linear_dw_tc_supported(M, N, K):
+    return bool(_lib.lib().rp_linear_dw_tc_supported(int(M), int(N), int(K)))
+
+
+def linear_dw_tc(x_planes, dy_planes):
+    """Weight gradient of nn.Linear on the implicit-GEMM kernel: x_planes bf16 [2,M,K], dy_planes bf16 [2,M,N] -> float32
+    [N,K] = dY^T X, both operands read in place (no transposed copies)."""
+    _req(x_planes, "x_planes", torch.bfloat16); _req(dy_planes, "dy_planes", torch.bfloat16)
+    P, M, K = x_planes.shape
+    N = dy_planes.shape[-1]
+    assert P == 2 and tuple(dy_planes.shape) == (2, M, N)
+    dev, st = _ctx(x_planes)
+    L = _lib.lib()
+    nb = L.rp_linear_dw_tc_workspace_bytes(M, N, K, dev)
+    assert nb > 0
+    ws = torch.empty((nb // 4,), dtype=torch.float32, device=x_planes.device)
+    dw = torch.empty((N, K), dtype=torch.float32, device=x_planes.device)
+    _tbegin(f"linear_dw_tcx3[{N}x{K}]", 2.0 * M * N * K, 2.0 * 2 * (x_planes[0].numel() + dy_planes[0].numel()) + 2.0 * nb)
+    _lib.check(L.rp_linear_dw_tc(_p(x_planes), _p(dy_planes), _p(dw), M, N, K, _p(ws), nb, dev, st), "rp_linear_dw_tc")
+    _count(2)
+    return dw
+
+
 def self_attention_tc_lse(qkv_planes):
     """Training forward: qkv_planes bf16 [P,n,576,576] -> (float32 out [n,576,192], float32 lse [n,3,576])."""
     _req(qkv_planes, "qkv_planes", torch.bfloat16)

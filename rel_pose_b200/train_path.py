@@ -106,6 +106,7 @@ def _ew(name, out, *args):
 # fp32 SIMT kernels (A/B measurements); tiny problems (the pose regressor at 6 rows) always stay there.
 TRAIN_TC = os.environ.get("RELPOSE_TRAIN_TC", "1") != "0"
 TRAIN_DW_TC = TRAIN_TC and os.environ.get("RELPOSE_TRAIN_DW_TC", "1") != "0"         # implicit-GEMM conv weight gradients
+TRAIN_LIN_DW_TC = TRAIN_DW_TC and os.environ.get("RELPOSE_TRAIN_LIN_DW_TC", "1") != "0"   # ... and nn.Linear weight gradients on the same kernel
 TRAIN_FLASH = TRAIN_TC and os.environ.get("RELPOSE_TRAIN_FLASH", "1") != "0"      # attention gradients without 576 x 576 tensors
 _TCP = 2                                   # bf16x3
 
@@ -120,18 +121,25 @@ def _lin_fwd(x2, w, b, act=ops.ACT_NONE):
     return ops.linear(x2, w, b, act=act)
 
 
-def _lin_dx(dy2, w):
-    """dy2 [M,N], w [N,K] -> dy2 @ w  [M,K]"""
+def _tc_rows(M, K, w):
+    return TRAIN_TC and M >= 64 and K % 8 == 0 and (M * K) % 8 == 0 and (w.numel() % 8) == 0
+
+
+def _lin_dx(dy2, w, dyp=None):
+    """dy2 [M,N], w [N,K] -> dy2 @ w  [M,K]   (dyp: the split planes of dy2 when the caller already has them)"""
     M, N = dy2.shape
-    if TRAIN_TC and M >= 64 and N % 8 == 0 and (M * N) % 8 == 0 and (w.numel() % 8) == 0:
-        return ops.linear_tc(ops.split_planes(dy2, _TCP), ops.split_planes(w.t().contiguous(), _TCP), None)[0]
+    if _tc_rows(M, N, w):
+        return ops.linear_tc(dyp if dyp is not None else ops.split_planes(dy2, _TCP), ops.split_planes(w.t().contiguous(), _TCP), None)[0]
     return mm(dy2, w)
 
 
-def _lin_dw(dy2, x2):
-    """dy2 [M,N], x2 [M,K] -> dy2^T @ x2  [N,K]"""
+def _lin_dw(dy2, x2, dyp=None, xp=None):
+    """dy2 [M,N], x2 [M,K] -> dy2^T @ x2  [N,K]   (x2 may be None when its planes xp are given)"""
     M, N = dy2.shape
-    K = x2.shape[1]
+    K = x2.shape[1] if x2 is not None else xp.shape[-1]
+    if TRAIN_LIN_DW_TC and ops.linear_dw_tc_supported(M, N, K):
+        # implicit-GEMM kernel of the convolution weight gradients: X and dY read in place as MN-major operands
+        return ops.linear_dw_tc(xp if xp is not None else ops.split_planes(x2, _TCP), dyp if dyp is not None else ops.split_planes(dy2, _TCP))
     if TRAIN_TC and M >= 512 and M % 8 == 0 and K % 4 == 0:
         return ops.linear_tc_splitk(ops.transpose_split_planes(dy2, _TCP), ops.transpose_split_planes(x2, _TCP))
     return mm(dy2, x2, ta=True)
@@ -139,14 +147,27 @@ def _lin_dw(dy2, x2):
 
 # ------------------------------------------------------------------------------------------ autograd functions
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b   (vision_transformer.py:323,331; mlp.py:21,24; model.py:91-98)"""
+    """y = x W^T + b   (vision_transformer.py:323,331; mlp.py:21,24; model.py:91-98).  When the weight gradient runs on
+    the implicit-GEMM kernel the forward keeps the bf16 planes of x it built for its own product (same bytes as x) and
+    the backward splits dy once for both of its products."""
 
     @staticmethod
     def forward(ctx, x, w, b):
         x = x.contiguous()
-        ctx.save_for_backward(x, w)
         N, K = w.shape
-        y = _lin_fwd(x.reshape(-1, K), w.detach().contiguous(), b.detach().contiguous() if b is not None else None)
+        x2 = x.reshape(-1, K)
+        M = x2.shape[0]
+        wd = w.detach().contiguous()
+        bd = b.detach().contiguous() if b is not None else None
+        ctx.planes = _tc_rows(M, K, w) and TRAIN_LIN_DW_TC and ops.linear_dw_tc_supported(M, N, K)
+        ctx.xshape = tuple(x.shape)
+        if ctx.planes:
+            xp = ops.split_planes(x2, _TCP)
+            y = ops.linear_tc(xp, ops.split_planes(wd, _TCP), bd)[0]
+            ctx.save_for_backward(xp, w)
+        else:
+            y = _lin_fwd(x2, wd, bd)
+            ctx.save_for_backward(x, w)
         return y.reshape(x.shape[:-1] + (N,))
 
     @staticmethod
@@ -154,9 +175,15 @@ class LinearFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         N, K = w.shape
         dy2 = dy.contiguous().reshape(-1, N)
-        x2 = x.reshape(-1, K)
-        dx = _lin_dx(dy2, w.detach().contiguous()).reshape(x.shape) if ctx.needs_input_grad[0] else None
-        dw = _lin_dw(dy2, x2) if ctx.needs_input_grad[1] else None
+        M = dy2.shape[0]
+        dyp = ops.split_planes(dy2, _TCP) if (ctx.planes or (ctx.needs_input_grad[0] and _tc_rows(M, N, w))) else None
+        dx = _lin_dx(dy2, w.detach().contiguous(), dyp).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        if not ctx.needs_input_grad[1]:
+            dw = None
+        elif ctx.planes:
+            dw = _lin_dw(dy2, None, dyp, x)
+        else:
+            dw = _lin_dw(dy2, x.reshape(-1, K), dyp)
         db = colsum(dy2) if ctx.needs_input_grad[2] else None
         return dx, dw, db
 

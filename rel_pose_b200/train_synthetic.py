@@ -125,20 +125,29 @@ def train_loop(a, dev, rank=0, world=1, local=0):
         for p in trainable:
             offs.append(o); o += (p.numel() + 3) // 4 * 4
         flat_grad = torch.zeros(o, dtype=torch.float32, device=dev)
-        for p, off in zip(trainable, offs):
-            p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        flat_views = [flat_grad[off:off + p.numel()].view_as(p) for p, off in zip(trainable, offs)]
+        for p, v in zip(trainable, flat_views):
+            p.grad = v
         static = [t.clone() for t in pool[0]]
         g_out = {}
 
         def fwd_bwd():
             images, poses, intr = static
             intr_w = intr.clone()
-            opt.zero_grad()
+            # no zero-fill + 123 accumulate kernels: autograd ASSIGNS fresh gradient tensors (p.grad is None), one
+            # multi-tensor copy packs them into the flat buffer the exchange step and the optimizer read
+            for p in trainable:
+                p.grad = None
             Ps = SE3(poses)
             poses_est = net(images, SE3.IdentityLike(Ps), intrinsics=intr_w)
             ltr, lrot, _ = geodesic_loss(SE3(Ps.data.clone()), poses_est, sync_metrics=False)
             loss = a.w_tr * ltr + a.w_rot * lrot
             loss.backward()
+            got = [(v, p.grad) for p, v in zip(trainable, flat_views) if p.grad is not None]
+            with torch.no_grad():
+                torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
+            for p, v in zip(trainable, flat_views):
+                p.grad = v
             g_out["loss"] = loss.detach()
 
         def exchange_grads():
