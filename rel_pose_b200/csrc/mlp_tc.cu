@@ -29,6 +29,7 @@
 // 161 (first fused version, one issuer, fc1 one chunk ahead) -> 150 (fc1 two ahead) -> 131 (three issuers,
 // N = 192 fc2) -> 116 (GELU chunk through TMEM, double buffered) -> 114 us.  Remaining bound: the N = 64 fc1
 // MMAs read 6 KB of shared memory per 32-cycle instruction (128 B/clk limit -> 48 cycles), tile-boundary drain.
+#include <cstdlib>
 #include "ln_rows.cuh"
 #include "rows_ln_epilogue.cuh"
 #include "tc_common.cuh"
@@ -41,7 +42,8 @@ constexpr int KB = D / 64;                                   // K blocks of fc1 
 constexpr int NT = D / 64;                                   // 64-column thirds of the fc2 output (3)
 constexpr int EPI_WARPS = 16;
 constexpr int CTRL_WARPS = 4;                                 // TMA producer, two fc1 issuers, fc2 issuer
-constexpr int NTHREADS = 32 * (CTRL_WARPS + EPI_WARPS);
+constexpr int OUT_WARPS = 4;                                  // in-place output warpgroup (one warp per TMEM lane quarter)
+constexpr int NTHREADS = 32 * (CTRL_WARPS + EPI_WARPS + OUT_WARPS);
 constexpr int TILE16K = BM * 64 * 2;                         // one [128 x 64] bf16 operand tile
 constexpr int UNIT1 = 64 * 64 * 2;                           // one plane of a weight unit (8 KiB)
 constexpr int NA1 = 3, LEAD = 2;                              // fc1 accumulators in TMEM; fc1 runs LEAD chunks ahead of fc2
@@ -79,7 +81,22 @@ struct MlpParams {
     const float* gamma2;
     const float* beta2;
     float eps2;
+    int stagger;           // start delay in cycles per CTA group (blockIdx.x % 8): see launch_mlp
+    int inplace;           // out == x: the output epilogue is a TMA reduce-add of acc + b2 into x (tmOut)
 };
+
+// Timeline probe (tools/probes/mlp_trace_probe.cu defines RP_MLP_TRACE and includes this file): lane 0 of every warp of
+// one CTA appends (clock64 << 8 | tag) to a per-warp list.  Compiles to nothing in the library.
+#ifdef RP_MLP_TRACE
+constexpr int TRACE_EV = 2048;
+__device__ long long g_mlp_trace[NTHREADS / 32][TRACE_EV];
+#define MLP_TR(tag)                                                                                         \
+    do {                                                                                                    \
+        if (blockIdx.x == RP_MLP_TRACE_CTA && lane == 0 && trn < TRACE_EV) g_mlp_trace[warp][trn++] = (clock64() << 8) | (tag); \
+    } while (0)
+#else
+#define MLP_TR(tag) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -112,6 +129,9 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xn_full + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef RP_MLP_TRACE
+    int trn = 0;
+#endif
     const int M = prm.M;
     const int ntiles = (M + BM - 1) / BM;
 
@@ -135,7 +155,7 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
             tc::mbar_init(&h_empty[i], 1);
         }
         tc::mbar_init(acc2_full, 1);
-        tc::mbar_init(acc2_empty, EPI_WARPS);
+        tc::mbar_init(acc2_empty, prm.inplace ? OUT_WARPS : EPI_WARPS);
         tc::mbar_init(&turn[0], 1);
         tc::mbar_init(&turn[1], 1);
         tc::fence_barrier_init();
@@ -143,6 +163,10 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
+    if (prm.stagger > 0) {
+        const long long t_start = clock64(), t_delay = (long long)(blockIdx.x & 7) * prm.stagger;
+        while (clock64() - t_start < t_delay) { }
+    }
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -157,6 +181,10 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     // that observes every phase in order.  The fc1 ring (units 0 .. 3 G1-1) is consumed by the two fc1 issuers,
     // the fc2 ring (the rest) by the fc2 issuer.  Where both fc1 issuers alternate on the same units (G1 odd),
     // the `turn` hand-off below makes the later one wait until the earlier one has observed ITS fill.
+    // Register budget: the CTA owns 768 x 80 registers; the control (40) and output (56) warpgroups give back exactly what
+    // the four GELU warpgroups take (96): 128 x 40 + 128 x 56 + 512 x 96 = 768 x 80.  setmaxnreg is per warpgroup
+    // (warps 0-3 | 4-19 | 20-23) and an increase can only draw on registers released inside the CTA.
+    if (warp < CTRL_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (convergent warp)
         // fc1 weights only: the fc2 issuer feeds its own ring, so a full fc2 ring (waiting for a GELU chunk) never
@@ -218,8 +246,10 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 // the other issuer has observed the previous chunk's fill (see the ring comment above)
                 if (sel == 0) { if (n > 0) tc::mbar_wait(&turn[0], (n - 1) & 1); }
                 else tc::mbar_wait(&turn[1], n & 1);
+                MLP_TR(1);
                 tc::mbar_wait(&acc1_empty[b], ((g / NA1) & 1) ^ 1);
                 tc::tcgen05_fence_after();
+                MLP_TR(2);
                 const uint32_t d = tmem_base + ACC1_COL + b * CH;
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
@@ -248,6 +278,7 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     }
                     __syncwarp();
                 }
+                MLP_TR(3);
             }
             if (AIN && sel == 1 && tile + (int)gridDim.x < ntiles) {
                 tc::mbar_wait(xn_free, it & 1);              // both issuers' last fc1 products of this tile have retired
@@ -282,7 +313,9 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 const uint32_t hb = c2 % C::NH;
                 const int u = 3 * C::G1 + 3 * (int)(c2 % C::G2);
                 const uint32_t fpar = (c2 / C::G2) & 1;
+                MLP_TR(4);
                 tc::mbar_wait(&h_full[hb], (c2 / C::NH) & 1);
+                MLP_TR(5);
                 if (j == 0) tc::mbar_wait(acc2_empty, (it & 1) ^ 1);
 #pragma unroll
                 for (int nn = 0; nn < NT; ++nn) tc::mbar_wait(&wfull[u + nn], fpar);
@@ -309,15 +342,18 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     if (j == NCH - 1) tc::umma_commit(acc2_full);
                 }
                 __syncwarp();
+                MLP_TR(6);
                 if (c2 + C::G2 < total) {       // refill this slot with the chunk G2 ahead as soon as it is free
 #pragma unroll
                     for (int nn = 0; nn < NT; ++nn) tc::mbar_wait(&wempty[u + nn], fpar);
                     load_chunk(c2 + C::G2);
                 }
+                MLP_TR(7);
             }
         }
-    } else {
+    } else if (warp < CTRL_WARPS + EPI_WARPS) {
         // ------------------------------------------------------------------ LayerNorm / GELU / output warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory");
         const int ew = warp - CTRL_WARPS;
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int part = ew >> 2;                        // which 16 of a chunk's 64 hidden columns / 48 of the 192 outputs
@@ -353,11 +389,13 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
             auto wait_acc = [&]() {
                 tc::mbar_wait(acc2_full, itp & 1);
                 tc::tcgen05_fence_after();
+                MLP_TR(20);
             };
             auto release = [&]() {                           // acc2 is in registers: fc2 of the following tile may overwrite it
                 tc::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(acc2_empty);
+                MLP_TR(21);
             };
             if (prm.ln_planes)
                 rowsln::epilogue<P>(t_lane + ACC2_COL, staging, q, part, lane, prm.b2, prm.x, prm.out, prm.ln_planes, prm.gamma2,
@@ -374,7 +412,7 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 #pragma unroll 1
             for (int j = 0; j < NCH; ++j, ++c2) {
                 const uint32_t b = b1;
-                if (j == 2 && prev_tile >= 0) out_epilogue(prev_tile, it - 1);
+                if (j == 2 && prev_tile >= 0 && !prm.inplace) { MLP_TR(17); out_epilogue(prev_tile, it - 1); MLP_TR(18); }
                 if (j == 2) {
                     // pull the next tile's rows towards L2 now; its LayerNorm runs before this tile's last two chunks
                     const int nrow = (tile + (int)gridDim.x) * BM + ew * 8 + (lane >> 2);
@@ -392,7 +430,9 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                     const float4 t = __ldg(reinterpret_cast<const float4*>(prm.b1 + j * CH + part * 16 + 4 * i));
                     bias[4 * i] = t.x; bias[4 * i + 1] = t.y; bias[4 * i + 2] = t.z; bias[4 * i + 3] = t.w;
                 }
+                MLP_TR(10);
                 tc::mbar_wait(&acc1_full[b], ph1);
+                MLP_TR(11);
                 if (++b1 == NA1) { b1 = 0; ph1 ^= 1; }
                 tc::tcgen05_fence_after();
                 uint32_t a[16];
@@ -405,8 +445,10 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = tc::gelu_fast(__uint_as_float(a[i]) + bias[i]);
                 const uint32_t hb = c2 % C::NH;
+                MLP_TR(12);
                 tc::mbar_wait(&h_empty[hb], ((c2 / C::NH) & 1) ^ 1);
                 tc::tcgen05_fence_after();
+                MLP_TR(13);
                 // the chunk goes back to TENSOR memory as the K-major A operand of fc2 (two bf16 per column): no
                 // shared-memory traffic, no generic->async proxy fence, and room for two buffers
 #pragma unroll
@@ -426,18 +468,66 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
                 tc::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&h_full[hb]);
+                MLP_TR(14);
                 if (ln_next) {
                     // LayerNorm of the NEXT tile right after the last GELU chunk: every fc1 product of this tile has
                     // been observed complete (chunk by chunk), so the LayerNorm planes are dead; while these warps are
                     // busy here the tensor pipe still has this tile's last three fc2 products queued (one more than
                     // when the LayerNorm ran before the last two chunks).
                     ln_load(tile + (int)gridDim.x);
+                    MLP_TR(15);
                     ln_finish();
+                    MLP_TR(16);
                 }
             }
             prev_tile = tile;
         }
-        if (prev_tile >= 0) out_epilogue(prev_tile, it - 1);
+        if (prev_tile >= 0 && !prm.inplace) out_epilogue(prev_tile, it - 1);
+    } else {
+        // ------------------------------------------------------------------ output warpgroup (in place: out == x)
+        // x += acc2 + b2 with vector reductions performed at the memory side: no residual loads, nothing for the GELU
+        // warps to do at all.  The timeline probe (tools/probes/mlp_trace_probe.cu) showed the sixteen GELU warps spending
+        // 6-9 k of the ~52 k cycles of a tile in the output epilogue (the SM's 32 B/clk store path: 98 KB per tile) with
+        // the GELU pipeline, and behind it the fc2 issuer waiting for acc2, parked; these four warps drain the
+        // accumulator while the GELU warps normalise the next tile's rows and release it long before fc2 needs it.
+        // Thread = one row (TMEM lane), six passes of 32 columns; a rounding-exact match of the load / add / store
+        // epilogue: (acc + b2) + x is one fp32 addition either way.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+        if (prm.inplace) {
+            const int q = warp & 3;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int row = tile * BM + q * 32 + lane;
+                float* dst = prm.out + (size_t)row * D;
+                tc::mbar_wait(acc2_full, it & 1);
+                tc::tcgen05_fence_after();
+                MLP_TR(20);
+#pragma unroll 1
+                for (int pass = 0; pass < 6; ++pass) {
+                    uint32_t a[2][16];
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) tc::tmem_ld_32x32b_x16(t_lane + ACC2_COL + pass * 32 + g * 16, a[g]);
+                    tc::tmem_ld_wait();
+                    if (pass == 5) {                              // acc2 is in registers: fc2 of the following tile may overwrite it
+                        tc::tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(acc2_empty);
+                        MLP_TR(21);
+                    }
+                    if (row < M) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 sh = __ldg(reinterpret_cast<const float4*>(prm.b2 + pass * 32 + 4 * i));
+                            const uint32_t* av = &a[i >> 2][4 * (i & 3)];
+                            tc::red_add_v4_f32(dst + pass * 32 + 4 * i, __uint_as_float(av[0]) + sh.x, __uint_as_float(av[1]) + sh.y,
+                                               __uint_as_float(av[2]) + sh.z, __uint_as_float(av[3]) + sh.w);
+                        }
+                    }
+                }
+                MLP_TR(18);
+            }
+        }
     }
 
     tc::tcgen05_fence_before();
@@ -495,7 +585,15 @@ extern "C" int rp_mlp_tc_ex(const float* x, const void* xn_planes, const float* 
         rc = tc::make_planes_tmap(&tmXN, xn_planes, P, M, D, BM);        // [P][M][192], box 128 rows x 64 K
         if (rc) return rc;
     }
-    MlpParams prm{x, ln_gamma, ln_beta, b1, b2, out, M, eps, static_cast<__nv_bfloat16*>(out_ln_planes), ln2_gamma, ln2_beta, eps2};
+    // All CTAs run the same tile schedule, so their memory phases (LayerNorm rows in, output rows out: 2 x 98 KB per tile)
+    // would hit L2 as 148-wide bursts; a start offset per CTA group spreads them (RELPOSE_MLP_STAGGER = cycles per group).
+    static const int stagger = [] { const char* e = getenv("RELPOSE_MLP_STAGGER"); return e ? atoi(e) : 0; }();
+    // out == x: the residual update happens at the memory side (the output warpgroup's vector reductions); RELPOSE_MLP_INPLACE=0
+    // keeps the load / add / store epilogue on the GELU warps for A/B runs.  Not combined with the LayerNorm-planes output
+    // (that one needs the sum in registers).
+    static const bool inplace_ok = [] { const char* e = getenv("RELPOSE_MLP_INPLACE"); return !(e && e[0] == '0'); }();
+    const int inplace = (out == x && !out_ln_planes && inplace_ok) ? 1 : 0;
+    MlpParams prm{x, ln_gamma, ln_beta, b1, b2, out, M, eps, static_cast<__nv_bfloat16*>(out_ln_planes), ln2_gamma, ln2_beta, eps2, stagger, inplace};
     cudaStream_t st = (cudaStream_t)stream;
     if (xn_planes) {
         if (P == 1) return launch_mlp<1, true>(tmW1, tmW2, tmXN, prm, device, st);

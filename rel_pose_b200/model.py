@@ -366,8 +366,9 @@ class ViTEss(nn.Module):
     def _mlp_tc(self, blk, x, P):
         """x + mlp(norm2(x)): one fused launch (LayerNorm -> fc1 -> GELU -> fc2 -> +x), hidden activation on chip."""
         if self.fused_mlp:
+            # x is this Block's own temporary (the projection's / em_project's output): updated in place
             return ops.mlp_tc(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, self._planes(blk.mlp.fc1.weight, P),
-                              blk.mlp.fc1.bias, self._planes(blk.mlp.fc2.weight, P), blk.mlp.fc2.bias)
+                              blk.mlp.fc1.bias, self._planes(blk.mlp.fc2.weight, P), blk.mlp.fc2.bias, inplace=True)
         h = ops.layernorm_planes(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, P)
         _, h = ops.linear_tc(h, self._planes(blk.mlp.fc1.weight, P), blk.mlp.fc1.bias, act=ops.ACT_GELU,
                              want_f32=False, planes_out=P)

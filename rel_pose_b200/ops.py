@@ -516,11 +516,13 @@ def planes_linear_tc(xn_planes, w_planes, bias=None, planes_out=0, residual=None
     return out, lnp
 
 
-def mlp_tc(x, gamma, beta, eps, w1_planes, b1, w2_planes, b2, xn_planes=None, ln_next=None):
+def mlp_tc(x, gamma, beta, eps, w1_planes, b1, w2_planes, b2, xn_planes=None, ln_next=None, inplace=False):
     """Fused `x + fc2(gelu(fc1(layernorm(x))))` on tcgen05 (csrc/mlp_tc.cu): x float32 [...,192],
     w1_planes bf16 [P,768,192], w2_planes bf16 [P,192,768] -> float32 [...,192].
     xn_planes: layernorm(x) already available as bf16 planes [P,...,192] (written by the producer of x).
-    ln_next = (gamma, beta, eps): also return LayerNorm(out) with these weights as bf16 planes -> (out, planes)."""
+    ln_next = (gamma, beta, eps): also return LayerNorm(out) with these weights as bf16 planes -> (out, planes).
+    inplace: x is overwritten with the result and returned (the kernel then adds fc2's tile to x at the memory side with
+    a TMA reduce-add instead of loading the residual rows and storing the sums); same bits as the out-of-place call."""
     _req(x, "x"); _req(b1, "b1"); _req(b2, "b2")
     _req(w1_planes, "w1_planes", torch.bfloat16); _req(w2_planes, "w2_planes", torch.bfloat16)
     P, hidden, dim = w1_planes.shape
@@ -531,7 +533,7 @@ def mlp_tc(x, gamma, beta, eps, w1_planes, b1, w2_planes, b2, xn_planes=None, ln
         assert xn_planes.shape[0] == P and xn_planes.numel() == P * M * dim
     else:
         _req(gamma, "gamma"); _req(beta, "beta")
-    out = torch.empty_like(x)
+    out = x if (inplace and ln_next is None) else torch.empty_like(x)
     lnp, g2, bt2, e2 = None, None, None, 0.0
     if ln_next is not None:
         g2, bt2, e2 = ln_next

@@ -178,6 +178,10 @@ def test_mlp_fused_tc(P, M):
     # bit-reproducible from run to run
     again = ops.mlp_tc(xg, cu(g), cu(be), 1e-6, w1p, cu(b1), w2p, cu(b2))
     assert torch.equal(got, again)
+    # in place (x += fc2 tile + b2 as a TMA reduce-add at the memory side): the same bits, x overwritten
+    xi = xg.clone()
+    ret = ops.mlp_tc(xi, cu(g), cu(be), 1e-6, w1p, cu(b1), w2p, cu(b2), inplace=True)
+    assert ret.data_ptr() == xi.data_ptr() and torch.equal(xi, got)
 
 
 @pytest.mark.parametrize("P", [1, 2])
