@@ -11,7 +11,7 @@
 //
 // Operands are split-bf16 planes as in gemm_tc.cu (P = 1 bf16, P = 2 "bf16x3" = fp32-class products).
 //
-// One persistent CTA per SM, 640 threads, one 128-row tile at a time:
+// One persistent CTA per SM, 768 threads, one 128-row tile at a time:
 //   warp 0      TMA producer of the fc1 weights: "units" [P][64 hidden rows][64 K] bf16 (128-byte swizzle), three
 //               per chunk, into the fc1 ring.
 //   warps 1, 2  fc1 issuers (even / odd chunks): 36 tcgen05.mma M128 x N64 x K16 per chunk (bf16x3), up to three
@@ -20,15 +20,31 @@
 //               [192 x 64] slice of W2, which this warp also loads (its ring slot is free exactly when its own
 //               MMAs retire).  Three issuer warps on three schedulers because a single issuer was the bottleneck.
 //   warps 4-19  LayerNorm of the tile's rows straight into the swizzled A-operand planes (no HBM round trip; the
-//               next tile's LayerNorm runs two chunks before the current tile ends), per-chunk GELU
-//               (TMEM -> registers -> TMEM), output epilogue (acc2 + bias + residual, transposed through shared
-//               memory for coalesced float4 stores).
+//               next tile's LayerNorm runs after the current tile's last GELU chunk), per-chunk GELU
+//               (TMEM -> registers -> TMEM); out != x only: output epilogue (acc2 + bias + residual, transposed
+//               through shared memory for coalesced float4 stores).
+//   warps 20-23 in place (out == x) only: output warpgroup, x += acc2 + b2 as vector reductions at the memory side.
+// Registers (setmaxnreg, per warpgroup): control 40, GELU 96, output 56 = the 768 x 80 the CTA is launched with.
 // Tensor memory (512 columns): acc1[3] = 0..191, acc2 = 192..383, GELU chunk buffers [2][P][32] = 384..511.
 //
 // Measured history at 64 pairs, bf16x3 (profiles/r01_mlp_fused_history.md): unfused 214 (+27 LayerNorm) us ->
 // 161 (first fused version, one issuer, fc1 one chunk ahead) -> 150 (fc1 two ahead) -> 131 (three issuers,
-// N = 192 fc2) -> 116 (GELU chunk through TMEM, double buffered) -> 114 us.  Remaining bound: the N = 64 fc1
-// MMAs read 6 KB of shared memory per 32-cycle instruction (128 B/clk limit -> 48 cycles), tile-boundary drain.
+// N = 192 fc2) -> 116 (GELU chunk through TMEM, double buffered) -> 114 us.
+//
+// Where a tile's ~48 k cycles go (tools/probes/mlp_trace_probe.cu, clock64 at every barrier of one CTA;
+// profiles/r02_mlp_trace_*.txt): twelve chunks at 3.0-3.3 k (tensor bound: 36 x 48 + 12 x 96 = 2 880 cycles of
+// tcgen05.mma per chunk; the N = 64 fc1 products read 6 KB of shared memory per 32-cycle instruction, 128 B/clk ->
+// 48 cycles) + ~9 k at the tile boundary, where the single 96 KB A-operand buffer serialises [last fc1 product
+// retires] -> LayerNorm of the next rows (1.3-2.3 k to issue the loads, 5.6 k to reduce / normalise / split / store: 16
+// warps in lockstep, ~570 dependent-ish instructions per thread) -> first fc1 chunk (1.7 k) with only three fc2
+// products (3.4 k) queued on the tensor pipe.  Tried against that boundary in round 2, all measured, none kept:
+// start offsets per CTA group (the phases are not bandwidth collisions between CTAs: +delay, no gain); TMA reduce-add of
+// 2 KB boxes from the GELU warps (bulk stores of small boxes cost ~220 cycles each: tma_store_probe.cu, 9 B/clk);
+// LayerNorm of the next tile by the output warpgroup into an L2-resident planes ring fetched by TMA
+// (profiles/r02_mlp_ln_ring_experiment.patch: one warp per scheduler executes its ~200-instruction dependent chain per
+// row pair at ~10 cycles per instruction, 30 k cycles per tile against the 16 warps' 7 k; the accumulator drain through
+// one 16 KB box buffer took 11 k and stalled fc2).  What is left is a second A-operand buffer, i.e. 96 KB of shared
+// memory this layout does not have.
 #include <cstdlib>
 #include "ln_rows.cuh"
 #include "rows_ln_epilogue.cuh"
@@ -81,7 +97,6 @@ struct MlpParams {
     const float* gamma2;
     const float* beta2;
     float eps2;
-    int stagger;           // start delay in cycles per CTA group (blockIdx.x % 8): see launch_mlp
     int inplace;           // out == x: the output epilogue is a TMA reduce-add of acc + b2 into x (tmOut)
 };
 
@@ -163,10 +178,6 @@ mlp_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_const
     rp::pdl_launch_dependents();                  // the next kernel may start its prologue (common.cuh)
     if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     rp::pdl_wait();                               // the previous kernel has completed: its outputs are visible
-    if (prm.stagger > 0) {
-        const long long t_start = clock64(), t_delay = (long long)(blockIdx.x & 7) * prm.stagger;
-        while (clock64() - t_start < t_delay) { }
-    }
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
@@ -585,15 +596,12 @@ extern "C" int rp_mlp_tc_ex(const float* x, const void* xn_planes, const float* 
         rc = tc::make_planes_tmap(&tmXN, xn_planes, P, M, D, BM);        // [P][M][192], box 128 rows x 64 K
         if (rc) return rc;
     }
-    // All CTAs run the same tile schedule, so their memory phases (LayerNorm rows in, output rows out: 2 x 98 KB per tile)
-    // would hit L2 as 148-wide bursts; a start offset per CTA group spreads them (RELPOSE_MLP_STAGGER = cycles per group).
-    static const int stagger = [] { const char* e = getenv("RELPOSE_MLP_STAGGER"); return e ? atoi(e) : 0; }();
     // out == x: the residual update happens at the memory side (the output warpgroup's vector reductions); RELPOSE_MLP_INPLACE=0
     // keeps the load / add / store epilogue on the GELU warps for A/B runs.  Not combined with the LayerNorm-planes output
     // (that one needs the sum in registers).
     static const bool inplace_ok = [] { const char* e = getenv("RELPOSE_MLP_INPLACE"); return !(e && e[0] == '0'); }();
     const int inplace = (out == x && !out_ln_planes && inplace_ok) ? 1 : 0;
-    MlpParams prm{x, ln_gamma, ln_beta, b1, b2, out, M, eps, static_cast<__nv_bfloat16*>(out_ln_planes), ln2_gamma, ln2_beta, eps2, stagger, inplace};
+    MlpParams prm{x, ln_gamma, ln_beta, b1, b2, out, M, eps, static_cast<__nv_bfloat16*>(out_ln_planes), ln2_gamma, ln2_beta, eps2, inplace};
     cudaStream_t st = (cudaStream_t)stream;
     if (xn_planes) {
         if (P == 1) return launch_mlp<1, true>(tmW1, tmW2, tmXN, prm, device, st);
