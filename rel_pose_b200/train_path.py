@@ -109,6 +109,7 @@ TRAIN_DW_TC = TRAIN_TC and os.environ.get("RELPOSE_TRAIN_DW_TC", "1") != "0"    
 TRAIN_LIN_DW_TC = TRAIN_DW_TC and os.environ.get("RELPOSE_TRAIN_LIN_DW_TC", "1") != "0"   # ... and nn.Linear weight gradients on the same kernel
 TRAIN_FLASH = TRAIN_TC and os.environ.get("RELPOSE_TRAIN_FLASH", "1") != "0"      # attention gradients without 576 x 576 tensors
 _TCP = 2                                   # bf16x3
+TOKENS_GRAD_HOOK = None                    # callable(grad) -> None, see forward_train
 
 
 def _lin_fwd(x2, w, b, act=ops.ACT_NONE):
@@ -755,6 +756,10 @@ def forward_train(model, images, Gs, intrinsics):
     y = _bn(_conv(y, e.conv2), e.norm2)
     x = _bn(_conv(x, e.downsample[0]), e.norm3, residual=y, relu=True)
     x = x.reshape(2 * B, NTOK, EMBED)                                 # A4: NHWC output is already [2B,576,192]
+    if TOKENS_GRAD_HOOK is not None and x.requires_grad:
+        # fires when the backward pass reaches the CNN: every gradient of the transformer, the Essential Matrix Module and
+        # the pose regressor exists by then (train_synthetic.py starts their all-reduce here, under the CNN's backward)
+        x.register_hook(TOKENS_GRAD_HOOK)
     x = AddPosFn.apply(x, vt.pos_embed)
     depth = model.transformer_depth
     for i in range(depth - 1):                                        # A5

@@ -16,7 +16,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from . import SE3, synthetic as S
+from . import SE3, synthetic as S, train_path
 from .losses import geodesic_loss
 
 
@@ -39,7 +39,7 @@ def make_batch(step, rank, B, H, W, device):
 def default_options(**over):
     """The reference's Matterport training flags (scripts/train_matterport.sh:6-9, train.py:200-233)."""
     d = dict(steps=30, warmup_steps=5, batch=6, size=[384, 512], lr=5e-4, weight_decay=1e-5, clip=2.5, w_tr=10.0, w_rot=10.0,
-             total_steps=120000, warmup=10000, optimizer="fused", pool=8, measure_allreduce=True, graph=True)
+             total_steps=120000, warmup=10000, optimizer="fused", pool=8, measure_allreduce=True, graph=True, overlap_exchange=True)
     d.update(over)
     return argparse.Namespace(**d)
 
@@ -111,9 +111,13 @@ def train_loop(a, dev, rank=0, world=1, local=0):
     # bound by the host (17 ms per step for 11 ms of kernels).  Two graphs are recorded once after a few eager steps and
     # replayed: G1 = zero_grad + forward + loss + backward, G2 = gradient norm + clipped Adam.  Between them, on more than
     # one rank, ONE NCCL all-reduce (average) of the flat gradient buffer -- every parameter's .grad is a view of it.
-    # It is the whole exchange step of train.py:66-67 in one call: 77 MB take 0.18 ms over NVLink, 1-2 % of the step, so
-    # there is nothing to gain from bucketing it into the backward the way DistributedDataParallel does (whose reducer
-    # cannot be captured: the attempt invalidated the capture, profiles/r02_train_2gpu_ddp_capture_attempt.json).
+    # It is the whole exchange step of train.py:66-67 in one call: 77 MB take 0.3 ms over NVLink = 5 % of the 5.9 ms step at
+    # 8 GPUs.  --overlap_exchange 1 (default) hides most of it: the gradients come in two buckets inside G1 -- everything
+    # behind the CNN (transformer, Essential Matrix Module, regressor: 92 % of the bytes) is all-reduced on a side stream
+    # from the moment the backward pass reaches the CNN (a hook on the token tensor's gradient, train_path.forward_train),
+    # the CNN's own gradients when the backward ends.  Same sums, same order of the two-operand adds inside NCCL per
+    # element: the losses are those of the single-call exchange.  (DistributedDataParallel's own reducer cannot be
+    # captured: the attempt invalidated the capture, profiles/r02_train_2gpu_ddp_capture_attempt.json.)
     # The batch is copied into static buffers and the two per-step optimizer scalars into a 2-float device buffer in
     # front of each replay.
     graph = None
@@ -130,6 +134,26 @@ def train_loop(a, dev, rank=0, world=1, local=0):
             p.grad = v
         static = [t.clone() for t in pool[0]]
         g_out = {}
+        # first parameter behind the CNN (model.parameters() follows the module order: resnet, extractor_final_conv, then the rest)
+        cnn_ids = {id(p) for m in (model.resnet, model.extractor_final_conv) for p in m.parameters()}
+        k0 = next((i for i, p in enumerate(trainable) if id(p) not in cnn_ids), len(trainable))
+        tail_ok = world > 1 and a.overlap_exchange and 0 < k0 < len(trainable) and all(id(p) not in cnn_ids for p in trainable[k0:])
+        ov = {"on": bool(tail_ok), "fired": False}
+        xstream = torch.cuda.Stream(device=dev) if tail_ok else None
+
+        def tokens_grad_hook(_g):
+            # backward has reached the CNN: pack and all-reduce the gradients behind it while the CNN's backward runs
+            tail = trainable[k0:]
+            if not ov["on"] or ov["fired"] or any(p.grad is None for p in tail):
+                return None
+            ov["fired"] = True
+            with torch.no_grad():
+                torch._foreach_copy_(flat_views[k0:], [p.grad for p in tail])
+            cur = torch.cuda.current_stream(dev)
+            xstream.wait_stream(cur)
+            with torch.cuda.stream(xstream):
+                dist.all_reduce(flat_grad[offs[k0]:], op=dist.ReduceOp.AVG)
+            return None
 
         def fwd_bwd():
             images, poses, intr = static
@@ -139,19 +163,29 @@ def train_loop(a, dev, rank=0, world=1, local=0):
             for p in trainable:
                 p.grad = None
             Ps = SE3(poses)
-            poses_est = net(images, SE3.IdentityLike(Ps), intrinsics=intr_w)
+            ov["fired"] = False
+            train_path.TOKENS_GRAD_HOOK = tokens_grad_hook if ov["on"] else None      # attached to the token tensor by the forward
+            try:
+                poses_est = net(images, SE3.IdentityLike(Ps), intrinsics=intr_w)
+            finally:
+                train_path.TOKENS_GRAD_HOOK = None
             ltr, lrot, _ = geodesic_loss(SE3(Ps.data.clone()), poses_est, sync_metrics=False)
             loss = a.w_tr * ltr + a.w_rot * lrot
             loss.backward()
-            got = [(v, p.grad) for p, v in zip(trainable, flat_views) if p.grad is not None]
+            lo = k0 if ov["fired"] else len(trainable)            # parameters not packed by the hook
+            got = [(v, p.grad) for p, v in zip(trainable[:lo], flat_views[:lo]) if p.grad is not None]
             with torch.no_grad():
                 torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
             for p, v in zip(trainable, flat_views):
                 p.grad = v
+            if ov["on"]:
+                # second bucket (or, if the hook could not fire, everything) on the main stream, then join the side stream
+                dist.all_reduce(flat_grad[:offs[k0]] if ov["fired"] else flat_grad, op=dist.ReduceOp.AVG)
+                torch.cuda.current_stream(dev).wait_stream(xstream)
             g_out["loss"] = loss.detach()
 
         def exchange_grads():
-            if world > 1:
+            if world > 1 and not ov["on"]:
                 dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
 
         def opt_part():
@@ -163,6 +197,11 @@ def train_loop(a, dev, rank=0, world=1, local=0):
         n_pre = max(1, min(a.warmup_steps, 2))
         pre_log = []
         try:
+            if ov["on"]:                                     # NCCL communicator of the side stream created outside the capture
+                xstream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(xstream):
+                    dist.all_reduce(torch.zeros(8, device=dev))
+                torch.cuda.current_stream(dev).wait_stream(xstream)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
@@ -175,17 +214,34 @@ def train_loop(a, dev, rank=0, world=1, local=0):
                     pre_log.append((g_out["loss"].clone(), g_out["gn"].clone()))
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            graph2 = torch.cuda.CUDAGraph()
-            opt.upload_step_scalars()
-            with torch.cuda.graph(graph):
-                fwd_bwd()
-            with torch.cuda.graph(graph2, pool=graph.pool()):
-                opt_part()
+
+            def capture():
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                opt.upload_step_scalars()
+                with torch.cuda.graph(g1):
+                    fwd_bwd()
+                with torch.cuda.graph(g2, pool=g1.pool()):
+                    opt_part()
+                return g1, g2
+
+            try:
+                graph, graph2 = capture()
+            except Exception:
+                if not ov["on"]:
+                    raise
+                ov["on"] = False                             # the exchange would not capture: one all-reduce between the graphs
+                torch.cuda.synchronize()
+                graph, graph2 = capture()
             assert all(p.grad.data_ptr() == flat_grad.data_ptr() + 4 * off for p, off in zip(trainable, offs)), \
                 "a gradient left the flat buffer"
-            graph_note = ("G1 = forward + loss + backward, " + ("one NCCL all-reduce (AVG) of the flat gradient buffer, "
-                          if world > 1 else "") + f"G2 = clip + Adam: CUDA graphs (first {n_pre} steps eager)")
+            if ov["on"]:
+                graph_note = ("G1 = forward + loss + backward WITH the gradient exchange inside: NCCL all-reduce (AVG) of the "
+                              f"gradients behind the CNN ({(flat_grad.numel() - offs[k0]) * 4} bytes) on a side stream under the "
+                              f"CNN's backward, of the CNN's ({offs[k0] * 4} bytes) at the end; G2 = clip + Adam: CUDA graphs "
+                              f"(first {n_pre} steps eager)" + ("" if ov["fired"] else "; hook did not fire: single all-reduce"))
+            else:
+                graph_note = ("G1 = forward + loss + backward, " + ("one NCCL all-reduce (AVG) of the flat gradient buffer, "
+                              if world > 1 else "") + f"G2 = clip + Adam: CUDA graphs (first {n_pre} steps eager)")
         except Exception as ex:
             graph = None
             graph_note = f"capture failed, eager: {type(ex).__name__}: {str(ex)[:160]}"
@@ -291,8 +347,12 @@ def train_loop(a, dev, rank=0, world=1, local=0):
                           "clip+adam+lr": round(phase[2], 3)}),
             "exchange": exchange if exchange is not None else (
                 "single rank: no gradient exchange" if world == 1 else
-                {"payload_bytes": int(flat_grad.numel()) * 4, "how": "one NCCL all-reduce (average) of the flat gradient buffer "
-                 "between the two graphs; its time is phase_ms['gradient all-reduce'] (CUDA events, max over ranks not taken)"})}
+                {"payload_bytes": int(flat_grad.numel()) * 4, "how": (
+                    "two NCCL all-reduces (average) inside G1: the gradients behind the CNN on a side stream while the CNN's backward "
+                    "runs, the CNN's at the end; phase_ms['gradient all-reduce'] is then ~0 and the exposed part is inside G1"
+                    if (graph is not None and ov["on"]) else
+                    "one NCCL all-reduce (average) of the flat gradient buffer between the two graphs; its time is "
+                    "phase_ms['gradient all-reduce'] (CUDA events, max over ranks not taken)")})}
 
 
 def main():
@@ -313,6 +373,8 @@ def main():
                     help="fused: rel_pose_b200.optim.FusedAdamOneCycle (clip + Adam + OneCycle in 3 launches, no host sync); "
                          "torch: the reference's own calls (clip_grad_norm_, Adam.step, OneCycleLR.step)")
     ap.add_argument("--pool", type=int, default=d.pool, help="synthetic batches generated up front on the device and cycled")
+    ap.add_argument("--overlap_exchange", type=int, default=1,
+                    help="graphs + several ranks: all-reduce the gradients behind the CNN under the CNN's backward (0: one call between the graphs)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the whole step as one CUDA graph (fused optimizer only); 0: eager")
     a = ap.parse_args()
     a.measure_allreduce = True

@@ -74,9 +74,9 @@ def test_gloo_world2_sharded_equals_unsharded(n_pairs, micro):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_pairs, micro, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=420) for _ in procs]
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
     ref = _fake_forward(torch.arange(n_pairs))
     for rank, full, tmax in res:
