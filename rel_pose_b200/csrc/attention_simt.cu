@@ -443,6 +443,82 @@ em_project_kernel(const float* __restrict__ bil, const float* __restrict__ W, co
     for (int cc = 0; cc < PJ_CC; ++cc) dst[(size_t)cc * RP_EMBED] = acc[cc] + bo;
 }
 
+// Second version (default; RELPOSE_EM_PROJECT_V1=1 selects the kernel above for A/B runs): ONE CTA per (pair, direction)
+// matrix, 384 threads = four column groups (18, 18, 18, 16 of the 70 columns c) x 96 threads, TWO outputs (o, o + 96)
+// per thread, Z read four k at a time.  The first version was bound by shared-memory instructions (one broadcast LDS.64
+// per two FMAs = 25 % of the FMA rate at best, 60 us for 0.72 GFLOP at 64 pairs) and staged the weights twice per
+// matrix; here every LDS.128 of Z feeds eight FMAs (18 + 8 shared-memory instructions per 144 FMAs: FMA bound), the
+// twelve warps sit three per scheduler and the weights are staged once per matrix.  Each output accumulates over k in
+// ascending order from zero exactly as before: results are bit-identical to the first version.
+constexpr int PJ2_G = 4, PJ2_CC = 18, PJ2_OT = RP_EMBED / 2;             // column groups, columns per group, threads per group
+constexpr int PJ2_THREADS = PJ2_G * PJ2_OT;                              // 384
+constexpr int PJ2_KC = 28, PJ2_ZP = PJ_K + 2;                            // K chunk of the staged weights; pitch of a Z row (212)
+constexpr int PJ2_SMEM = (PJ2_G * PJ2_CC * PJ2_ZP + RP_EMBED * (PJ2_KC + 1)) * 4;
+static_assert(PJ2_G * PJ2_CC >= EMW && PJ2_ZP % 4 == 0 && PJ2_KC % 4 == 0 && (PJ_K % PJ2_KC) % 2 == 0, "em_project2 tiling");
+
+__global__ void __launch_bounds__(PJ2_THREADS)
+em_project2_kernel(const float* __restrict__ bil, const float* __restrict__ W, const float* __restrict__ bias,
+                   float* __restrict__ out) {
+    extern __shared__ __align__(16) float pj_smem[];
+    float (*Zs)[PJ2_ZP] = reinterpret_cast<float (*)[PJ2_ZP]>(pj_smem);                       // Z[c][h*70+a], rows >= 70 zero
+    float (*Ws)[PJ2_KC + 1] = reinterpret_cast<float (*)[PJ2_KC + 1]>(pj_smem + PJ2_G * PJ2_CC * PJ2_ZP);
+    const int tid = threadIdx.x;
+    const int g = tid / PJ2_OT, o = tid % PJ2_OT;          // warp-uniform column group; outputs o and o + 96
+    const int dir = blockIdx.x & 1, b = blockIdx.x >> 1;
+    const float* F = bil + ((size_t)b * 2 + dir) * RP_HEADS * EMW * EMW;
+    for (int e = tid; e < PJ_K * EMW; e += PJ2_THREADS) {
+        int k = e / EMW, c = e % EMW;                       // c fastest: contiguous in global
+        Zs[c][k] = F[e];                                    // F[h][a][c] with k = h*70+a
+    }
+    for (int e = tid; e < (PJ2_G * PJ2_CC - EMW) * PJ2_ZP; e += PJ2_THREADS) Zs[EMW + e / PJ2_ZP][e % PJ2_ZP] = 0.f;
+    float acc0[PJ2_CC], acc1[PJ2_CC];
+#pragma unroll
+    for (int cc = 0; cc < PJ2_CC; ++cc) acc0[cc] = acc1[cc] = 0.f;
+    const float (*Zg)[PJ2_ZP] = Zs + g * PJ2_CC;
+    for (int k0 = 0; k0 < PJ_K; k0 += PJ2_KC) {
+        const int kc = (PJ_K - k0 < PJ2_KC) ? (PJ_K - k0) : PJ2_KC;      // 28 x 7, then 14
+        __syncthreads();
+        for (int e = tid; e < RP_EMBED * kc; e += PJ2_THREADS) {
+            int r = e / kc, kk = e % kc;
+            Ws[r][kk] = W[(size_t)r * PJ_K + k0 + kk];
+        }
+        __syncthreads();
+        int kk = 0;
+        for (; kk + 4 <= kc; kk += 4) {
+            const float a0 = Ws[o][kk], a1 = Ws[o][kk + 1], a2 = Ws[o][kk + 2], a3 = Ws[o][kk + 3];
+            const float b0 = Ws[o + PJ2_OT][kk], b1 = Ws[o + PJ2_OT][kk + 1], b2 = Ws[o + PJ2_OT][kk + 2], b3 = Ws[o + PJ2_OT][kk + 3];
+#pragma unroll
+            for (int cc = 0; cc < PJ2_CC; ++cc) {
+                const float4 z = *reinterpret_cast<const float4*>(&Zg[cc][k0 + kk]);
+                acc0[cc] = fmaf(z.x, a0, acc0[cc]); acc1[cc] = fmaf(z.x, b0, acc1[cc]);
+                acc0[cc] = fmaf(z.y, a1, acc0[cc]); acc1[cc] = fmaf(z.y, b1, acc1[cc]);
+                acc0[cc] = fmaf(z.z, a2, acc0[cc]); acc1[cc] = fmaf(z.z, b2, acc1[cc]);
+                acc0[cc] = fmaf(z.w, a3, acc0[cc]); acc1[cc] = fmaf(z.w, b3, acc1[cc]);
+            }
+        }
+        for (; kk + 2 <= kc; kk += 2) {                     // the last chunk (14) ends with one pair
+            const float a0 = Ws[o][kk], a1 = Ws[o][kk + 1];
+            const float b0 = Ws[o + PJ2_OT][kk], b1 = Ws[o + PJ2_OT][kk + 1];
+#pragma unroll
+            for (int cc = 0; cc < PJ2_CC; ++cc) {
+                const float2 z = *reinterpret_cast<const float2*>(&Zg[cc][k0 + kk]);
+                acc0[cc] = fmaf(z.x, a0, acc0[cc]); acc1[cc] = fmaf(z.x, b0, acc1[cc]);
+                acc0[cc] = fmaf(z.y, a1, acc0[cc]); acc1[cc] = fmaf(z.y, b1, acc1[cc]);
+            }
+        }
+    }
+    const float bo0 = bias[o], bo1 = bias[o + PJ2_OT];
+    const int c0 = g * PJ2_CC;
+    float* dst = out + ((size_t)(2 * b + (1 - dir)) * EMW + c0) * RP_EMBED + o;
+#pragma unroll
+    for (int cc = 0; cc < PJ2_CC; ++cc) {
+        if (c0 + cc < EMW) {
+            dst[(size_t)cc * RP_EMBED] = acc0[cc] + bo0;
+            dst[(size_t)cc * RP_EMBED + PJ2_OT] = acc1[cc] + bo1;
+        }
+    }
+}
+
 int set_smem(const void* fn, int bytes, const char* what) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) {
@@ -523,6 +599,13 @@ extern "C" int rp_em_project_f32(const float* bil, const float* W, const float* 
                                  void* stream) {
     RP_REQUIRE(bil && W && bias && out && B > 0, RP_EINVAL, "rp_em_project: bad argument");
     RP_GUARD(device);
-    em_project_kernel<<<dim3(EMW / PJ_CC, B * 2), RP_EMBED, 0, (cudaStream_t)stream>>>(bil, W, bias, out);
+    const char* env = std::getenv("RELPOSE_EM_PROJECT_V1");     // read per call: the GPU test toggles it in-process
+    if (env && env[0] == '1') {
+        em_project_kernel<<<dim3(EMW / PJ_CC, B * 2), RP_EMBED, 0, (cudaStream_t)stream>>>(bil, W, bias, out);
+    } else {
+        int rc = set_smem((const void*)em_project2_kernel, PJ2_SMEM, "rp_em_project");
+        if (rc) return rc;
+        em_project2_kernel<<<B * 2, PJ2_THREADS, PJ2_SMEM, (cudaStream_t)stream>>>(bil, W, bias, out);
+    }
     return rp::finish_launch("rp_em_project");
 }

@@ -69,7 +69,7 @@ template <int P, int CPS>
 __global__ void __launch_bounds__(ATT_THREADS, CPS)
 self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_planes, int p_out, int n_img,
-                         float scale_log2, int kv_xor, float* __restrict__ lse_out) {
+                         float scale_log2, int kv_xor, float* __restrict__ lse_out, int skip_dead) {
     using C = ACfg<P, CPS>;
     constexpr int V_STAGES = C::V_STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -266,6 +266,24 @@ self_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int qt = tile % QTILES, h = (tile / QTILES) % HEADS, img = tile / (QTILES * HEADS);
+            if (skip_dead && qt * BM + quarter * 32 >= NTOK) {
+                // Rows past the last token (lane quarters 2 and 3 of the fifth query tile: zero-filled Q, nothing is ever
+                // stored): keep the barrier protocol in lock step with the live warps -- same waits, same arrivals -- and
+                // skip the arithmetic; the issue slots go to the live quarters and to the SM's other CTA.  Both warps of
+                // a quarter take this branch together, so the row exchanges (bar.sync) are skipped by both.
+                for (int j = 0; j < NBLK; ++j, ++g) {
+                    tc::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+                    if constexpr (CPS == 1) {
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&s_free[g & 1]);
+                    }
+                    if (j > 0) tc::mbar_wait(pv_done, (g - 1) & 1);   // P_j may not be announced before PV_{j-1} retired
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(p_ready);
+                }
+                tc::mbar_wait(pv_done, (g - 1) & 1);
+                continue;
+            }
             float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
             float o[HO];
 #pragma unroll
@@ -468,8 +486,10 @@ int launch_attention_cps(const void* qkv_planes, float* out_f32, void* out_plane
     const int slots = CPS * rp::num_sms(device);
     const int grid = ntiles < slots ? ntiles : slots;
     const float scale_log2 = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
+    // RELPOSE_ATT_SKIP_DEAD=0: the softmax warps of the rows past the last token do the full arithmetic (A/B measurements)
+    static const int skip_dead = [] { const char* e = getenv("RELPOSE_ATT_SKIP_DEAD"); return (e && e[0] == '0') ? 0 : 1; }();
     rp::launch(self_attention_tc_kernel<P, CPS>, dim3(grid), dim3(ATT_THREADS), (size_t)(C::SMEM), st, tmQ, tmKV, out_f32, static_cast<__nv_bfloat16*>(out_planes),
-                                                                       p_out, n_img, scale_log2, kv_xor, lse_out);
+                                                                       p_out, n_img, scale_log2, kv_xor, lse_out, skip_dead);
     return rp::finish_launch("rp_self_attention_tc");
 }
 

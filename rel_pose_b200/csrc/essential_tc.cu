@@ -55,7 +55,7 @@ struct SCfg {
 template <int P>
 __global__ void __launch_bounds__(EM_THREADS, 2)
 em_stats_tc_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC,
-                   float* __restrict__ lse2, int B) {
+                   float* __restrict__ lse2, int B, int skip_dead) {
     using C = SCfg<P>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a SHARED pointer (LDS / STS)
@@ -175,8 +175,13 @@ em_stats_tc_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
             int tile, h, which, dir, b;
             decode(item, tile, h, which, dir, b);
             float m = -INFINITY, l = 0.f;
+            const bool dead = skip_dead && tile * BM + quarter * 32 >= NTOK;   // lane quarter entirely past the last token: nothing to compute or store
             for (int j = 0; j < NBLK; ++j, ++g) {
                 tc::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+                if (dead) {                                       // keep the protocol (every thread arrives), skip the arithmetic
+                    tc::mbar_arrive(&s_free[g & 1]);
+                    continue;
+                }
                 tc::tcgen05_fence_after();
                 uint32_t s[BKV];
                 {
@@ -711,6 +716,8 @@ constexpr int EM2_CTRL = 4, EM2_SPLIT = 4, EM2_THREADS = 32 * (EM2_CTRL + 4 * EM
 constexpr int HB2 = BKV / EM2_SPLIT, HT2 = HD / EM2_SPLIT;                                     // 24 score / 16 T_v columns per thread
 constexpr int A_PLANE = BKV / 2;                                                               // 48 columns per bf16 plane of A_ij
 
+constexpr int EM_INTERNAL_NO_SKIP_DEAD = 1 << 30;   // launcher-only bit of em_flags (RELPOSE_EM_SKIP_DEAD=0, A/B measurements)
+
 template <int P>
 __global__ void __launch_bounds__(EM2_THREADS, 1)
 em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
@@ -1032,6 +1039,11 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             asm volatile("bar.sync 1, 512;" ::: "memory");
             const int row = tile * BM + r;
             const float rl = row < NTOK ? lse_r[row] : INFINITY;    // rows past the end contribute exactly 0
+            // Lane quarters that lie entirely past the last token (quarters 2 and 3 of the fifth row tile): Q is zero-filled,
+            // so S_ij = 0 exactly, and the zero bits already sitting in the S buffer ARE the A_ij planes these rows would
+            // write (2^-inf = 0).  Such a warp keeps every wait / arrival of the protocol and skips the loads, exponentials,
+            // plane split and T_j folds (its T rows stay 0); all four warps of a quarter agree, so its bar.sync is skipped too.
+            const bool dead = !(em_flags & EM_INTERNAL_NO_SKIP_DEAD) && tile * BM + quarter * 32 >= NTOK;
             float tacc[HT2], tpos[8];
 #pragma unroll
             for (int i = 0; i < HT2; ++i) tacc[i] = 0.f;
@@ -1055,6 +1067,7 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int j = 0; j < NBLK; ++j, ++g) {
                 tc::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
                 tc::tcgen05_fence_after();
+                if (!dead) {
                 uint32_t s[HB2];
                 {
                     const uint32_t t_s = t_lane + T_S + (g & 1) * BKV + hsel * HB2;
@@ -1090,12 +1103,13 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tc::tmem_st_32x32b_x8(t_a, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
                     tc::tmem_st_32x32b_x4(t_a + 8, *reinterpret_cast<uint32_t(*)[4]>(&w[8]));
                 }
+                }   // !dead
                 // the T / F accumulator region must be drained before T_j may be issued: fold the previous block's
                 // product (inside a unit) or the previous unit's F_t
                 if (j > 0) {
                     tc::mbar_wait(pv_done, (g - 1) & 1);
                     tc::tcgen05_fence_after();
-                    fold_t();
+                    if (!dead) fold_t();
                 } else if (tt > 0) {
                     tc::mbar_wait(f_done, (tt - 1) & 1);
                     tc::tcgen05_fence_after();
@@ -1109,7 +1123,7 @@ em_accum2_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // last block product of the unit, then T_i (registers) -> bf16 planes in shared memory (MN-major operand)
             tc::mbar_wait(pv_done, (g - 1) & 1);
             tc::tcgen05_fence_after();
-            fold_t();
+            if (!dead) fold_t();
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
                 if (cc == 2 && !(has_pos && hsel == 0)) break;
@@ -1251,7 +1265,9 @@ int launch_essential(const void* qkv_planes, const float* pos, float* bil, int B
     }
     const int sms = rp::num_sms(device);
     const int n_stats = B * 2 * 2 * HEADS * RTILES, n_acc = B * 2 * HEADS;
-    rp::launch(em_stats_tc_kernel<P>, dim3(n_stats < 2 * sms ? n_stats : 2 * sms), dim3(EM_THREADS), (size_t)(SCfg<P>::SMEM), st, tmR, tmC, lse2, B);
+    // RELPOSE_EM_SKIP_DEAD=0: the softmax warps of lane quarters past the last token do the full arithmetic (A/B measurements)
+    static const int no_skip = [] { const char* e = getenv("RELPOSE_EM_SKIP_DEAD"); return (e && e[0] == '0') ? EM_INTERNAL_NO_SKIP_DEAD : 0; }();
+    rp::launch(em_stats_tc_kernel<P>, dim3(n_stats < 2 * sms ? n_stats : 2 * sms), dim3(EM_THREADS), (size_t)(SCfg<P>::SMEM), st, tmR, tmC, lse2, B, no_skip ? 0 : 1);
     rc = rp::finish_launch("rp_essential_tc(stats)");
     if (rc) return rc;
     if (em_use_v1()) {
@@ -1259,7 +1275,7 @@ int launch_essential(const void* qkv_planes, const float* pos, float* bil, int B
         return rp::finish_launch("rp_essential_tc(accum)");
     }
     const int n_units = n_acc * RTILES;
-    rp::launch(em_accum2_tc_kernel<P>, dim3(n_units < sms ? n_units : sms), dim3(EM2_THREADS), (size_t)(ECfg<P>::SMEM), st, tmR, tmC, tmPos, lse2, part, B, width, flags);
+    rp::launch(em_accum2_tc_kernel<P>, dim3(n_units < sms ? n_units : sms), dim3(EM2_THREADS), (size_t)(ECfg<P>::SMEM), st, tmR, tmC, tmPos, lse2, part, B, width, flags | no_skip);
     rc = rp::finish_launch("rp_essential_tc(accum)");
     if (rc) return rc;
     const long long total = (long long)n_acc * width * width;

@@ -169,6 +169,23 @@ def test_essential_module(B, scale):
     report("em_project slot1 (=Y1)", out[:, 1], y1, atol=1e-5 * np.abs(y1).max(), rtol=2e-4)
 
 
+@pytest.mark.parametrize("B", [1, 5])
+def test_em_project_versions_are_bit_identical(B, monkeypatch):
+    """proj_fundamental (vision_transformer.py:225-231): the one-CTA-per-matrix kernel (default) accumulates every output
+    over k in the same order as the first kernel (RELPOSE_EM_PROJECT_V1=1) -> identical bits; and it matches float64."""
+    bil = rnd(31, B, 2, 3, 70, 70, scale=3.0)
+    pw = rnd(32, 192, 210, scale=1 / np.sqrt(210)); pb = rnd(33, 192, scale=0.1)
+    monkeypatch.delenv("RELPOSE_EM_PROJECT_V1", raising=False)
+    new = ops.em_project(cu(bil), cu(pw), cu(pb)).cpu().numpy()
+    monkeypatch.setenv("RELPOSE_EM_PROJECT_V1", "1")
+    old = ops.em_project(cu(bil), cu(pw), cu(pb)).cpu().numpy()
+    monkeypatch.delenv("RELPOSE_EM_PROJECT_V1", raising=False)
+    assert new.shape == (2 * B, 70, 192) and np.array_equal(new, old)
+    z = bil.astype(np.float64).reshape(B, 2, 210, 70).transpose(0, 1, 3, 2)            # [b, dir, c, h*70+a]
+    ref = (z @ pw.astype(np.float64).T + pb.astype(np.float64))[:, ::-1].reshape(2 * B, 70, 192)   # slot = 1 - dir
+    report("em_project vs float64", new, ref, atol=1e-5 * np.abs(ref).max(), rtol=2e-4)
+
+
 class _BN:
     def __init__(self, seed, C):
         self.weight = cu(1 + 0.2 * rnd(seed, C)); self.bias = cu(0.1 * rnd(seed + 1, C))
