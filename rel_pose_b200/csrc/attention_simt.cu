@@ -456,6 +456,28 @@ constexpr int PJ2_KC = 28, PJ2_ZP = PJ_K + 2;                            // K ch
 constexpr int PJ2_SMEM = (PJ2_G * PJ2_CC * PJ2_ZP + RP_EMBED * (PJ2_KC + 1)) * 4;
 static_assert(PJ2_G * PJ2_CC >= EMW && PJ2_ZP % 4 == 0 && PJ2_KC % 4 == 0 && (PJ_K % PJ2_KC) % 2 == 0, "em_project2 tiling");
 
+constexpr int PJ2_WREG = RP_EMBED * PJ2_KC / PJ2_THREADS;                // staged weights per thread and chunk (14)
+constexpr int PJ2_ZB = 13;                                               // loads of Z in flight per thread and round
+static_assert(RP_EMBED * PJ2_KC % PJ2_THREADS == 0, "em_project2 staging");
+
+// chunk [k0, k0 + KC) of W [192][210] -> registers: all loads of a thread are in flight together
+template <int KC>
+__device__ __forceinline__ void pj2_load_w(const float* __restrict__ W, int k0, int tid, float (&wn)[PJ2_WREG]) {
+#pragma unroll
+    for (int i = 0; i < PJ2_WREG; ++i) {
+        const int e = tid + i * PJ2_THREADS;
+        wn[i] = (e < RP_EMBED * KC) ? W[(size_t)(e / KC) * PJ_K + k0 + e % KC] : 0.f;
+    }
+}
+template <int KC>
+__device__ __forceinline__ void pj2_store_w(float (*Ws)[PJ2_KC + 1], int tid, const float (&wn)[PJ2_WREG]) {
+#pragma unroll
+    for (int i = 0; i < PJ2_WREG; ++i) {
+        const int e = tid + i * PJ2_THREADS;
+        if (e < RP_EMBED * KC) Ws[e / KC][e % KC] = wn[i];
+    }
+}
+
 __global__ void __launch_bounds__(PJ2_THREADS)
 em_project2_kernel(const float* __restrict__ bil, const float* __restrict__ W, const float* __restrict__ bias,
                    float* __restrict__ out) {
@@ -466,23 +488,40 @@ em_project2_kernel(const float* __restrict__ bil, const float* __restrict__ W, c
     const int g = tid / PJ2_OT, o = tid % PJ2_OT;          // warp-uniform column group; outputs o and o + 96
     const int dir = blockIdx.x & 1, b = blockIdx.x >> 1;
     const float* F = bil + ((size_t)b * 2 + dir) * RP_HEADS * EMW * EMW;
-    for (int e = tid; e < PJ_K * EMW; e += PJ2_THREADS) {
-        int k = e / EMW, c = e % EMW;                       // c fastest: contiguous in global
-        Zs[c][k] = F[e];                                    // F[h][a][c] with k = h*70+a
+    // One CTA per SM and twelve warps: global-memory latency is not hidden by occupancy, so every staging step issues all
+    // of a thread's loads before it touches any of them (the first version of this kernel staged element by element and
+    // spent 80 % of its time on the long scoreboard), and the next chunk of W is fetched while the current one is used.
+    float wn[PJ2_WREG];
+    pj2_load_w<PJ2_KC>(W, 0, tid, wn);
+#pragma unroll 1
+    for (int e0 = 0; e0 < PJ_K * EMW; e0 += PJ2_ZB * PJ2_THREADS) {      // three rounds of 13 loads in flight per thread
+        float zr[PJ2_ZB];
+#pragma unroll
+        for (int i = 0; i < PJ2_ZB; ++i) {
+            const int e = e0 + tid + i * PJ2_THREADS;       // F[h][a][c] flat = k * 70 + c with k = h*70+a: coalesced
+            zr[i] = (e < PJ_K * EMW) ? F[e] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < PJ2_ZB; ++i) {
+            const int e = e0 + tid + i * PJ2_THREADS;
+            if (e < PJ_K * EMW) Zs[e % EMW][e / EMW] = zr[i];
+        }
     }
     for (int e = tid; e < (PJ2_G * PJ2_CC - EMW) * PJ2_ZP; e += PJ2_THREADS) Zs[EMW + e / PJ2_ZP][e % PJ2_ZP] = 0.f;
     float acc0[PJ2_CC], acc1[PJ2_CC];
 #pragma unroll
     for (int cc = 0; cc < PJ2_CC; ++cc) acc0[cc] = acc1[cc] = 0.f;
     const float (*Zg)[PJ2_ZP] = Zs + g * PJ2_CC;
-    for (int k0 = 0; k0 < PJ_K; k0 += PJ2_KC) {
-        const int kc = (PJ_K - k0 < PJ2_KC) ? (PJ_K - k0) : PJ2_KC;      // 28 x 7, then 14
-        __syncthreads();
-        for (int e = tid; e < RP_EMBED * kc; e += PJ2_THREADS) {
-            int r = e / kc, kk = e % kc;
-            Ws[r][kk] = W[(size_t)r * PJ_K + k0 + kk];
-        }
-        __syncthreads();
+    constexpr int NFULL = PJ_K / PJ2_KC, KTAIL = PJ_K - NFULL * PJ2_KC;      // 7 chunks of 28, then 14
+    static_assert(KTAIL > 0 && KTAIL % 2 == 0, "tail chunk");
+    for (int ch = 0; ch <= NFULL; ++ch) {
+        const int k0 = ch * PJ2_KC;
+        const int kc = ch < NFULL ? PJ2_KC : KTAIL;
+        __syncthreads();                                    // the previous chunk of Ws has been consumed (first pass: nothing)
+        if (ch < NFULL) pj2_store_w<PJ2_KC>(Ws, tid, wn); else pj2_store_w<KTAIL>(Ws, tid, wn);
+        __syncthreads();                                    // also orders the fill of Zs before its first use
+        if (ch + 1 < NFULL) pj2_load_w<PJ2_KC>(W, k0 + PJ2_KC, tid, wn);
+        else if (ch + 1 == NFULL) pj2_load_w<KTAIL>(W, k0 + PJ2_KC, tid, wn);
         int kk = 0;
         for (; kk + 4 <= kc; kk += 4) {
             const float a0 = Ws[o][kk], a1 = Ws[o][kk + 1], a2 = Ws[o][kk + 2], a3 = Ws[o][kk + 3];
