@@ -5,7 +5,7 @@
 // (x = x0 + x1; every product is evaluated as a0 b0 + a0 b1 + a1 b0 into one fp32 TMEM accumulator, fp32 class).
 //
 // Work item = (image, head, 128-query tile); 576 = 4.5 tiles, the 5th tile is half empty (TMA zero fill, rows
-// never stored).  Keys/values stream in 6 blocks of 96.  Persistent CTAs (one or two per SM), 384 threads:
+// never stored; the softmax warps of its two empty lane quarters keep the barrier protocol and skip the arithmetic).  Keys/values stream in 6 blocks of 96.  Persistent CTAs (one or two per SM), 384 threads:
 //   warp 0      TMA producer: Q tile (once per item), K and V blocks through two independent 2-stage rings
 //   warp 1      S issuer + TMEM owner:  S_j = Q K_j^T   M=128 N=96 K=64, A,B K-major SWIZZLE_128B -> TMEM S[j&1];
 //               runs up to two key blocks ahead of the softmax (s_free mbarriers)

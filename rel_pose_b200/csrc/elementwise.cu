@@ -2,6 +2,7 @@
 // Reference rows: A1 (src/model.py:114-125), A4 (:136-141,172), LayerNorm (vision_transformer.py:396),
 // A6 (vision_transformer.py:90-158), A10 (src/model.py:145-152).
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 #include <stdlib.h>
 #include <string.h>
@@ -357,13 +358,120 @@ __global__ void __launch_bounds__(RT_H) regressor_tail_kernel(const float* __res
     }
 }
 
+// Second version (default; RELPOSE_REGRESSOR_TAIL_V1=1 selects the kernel above for A/B runs).  The first version gave every
+// row its own CTA, so every CTA pulled the whole 1 MB layer-1 weight through its SM's L2 port (~26 k cycles = 13 us, the
+// kernel's 32 us together with the serial layer-2 dots).  Here a thread-block CLUSTER of 8 CTAs takes 8 rows: CTA `rank` owns
+// hidden units [64 rank, 64 rank + 64) for all 8 rows (128 KB of weights + 16 KB of h per CTA), four k-slices per CTA summed in
+// a fixed order, and hands row r of its [8 x 64] ReLU block to CTA r through distributed shared memory; after one cluster
+// barrier CTA r holds all 512 hidden values of row r and forms its 14 outputs (one warp per output, loads batched).
+constexpr int RT2_ROWS = 8, RT2_J = RT_H / RT2_ROWS /* 64 hidden units per CTA */, RT2_KS = 4, RT2_THREADS = RT2_J * RT2_KS;
+constexpr int RT2_SMEM = (RT_H * RT2_J + RT_H * RT2_ROWS + RT2_KS * RT2_ROWS * RT2_J + RT_H) * 4;   // Ws, hs, part, h2row
+static_assert(RT2_ROWS == 8 && RT2_THREADS == 256 && RT_H % RT2_KS == 0 && (RT_H * RT2_J / 4) % RT2_THREADS == 0, "regressor_tail2 tiling");
+
+__global__ void __cluster_dims__(RT2_ROWS, 1, 1) __launch_bounds__(RT2_THREADS)
+regressor_tail2_kernel(const float* __restrict__ h, const float* __restrict__ W1T, const float* __restrict__ b1,
+                       const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ out, int B) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) float rt_smem[];
+    float (*Ws)[RT2_J] = reinterpret_cast<float (*)[RT2_J]>(rt_smem);                       // W1T[k][64 rank + jj], 128 KB
+    float (*hs)[RT2_ROWS] = reinterpret_cast<float (*)[RT2_ROWS]>(rt_smem + RT_H * RT2_J);  // h of the 8 rows, k-major
+    float (*part)[RT2_ROWS][RT2_J] = reinterpret_cast<float (*)[RT2_ROWS][RT2_J]>(rt_smem + RT_H * RT2_J + RT_H * RT2_ROWS);
+    float* h2row = rt_smem + RT_H * RT2_J + RT_H * RT2_ROWS + RT2_KS * RT2_ROWS * RT2_J;   // row `rank` of relu(W1 h + b1)
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster.block_rank();                      // = blockIdx.x % 8
+    const int row0 = (blockIdx.x / RT2_ROWS) * RT2_ROWS;
+    rp::pdl_launch_dependents();
+    rp::pdl_wait();
+    // the CTA's slice of the layer-1 weight: 8192 16-byte asynchronous copies, all in flight together under the loads of h
+#pragma unroll
+    for (int i = 0; i < RT_H * RT2_J / 4 / RT2_THREADS; ++i) {
+        const int c = tid + i * RT2_THREADS, k = c / (RT2_J / 4), q = c % (RT2_J / 4);
+        rp::cp_async16(&Ws[k][4 * q], W1T + (size_t)k * RT_H + rank * RT2_J + 4 * q);
+    }
+    rp::cp_async_commit();
+    {
+        float v[RT2_ROWS * RT_H / RT2_THREADS];                      // 16 loads in flight
+#pragma unroll
+        for (int i = 0; i < RT2_ROWS * RT_H / RT2_THREADS; ++i) {
+            const int e = tid + i * RT2_THREADS, r = e / RT_H;
+            v[i] = (row0 + r < B) ? h[(size_t)(row0 + r) * RT_H + (e % RT_H)] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < RT2_ROWS * RT_H / RT2_THREADS; ++i) {
+            const int e = tid + i * RT2_THREADS;
+            hs[e % RT_H][e / RT_H] = v[i];
+        }
+    }
+    rp::cp_async_wait<0>();
+    __syncthreads();
+    const int jj = tid % RT2_J, ks = tid / RT2_J;
+    constexpr int KSL = RT_H / RT2_KS;                               // 128 k per slice
+    float acc[RT2_ROWS];
+#pragma unroll
+    for (int r = 0; r < RT2_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 8
+    for (int k = ks * KSL; k < ks * KSL + KSL; ++k) {
+        const float w = Ws[k][jj];
+        const float4 x0 = *reinterpret_cast<const float4*>(&hs[k][0]);
+        const float4 x1 = *reinterpret_cast<const float4*>(&hs[k][4]);
+        acc[0] = fmaf(x0.x, w, acc[0]); acc[1] = fmaf(x0.y, w, acc[1]);
+        acc[2] = fmaf(x0.z, w, acc[2]); acc[3] = fmaf(x0.w, w, acc[3]);
+        acc[4] = fmaf(x1.x, w, acc[4]); acc[5] = fmaf(x1.y, w, acc[5]);
+        acc[6] = fmaf(x1.z, w, acc[6]); acc[7] = fmaf(x1.w, w, acc[7]);
+    }
+#pragma unroll
+    for (int r = 0; r < RT2_ROWS; ++r) part[ks][r][jj] = acc[r];
+    __syncthreads();
+    // [8 rows x 64 units] of this CTA: slices summed in order, bias, ReLU; row r goes to CTA r of the cluster
+    for (int e = tid; e < RT2_ROWS * RT2_J; e += RT2_THREADS) {
+        const int r = e / RT2_J, c = e % RT2_J;
+        float v = part[0][r][c];
+#pragma unroll
+        for (int s2 = 1; s2 < RT2_KS; ++s2) v += part[s2][r][c];
+        v = fmaxf(v + b1[rank * RT2_J + c], 0.f);
+        float* remote = cluster.map_shared_rank(h2row, r);
+        remote[rank * RT2_J + c] = v;
+    }
+    cluster.sync();                                                  // release / acquire: every CTA's h2row is complete and visible
+    const int row = row0 + rank;
+    if (row < B) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int n = warp; n < RT_OUT; n += RT2_THREADS / 32) {
+            float wv[RT_H / 32];
+#pragma unroll
+            for (int i = 0; i < RT_H / 32; ++i) wv[i] = __ldg(W2 + (size_t)n * RT_H + lane + 32 * i);
+            float s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < RT_H / 32; ++i) s2 = fmaf(h2row[lane + 32 * i], wv[i], s2);
+            s2 = rp::warp_sum(s2);
+            if (lane == 0) out[(size_t)row * RT_OUT + n] = s2 + b2[n];
+        }
+    }
+}
+
 extern "C" int rp_regressor_tail_f32(const float* h, const float* W1T, const float* b1, const float* W2, const float* b2,
                                      float* out, int B, int hidden, int n_out, int device, void* stream) {
     RP_REQUIRE(h && W1T && b1 && W2 && b2 && out && B > 0, RP_EINVAL, "rp_regressor_tail: bad argument");
     RP_REQUIRE(hidden == RT_H && n_out == RT_OUT, RP_EINVAL, "rp_regressor_tail: built for 512 hidden units and 14 outputs (got %d, %d)",
                hidden, n_out);
     RP_GUARD(device);
-    rp::launch(regressor_tail_kernel, dim3((B + RT_ROWS - 1) / RT_ROWS), dim3(RT_H), (size_t)(0), (cudaStream_t)stream, h, W1T, b1, W2, b2, out, B);
+    const char* env = getenv("RELPOSE_REGRESSOR_TAIL_V1");       // read per call: the GPU test toggles it in-process
+    if ((env && env[0] == '1') || !rp::aligned16(W1T))            // v2 stages the weight with 16-byte asynchronous copies
+        rp::launch(regressor_tail_kernel, dim3((B + RT_ROWS - 1) / RT_ROWS), dim3(RT_H), (size_t)(0), (cudaStream_t)stream, h, W1T, b1, W2, b2, out, B);
+    else {
+        static bool attr_set[64] = {false};
+        if (device >= 0 && device < 64 && !attr_set[device]) {
+            cudaError_t e = cudaFuncSetAttribute(regressor_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT2_SMEM);
+            if (e != cudaSuccess) {
+                rp::set_error("rp_regressor_tail: cudaFuncSetAttribute(%d): %s", RT2_SMEM, cudaGetErrorString(e));
+                return (int)e;
+            }
+            attr_set[device] = true;
+        }
+        rp::launch(regressor_tail2_kernel, dim3(RT2_ROWS * ((B + RT2_ROWS - 1) / RT2_ROWS)), dim3(RT2_THREADS), (size_t)(RT2_SMEM), (cudaStream_t)stream, h, W1T,
+                   b1, W2, b2, out, B);
+    }
     return rp::finish_launch("rp_regressor_tail");
 }
 

@@ -638,7 +638,15 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= mn) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s2 = 0; s2 < nsplit; ++s2) {
+    int s2 = 0;
+    for (; s2 + 8 <= nsplit; s2 += 8) {                    // eight partial loads in flight, added in split order
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(part + (size_t)(s2 + u) * mn + i));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; s2 < nsplit; ++s2) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)s2 * mn + i));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }

@@ -546,10 +546,12 @@ class ViTEss(nn.Module):
                 feat, w0 = self._pool_attn_head(x, B)
             else:
                 feat, w0 = x.reshape(B, -1), reg[0].weight
-            if self._tc_planes() == 2 and self.tc_regressor:
-                # 26880 -> 512: 55 MB of weights for 64 rows; split-K on the tensor cores (bf16x3, short accumulation chains)
-                w0p = self._pool_head_planes("w0", 2) if (self.noess or self.cnn_only) else self._planes(w0, 2)
-                h = ops.linear_tc_splitk(ops.split_planes(feat.contiguous(), 2), w0p, reg[0].bias, act=ops.ACT_RELU)
+            Pr = self._tc_planes()
+            if Pr >= 1 and self.tc_regressor:
+                # 26880 -> 512: 55 MB of weights for 64 rows; split-K on the tensor cores (short accumulation chains), in the
+                # precision of the rest of the path: bf16x3 planes, or one bf16 plane in the throughput mode of config 4
+                w0p = self._pool_head_planes("w0", Pr) if (self.noess or self.cnn_only) else self._planes(w0, Pr)
+                h = ops.linear_tc_splitk(ops.split_planes(feat.contiguous(), Pr), w0p, reg[0].bias, act=ops.ACT_RELU)
             else:
                 h = ops.linear(feat, w0, reg[0].bias, act=ops.ACT_RELU)
             if self.H2 == 512:

@@ -129,6 +129,26 @@ def test_regressor_tail(B):
     report(f"regressor_tail B={B}", got, ref, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("B", [1, 7, 8, 9, 64, 256])
+def test_regressor_tail_cluster_kernel_against_first_version(B, monkeypatch):
+    """The cluster kernel (8 CTAs per 8 rows, rows exchanged through distributed shared memory; default) against the
+    one-row-per-CTA kernel (RELPOSE_REGRESSOR_TAIL_V1=1) and float64: partial clusters, exact multiples, several clusters."""
+    h = np.maximum(rnd(45, B, 512), 0); w1 = rnd(46, 512, 512, scale=1.0 / np.sqrt(512)); b1 = rnd(47, 512, scale=0.1)
+    w2 = rnd(48, 14, 512, scale=1.0 / np.sqrt(512)); b2 = rnd(49, 14, scale=0.1)
+    args = (cu(h), cu(np.ascontiguousarray(w1.T)), cu(b1), cu(w2), cu(b2))
+    monkeypatch.delenv("RELPOSE_REGRESSOR_TAIL_V1", raising=False)
+    new = ops.regressor_tail(*args).cpu().numpy()
+    again = ops.regressor_tail(*args).cpu().numpy()
+    monkeypatch.setenv("RELPOSE_REGRESSOR_TAIL_V1", "1")
+    old = ops.regressor_tail(*args).cpu().numpy()
+    monkeypatch.delenv("RELPOSE_REGRESSOR_TAIL_V1", raising=False)
+    assert np.array_equal(new, again)                                    # fixed summation order: deterministic
+    h2 = np.maximum(h.astype(np.float64) @ w1.astype(np.float64).T + b1, 0)
+    ref = h2 @ w2.astype(np.float64).T + b2
+    report(f"regressor_tail v2 B={B}", new, ref, atol=1e-5, rtol=1e-5)
+    report(f"regressor_tail v2 vs v1 B={B}", new, old, atol=1e-5, rtol=1e-5)
+
+
 def test_linear_residual_may_alias_output():
     a = rnd(1, 300, 192); w = rnd(2, 192, 192, scale=0.07); b = rnd(3, 192, scale=0.1); r = rnd(4, 300, 192)
     x = cu(r)
