@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 
 from rel_pose_b200 import ViTEss, ops, synthetic as S  # noqa: E402
 from rel_pose_b200.lietorch import SE3  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (nvidia-smi clocks / throttle reasons sampled while the GPU is loaded)
 
 VARIANTS = [
     ("default", {}),
@@ -41,6 +42,8 @@ def main():
     Gs = SE3.Identity(B, 2, device=dev)
     out = {"workload": f"{B} synthetic {a.size}x{a.size} pairs per step, device-resident float32 images, "
                        f"{a.steps} timed steps after {a.warmup} warm-up steps, CUDA events", "variants": {}}
+    sampler = ClockSampler(0)
+    sampler.start()
     for name, over in VARIANTS:
         margs = argparse.Namespace(noess=False, pool_size=60, fc_hidden_size=512, fusion_transformer=True, transformer_depth=6,
                                    cross_features=False, use_single_softmax=False, no_pos_encoding=False, l1_pos_encoding=False)
@@ -67,8 +70,10 @@ def main():
                                  "launches_per_step": (ops.launches() - l0) // a.steps,
                                  "engine": "fp32 SIMT" if model._tc_planes() == 0 else
                                            ("bf16x3 tcgen05" + (" (module flags on rp_essential_ex_tc)" if model.em_flags else ""))}
+        out["variants"][name]["clocks"] = sampler.mark()
         del model
         torch.cuda.empty_cache()
+    out["clocks"] = sampler.stop()
     print(json.dumps(out))
 
 
