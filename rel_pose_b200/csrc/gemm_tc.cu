@@ -66,7 +66,6 @@ struct EpiParams {
     __nv_bfloat16* out_planes;   // [P_out][M][N] or null
     int p_out;
     int act;
-    int red;                 // nn.Linear with residual == out_f32 (in place): out_f32 += acc + shift as vector reductions
 };
 
 using tc::gelu_fast;
@@ -282,27 +281,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int ci = 0; ci < CH_PER_PART; ++ci) {
                 const int c0 = (part * CH_PER_PART + ci) * 16;
                 if (n0 + c0 >= N) break;                 // warp-uniform
-                if (ep.red) {
-                    // In place (x += proj(a) + b, vision_transformer.py:350): the thread keeps its TMEM row and adds acc + bias
-                    // into the residual stream with 16-byte reductions at the memory side -- no transposing patch, no residual
-                    // loads, the same single rounding per element as the load-add-store epilogue (bit-identical results).
-                    uint32_t r[16];
-                    tc::tmem_ld_32x32b_x16(t_row + c0, r);
-                    float4 b4[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        b4[j] = ep.shift ? __ldg(reinterpret_cast<const float4*>(ep.shift + n0 + c0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    tc::tmem_ld_wait();
-                    const int rt = q * 32 + lane;
-                    if (rt < valid_rows) {
-                        float* dst = out_f32 + (size_t)(row_base + rt) * N + n0 + c0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tc::red_add_v4_f32(dst + 4 * j, __uint_as_float(r[4 * j]) + b4[j].x, __uint_as_float(r[4 * j + 1]) + b4[j].y,
-                                               __uint_as_float(r[4 * j + 2]) + b4[j].z, __uint_as_float(r[4 * j + 3]) + b4[j].w);
-                    }
-                    continue;
-                }
                 const int col = n0 + c0 + cq * 4;        // the lane's 4 columns: the same for all row groups
                 const bool colv = vec4 && col < N;
                 float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -749,14 +727,6 @@ extern "C" int rp_linear_tc(const void* A_planes, const void* W_planes, const fl
     rc = tc::make_planes_tmap(&tmB, W_planes, P, N, K, BN);
     if (rc) return rc;
     EpiParams ep{nullptr, bias, nullptr, residual, 0, out_f32, static_cast<__nv_bfloat16*>(out_planes), P_out, act};
-    // residual == out_f32 (the caller updates the residual stream in place): reductions at the memory side instead of
-    // load + add + store.  RELPOSE_LINEAR_RED=0 keeps the load-add-store epilogue (A/B measurements; same bits either way).
-    static const bool red_ok = [] { const char* e = getenv("RELPOSE_LINEAR_RED"); return !(e && e[0] == '0'); }();
-    if (red_ok && residual && residual == out_f32 && !out_planes && act == RP_ACT_NONE && (N % 16) == 0 && rp::aligned16(out_f32) &&
-        rp::aligned16(bias)) {
-        ep.res_post = nullptr;
-        ep.red = 1;
-    }
     Geom g{};
     g.M = M; g.N = N; g.K = K;
     int ntiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);

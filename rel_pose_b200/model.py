@@ -336,10 +336,7 @@ class ViTEss(nn.Module):
             return self._block_chained(blk, blk.attn, x, xn, next_norm, P)
         qkv = self._ln_qkv_tc(x, blk.norm1, blk.attn.qkv, P)
         _, a = ops.self_attention_tc(qkv, planes_out=P)
-        # x is the residual stream's own buffer (the CNN's token tensor / the previous Block's output): updated in place
-        # unless the caller collects per-stage tensors, which must stay distinct
-        x, _ = ops.linear_tc(a, self._planes(blk.attn.proj.weight, P), blk.attn.proj.bias, residual=x,
-                             inplace=self.__dict__.get("_proj_inplace", False))
+        x, _ = ops.linear_tc(a, self._planes(blk.attn.proj.weight, P), blk.attn.proj.bias, residual=x)
         return self._mlp_tc(blk, x, P), None
 
     def _block_chained(self, blk, attn, x, xn, next_norm, P, cross=False):
@@ -419,8 +416,7 @@ class ViTEss(nn.Module):
             return self._block_chained(blk, ca, x, xn, None, P, cross=True)[0]
         qkv = self._ln_qkv_tc(x, blk.norm1, ca.qkv, P)
         _, a = ops.self_attention_tc(qkv, planes_out=P, cross=True)
-        x, _ = ops.linear_tc(a, self._planes(ca.proj.weight, P), ca.proj.bias, residual=x,
-                             inplace=self.__dict__.get("_proj_inplace", False))
+        x, _ = ops.linear_tc(a, self._planes(ca.proj.weight, P), ca.proj.bias, residual=x)
         return self._mlp_tc(blk, x, P)
 
     def _pool_head_params(self):
@@ -531,7 +527,6 @@ class ViTEss(nn.Module):
             if stages is not None:
                 stages["tokens"] = x if self.cnn_only else x - vt.pos_embed
             xn = None                                                         # norm1(x) of the next Block as bf16 planes
-            self.__dict__["_proj_inplace"] = stages is None                   # see _block
             for i in range(0 if self.cnn_only else self.transformer_depth - 1):   # A5
                 x, xn = self._block(vt.blocks[i], x, xn, vt.blocks[i + 1].norm1)
                 if stages is not None:

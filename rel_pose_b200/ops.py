@@ -393,10 +393,8 @@ def layernorm_planes(x, gamma, beta, eps=1e-6, P=2):
     return out
 
 
-def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f32=True, planes_out=0, inplace=False):
-    """tcgen05 GEMM: a_planes [P,...,K] bf16, w_planes [P,N,K] bf16 -> (float32 [...,N] | None, planes | None).
-    inplace (with a residual, float32 output only, no activation): the result is written INTO `residual` (the residual stream
-    is updated in place by reductions at the memory side; same bits as the out-of-place call) and that tensor is returned."""
+def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f32=True, planes_out=0):
+    """tcgen05 GEMM: a_planes [P,...,K] bf16, w_planes [P,N,K] bf16 -> (float32 [...,N] | None, planes | None)."""
     _req(a_planes, "a_planes", torch.bfloat16); _req(w_planes, "w_planes", torch.bfloat16)
     P = a_planes.shape[0]
     assert w_planes.shape[0] == P and w_planes.dim() == 3
@@ -409,11 +407,7 @@ def linear_tc(a_planes, w_planes, bias=None, act=ACT_NONE, residual=None, want_f
     if residual is not None:
         _req(residual, "residual")
         assert residual.numel() == M * N
-    inplace = bool(inplace and residual is not None and want_f32 and not planes_out and act == ACT_NONE and N % 16 == 0)
-    if inplace:
-        out = residual.view(lead + (N,))
-    else:
-        out = torch.empty(lead + (N,), dtype=torch.float32, device=a_planes.device) if want_f32 else None
+    out = torch.empty(lead + (N,), dtype=torch.float32, device=a_planes.device) if want_f32 else None
     outp = torch.empty((planes_out,) + lead + (N,), dtype=torch.bfloat16, device=a_planes.device) if planes_out else None
     dev, st = _ctx(a_planes)
     _tbegin(f"linear_tc{'x3' if P == 2 else ''}[{N}x{K}]", 2.0 * M * N * K,

@@ -108,23 +108,6 @@ def test_linear_tc_splitk(M, N, K, act):
     assert torch.equal(out, again)
 
 
-@pytest.mark.parametrize("P", [1, 2])
-@pytest.mark.parametrize("M,N,K", [(1152, 192, 192), (140, 192, 192), (73728, 192, 192), (300, 208, 72), (77, 64, 768)])
-def test_linear_tc_inplace_residual_is_bit_identical(P, M, N, K):
-    """x += a W^T + b (attention projection, vision_transformer.py:350): the in-place call (16-byte reductions at the memory
-    side, residual == output) must give the bits of the out-of-place load-add-store epilogue; ragged last tiles included."""
-    a = rnd(51, M, K); w = rnd(52, N, K, scale=1.0 / np.sqrt(K)); b = rnd(53, N, scale=0.1); r = rnd(54, M, N)
-    ap = ops.split_planes(cu(a), P); wp = ops.split_planes(cu(w), P)
-    ref, _ = ops.linear_tc(ap, wp, cu(b), residual=cu(r))
-    x = cu(r)
-    out, _ = ops.linear_tc(ap, wp, cu(b), residual=x, inplace=True)
-    torch.cuda.synchronize()
-    assert out.data_ptr() == x.data_ptr()
-    assert torch.equal(out, ref)
-    y = a.astype(np.float64) @ w.astype(np.float64).T + b + r
-    assert np.abs(out.cpu().numpy() - y).max() <= (3e-5 if P == 2 else 2e-2) * np.abs(y).max() * max(1.0, (K / 192.0) ** 0.5)
-
-
 def test_linear_tc_only_planes_output():
     a = rnd(9, 256, 192); w = rnd(10, 768, 192, scale=0.07)
     out, outp = ops.linear_tc(ops.split_planes(cu(a), 2), ops.split_planes(cu(w), 2), None, act=1, want_f32=False, planes_out=2)
