@@ -382,6 +382,7 @@ regressor_tail2_kernel(const float* __restrict__ h, const float* __restrict__ W1
     const int rank = (int)cluster.block_rank();                      // = blockIdx.x % 8
     const int row0 = (blockIdx.x / RT2_ROWS) * RT2_ROWS;
     rp::pdl_launch_dependents();
+    cluster.barrier_arrive();                                        // phase 1: "this CTA is running" (awaited before the first remote write)
     rp::pdl_wait();
     // the CTA's slice of the layer-1 weight: 8192 16-byte asynchronous copies, all in flight together under the loads of h
 #pragma unroll
@@ -423,7 +424,9 @@ regressor_tail2_kernel(const float* __restrict__ h, const float* __restrict__ W1
 #pragma unroll
     for (int r = 0; r < RT2_ROWS; ++r) part[ks][r][jj] = acc[r];
     __syncthreads();
-    // [8 rows x 64 units] of this CTA: slices summed in order, bias, ReLU; row r goes to CTA r of the cluster
+    // [8 rows x 64 units] of this CTA: slices summed in order, bias, ReLU; row r goes to CTA r of the cluster.  Distributed shared
+    // memory may only be written once the owning CTA has started: every CTA arrived at phase 1 as its first action.
+    cluster.barrier_wait();
     for (int e = tid; e < RT2_ROWS * RT2_J; e += RT2_THREADS) {
         const int r = e / RT2_J, c = e % RT2_J;
         float v = part[0][r][c];
